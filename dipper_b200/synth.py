@@ -1,0 +1,155 @@
+"""Seeded synthetic "alisim-shaped" inputs for tests and bench.py.
+
+iqtree2/alisim is not installed, so the generator lives here: Yule-Harding tree, Exp
+branch lengths clipped to [min,max], JC69 substitutions (uniformisation), optional
+Gamma(0.5)x4 + invariant-site rate heterogeneity, gap runs + gap columns.  Codes are
+the reference's 4-bit alphabet: A0 C1 G2 T3, 4 = anything else
+(src/fourBitCompressor.cpp:17-36).
+"""
+import numpy as np
+
+REGIMES = {
+    # name: (min, mean, max) branch length in substitutions/site
+    "alisim": (2e-6, 2e-5, 2e-4),     # scripts/alisim.sh-like: tie-heavy, many identical tips
+    "tiefree": (1e-3, 1e-2, 1e-1),    # used for the strict RF = 0 gates and the bench
+}
+
+
+def yule_tree(n, rng, regime="tiefree"):
+    """Returns (parent, bl, children, leaf_nodes): nodes 0..2n-2, root = 0."""
+    lo, mean, hi = REGIMES[regime]
+    parent = [-1]
+    children = [[]]
+    leaves = [0]
+    while len(leaves) < n:
+        k = int(rng.integers(0, len(leaves)))
+        v = leaves[k]
+        a, b = len(parent), len(parent) + 1
+        parent += [v, v]
+        children += [[], []]
+        children[v] = [a, b]
+        leaves[k] = a
+        leaves.append(b)
+    m = len(parent)
+    bl = np.clip(rng.exponential(mean, m), lo, hi)
+    bl[0] = 0.0
+    return np.array(parent), bl, children, leaves
+
+
+def evolve(n, L, seed=1, regime="tiefree", rate_het=False, gap_cols=0.03, gap_runs=True, tree=None):
+    """uint8 codes [n, L] for tips in tree-leaf order shuffled by the seed, plus the tree.
+
+    Returns (codes, info) with info = dict(parent, bl, children, leaves, order) where
+    order[i] = tree node of output row i.
+    """
+    rng = np.random.default_rng(seed)
+    parent, bl, children, leaves = tree if tree is not None else yule_tree(n, rng, regime)
+    if rate_het:
+        cat = np.array([0.0334, 0.2519, 0.8203, 2.8944])  # Gamma(alpha=0.5) 4-category means
+        rates = cat[rng.integers(0, 4, L)]
+        rates[rng.random(L) < 0.2] = 0.0
+        rates = rates / max(rates.mean(), 1e-12)
+        cdf = np.cumsum(rates) / rates.sum()
+    order = np.array(leaves)
+    rng.shuffle(order)
+    row_of = {int(v): i for i, v in enumerate(order)}
+    codes = np.empty((n, L), np.uint8)
+    root_seq = rng.integers(0, 4, L).astype(np.uint8)
+    stack = [(0, root_seq)]
+    while stack:
+        v, seq = stack.pop()
+        if not children[v]:
+            codes[row_of[v]] = seq
+            continue
+        for c in children[v]:
+            s = seq.copy()
+            ev = rng.poisson(L * bl[c] * 4.0 / 3.0)
+            if ev:
+                if rate_het:
+                    pos = np.searchsorted(cdf, rng.random(ev))
+                else:
+                    pos = rng.integers(0, L, ev)
+                s[pos] = rng.integers(0, 4, ev).astype(np.uint8)
+            stack.append((c, s))
+    if gap_cols:
+        ncol = int(L * gap_cols)
+        if ncol:
+            cols = rng.choice(L, ncol, replace=False)
+            for c in cols:
+                codes[rng.random(n) < 0.5, c] = 4
+    if gap_runs:
+        for i in range(n):
+            for _ in range(int(rng.integers(0, 3))):
+                st = int(rng.integers(0, L))
+                ln = int(rng.integers(1, 51))
+                codes[i, st:st + ln] = 4
+    return codes, dict(parent=parent, bl=bl, children=children, leaves=leaves, order=order)
+
+
+_LET = np.frombuffer(b"ACGT-", np.uint8)
+
+
+def codes_to_strings(codes):
+    return [_LET[row].tobytes().decode() for row in codes]
+
+
+def names(n):
+    return ["T%d" % (i + 1) for i in range(n)]
+
+
+def pack4_np(codes):
+    """[n, L] codes -> uint64 [n, ceil(L/16)], bit-identical to fourBitCompressor."""
+    n, L = codes.shape
+    W = (L + 15) // 16
+    out = np.zeros((n, W), np.uint64)
+    sh = (np.arange(16, dtype=np.uint64) * np.uint64(4))
+    step = max(1, (1 << 24) // max(W * 16, 1))
+    for r0 in range(0, n, step):
+        blk = codes[r0:r0 + step]
+        pad = np.zeros((blk.shape[0], W * 16), np.uint64)
+        pad[:, :L] = blk
+        out[r0:r0 + step] = (pad.reshape(blk.shape[0], W, 16) << sh).sum(axis=2, dtype=np.uint64)
+    return out
+
+
+def pack2_np(seq_codes):
+    """1-D codes (0..3; anything else -> 0) -> uint64 [ceil(len/32)], as twoBitCompressor."""
+    L = len(seq_codes)
+    W = (L + 31) // 32
+    pad = np.zeros(W * 32, np.uint64)
+    c = np.asarray(seq_codes, np.uint64)
+    pad[:L] = np.where(c < 4, c, 0)
+    sh = (np.arange(32, dtype=np.uint64) * np.uint64(2))
+    return (pad.reshape(W, 32) << sh).sum(axis=1, dtype=np.uint64)
+
+
+def unaligned(codes):
+    """Strip gap codes: list of 1-D code arrays (ragged)."""
+    return [row[row < 4] for row in codes]
+
+
+def flatten2(seqs2):
+    """Ragged 2-bit packed sequences -> (flat words, word offsets, lengths in bases)."""
+    packed = [pack2_np(s) for s in seqs2]
+    lens = np.array([len(s) for s in seqs2], np.uint64)
+    offs = np.zeros(len(seqs2), np.uint64)
+    if len(packed) > 1:
+        offs[1:] = np.cumsum([len(p) for p in packed[:-1]])
+    flat = np.concatenate(packed) if packed else np.zeros(0, np.uint64)
+    return flat, offs, lens
+
+
+def write_fasta(path, names_, seqs):
+    with open(path, "w") as f:
+        for nm, s in zip(names_, seqs):
+            f.write(">%s\n%s\n" % (nm, s))
+
+
+def write_phylip(path, names_, D, lower=True):
+    """`%.6f` PHYLIP text; lower-triangular rows carry j < i entries (src/matrix_reader.cu:23-42)."""
+    n = len(names_)
+    with open(path, "w") as f:
+        f.write("%d\n" % n)
+        for i in range(n):
+            vals = D[i, :i] if lower else D[i]
+            f.write(names_[i] + (" " if len(vals) else "") + " ".join("%.6f" % v for v in vals) + "\n")

@@ -1,0 +1,820 @@
+/*
+ * dipper_oracle.c -- CPU restatement of DIPPER's hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity oracle for dipper_b200.  It is linked/loaded only by
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs.  The product path (libdipper_b200.so) never calls into it.
+ *
+ * Parity status: the reference ships no golden vectors or tests, so
+ * this oracle is pinned two ways:
+ *   (1) MurmurHash3_x64_128 against the public SMHasher known answers
+ *       (tests/test_oracle.py) and
+ *   (2) against outputs of the reference's own CUDA objects built by
+ *       oracle/build_ref.sh into oracle/_ref/ and run on the GPU box
+ *       (tests/test_ref_parity.py, -m gpu).
+ *
+ * Every function cites the reference file:line (paths relative to /root/reference)
+ * whose behaviour it restates.  Nothing here is copied from the reference; loops
+ * are re-derived from SURVEY.md Appendix A.
+ *
+ * Build: gcc -O2 -fopenmp -ffp-contract=off -shared -fPIC (see oracle/Makefile).
+ * -ffp-contract=off keeps a*b+c un-fused: the reference's NJ / placement
+ * expressions contain no multiply feeding an add, so nvcc's FMA
+ * contraction does not change them either.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------- */
+/* A.1 encoders                                                              */
+/* ------------------------------------------------------------------------- */
+
+/* src/fourBitCompressor.cpp:5-41 : A0 C1 G2 T/U3 other 4; 16 sites per word, LSB first */
+ORC_API void orc_pack4(const char *seq, uint64_t len, uint64_t *out) {
+    uint64_t nw = (len + 15) / 16;
+    for (uint64_t w = 0; w < nw; w++) out[w] = 0;
+    for (uint64_t s = 0; s < len; s++) {
+        uint64_t code;
+        switch (seq[s]) {
+            case 'A': code = 0; break;
+            case 'C': code = 1; break;
+            case 'G': code = 2; break;
+            case 'T': case 'U': code = 3; break;
+            default: code = 4; break;
+        }
+        out[s >> 4] |= code << (4 * (s & 15));
+    }
+}
+
+/* src/twoBitCompressor.cpp:5-41 : same letters, anything else -> 0; 32 bases per word */
+ORC_API void orc_pack2(const char *seq, uint64_t len, uint64_t *out) {
+    uint64_t nw = (len + 31) / 32;
+    for (uint64_t w = 0; w < nw; w++) out[w] = 0;
+    for (uint64_t s = 0; s < len; s++) {
+        uint64_t code;
+        switch (seq[s]) {
+            case 'C': code = 1; break;
+            case 'G': code = 2; break;
+            case 'T': case 'U': code = 3; break;
+            default: code = 0; break;
+        }
+        out[s >> 5] |= code << (2 * (s & 31));
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* A.2 aligned pair statistics and distance models                           */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+    int useful;   /* sites where either is ACGT            src/MSA.cu:96,121 */
+    int match;    /* sites both ACGT and equal             src/MSA.cu:97,122 */
+    int tot;      /* sites both ACGT                       DC/msa.cu:114     */
+    int ts;       /* both valid, differ, same parity       DC/msa.cu:161     */
+    int tv;       /* both valid, differ, other parity      DC/msa.cu:162     */
+    int frac[4];  /* code occurrences over both-valid sites, both seqs  DC/msa.cu:115 */
+    int pr[4];    /* unordered pairs {A,G},{A,T},{C,G},{C,T}             DC/msa.cu:121-124 */
+    int gc_row;   /* mismatching sites where the ROW seq is C/G         DC/msa.cu:195 */
+    int gc_col;   /* mismatching sites where the COLUMN seq is C/G      DC/msa.cu:196 */
+} orc_pair_stats;
+
+static inline int nib(const uint64_t *s, int site) { return (int)((s[site >> 4] >> (4 * (site & 15))) & 15); }
+
+/* row = the sequence called rowId in the reference, col = the j<rowId partner */
+ORC_API void orc_pair_stats_compute(const uint64_t *row, const uint64_t *col, int seqLen, orc_pair_stats *st) {
+    memset(st, 0, sizeof(*st));
+    for (int s = 0; s < seqLen; s++) {
+        int r = nib(row, s), c = nib(col, s);
+        if (r < 4 || c < 4) st->useful++;
+        if (r < 4 && r == c) st->match++;
+        if (r >= 4 || c >= 4) continue;
+        st->tot++;
+        st->frac[r]++; st->frac[c]++;
+        if (r == c) continue;
+        if ((r & 1) == (c & 1)) st->ts++; else st->tv++;
+        int lo = r < c ? r : c, hi = r < c ? c : r;
+        if (lo == 0 && hi == 2) st->pr[0]++;
+        else if (lo == 0 && hi == 3) st->pr[1]++;
+        else if (lo == 1 && hi == 2) st->pr[2]++;
+        else if (lo == 1 && hi == 3) st->pr[3]++;
+        if (r == 1 || r == 2) st->gc_row++;
+        if (c == 1 || c == 2) st->gc_col++;
+    }
+}
+
+/* distance from the statistics.  types: 1 p, 2 JC (src/MSA.cu:233-235);
+ * 3 Tajima-Nei, 4 K2P, 5 Tamura, 6 Jin-Nei (DC/msa.cu:238-264). */
+ORC_API double orc_dist_from_stats(const orc_pair_stats *st, int type) {
+    if (type == 1 || type == 2) {
+        double p = 1 - (double)st->match / st->useful;
+        if (type == 1) return p;
+        return -0.75 * log(1.0 - p / 0.75);
+    }
+    if (type == 3) {
+        double fr[4];
+        for (int i = 0; i < 4; i++) fr[i] = (double)st->frac[i] / st->tot / 2.0;
+        double h = 0;
+        h += 0.5 * st->pr[0] * fr[0] * fr[2];
+        h += 0.5 * st->pr[1] * fr[0] * fr[3];
+        h += 0.5 * st->pr[2] * fr[1] * fr[2];
+        h += 0.5 * st->pr[3] * fr[1] * fr[3];
+        double D = (double)(st->tot - st->match) / st->tot;
+        double b = 0.5 * (1.0 - fr[0] * fr[0] - fr[2] * fr[2] + D * D / h);
+        return -b * log(1.0 - D / b);
+    }
+    if (type == 4 || type == 6) {
+        double pp = (double)st->ts / st->tot, qq = (double)st->tv / st->tot;
+        if (type == 4) return -0.5 * log((1 - 2 * pp - qq) * sqrt(1 - 2 * qq));
+        return 0.5 * (1.0 / (1 - 2 * pp - qq) + 0.5 / (1 - qq * 2) - 1.5);
+    }
+    if (type == 5) {
+        double pp = (double)st->ts / st->tot, qq = (double)st->tv / st->tot;
+        double c = (double)st->gc_row / st->tot + (double)st->gc_col / st->tot
+                 - 2 * (double)st->gc_row * (double)st->gc_col / st->tot / st->tot;
+        return -c * log(1 - pp / c - qq) - 0.5 * (1 - c) * log(1 - 2 * qq);
+    }
+    return 0.0;
+}
+
+/* counts for a rectangle of pairs: test hook twin of dipb_msa_counts */
+ORC_API void orc_msa_counts(const uint64_t *seqs, int n, int seqLen, int i0, int i1, int j0, int j1,
+                            int32_t *match, int32_t *useful) {
+    int comp = (seqLen + 15) / 16;
+    (void)n;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int i = i0; i < i1; i++)
+        for (int j = j0; j < j1; j++) {
+            orc_pair_stats st;
+            orc_pair_stats_compute(seqs + (size_t)i * comp, seqs + (size_t)j * comp, seqLen, &st);
+            match[(size_t)(i - i0) * (j1 - j0) + (j - j0)] = st.match;
+            useful[(size_t)(i - i0) * (j1 - j0) + (j - j0)] = st.useful;
+        }
+}
+
+/* one reference-shaped row: out[j] = d(row, j) for j < row.  src/MSA.cu:271-282 */
+ORC_API void orc_msa_dist_row(const uint64_t *seqs, int seqLen, int row, int type, double *out) {
+    int comp = (seqLen + 15) / 16;
+    for (int j = 0; j < row; j++) {
+        orc_pair_stats st;
+        orc_pair_stats_compute(seqs + (size_t)row * comp, seqs + (size_t)j * comp, seqLen, &st);
+        out[j] = orc_dist_from_stats(&st, type);
+    }
+}
+
+/* Word-parallel twin of the (useful, match) count used only to make the timed CPU
+ * baseline a fair one (the nibble loop above is the readable statement).  Verified
+ * against orc_pair_stats_compute in tests/test_oracle.py. */
+static inline void fast_counts(const uint64_t *a, const uint64_t *b, int seqLen, int *useful, int *match) {
+    int comp = (seqLen + 15) / 16, u = 0, m = 0;
+    const uint64_t L = 0x1111111111111111ULL;
+    for (int w = 0; w < comp; w++) {
+        uint64_t x = a[w], y = b[w];
+        uint64_t mask = ~0ULL;
+        if (w == comp - 1 && (seqLen & 15)) mask = (1ULL << (4 * (seqLen & 15))) - 1;
+        uint64_t ia = (x >> 2) & L, ib = (y >> 2) & L;      /* bit2 set <=> code 4 (invalid) */
+        uint64_t d = x ^ y;
+        uint64_t ne = (d | (d >> 1) | (d >> 2) | (d >> 3)) & L;
+        u += __builtin_popcountll(~(ia & ib) & L & mask);
+        m += __builtin_popcountll(~ne & ~ia & L & mask);
+    }
+    *useful = u; *match = m;
+}
+
+/* full matrix as NJDeviceArrays::getDismatrix + fillDismatrix produce it
+ * (src/neighborJoining.cu:20-85): lower triangle from rows, mirrored, zero diagonal. */
+ORC_API void orc_msa_dist_matrix(const uint64_t *seqs, int n, int seqLen, int type, double *D) {
+    int comp = (seqLen + 15) / 16;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int i = 0; i < n; i++) {
+        D[(size_t)i * n + i] = 0;
+        for (int j = 0; j < i; j++) {
+            double d;
+            if (type == 1 || type == 2) {
+                orc_pair_stats st;
+                fast_counts(seqs + (size_t)i * comp, seqs + (size_t)j * comp, seqLen, &st.useful, &st.match);
+                d = orc_dist_from_stats(&st, type);
+            } else {
+                orc_pair_stats st;
+                orc_pair_stats_compute(seqs + (size_t)i * comp, seqs + (size_t)j * comp, seqLen, &st);
+                d = orc_dist_from_stats(&st, type);
+            }
+            D[(size_t)i * n + j] = d;
+            D[(size_t)j * n + i] = d;
+        }
+    }
+}
+
+ORC_API void orc_fast_counts(const uint64_t *a, const uint64_t *b, int seqLen, int *useful, int *match) {
+    fast_counts(a, b, seqLen, useful, match);
+}
+
+/* ------------------------------------------------------------------------- */
+/* A.3 sketching                                                             */
+/* ------------------------------------------------------------------------- */
+
+static inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+static inline uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return k;
+}
+
+/* Public-domain MurmurHash3_x64_128 (Appleby), as used by src/mash.cu:159-236.
+ * Written from the published algorithm; pinned by SMHasher vectors in tests. */
+ORC_API void orc_murmur3_x64_128(const void *key, int len, uint32_t seed, uint64_t out[2]) {
+    const uint8_t *data = (const uint8_t *)key;
+    int nblocks = len / 16;
+    uint64_t h1 = seed, h2 = seed;
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    for (int i = 0; i < nblocks; i++) {
+        uint64_t k1, k2;
+        memcpy(&k1, data + 16 * i, 8);
+        memcpy(&k2, data + 16 * i + 8, 8);
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    const uint8_t *tail = data + nblocks * 16;
+    uint64_t k1 = 0, k2 = 0;
+    int rem = len & 15;
+    for (int i = rem - 1; i >= 8; i--) k2 ^= (uint64_t)tail[i] << (8 * (i - 8));
+    if (rem > 8) { k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+    for (int i = (rem > 8 ? 7 : rem - 1); i >= 0; i--) k1 ^= (uint64_t)tail[i] << (8 * i);
+    if (rem > 0) { k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+    h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2; h2 += h1;
+    out[0] = h1; out[1] = h2;
+}
+
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* canonical k-mer hash at start position j.  src/mash.cu:239-258,298-323 */
+ORC_API uint64_t orc_kmer_hash(const uint64_t *seq2, uint64_t j, int k) {
+    char fwd[32], rev[32];
+    static const char lut[4] = {'A', 'C', 'G', 'T'};
+    for (int t = 0; t < k; t++) {
+        uint64_t p = j + t;
+        int code = (int)((seq2[p >> 5] >> (2 * (p & 31))) & 3);
+        fwd[t] = lut[code];
+        rev[k - 1 - t] = lut[3 - code];
+    }
+    const char *use = memcmp(fwd, rev, (size_t)k) <= 0 ? fwd : rev;
+    uint64_t h[2];
+    orc_murmur3_x64_128(use, k, 42, h);
+    return h[0];
+}
+
+/* bottom-s multiset of canonical k-mer hashes, ascending, padded with ~0.
+ * src/mash.cu:260-369 (duplicates are kept: the reference never de-duplicates). */
+ORC_API void orc_sketch(const uint64_t *seq2, uint64_t len, int k, int s, uint64_t *out) {
+    for (int t = 0; t < s; t++) out[t] = ~0ULL;
+    if (len < (uint64_t)k) return;
+    uint64_t nk = len - k + 1;
+    uint64_t *h = (uint64_t *)malloc(nk * sizeof(uint64_t));
+    for (uint64_t j = 0; j < nk; j++) h[j] = orc_kmer_hash(seq2, j, k);
+    qsort(h, nk, sizeof(uint64_t), cmp_u64);
+    for (uint64_t t = 0; t < nk && t < (uint64_t)s; t++) out[t] = h[t];
+    free(h);
+}
+
+/* all sketches, row-major [n][s]; seqs ragged, offsets in words (exclusive scan of ceil(len/32)).
+ * src/mash.cu:14-122 layout. */
+ORC_API void orc_sketch_all(const uint64_t *flat, const uint64_t *offsets, const uint64_t *lens, int n, int k, int s,
+                            uint64_t *out) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < n; i++) orc_sketch(flat + offsets[i], lens[i], k, s, out + (size_t)i * s);
+}
+
+/* A.4 Mash distance: A = the column sequence (idx < rowId), B = the row sequence.
+ * src/mash.cu:437-454, row-major twin DC/mash.cpp:23-39. */
+ORC_API double orc_mash_dist(const uint64_t *A, const uint64_t *B, int s, int k) {
+    int uni = 0, inter = 0, b = 0;
+    for (int a = 0; uni < s; a++, uni++) {
+        uint64_t av = A[a];
+        while (uni < s && b < s) {
+            uint64_t bv = B[b];
+            if (bv > av) break;
+            if (bv < av) uni++; else inter++;
+            b++;
+        }
+        if (uni >= s) break;
+    }
+    double jac = (inter > 1 ? (double)inter : 1.0) / uni;
+    double d = fabs(log(2.0 * jac / (1.0 + jac)) / k);
+    return d < 1.0 ? d : 1.0;
+}
+
+ORC_API void orc_mash_inter_uni(const uint64_t *A, const uint64_t *B, int s, int *inter_out, int *uni_out) {
+    int uni = 0, inter = 0, b = 0;
+    for (int a = 0; uni < s; a++, uni++) {
+        uint64_t av = A[a];
+        while (uni < s && b < s) {
+            uint64_t bv = B[b];
+            if (bv > av) break;
+            if (bv < av) uni++; else inter++;
+            b++;
+        }
+        if (uni >= s) break;
+    }
+    *inter_out = inter; *uni_out = uni;
+}
+
+ORC_API void orc_mash_dist_row(const uint64_t *sk, int s, int k, int row, double *out) {
+    for (int j = 0; j < row; j++) out[j] = orc_mash_dist(sk + (size_t)j * s, sk + (size_t)row * s, s, k);
+}
+
+ORC_API void orc_mash_dist_matrix(const uint64_t *sk, int n, int s, int k, double *D) {
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int i = 0; i < n; i++) {
+        D[(size_t)i * n + i] = 0;
+        for (int j = 0; j < i; j++) {
+            double d = orc_mash_dist(sk + (size_t)j * s, sk + (size_t)i * s, s, k);
+            D[(size_t)i * n + j] = d;
+            D[(size_t)j * n + i] = d;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* A.5 neighbor joining                                                      */
+/* ------------------------------------------------------------------------- */
+
+/* The reference accumulates U with fp64 atomics in unspecified order
+ * (src/neighborJoining.cu:106,176,190).  dipper_b200 fixes one order and this oracle
+ * restates the same one so that trees are bit-reproducible:
+ *   block of 1024 consecutive addends -> 32 groups of 32, each reduced by the
+ *   stride-halving tree (16,8,4,2,1); the 32 group sums reduced by the same tree;
+ *   block results added in ascending block order. */
+static double tree32(double *a) {
+    for (int s = 16; s >= 1; s >>= 1)
+        for (int t = 0; t < s; t++) a[t] += a[t + s];
+    return a[0];
+}
+static double canon_block_sum(const double *v, int cnt) { /* cnt <= 1024, missing slots are +0.0 */
+    double g[32];
+    for (int w = 0; w < 32; w++) {
+        double a[32];
+        for (int l = 0; l < 32; l++) { int t = w * 32 + l; a[l] = t < cnt ? v[t] : 0.0; }
+        g[w] = tree32(a);
+    }
+    return tree32(g);
+}
+ORC_API double orc_canon_sum(const double *v, int n) {
+    double acc = 0.0;
+    for (int b = 0; b * 1024 < n; b++) {
+        int cnt = n - b * 1024; if (cnt > 1024) cnt = 1024;
+        acc += canon_block_sum(v + (size_t)b * 1024, cnt);
+    }
+    return acc;
+}
+
+typedef struct { double val; int i, j; } nj_cand;
+
+/* reference total order on equal values: (rowblock(i), j mod 256, j, i)
+ * src/neighborJoining.cu:124-146 + thrust::min_element first-minimum (:214) */
+static inline int rowblock_of(int i, int n) {
+    int sz = n / 256, rem = n % 256;
+    /* blocks b < rem own sz+1 rows, the rest own sz rows */
+    long long split = (long long)(sz + 1) * rem;
+    if (i < split) return i / (sz + 1);
+    if (sz == 0) return 256; /* unreachable: i < n */
+    return rem + (int)((i - split) / sz);
+}
+static inline int cand_before(const nj_cand *a, const nj_cand *b, int n) {
+    if (a->val < b->val) return 1;
+    if (a->val > b->val) return 0;
+    int ba = rowblock_of(a->i, n), bb = rowblock_of(b->i, n);
+    if (ba != bb) return ba < bb;
+    int ta = a->j & 255, tb = b->j & 255;
+    if (ta != tb) return ta < tb;
+    if (a->j != b->j) return a->j < b->j;
+    return a->i < b->i;
+}
+
+/* D: n*n fp64 row-major, symmetric, zero diagonal (copied; caller's buffer untouched).
+ * Outputs for internal nodes n..2n-2 at index (node-n): children ids and lengths in
+ * the order the reference pushes them (src/neighborJoining.cu:233-234,248-249).
+ * Returns 0, or -1 on allocation failure. */
+ORC_API int orc_nj(const double *Din, int n, int32_t *child0, int32_t *child1, double *len0, double *len1) {
+    size_t N = (size_t)n;
+    double *D = (double *)malloc(N * N * sizeof(double));
+    double *U = (double *)malloc(N * sizeof(double));
+    double *val = (double *)malloc(N * sizeof(double));
+    int *realID = (int *)malloc(N * sizeof(int));
+    if (!D || !U || !val || !realID) return -1;
+    memcpy(D, Din, N * N * sizeof(double));
+    for (int i = 0; i < n; i++) realID[i] = i;
+    /* calculateU :94-115 (diagonal is zero, so including it adds +0.0) */
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) U[i] = orc_canon_sum(D + (size_t)i * N, n);
+    int ID = n;
+    for (int it = 0; it < n - 2; it++) {
+        int m = n - it; /* active size */
+        double denom = (double)(m - 2);
+        nj_cand best = {10000.0, 0, 0};
+        /* findMinDist :117-148: candidate (i,j), i != j, value (d - U[i]/(m-2)) - U[j]/(m-2) */
+#pragma omp parallel
+        {
+            nj_cand loc = {10000.0, 0, 0};
+            int have = 0;
+#pragma omp for schedule(static) nowait
+            for (int i = 0; i < m; i++) {
+                double ui = U[i] / denom;
+                const double *row = D + (size_t)i * N;
+                for (int j = 0; j < m; j++) {
+                    if (i == j) continue;
+                    double t = row[j] - ui - U[j] / denom;
+                    if (t < 10000.0 && (!have || t <= loc.val)) {
+                        nj_cand c = {t, i, j};
+                        if (!have || cand_before(&c, &loc, m)) { loc = c; have = 1; }
+                    }
+                }
+            }
+#pragma omp critical
+            { if (have && (best.val == 10000.0 ? 1 : cand_before(&loc, &best, m))) best = loc; }
+        }
+        int x = best.i, y = best.j;
+        if (x > y) { int t = x; x = y; y = t; }
+        double dxy = D[(size_t)x * N + y];
+        double blX = (dxy + U[x] / denom - U[y] / denom) * 0.5;
+        double blY = dxy - blX;
+        if (blX < 0) { blY += blX; blX = 0; }
+        if (blY < 0) { blX += blY; blY = 0; }
+        child0[ID - n] = realID[x]; len0[ID - n] = blX;
+        child1[ID - n] = realID[y]; len1[ID - n] = blY;
+        realID[x] = ID++; realID[y] = realID[m - 1];
+        /* updateDisMatrix :161-194 */
+        int last = m - 1;
+        for (int i = 0; i < last; i++) {
+            if (i == x || i == y) { val[i] = 0.0; continue; }
+            double a = D[(size_t)x * N + i], b = D[(size_t)y * N + i];
+            double v = (a + b - dxy) * 0.5;
+            double far = D[(size_t)last * N + i];
+            U[i] += -a - b + v;
+            val[i] = v;
+            D[(size_t)x * N + i] = v; D[(size_t)i * N + x] = v;
+            D[(size_t)y * N + i] = far; D[(size_t)i * N + y] = far;
+        }
+        /* the old last row, now living at y (:184-192) */
+        {
+            double a = D[(size_t)x * N + last], b = D[(size_t)y * N + last];
+            double v = (a + b - dxy) * 0.5;
+            if (y != last) {
+                U[y] = U[last];
+                U[y] += -a - b + v;
+                val[y] = v;
+                D[(size_t)x * N + y] = v; D[(size_t)y * N + x] = v;
+            } else {
+                /* y is itself the last row: the reference's thread-0 block reads
+                 * d[y][last] = d[y][y] = 0 and writes d[x][y]; row y is dropped anyway. */
+                val[y] = 0.0;
+            }
+        }
+        /* U[x] = sum of the new row, canonical order over slots 0..last-1 (x and, when
+         * y==last, nothing else contribute +0.0) */
+        U[x] = orc_canon_sum(val, last);
+        D[(size_t)y * N + y] = 0.0;
+    }
+    double d01 = D[1];
+    child0[n - 2] = realID[0]; len0[n - 2] = d01 * 0.5;
+    child1[n - 2] = realID[1]; len1[n - 2] = d01 * 0.5;
+    free(D); free(U); free(val); free(realID);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* A.6 k-closest placement (K = 5)                                           */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+    int n;          /* total leaves (numSequences) */
+    int node_off;   /* internal node of tip i is i + node_off - 1 ; = n for src/, totalN for DC */
+    int *head, *e, *nxt, *belong, *cid;
+    double *len, *cdis;
+    int *q_id, *q_from; double *q_dis; /* BFS scratch */
+} orc_ptree;
+
+#define KC 5
+
+ORC_API orc_ptree *orc_ptree_new(int n) {
+    orc_ptree *t = (orc_ptree *)calloc(1, sizeof(orc_ptree));
+    size_t N = (size_t)n;
+    t->n = n; t->node_off = n;
+    t->head = (int *)malloc(2 * N * sizeof(int));
+    t->e = (int *)malloc(8 * N * sizeof(int));
+    t->nxt = (int *)malloc(8 * N * sizeof(int));
+    t->belong = (int *)malloc(8 * N * sizeof(int));
+    t->len = (double *)malloc(8 * N * sizeof(double));
+    t->cid = (int *)malloc(8 * N * KC * sizeof(int));
+    t->cdis = (double *)malloc(8 * N * KC * sizeof(double));
+    t->q_id = (int *)malloc(2 * N * sizeof(int));
+    t->q_from = (int *)malloc(2 * N * sizeof(int));
+    t->q_dis = (double *)malloc(2 * N * sizeof(double));
+    /* initialize :266-289 */
+    for (size_t i = 0; i < 2 * N; i++) t->head[i] = -1;
+    for (size_t i = 0; i < 8 * N; i++) {
+        t->e[i] = -1; t->nxt[i] = -1; t->belong[i] = -1; t->len[i] = 2;
+        for (int k = 0; k < KC; k++) { t->cid[i * KC + k] = -1; t->cdis[i * KC + k] = 2; }
+    }
+    return t;
+}
+ORC_API void orc_ptree_free(orc_ptree *t) {
+    if (!t) return;
+    free(t->head); free(t->e); free(t->nxt); free(t->belong); free(t->len);
+    free(t->cid); free(t->cdis); free(t->q_id); free(t->q_from); free(t->q_dis); free(t);
+}
+
+static void link_slot(orc_ptree *t, int slot, int from, int to, double l) {
+    t->e[slot] = to; t->len[slot] = l; t->nxt[slot] = t->head[from]; t->head[from] = slot; t->belong[slot] = from;
+}
+
+/* buildInitialTree :530-554 */
+ORC_API void orc_ptree_init2(orc_ptree *t, double d01) {
+    int nv = t->node_off;
+    link_slot(t, 0, 0, nv, d01 / 2);
+    link_slot(t, 1, 1, nv, d01 / 2);
+    link_slot(t, 2, nv, 0, d01 / 2);
+    link_slot(t, 3, nv, 1, d01 / 2);
+}
+
+/* updateClosestNodes :86-124, with the intended queue seed (slot 0 = (x,-1,0); App. B10) */
+ORC_API void orc_ptree_bfs(orc_ptree *t, int x) {
+    int l = 0, r = 0;
+    t->q_id[0] = x; t->q_dis[0] = 0; t->q_from[0] = -1;
+    while (l <= r) {
+        int node = t->q_id[l], fb = t->q_from[l];
+        double d = t->q_dis[l];
+        l++;
+        for (int s = t->head[node]; s != -1; s = t->nxt[s]) {
+            if (t->e[s] == fb) continue;
+            for (int j = 0; j < KC; j++) {
+                if (t->cdis[s * KC + j] > d) {
+                    for (int k = KC - 1; k > j; k--) {
+                        t->cdis[s * KC + k] = t->cdis[s * KC + k - 1];
+                        t->cid[s * KC + k] = t->cid[s * KC + k - 1];
+                    }
+                    t->cdis[s * KC + j] = d; t->cid[s * KC + j] = x;
+                    r++;
+                    t->q_id[r] = t->e[s]; t->q_dis[r] = d + t->len[s]; t->q_from[r] = node;
+                    break;
+                }
+            }
+        }
+    }
+}
+
+typedef struct { int slot; double frac; double add; } orc_place_cand;
+
+/* calculateBranchLength :309-358 for one slot */
+static int edge_candidate(const orc_ptree *t, const double *dis, int q, orc_place_cand *c) {
+    if (t->belong[q] < t->e[q]) return 0;
+    int x = t->belong[q], oth = t->e[q];
+    double d1 = 0, d2 = 0, v;
+    for (int k = 0; k < KC; k++)
+        if (t->cid[q * KC + k] != -1) { v = dis[t->cid[q * KC + k]] - t->cdis[q * KC + k]; if (v > d1) d1 = v; }
+    int r = t->head[oth];
+    while (t->e[r] != x) r = t->nxt[r];
+    for (int k = 0; k < KC; k++)
+        if (t->cid[r * KC + k] != -1) { v = dis[t->cid[r * KC + k]] - t->cdis[r * KC + k]; if (v > d2) d2 = v; }
+    double L = t->len[q];
+    double add = (d1 + d2 - L) / 2;
+    if (add < 0) add = 0;
+    d1 -= add; d2 -= add;
+    if (d1 < 0) d1 = 0;
+    if (d2 < 0) d2 = 0;
+    if (d1 > L) { add += d1 - L; d1 = L; }
+    if (d2 > L) { add += d2 - L; d2 = L; }
+    double rest = L - d1 - d2;
+    d1 += rest / 2; d2 += rest / 2;
+    c->slot = q; c->frac = d1; c->add = add;
+    return 1;
+}
+
+/* argmin over slots [0, nslots): non-candidates emit (0,0,2); first minimum wins (:326-329,:807) */
+ORC_API void orc_ptree_best_edge(const orc_ptree *t, const double *dis, int nslots, int *slot, double *frac, double *add) {
+    orc_place_cand best = {0, 0, 2};
+    int have = 0;
+    for (int q = 0; q < nslots; q++) {
+        orc_place_cand c = {0, 0, 2};
+        edge_candidate(t, dis, q, &c);
+        if (!have || c.add < best.add) { best = c; have = 1; }
+    }
+    *slot = best.slot; *frac = best.frac; *add = best.add;
+}
+
+/* updateTreeStructure :446-528 */
+ORC_API void orc_ptree_insert(orc_ptree *t, int eid, double fracLen, double addLen, int placeId, int edgeCount) {
+    int middle = placeId + t->node_off - 1, outside = placeId;
+    int x = t->belong[eid], y = t->e[eid];
+    double orig = t->len[eid];
+    int xe = -1, ye = -1;
+    for (int s = t->head[x]; s != -1; s = t->nxt[s])
+        if (t->e[s] == y) { t->e[s] = middle; t->len[s] = fracLen; xe = s; break; }
+    for (int s = t->head[y]; s != -1; s = t->nxt[s])
+        if (t->e[s] == x) { t->e[s] = middle; t->len[s] -= fracLen; ye = s; break; }
+    int c0 = edgeCount, c1 = edgeCount + 1, c2 = edgeCount + 2, c3 = edgeCount + 3;
+    link_slot(t, c0, middle, x, fracLen);
+    for (int k = 0; k < KC; k++)
+        if (t->cid[ye * KC + k] != -1) {
+            t->cid[c0 * KC + k] = t->cid[ye * KC + k];
+            t->cdis[c0 * KC + k] = t->cdis[ye * KC + k] + orig - fracLen;
+        }
+    link_slot(t, c1, middle, y, orig - fracLen);
+    for (int k = 0; k < KC; k++)
+        if (t->cid[xe * KC + k] != -1) {
+            t->cid[c1 * KC + k] = t->cid[xe * KC + k];
+            t->cdis[c1 * KC + k] = t->cdis[xe * KC + k] + fracLen;
+        }
+    link_slot(t, c2, outside, middle, addLen);
+    link_slot(t, c3, middle, outside, addLen);
+    int src[2] = {c1, c0};
+    for (int w = 0; w < 2; w++) {
+        int sidx = src[w];
+        for (int i = 0; i < KC; i++) {
+            if (t->cid[sidx * KC + i] == -1) break;
+            for (int j = 0; j < KC; j++)
+                if (t->cdis[c3 * KC + j] > t->cdis[sidx * KC + i]) {
+                    for (int k = KC - 1; k > j; k--) {
+                        t->cdis[c3 * KC + k] = t->cdis[c3 * KC + k - 1];
+                        t->cid[c3 * KC + k] = t->cid[c3 * KC + k - 1];
+                    }
+                    t->cdis[c3 * KC + j] = t->cdis[sidx * KC + i];
+                    t->cid[c3 * KC + j] = t->cid[sidx * KC + i];
+                    break;
+                }
+        }
+    }
+}
+
+/* findPlacementTree :646-854 driven by a caller-supplied row source:
+ * rows(ctx, i, out) must fill out[j] = d(i, j), j < i. */
+typedef void (*orc_row_fn)(void *ctx, int row, double *out);
+
+ORC_API orc_ptree *orc_place_all(int n, orc_row_fn rows, void *ctx) {
+    orc_ptree *t = orc_ptree_new(n);
+    double *dis = (double *)calloc((size_t)n, sizeof(double));
+    rows(ctx, 1, dis);
+    orc_ptree_init2(t, dis[0]);
+    int idx = 4;
+    orc_ptree_bfs(t, 0);
+    orc_ptree_bfs(t, 1);
+    for (int i = 2; i < n; i++) {
+        rows(ctx, i, dis);
+        int slot; double frac, add;
+        orc_ptree_best_edge(t, dis, 4 * i - 4, &slot, &frac, &add);
+        orc_ptree_insert(t, slot, frac, add, i, idx);
+        idx += 4;
+        orc_ptree_bfs(t, i);
+    }
+    free(dis);
+    return t;
+}
+
+/* matrix-backed convenience: D is n*n row-major */
+typedef struct { const double *D; int n; } mat_ctx;
+static void mat_rows(void *c, int row, double *out) {
+    mat_ctx *m = (mat_ctx *)c;
+    memcpy(out, m->D + (size_t)row * m->n, (size_t)row * sizeof(double));
+}
+ORC_API orc_ptree *orc_place_all_matrix(const double *D, int n) {
+    mat_ctx c = {D, n};
+    return orc_place_all(n, mat_rows, &c);
+}
+
+/* addQuery :858-990 on a tree already loaded with B backbone leaves (slots 0..4B-5) */
+ORC_API void orc_place_add_matrix(orc_ptree *t, const double *D, int n, int B) {
+    double *dis = (double *)calloc((size_t)n, sizeof(double));
+    int idx = 4 * B - 4;
+    for (int i = B; i < n; i++) {
+        memcpy(dis, D + (size_t)i * n, (size_t)i * sizeof(double));
+        int slot; double frac, add;
+        orc_ptree_best_edge(t, dis, 4 * i - 4, &slot, &frac, &add);
+        orc_ptree_insert(t, slot, frac, add, i, idx);
+        idx += 4;
+        orc_ptree_bfs(t, i);
+    }
+    free(dis);
+}
+
+/* raw array access for the Python side */
+ORC_API int *orc_ptree_head(orc_ptree *t) { return t->head; }
+ORC_API int *orc_ptree_e(orc_ptree *t) { return t->e; }
+ORC_API int *orc_ptree_nxt(orc_ptree *t) { return t->nxt; }
+ORC_API int *orc_ptree_belong(orc_ptree *t) { return t->belong; }
+ORC_API double *orc_ptree_len(orc_ptree *t) { return t->len; }
+ORC_API int *orc_ptree_cid(orc_ptree *t) { return t->cid; }
+ORC_API double *orc_ptree_cdis(orc_ptree *t) { return t->cdis; }
+
+/* initializeDeviceArrays(Tree*) :160-183 given a parsed backbone in parent-array form:
+ * post-order dfs over children lists; per non-root node two slots child->parent,
+ * parent->child.  children are given CSR-style in Newick order. */
+ORC_API void orc_ptree_load_backbone(orc_ptree *t, int root, const int *child_off, const int *child_idx,
+                                     const int *parent, const double *bl, int B) {
+    /* iterative post-order */
+    int cap = 4 * t->n + 16;
+    int *stack = (int *)malloc(cap * sizeof(int)), *state = (int *)malloc(cap * sizeof(int));
+    int sp = 0, edge = 0;
+    stack[0] = root; state[0] = 0; sp = 1;
+    while (sp) {
+        int node = stack[sp - 1];
+        int k = state[sp - 1];
+        int nc = child_off[node + 1] - child_off[node];
+        if (k < nc) {
+            state[sp - 1]++;
+            stack[sp] = child_idx[child_off[node] + k]; state[sp] = 0; sp++;
+            continue;
+        }
+        sp--;
+        if (parent[node] < 0) continue;
+        int x = node, y = parent[node];
+        link_slot(t, edge, x, y, bl[node]); edge++;
+        link_slot(t, edge, y, x, bl[node]); edge++;
+    }
+    free(stack); free(state);
+    for (int i = 0; i < B; i++) orc_ptree_bfs(t, i);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Newick writers                                                            */
+/* ------------------------------------------------------------------------- */
+
+typedef struct { char *p; size_t len, cap; } sbuf;
+static void sb_put(sbuf *b, const char *s, size_t n) {
+    if (b->len + n + 1 > b->cap) { while (b->len + n + 1 > b->cap) b->cap = b->cap ? b->cap * 2 : 4096; b->p = (char *)realloc(b->p, b->cap); }
+    memcpy(b->p + b->len, s, n); b->len += n; b->p[b->len] = 0;
+}
+static void sb_dbl(sbuf *b, double v) { char t[64]; int n = snprintf(t, sizeof t, "%g", v); sb_put(b, t, (size_t)n); }
+
+/* NJ print: src/neighborJoining.cu:252-270 (ostream<<double == %g).  names: n C strings. */
+ORC_API char *orc_nj_newick(int n, const int32_t *c0, const int32_t *c1, const double *l0, const double *l1,
+                            const char *const *names) {
+    sbuf b = {0, 0, 0};
+    /* iterative: frames (node, stage) */
+    int *st_node = (int *)malloc((size_t)(2 * n + 2) * sizeof(int));
+    int *st_stage = (int *)malloc((size_t)(2 * n + 2) * sizeof(int));
+    int sp = 0;
+    st_node[0] = 2 * n - 2; st_stage[0] = 0; sp = 1;
+    while (sp) {
+        int node = st_node[sp - 1];
+        if (node < n) { sb_put(&b, names[node], strlen(names[node])); sp--; continue; }
+        int k = node - n, stg = st_stage[sp - 1]++;
+        if (stg == 0) { sb_put(&b, "(", 1); st_node[sp] = c0[k]; st_stage[sp] = 0; sp++; }
+        else if (stg == 1) { sb_put(&b, ":", 1); sb_dbl(&b, l0[k]); sb_put(&b, ",", 1); st_node[sp] = c1[k]; st_stage[sp] = 0; sp++; }
+        else { sb_put(&b, ":", 1); sb_dbl(&b, l1[k]); sb_put(&b, ")", 1); sp--; }
+    }
+    sb_put(&b, ";\n", 2);
+    free(st_node); free(st_stage);
+    return b.p;
+}
+
+/* placement print: src/placement_close_k.cu:575-594,640: start at node root_node with
+ * from=-1; a node is a leaf iff it has exactly one adjacency; children in adjacency order. */
+ORC_API char *orc_ptree_newick(const orc_ptree *t, int root_node, const char *const *names) {
+    sbuf b = {0, 0, 0};
+    int cap = 2 * t->n + 4;
+    int *st_node = (int *)malloc((size_t)cap * sizeof(int)), *st_from = (int *)malloc((size_t)cap * sizeof(int));
+    int *st_slot = (int *)malloc((size_t)cap * sizeof(int)), *st_open = (int *)malloc((size_t)cap * sizeof(int));
+    int sp = 1;
+    st_node[0] = root_node; st_from[0] = -1; st_slot[0] = -2; st_open[0] = 0;
+    while (sp) {
+        int f = sp - 1, node = st_node[f];
+        if (t->nxt[t->head[node]] == -1) { sb_put(&b, names[node], strlen(names[node])); sp--; continue; }
+        int s;
+        if (st_slot[f] == -2) { sb_put(&b, "(", 1); s = t->head[node]; }
+        else {
+            /* returning from child via slot st_slot[f]: print its length, then separator decided below */
+            sb_put(&b, ":", 1); sb_dbl(&b, t->len[st_slot[f]]);
+            s = t->nxt[st_slot[f]];
+        }
+        while (s != -1 && t->e[s] == st_from[f]) s = t->nxt[s];
+        if (s == -1) { sb_put(&b, ")", 1); sp--; continue; }
+        if (st_slot[f] != -2) sb_put(&b, ",", 1);
+        st_slot[f] = s;
+        st_node[sp] = t->e[s]; st_from[sp] = node; st_slot[sp] = -2; st_open[sp] = 0; sp++;
+    }
+    sb_put(&b, ";\n", 2);
+    free(st_node); free(st_from); free(st_slot); free(st_open);
+    return b.p;
+}
+
+ORC_API void orc_free(void *p) { free(p); }
+ORC_API int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
