@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline: pairwise distances/s and NJ wall time at N tips.
+
+Workload (config C3, BASELINE.json configs[2]): synthetic aligned MSA, 30 000 tips x
+30 000 sites, JC distance matrix (-d 2) then conventional NJ (-m 2).  One "step" = one
+full pass: packed sequences -> fp64 distance matrix -> NJ tree.
+
+  value   whole-job pairs/s with the packed sequences already resident in HBM
+          (distance matrix + NJ, device-timed with CUDA events on the library stream)
+  e2e     same metric through the public C ABI from HOST buffers: H2D of the 4-bit
+          sequences + repack + distances + NJ + D2H of the tree, wall-clocked
+  roofline  the NJ search (dominant phase) against the measured HBM copy bandwidth;
+          algorithmic bytes = the reference's full-scan cost  sum_n (n^2+4n)*8  (SURVEY.md
+          §8d) -- a pruned exact search may exceed 1.0 of this yard-stick; the distance
+          kernel's integer-pipe figure is reported beside it under "dist_kernel"
+  cpu_baseline  the OpenMP oracle port on a bounded sample (rank 0, N=1 only)
+
+`--impl reference` runs the reference's own CUDA objects (oracle/_ref/dipper_ref; the
+reference has no CPU path) on a bounded sample of the same workload.
+Multi-GPU (torchrun): the distance matrix is row-block sharded over ranks and summed
+onto rank 0 (NCCL reduce), NJ runs on rank 0 (BASELINE.json configs[2]).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pairwise distances/sec (JC distance matrix + NJ tree, whole job)"
+UNIT = "pairs/s"
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_data(n, L, seed):
+    from dipper_b200 import synth
+    cache = os.path.join(tempfile.gettempdir(), "dipb_bench_%d_%d_%d.npy" % (n, L, seed))
+    if os.path.exists(cache):
+        return np.load(cache)
+    codes, _ = synth.evolve(n, L, seed=seed, regime="tiefree", gap_cols=0.03, gap_runs=False)
+    P = synth.pack4_np(codes)
+    try:
+        np.save(cache, P)
+    except Exception:
+        pass
+    return P
+
+
+def nj_algorithmic_bytes(n):
+    # full-scan definition, (m^2 + 4m)*8 B per iteration with m active rows
+    m = np.arange(3, n + 1, dtype=np.float64)
+    return float(((m * m + 4 * m) * 8).sum())
+
+
+def dist_algorithmic_intops(n, L):
+    # pairs x ceil(L/32) x (4 LOP3 + 2 POPC + 2 IADD)
+    return n * (n - 1) / 2 * ((L + 31) // 32) * 8.0
+
+
+def write_ref_bin(path, P, L):
+    with open(path, "wb") as f:
+        np.array([P.shape[0], 4], np.int64).tofile(f)
+        np.full(P.shape[0], L, np.uint64).tofile(f)
+        P.tofile(f)
+
+
+def run_reference(args):
+    """The reference's own CUDA objects on a bounded sample (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    exe = os.path.join(ROOT, "oracle", "_ref", "dipper_ref")
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True}
+    if not os.path.exists(exe):
+        print(json.dumps(dict(base, unavailable="oracle/_ref/dipper_ref not built (reference sources absent at build time)")))
+        return
+    n, L = args.ref_tips, args.sites
+    P = gen_data(n, L, args.seed)
+    tmp = tempfile.mkdtemp(prefix="dipb_ref_")
+    inp = os.path.join(tmp, "in.bin")
+    write_ref_bin(inp, P, L)
+    times = []
+    for it in range(args.warmup + args.steps):
+        p = subprocess.run([exe, "msa_nj", inp, os.path.join(tmp, "o"), "2"], capture_output=True, text=True)
+        if p.returncode != 0:
+            print(json.dumps(dict(base, unavailable="dipper_ref failed: " + p.stderr[-200:].replace("\n", " "))))
+            return
+        j = json.loads(p.stdout.strip().splitlines()[-1])
+        if it >= args.warmup:
+            times.append((j["dist_ms"], j["tree_ms"], j["alloc_ms"]))
+    t = np.array(times)
+    dist_ms, nj_ms = float(t[:, 0].mean()), float(t[:, 1].mean())
+    pairs = n * (n - 1) / 2
+    val = pairs / ((dist_ms + nj_ms) / 1e3)
+    sample = "%d tips x %d sites (bounded sample of the 30000-tip workload), reference CUDA objects on 1 B200" % (n, L)
+    print(json.dumps(dict(base, value=val, ms_per_step=dist_ms + nj_ms, scaling="strong", vs_baseline=None,
+                          dtype="int32 counts + f64", data="synthetic",
+                          config={"workload": "C3 sample: aligned MSA %d tips x %d sites, JC matrix + NJ" % (n, L),
+                                  "inputs": "larger than L2"},
+                          phases={"dist_ms": dist_ms, "nj_ms": nj_ms, "alloc_ms": float(t[:, 2].mean())},
+                          cpu_baseline={"value": val, "unit": UNIT, "cores": 0, "kind": "reference", "sample": sample},
+                          e2e={"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})))
+
+
+def cpu_baseline(args, L):
+    from oracle import oracle as O       # checker / baseline leg only
+    n = args.cpu_tips
+    P = gen_data(n, L, args.seed)
+    t0 = time.time()
+    D = O.msa_dist_matrix(P, L, 2)
+    t1 = time.time()
+    O.nj(D)
+    t2 = time.time()
+    pairs = n * (n - 1) / 2
+    return {"value": pairs / (t2 - t0), "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+            "sample": "%d tips x %d sites, OpenMP oracle: dist %.2f s + NJ %.2f s" % (n, L, t1 - t0, t2 - t1)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tips", type=int, default=30000)
+    ap.add_argument("--sites", type=int, default=30000)
+    ap.add_argument("--ref-tips", type=int, default=12000)
+    ap.add_argument("--cpu-tips", type=int, default=2000)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--nj-algo", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from dipper_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, L = args.tips, args.sites
+    P = gen_data(n, L, args.seed)
+    lens = np.full(n, L, np.uint64)
+    ctx = api.Context(local)
+    prm = api.Param(distanceType=2, in_="m")
+    pairs = n * (n - 1) / 2
+
+    # row-block shard of the lower triangle, balanced by area, aligned to 128-row tiles
+    def shard(r):
+        cuts = [int(round(n * np.sqrt(k / world) / 128.0)) * 128 for k in range(world + 1)]
+        cuts[0], cuts[-1] = 0, n
+        return cuts[r], cuts[r + 1]
+
+    class DevView:   # __cuda_array_interface__ over the library's matrix for NCCL
+        def __init__(self, ptr, count):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(msa, timed):
+        """resident-input step: distances (sharded) -> reduce -> NJ on rank 0. Returns (dist_ms, comm_ms, nj_ms)."""
+        r0, r1 = shard(rank)
+        if world == 1:
+            M = msa.distMatrix(prm)
+        else:
+            M = msa.distMatrix(prm, r0, r1)
+        d_ms = ctx.elapsed_ms(api.T_MSA_DIST)
+        c_ms = 0.0
+        if world > 1:
+            from dipper_b200._lib import lib
+            ptr = lib().dipb_matrix_device_ptr(M.h)
+            t = torch.as_tensor(DevView(ptr, n * n), device="cuda")
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.reduce(t, dst=0)
+            e1.record()
+            torch.cuda.synchronize()
+            c_ms = e0.elapsed_time(e1)
+        nj_ms = 0.0
+        if rank == 0:
+            nj = api.NJDeviceArrays(ctx)
+            nj.matrix, nj.d_numSequences = M, n
+            nj.findNeighbourJoiningTree(["T%d" % (i + 1) for i in range(n)], args.nj_algo)
+            nj_ms = ctx.elapsed_ms(api.T_NJ)
+            nj.deallocateDeviceArrays()
+        else:
+            M.free()
+        return d_ms, c_ms, nj_ms
+
+    msa = api.MSADeviceArrays(ctx)
+    msa.allocateDeviceArrays(P, lens, n, prm)
+    for _ in range(args.warmup):
+        one_step(msa, False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches()
+    t_wall0 = time.time()
+    phases = []
+    for _ in range(args.steps):
+        phases.append(one_step(msa, True))
+    barrier()
+    t_wall = time.time() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.kernel_launches() - launches0
+    ph = np.array(phases)
+    # device time of a step = dist (max over ranks) + comm + nj; reduce the per-rank maxima
+    step_ms = ph.sum(axis=1).mean()
+    if world > 1:
+        tt = torch.tensor([ph[:, 0].mean(), ph[:, 1].mean(), ph[:, 2].mean(), float(launches)], device="cuda", dtype=torch.float64)
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        d_ms, c_ms, nj_ms = float(mx[0]), float(mx[1]), float(mx[2])
+        launches = int(sm[3])
+        step_ms = d_ms + c_ms + nj_ms
+    else:
+        d_ms, c_ms, nj_ms = ph[:, 0].mean(), ph[:, 1].mean(), ph[:, 2].mean()
+    nj_stats = ctx.nj_stats() if rank == 0 else {}
+
+    # ---- e2e from host buffers through the C ABI (rank 0 drives; shards upload their own copy) ----
+    e2e_t = []
+    msa.deallocateDeviceArrays()
+    for it in range(1 + max(1, args.steps)):
+        barrier()
+        t0 = time.time()
+        m2 = api.MSADeviceArrays(ctx)
+        m2.allocateDeviceArrays(P, lens, n, prm)              # H2D + repack inside
+        one_step(m2, True)                                    # distances + NJ + D2H of the tree
+        barrier()
+        if it > 0:
+            e2e_t.append(time.time() - t0)
+        m2.deallocateDeviceArrays()
+    e2e_s = float(np.mean(e2e_t))
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt[0])
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        nj_bytes = nj_algorithmic_bytes(n)
+        ach = nj_bytes / (nj_ms / 1e3) / 1e9
+        scanned = nj_stats.get("rows_scanned", 0)
+        out = {
+            "metric": METRIC, "value": pairs / (step_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32 counts + f64", "data": "synthetic",
+            "config": {"workload": "C3: aligned MSA %d tips x %d sites, JC distance matrix (row-block sharded over %d GPU) + single-GPU NJ" % (n, L, world),
+                       "inputs": "larger than L2 (450 MB packed sequences, 7.2 GB fp64 matrix)", "nj_algo": args.nj_algo},
+            "phases": {"dist_ms": d_ms, "reduce_ms": c_ms, "nj_ms": nj_ms,
+                       "dist_pairs_per_sec": pairs / (d_ms / 1e3), "nj_wall_s": nj_ms / 1e3},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "NJ search+update loop",
+                         "algorithmic_bytes": nj_bytes,
+                         "note": "yard-stick = reference full-scan bytes; rows actually rescanned: %d" % scanned},
+            "dist_kernel": {"bound": "integer pipe", "int_ops": dist_algorithmic_intops(n, L),
+                            "achieved_Tops": dist_algorithmic_intops(n, L) / (d_ms / 1e3) / 1e12 / max(world, 1)},
+            "e2e": {"value": pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(P.nbytes + lens.nbytes),
+                    "d2h_bytes_per_step": int((n - 1) * 24), "seconds": e2e_s},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, L)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,45 @@
+/*
+ * dipper_host.h -- host-side C ABI of dipper_b200: the encoders, readers and Newick
+ * code that stay on the CPU in the reference as well (L1/L5 in SURVEY.md).  Exported
+ * from the same libdipper_b200.so so that the CLI, the tests and foreign bindings
+ * share one implementation.  Paths cited are relative to the reference root.
+ */
+#ifndef DIPPER_HOST_H
+#define DIPPER_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* fourBitCompressor(std::string, size_t, uint64_t*)  src/fourBitCompressor.cpp:5-41 */
+void dipb_pack4(const char *seq, size_t len, uint64_t *out /* ceil(len/16) words */);
+/* twoBitCompressor(std::string, size_t, uint64_t*)   src/twoBitCompressor.cpp:5-41 */
+void dipb_pack2(const char *seq, size_t len, uint64_t *out /* ceil(len/32) words */);
+
+/* Newick of an NJ result (src/neighborJoining.cu:252-270: children in push order,
+ * lengths as ostream<<double, trailing ";\n").  Returns a malloc'd string (dipb_free_str). */
+char *dipb_nj_newick(int n, const int32_t *child0, const int32_t *child1, const double *len0, const double *len1,
+                     const char *const *names);
+/* Newick of a placement tree (src/placement_close_k.cu:568-643): root_node = n for
+ * dipper's own trees, children in adjacency-list order, leaf = single adjacency. */
+char *dipb_tree_newick(int n_nodes, int root_node, const int32_t *head, const int32_t *e, const int32_t *nxt,
+                       const double *len, const char *const *names);
+void dipb_free_str(char *s);
+
+/* Tree(std::string newick, size_t totalLeaves) + KPlacementDeviceArrays::initializeDeviceArrays
+ * host half (src/tree.cpp:216-361, src/placement_close_k.cu:144-183): parses a rooted
+ * Newick whose every non-root node carries a branch length; leaves are numbered in order
+ * of appearance, internal nodes total_leaves, total_leaves+1, ... in order of '('.
+ * Fills the adjacency arrays (sizes: head 2*total_leaves, others 8*total_leaves) and
+ * returns the number of backbone leaves, or a negative DIPB_E_* code.
+ * leaf_names_out receives a malloc'd, '\n'-separated list of leaf names in index order. */
+int dipb_backbone_from_newick(const char *newick, int total_leaves, int32_t *head, int32_t *e, int32_t *nxt,
+                              int32_t *belong, double *len, char **leaf_names_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,26 @@
+#!/bin/bash
+# Compiles the reference's own kernel files, in place from /root/reference, for sm_100a
+# and links them with oracle/ref_driver.cu into oracle/_ref/dipper_ref.
+# Outputs go only to oracle/_ref/ (git-ignored, shipped to the GPU box by gpurun).
+# No reference source is copied into this repository.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${DIPPER_REFERENCE:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -d "$REF/src" ]; then echo "build_ref: $REF not present, skipping"; exit 0; fi
+mkdir -p "$OUT"
+NVCC=/usr/local/cuda/bin/nvcc
+FLAGS="-gencode arch=compute_100a,code=sm_100a -rdc=true --extended-lambda -std=c++17 -O3 -w -ccbin /usr/bin/g++ -I$HERE/stubs -I$REF/src"
+SRCS="src/MSA.cu src/mash.cu src/neighborJoining.cu src/placement_close_k.cu src/matrix_reader.cu src/tree.cpp"
+pids=""
+for s in $SRCS; do
+  o="$OUT/$(basename ${s%.*}).o"
+  if [ ! -f "$o" ] || [ "$REF/$s" -nt "$o" ]; then
+    ( $NVCC $FLAGS -x cu -dc "$REF/$s" -o "$o" ) &
+    pids="$pids $!"
+  fi
+done
+for p in $pids; do wait $p; done
+$NVCC $FLAGS -dc "$HERE/ref_driver.cu" -o "$OUT/ref_driver.o"
+$NVCC -gencode arch=compute_100a,code=sm_100a -rdc=true -ccbin /usr/bin/g++ -o "$OUT/dipper_ref" "$OUT"/*.o
+echo "build_ref: built $OUT/dipper_ref"

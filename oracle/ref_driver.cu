@@ -1,0 +1,125 @@
+// ref_driver.cu -- replacement main() for the reference's own CUDA objects.
+// TEST / BASELINE INFRASTRUCTURE ONLY (lives under oracle/, built into oracle/_ref/).
+//
+// src/tree_generation.cu cannot be built here (needs Boost.program_options and TBB,
+// neither installed, no network), so this file drives the reference's UNMODIFIED
+// kernel files (compiled in place from /root/reference by oracle/build_ref.sh) through
+// the struct API of src/mash_placement.cuh.  Documented deviations from the
+// reference's main: device 0 instead of the hard-coded device 1;
+// input order is whatever the input file holds (the caller pins the permutation)
+// instead of a time-seeded shuffle; for Mash + NJ the missing allocateDeviceArrays +
+// sketchConstructionOnGpu calls are inserted (reference bug, tree_generation.cu:576-587).
+//
+// usage: dipper_ref <mode> <input.bin> <out_prefix> [dist_type] [k]
+//   input.bin: int64 n, int64 bits (4 = aligned 4-bit, 2 = unaligned 2-bit),
+//              uint64 len[n], then each sequence's packed words back to back.
+//   modes: msa_rows   -> <out>.rows   lower-triangle distances (row i: i doubles)
+//          msa_nj     -> <out>.nwk    conventional NJ tree from aligned input
+//          msa_place  -> <out>.nwk    k-closest placement tree from aligned input
+//          mash_sketch-> <out>.sk     uint64 [n][1000] sketches
+//          mash_rows  -> <out>.rows
+//          mash_nj    -> <out>.nwk
+//          mash_place -> <out>.nwk
+//   every mode prints one JSON line with wall-clock phase times (cudaDeviceSynchronize
+//   on both sides) to stdout.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "mash_placement.cuh"
+
+using Clock = std::chrono::high_resolution_clock;
+static double ms_since(Clock::time_point t0) {
+    cudaDeviceSynchronize();
+    return std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+}
+
+int main(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: dipper_ref <mode> <input.bin> <out_prefix> [dist_type] [k]\n"); return 2; }
+    std::string mode = argv[1], in = argv[2], out = argv[3];
+    int distType = argc > 4 ? atoi(argv[4]) : 2;
+    int k = argc > 5 ? atoi(argv[5]) : 15;
+    if (cudaSetDevice(0) != cudaSuccess) { fprintf(stderr, "no CUDA device\n"); return 3; }
+    FILE* f = fopen(in.c_str(), "rb");
+    if (!f) { fprintf(stderr, "cannot open %s\n", in.c_str()); return 2; }
+    int64_t n = 0, bits = 0;
+    if (fread(&n, 8, 1, f) != 1 || fread(&bits, 8, 1, f) != 1) return 2;
+    std::vector<uint64_t> lens(n);
+    if (fread(lens.data(), 8, n, f) != (size_t)n) return 2;
+    uint64_t** seqs = new uint64_t*[n];
+    int per = bits == 4 ? 16 : 32;
+    for (int64_t i = 0; i < n; i++) {
+        size_t w = (lens[i] + per - 1) / per;
+        seqs[i] = new uint64_t[w + 1];
+        seqs[i][w] = 0;
+        if (fread(seqs[i], 8, w, f) != w) return 2;
+    }
+    fclose(f);
+    std::vector<std::string> names(n);
+    for (int64_t i = 0; i < n; i++) names[i] = "T" + std::to_string(i + 1);
+
+    bool msa = mode.rfind("msa_", 0) == 0;
+    MashPlacement::Param params(k, 1000, 1, distType, msa ? "m" : "r", "t");
+    double t_alloc = 0, t_sketch = 0, t_dist = 0, t_tree = 0;
+    cudaDeviceSynchronize();
+    auto t0 = Clock::now();
+    if (msa) MashPlacement::msaDeviceArrays.allocateDeviceArrays(seqs, lens.data(), n, params);
+    else MashPlacement::mashDeviceArrays.allocateDeviceArrays(seqs, lens.data(), n, params);
+    t_alloc = ms_since(t0);
+    if (!msa) {
+        t0 = Clock::now();
+        MashPlacement::mashDeviceArrays.sketchConstructionOnGpu(params);
+        t_sketch = ms_since(t0);
+    }
+    if (mode == "mash_sketch") {
+        // h_hashList holds the transposed layout hash[t*n + seq] (src/mash.cu:381-383,418-419)
+        std::vector<uint64_t> sk((size_t)n * 1000);
+        for (int64_t s = 0; s < n; s++)
+            for (int t = 0; t < 1000; t++) sk[s * 1000 + t] = MashPlacement::mashDeviceArrays.h_hashList[(size_t)t * n + s];
+        FILE* o = fopen((out + ".sk").c_str(), "wb");
+        fwrite(sk.data(), 8, sk.size(), o);
+        fclose(o);
+    } else if (mode == "msa_rows" || mode == "mash_rows") {
+        double* d_row;
+        cudaMalloc(&d_row, sizeof(double) * n);
+        std::vector<double> h(n);
+        FILE* o = fopen((out + ".rows").c_str(), "wb");
+        t0 = Clock::now();
+        for (int i = 1; i < n; i++) {
+            if (msa) MashPlacement::msaDeviceArrays.distConstructionOnGpu(params, i, d_row);
+            else MashPlacement::mashDeviceArrays.distConstructionOnGpu(params, i, d_row);
+            cudaMemcpy(h.data(), d_row, sizeof(double) * i, cudaMemcpyDeviceToHost);
+            fwrite(h.data(), 8, i, o);
+        }
+        t_dist = ms_since(t0);
+        fclose(o);
+    } else if (mode == "msa_nj" || mode == "mash_nj") {
+        std::ofstream os(out + ".nwk");
+        t0 = Clock::now();
+        MashPlacement::njDeviceArrays.getDismatrix((int)n, params, MashPlacement::mashDeviceArrays,
+                                                   MashPlacement::matrixReader, MashPlacement::msaDeviceArrays);
+        t_dist = ms_since(t0);
+        t0 = Clock::now();
+        MashPlacement::njDeviceArrays.findNeighbourJoiningTree(names, os);
+        t_tree = ms_since(t0);
+    } else if (mode == "msa_place" || mode == "mash_place") {
+        std::ofstream os(out + ".nwk");
+        MashPlacement::kplacementDeviceArrays.allocateDeviceArrays(n);
+        t0 = Clock::now();
+        MashPlacement::kplacementDeviceArrays.findPlacementTree(params, MashPlacement::mashDeviceArrays,
+                                                                MashPlacement::matrixReader, MashPlacement::msaDeviceArrays);
+        t_tree = ms_since(t0);
+        MashPlacement::kplacementDeviceArrays.printTree(names, os);
+    } else {
+        fprintf(stderr, "unknown mode %s\n", mode.c_str());
+        return 2;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("{\"impl\": \"reference-cuda\", \"mode\": \"%s\", \"n\": %lld, \"alloc_ms\": %.3f, \"sketch_ms\": %.3f, "
+           "\"dist_ms\": %.3f, \"tree_ms\": %.3f, \"cuda_status\": \"%s\"}\n",
+           mode.c_str(), (long long)n, t_alloc, t_sketch, t_dist, t_tree, cudaGetErrorString(e));
+    return e == cudaSuccess ? 0 : 4;
+}

@@ -1,0 +1,121 @@
+"""GPU parity: aligned-MSA counts / distances through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from dipper_b200 import api, synth
+from conftest import make_msa
+
+pytestmark = pytest.mark.gpu
+
+
+def upload(ctx, P, L):
+    m = api.MSADeviceArrays(ctx)
+    m.allocateDeviceArrays(P, np.full(P.shape[0], L, np.uint64), P.shape[0], api.Param(distanceType=2, in_="m"))
+    return m
+
+
+@pytest.mark.parametrize("n,L", [(2, 1), (3, 15), (17, 16), (17, 17), (5, 31), (130, 33), (257, 1000), (300, 515)])
+def test_counts_bit_exact(ctx, oracle, n, L):
+    codes, P, _ = make_msa(n, L, seed=n * 1000 + L, gap_cols=0.1)
+    msa = upload(ctx, P, L)
+    m, u = msa.counts(0, n, 0, n)
+    om, ou = oracle.msa_counts(P, L, 0, n, 0, n)
+    assert np.array_equal(m, om)
+    assert np.array_equal(u, ou)
+
+
+def test_counts_with_lowercase_and_N(ctx, oracle):
+    rng = np.random.default_rng(2)
+    n, L = 20, 777
+    seqs = ["".join(rng.choice(list("ACGTUacgtN-RY"), L, p=[.2, .2, .2, .15, .05, .02, .02, .02, .02, .04, .04, .01, .01]))
+            for _ in range(n)]
+    P = np.stack([oracle.pack4(s) for s in seqs])
+    msa = upload(ctx, P, L)
+    m, u = msa.counts(0, n, 0, n)
+    om, ou = oracle.msa_counts(P, L, 0, n, 0, n)
+    assert np.array_equal(m, om) and np.array_equal(u, ou)
+
+
+def test_long_alignment_segments(ctx, oracle):
+    # > 65 024 sites forces the multi-segment (int32-accumulating) path
+    n, L = 6, 70001
+    codes, P, _ = make_msa(n, L, seed=9, gap_cols=0.01, gap_runs=False)
+    msa = upload(ctx, P, L)
+    m, u = msa.counts(0, n, 0, n)
+    om, ou = oracle.msa_counts(P, L, 0, n, 0, n)
+    assert np.array_equal(m, om) and np.array_equal(u, ou)
+    D = msa.distMatrix(api.Param(distanceType=2, in_="m")).to_host()
+    O = oracle.msa_dist_matrix(P, L, 2)
+    assert np.allclose(D, O, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("dist_type", [1, 2, 3, 4, 5, 6])
+def test_distance_rows_all_models(ctx, oracle, dist_type):
+    n, L = 150, 2000
+    codes, P, _ = make_msa(n, L, seed=21, gap_cols=0.05)
+    msa = upload(ctx, P, L)
+    prm = api.Param(distanceType=dist_type, in_="m")
+    for row in (1, 2, 77, 128, 149):
+        got = msa.distConstructionOnGpu(prm, row)
+        exp = oracle.msa_dist_row(P, L, row, dist_type)
+        ok = np.isfinite(exp)
+        assert np.array_equal(np.isfinite(got), ok)
+        assert np.allclose(got[ok], exp[ok], rtol=1e-6, atol=0), (row, dist_type)   # north_star: 1e-6 relative
+
+
+@pytest.mark.parametrize("dist_type", [1, 2, 4])
+@pytest.mark.parametrize("n", [2, 3, 129, 400])
+def test_full_matrix(ctx, oracle, n, dist_type):
+    L = 1200
+    codes, P, _ = make_msa(n, L, seed=n, gap_cols=0.03)
+    msa = upload(ctx, P, L)
+    D = msa.distMatrix(api.Param(distanceType=dist_type, in_="m")).to_host()
+    O = oracle.msa_dist_matrix(P, L, dist_type)
+    assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+    ok = np.isfinite(O)
+    assert np.allclose(D[ok], O[ok], rtol=1e-6, atol=0)
+    if dist_type == 1:
+        assert np.array_equal(D, O)     # p-distance is one fp64 division: bit-exact
+
+
+def test_all_gap_pair_is_nan_like_reference(ctx, oracle):
+    # useful == 0 -> 0/0 (src/MSA.cu:233 has no guard)
+    P = np.stack([oracle.pack4("----"), oracle.pack4("NNNN"), oracle.pack4("ACGT")])
+    msa = upload(ctx, P, 4)
+    row = msa.distConstructionOnGpu(api.Param(distanceType=1, in_="m"), 1)
+    assert np.isnan(row[0])
+    row2 = msa.distConstructionOnGpu(api.Param(distanceType=1, in_="m"), 2)
+    assert row2[0] == 1.0 and row2[1] == 1.0   # base opposite a gap counts as a mismatch
+
+
+def test_golden_fixtures_through_cuda(ctx):
+    import glob, os
+    for fn in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*msa*.npz"))):
+        z = np.load(fn)
+        P, L = z["packed"], int(z["seq_len"])
+        msa = upload(ctx, P, L)
+        m, u = msa.counts(0, P.shape[0], 0, P.shape[0])
+        assert np.array_equal(m, z["match"]) and np.array_equal(u, z["useful"]), fn
+        for t in z["dist_types"]:
+            D = msa.distMatrix(api.Param(distanceType=int(t), in_="m")).to_host()
+            G = z["dist_%d" % t]
+            ok = np.isfinite(G)
+            assert np.allclose(D[ok], G[ok], rtol=1e-6, atol=0), (fn, t)
+
+
+def test_upload_rejects_ragged(ctx, oracle):
+    rows = [oracle.pack4("ACGTACGT"), oracle.pack4("ACGT")]
+    m = api.MSADeviceArrays(ctx)
+    with pytest.raises(api.DipperError):
+        m.allocateDeviceArrays(rows, np.array([8, 4], np.uint64), 2, api.Param(in_="m"))
+
+
+def test_row_sharded_matrix_sums_to_full(ctx, oracle):
+    n, L = 515, 640
+    codes, P, _ = make_msa(n, L, seed=31)
+    msa = upload(ctx, P, L)
+    prm = api.Param(distanceType=2, in_="m")
+    full = msa.distMatrix(prm).to_host()
+    a = msa.distMatrix(prm, 0, 256).to_host()
+    b = msa.distMatrix(prm, 256, n).to_host()
+    assert np.array_equal(a + b, full)
