@@ -1,0 +1,461 @@
+// K4 (pruned): exact neighbor-joining search with lower-bound row pruning (sm_100a).
+//
+// Same result as the exhaustive search in nj.cu / the reference's findMinDist +
+// thrust::min_element (src/neighborJoining.cu:117-148,214), including the tie-break,
+// but only rows that can still hold the minimum are read.  The reference reads
+// n^2 doubles per iteration (72 TB over a 30 000-tip run).
+//
+// Bound.  For every active row i we keep
+//     K[i] >= -inf  with   min_{j != i} (d(i,j) - u_j(now)) >= K[i] - C(now)
+// where u_j = U[j]/(n-2) and C accumulates, per merge, max_j (u_j(new) - u_j(old)) over
+// surviving columns.  A rescan of row i sets K[i] = min_j (d(i,j) - u_j) + C exactly;
+// the column created by a merge is folded into every K explicitly.  Then
+//     min_j q(i,j) >= K[i] - C - u_i =: lb_i
+// and with ub = the smallest exactly-evaluated candidate we know (each row's last
+// argmin partner re-evaluated with the current u, plus the new column), every row with
+// lb_i - margin > ub is skipped: all of its candidates are strictly larger than the
+// true minimum, so neither the argmin nor any tie is lost.  Rows that pass are
+// rescanned with the reference's exact expression (d - u_i) - u_j and tie order.
+//
+// Execution: ONE persistent cooperative kernel runs all N-2 iterations (one CTA per
+// SM, 4 grid barriers per iteration); no host round trips.  Phases per iteration:
+//   A  merge update of rows/columns x,y (as updateDisMatrix :161-194), deterministic U,
+//      max u-drift, partner/K bookkeeping for the moved row
+//   B  fold the new column into K, re-evaluate partners -> per-CTA upper bounds
+//   C1 select rows with lb <= ub into a work list
+//   C2 all CTAs scan (row, 4096-column chunk) items of the list
+//   D  every CTA reduces the per-CTA winners to the same (x, y); CTA 0 records the tree
+#include <vector>
+#include "common.cuh"
+#include "nj.cuh"
+
+namespace dipb {
+
+namespace {
+
+constexpr int PT = 1024;        // threads per CTA
+constexpr int CHUNK = 4 * PT;   // columns per scan item
+
+struct PCand {
+    double t;   // candidate value, 1e300 = empty
+    int i, j;
+    double d, ui, uj;
+};
+
+struct PShared {
+    unsigned int bar_count;
+    unsigned int bar_gen;
+    unsigned int sel_count;
+    unsigned int pad;
+    unsigned long long rows_scanned, iters;
+};
+
+__device__ __forceinline__ unsigned long long enc_f64(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_f64(unsigned long long e) {
+    unsigned long long b = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ unsigned int enc_f32(float v) {
+    unsigned int b = __float_as_uint(v);
+    return (b >> 31) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ int p_rowblock_of(int i, int n) {
+    int sz = n / 256, rem = n % 256;
+    long long split = (long long)(sz + 1) * rem;
+    if (i < split) return i / (sz + 1);
+    return rem + (int)((i - split) / sz);
+}
+__device__ __forceinline__ unsigned long long p_tie_key(int i, int j, int n) {
+    return ((unsigned long long)p_rowblock_of(i, n) << 56) | ((unsigned long long)(j & 255) << 48) |
+           ((unsigned long long)j << 24) | (unsigned long long)i;
+}
+__device__ __forceinline__ bool p_before(double ta, int ia, int ja, double tb, int ib, int jb, int n) {
+    if (ta < tb) return true;
+    if (ta > tb) return false;
+    if (ta >= 10000.0) return false;
+    return p_tie_key(ia, ja, n) < p_tie_key(ib, jb, n);
+}
+
+__device__ __forceinline__ void grid_barrier(PShared* ps, unsigned int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int* gen = &ps->bar_gen;
+        unsigned int g = *gen;
+        __threadfence();
+        if (atomicAdd(&ps->bar_count, 1u) == nblocks - 1) {
+            ps->bar_count = 0;
+            __threadfence();
+            atomicAdd(&ps->bar_gen, 1u);
+        } else {
+            while (*gen == g) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double block_min(double v, double* sh) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, s));
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double r = sh[lane];
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) r = fmin(r, __shfl_xor_sync(0xffffffffu, r, s));
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double* sh) { return -block_min(-v, sh); }
+
+}  // namespace
+
+__global__ void __launch_bounds__(PT, 1)
+nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, double* __restrict__ u,
+                 unsigned long long* __restrict__ K, unsigned long long* __restrict__ PP, double* __restrict__ partial_sum,
+                 double* __restrict__ partial_max, double* __restrict__ partial_ub, int* __restrict__ sel_rows,
+                 PCand* __restrict__ cta_best, PShared* ps, int* __restrict__ realID, int32_t* __restrict__ child0,
+                 int32_t* __restrict__ child1, double* __restrict__ len0, double* __restrict__ len1, int n_total,
+                 double dmax) {
+    __shared__ double sh[32];
+    __shared__ PCand shc[32];
+    __shared__ double s_ux, s_C, s_ub;
+    const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int n = n_total;
+    double C = 0.0;
+    int next_id = n_total;
+    int x = -1, y = -1;
+    double dxy = 0.0;
+    bool first = true;
+    unsigned long long my_rows = 0;
+
+    while (n > 2) {
+        double ub = 1e300;
+        if (!first) {
+            // ------------------------------------------------ Phase A: merge update
+            const int last = n - 1;
+            const double den_new = (double)(n - 3);
+            for (int blk = cta; blk * PT < last; blk += G) {
+                const int i = blk * PT + tid;
+                double slot = 0.0, dlt = -1e300;
+                if (i < last && i != x) {
+                    if (i != y) {
+                        double a = __ldcg(&D[(size_t)x * ld + i]), b = __ldcg(&D[(size_t)y * ld + i]);
+                        double val = (a + b - dxy) * 0.5;
+                        double far = __ldcg(&D[(size_t)last * ld + i]);
+                        double Ui = __ldcg(&U[i]);
+                        Ui += -a - b + val;
+                        U[i] = Ui;
+                        D[(size_t)x * ld + i] = val;
+                        D[(size_t)i * ld + x] = val;
+                        D[(size_t)y * ld + i] = far;
+                        D[(size_t)i * ld + y] = far;
+                        slot = val;
+                        if (n > 3) {
+                            double un = Ui / den_new;
+                            dlt = un - __ldcg(&u[i]);
+                            u[i] = un;
+                        }
+                        // partner remap: merged rows vanish, the last row now lives at y
+                        unsigned long long pp = __ldcg(&PP[i]);
+                        int p = (int)(unsigned int)(pp & 0xffffffffull);
+                        if (p == x || p == y) PP[i] = pp | 0xffffffffull;
+                        else if (p == last) PP[i] = (pp & 0xffffffff00000000ull) | (unsigned int)y;
+                    } else {
+                        double a = __ldcg(&D[(size_t)x * ld + last]), b = __ldcg(&D[(size_t)y * ld + last]);
+                        double val = (a + b - dxy) * 0.5;
+                        double uy = __ldcg(&U[last]);
+                        uy += -a - b + val;
+                        U[y] = uy;
+                        D[(size_t)x * ld + y] = val;
+                        D[(size_t)y * ld + x] = val;
+                        slot = val;
+                        if (n > 3) {
+                            double un = uy / den_new;
+                            dlt = un - __ldcg(&u[last]);
+                            u[y] = un;
+                        }
+                        K[y] = __ldcg(&K[last]);
+                        unsigned long long pp = __ldcg(&PP[last]);
+                        int p = (int)(unsigned int)(pp & 0xffffffffull);
+                        if (p == x || p == y) pp |= 0xffffffffull;
+                        PP[y] = pp;
+                    }
+                }
+                // canonical block sum (same order as nj.cu / the oracle) and max drift
+                double v = warp_tree_sum(slot);
+                if (lane == 0) sh[w] = v;
+                __syncthreads();
+                if (w == 0) {
+                    double g = warp_tree_sum(sh[lane]);
+                    if (lane == 0) partial_sum[blk] = g;
+                }
+                __syncthreads();
+                double mx = block_max(dlt, sh);
+                if (tid == 0) partial_max[blk] = mx;
+            }
+            grid_barrier(ps, G);
+
+            // ------------------------------------------------ Phase B: finalise U[x], fold column x, upper bound
+            n = last;
+            if (n <= 2) break;
+            if (tid == 0) {
+                double acc = 0.0, mx = -1e300;
+                int nb = (last + PT - 1) / PT;
+                for (int b = 0; b < nb; b++) {
+                    acc += __ldcg(&partial_sum[b]);
+                    mx = fmax(mx, __ldcg(&partial_max[b]));
+                }
+                s_ux = acc / (double)(n - 2);
+                s_C = C + mx;
+                if (cta == 0) { U[x] = acc; u[x] = s_ux; }
+            }
+            __syncthreads();
+            const double ux = s_ux;
+            C = s_C;
+            {
+                const int seg = (n + G - 1) / G;
+                double loc = 1e300;
+                for (int k = tid; k < seg; k += PT) {
+                    int i = cta * seg + k;
+                    if (i >= n) break;
+                    if (i == x) {
+                        K[x] = 0ull;  // encoded value below every double: forces a rescan of the new row
+                        PP[x] = 0xffffffffffffffffull;
+                        continue;
+                    }
+                    double ui = __ldcg(&u[i]);
+                    double dix = __ldcg(&D[(size_t)i * ld + x]);
+                    unsigned long long kc = enc_f64((dix - ux) + C);
+                    unsigned long long ko = __ldcg(&K[i]);
+                    if (kc < ko) K[i] = kc;
+                    double t = (dix - ui) - ux;
+                    loc = fmin(loc, t);
+                    int p = (int)(unsigned int)(__ldcg(&PP[i]) & 0xffffffffull);
+                    if (p >= 0 && p < n && p != i) {
+                        double up = (p == x) ? ux : __ldcg(&u[p]);
+                        double tp = (__ldcg(&D[(size_t)i * ld + p]) - ui) - up;
+                        loc = fmin(loc, tp);
+                    }
+                }
+                double m = block_min(loc, sh);
+                if (tid == 0) partial_ub[cta] = m;
+            }
+            grid_barrier(ps, G);
+            if (tid == 0) {
+                double m = 1e300;
+                for (int b = 0; b < G; b++) m = fmin(m, __ldcg(&partial_ub[b]));
+                s_ub = m;
+            }
+            __syncthreads();
+            ub = s_ub;
+        }
+
+        // ---------------------------------------------------- Phase C1: select rows
+        {
+            const double margin = 1e-9 * (4.0 * dmax + fabs(C));
+            const int seg = (n + G - 1) / G;
+            for (int k = tid; k < seg; k += PT) {
+                int i = cta * seg + k;
+                if (i >= n) break;
+                unsigned long long ke = __ldcg(&K[i]);
+                bool take = (ke == 0ull);
+                if (!take) {
+                    double lb = (dec_f64(ke) - C) - __ldcg(&u[i]) - margin;
+                    take = !(lb > ub);
+                }
+                if (take) {
+                    unsigned int pos = atomicAdd(&ps->sel_count, 1u);
+                    sel_rows[pos] = i;
+                    K[i] = 0xffffffffffffffffull;   // reset, the scan atomically lowers it
+                    PP[i] = 0xffffffffffffffffull;
+                }
+            }
+        }
+        grid_barrier(ps, G);
+
+        // ---------------------------------------------------- Phase C2: scan (row, chunk) items
+        {
+            const int nsel = (int)*((volatile unsigned int*)&ps->sel_count);
+            const int nchunk = (n + CHUNK - 1) / CHUNK;
+            const long long items = (long long)nsel * nchunk;
+            double bt = 1e300; int bi = 0, bj = 0; double bd = 0, bui = 0, buj = 0;
+            for (long long it = cta; it < items; it += G) {
+                const int r = __ldcg(&sel_rows[(int)(it / nchunk)]);
+                const int c0 = (int)(it % nchunk) * CHUNK;
+                const double ur = __ldcg(&u[r]);
+                const double* row = D + (size_t)r * ld;
+                double lt = 1e300, lm = 1e300, ld_ = 0, luj = 0; int lj = -1;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    int j = c0 + q * PT + tid;
+                    if (j < n && j != r) {
+                        double d = __ldcg(&row[j]);
+                        double uj = __ldcg(&u[j]);
+                        double t = (d - ur) - uj;
+                        double m = d - uj;
+                        lm = fmin(lm, m);
+                        if (t < 10000.0 && (t < lt || (t == lt && (((j & 255) < (lj & 255)) || ((j & 255) == (lj & 255) && j < lj))))) {
+                            lt = t; lj = j; ld_ = d; luj = uj;
+                        }
+                    }
+                }
+                // block-reduce: min m; best (t, j) in the reference order within row r
+                double mm = block_min(lm, sh);
+                // pack per-thread candidate for a shuffle reduction
+                double rt = lt; int rj = lj; double rd = ld_, ruj = luj;
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                    double ot = __shfl_xor_sync(0xffffffffu, rt, s);
+                    int oj = __shfl_xor_sync(0xffffffffu, rj, s);
+                    double od = __shfl_xor_sync(0xffffffffu, rd, s);
+                    double ouj = __shfl_xor_sync(0xffffffffu, ruj, s);
+                    bool take = oj >= 0 && (rj < 0 || ot < rt || (ot == rt && (((oj & 255) < (rj & 255)) || ((oj & 255) == (rj & 255) && oj < rj))));
+                    if (take) { rt = ot; rj = oj; rd = od; ruj = ouj; }
+                }
+                if (lane == 0) { shc[w].t = rt; shc[w].j = rj; shc[w].d = rd; shc[w].uj = ruj; }
+                __syncthreads();
+                if (w == 0) {
+                    rt = shc[lane].t; rj = shc[lane].j; rd = shc[lane].d; ruj = shc[lane].uj;
+#pragma unroll
+                    for (int s = 16; s >= 1; s >>= 1) {
+                        double ot = __shfl_xor_sync(0xffffffffu, rt, s);
+                        int oj = __shfl_xor_sync(0xffffffffu, rj, s);
+                        double od = __shfl_xor_sync(0xffffffffu, rd, s);
+                        double ouj = __shfl_xor_sync(0xffffffffu, ruj, s);
+                        bool take = oj >= 0 && (rj < 0 || ot < rt || (ot == rt && (((oj & 255) < (rj & 255)) || ((oj & 255) == (rj & 255) && oj < rj))));
+                        if (take) { rt = ot; rj = oj; rd = od; ruj = ouj; }
+                    }
+                    if (lane == 0) {
+                        if (mm < 1e299) atomicMin(&K[r], enc_f64(mm + C));
+                        if (rj >= 0) {
+                            atomicMin(&PP[r], ((unsigned long long)enc_f32((float)rt) << 32) | (unsigned int)rj);
+                            if (p_before(rt, r, rj, bt, bi, bj, n)) { bt = rt; bi = r; bj = rj; bd = rd; bui = ur; buj = ruj; }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (c0 == 0 && tid == 0) my_rows++;
+            }
+            if (tid == 0) {
+                PCand c; c.t = bt; c.i = bi; c.j = bj; c.d = bd; c.ui = bui; c.uj = buj;
+                cta_best[cta] = c;
+            }
+        }
+        grid_barrier(ps, G);
+
+        // ---------------------------------------------------- Phase D: pick (identical in every CTA)
+        {
+            double t = 1e300; int ci = 0, cj = 0; double cd = 0, cui = 0, cuj = 0;
+            if (tid < G) {
+                const PCand* cb = cta_best + tid;
+                t = __ldcg(&cb->t); ci = __ldcg(&cb->i); cj = __ldcg(&cb->j);
+                cd = __ldcg(&cb->d); cui = __ldcg(&cb->ui); cuj = __ldcg(&cb->uj);
+            }
+            // reduce over the first ceil(G/32) warps
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                double ot = __shfl_xor_sync(0xffffffffu, t, s);
+                int oi = __shfl_xor_sync(0xffffffffu, ci, s), oj = __shfl_xor_sync(0xffffffffu, cj, s);
+                double od = __shfl_xor_sync(0xffffffffu, cd, s), oui = __shfl_xor_sync(0xffffffffu, cui, s),
+                       ouj = __shfl_xor_sync(0xffffffffu, cuj, s);
+                if (p_before(ot, oi, oj, t, ci, cj, n)) { t = ot; ci = oi; cj = oj; cd = od; cui = oui; cuj = ouj; }
+            }
+            if (lane == 0) { shc[w].t = t; shc[w].i = ci; shc[w].j = cj; shc[w].d = cd; shc[w].ui = cui; shc[w].uj = cuj; }
+            __syncthreads();
+            if (w == 0) {
+                t = shc[lane].t; ci = shc[lane].i; cj = shc[lane].j; cd = shc[lane].d; cui = shc[lane].ui; cuj = shc[lane].uj;
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                    double ot = __shfl_xor_sync(0xffffffffu, t, s);
+                    int oi = __shfl_xor_sync(0xffffffffu, ci, s), oj = __shfl_xor_sync(0xffffffffu, cj, s);
+                    double od = __shfl_xor_sync(0xffffffffu, cd, s), oui = __shfl_xor_sync(0xffffffffu, cui, s),
+                           ouj = __shfl_xor_sync(0xffffffffu, cuj, s);
+                    if (p_before(ot, oi, oj, t, ci, cj, n)) { t = ot; ci = oi; cj = oj; cd = od; cui = oui; cuj = ouj; }
+                }
+                if (lane == 0) { shc[0].t = t; shc[0].i = ci; shc[0].j = cj; shc[0].d = cd; shc[0].ui = cui; shc[0].uj = cuj; }
+            }
+            __syncthreads();
+            int wi = shc[0].i, wj = shc[0].j;
+            double wd = shc[0].d, wui = shc[0].ui, wuj = shc[0].uj;
+            __syncthreads();
+            double uxo, uyo;
+            if (wi < wj) { x = wi; y = wj; uxo = wui; uyo = wuj; } else { x = wj; y = wi; uxo = wuj; uyo = wui; }
+            dxy = wd;
+            if (cta == 0 && tid == 0) {
+                // host step of the reference, src/neighborJoining.cu:219-237
+                double blX = (dxy + uxo - uyo) * 0.5;
+                double blY = dxy - blX;
+                if (blX < 0) { blY += blX; blX = 0; }
+                if (blY < 0) { blX += blY; blY = 0; }
+                child0[next_id - n_total] = realID[x]; len0[next_id - n_total] = blX;
+                child1[next_id - n_total] = realID[y]; len1[next_id - n_total] = blY;
+                realID[x] = next_id; realID[y] = realID[n - 1];
+                ps->sel_count = 0;   // next use is after two more grid barriers
+                ps->iters += 1;
+            }
+            next_id++;
+        }
+        first = false;
+    }
+    if (tid == 0 && my_rows) atomicAdd(&ps->rows_scanned, my_rows);
+}
+
+int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJState* st, int* realID, int32_t* c0,
+                   int32_t* c1, double* l0, double* l1) {
+    (void)partial; (void)st;
+    dipb_ctx* c = m->ctx;
+    const int n = m->n;
+    int G = c->num_sms;
+    int max_blocks = 0;
+    DIPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, nj_pruned_kernel, PT, 0));
+    if (max_blocks < 1) { set_error("nj_pruned: kernel does not fit an SM"); return DIPB_E_CUDA; }
+    unsigned long long *K = nullptr, *PP = nullptr;
+    double *psum = nullptr, *pmax = nullptr, *pub = nullptr, *dmax_d = nullptr;
+    int* sel = nullptr;
+    PCand* cb = nullptr;
+    PShared* ps = nullptr;
+    const int nblk = (n + PT - 1) / PT + 1;
+    DIPB_CUDA(cudaMalloc(&K, sizeof(unsigned long long) * n));
+    DIPB_CUDA(cudaMalloc(&PP, sizeof(unsigned long long) * n));
+    DIPB_CUDA(cudaMalloc(&psum, sizeof(double) * nblk));
+    DIPB_CUDA(cudaMalloc(&pmax, sizeof(double) * nblk));
+    DIPB_CUDA(cudaMalloc(&pub, sizeof(double) * G));
+    DIPB_CUDA(cudaMalloc(&sel, sizeof(int) * n));
+    DIPB_CUDA(cudaMalloc(&cb, sizeof(PCand) * G));
+    DIPB_CUDA(cudaMalloc(&ps, sizeof(PShared)));
+    DIPB_CUDA(cudaMalloc(&dmax_d, sizeof(double)));
+    DIPB_CUDA(cudaMemsetAsync(ps, 0, sizeof(PShared), c->stream));
+    DIPB_CUDA(cudaMemsetAsync(K, 0, sizeof(unsigned long long) * n, c->stream));       // 0 = "rescan me"
+    DIPB_CUDA(cudaMemsetAsync(PP, 0xff, sizeof(unsigned long long) * n, c->stream));   // no partner
+    // scale for the safety margin: the initial row sums bound every later |d| and |u|
+    double dmax = 0.0;
+    {
+        // max_i U[i] / (n-2) * 2 is a cheap, safe scale (u values stay within the initial range of row means)
+        std::vector<double> hu(n);
+        DIPB_CUDA(cudaMemcpyAsync(hu.data(), u, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        DIPB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < n; i++) { double a = hu[i] < 0 ? -hu[i] : hu[i]; if (a == a && a > dmax && a < 1e300) dmax = a; }
+        dmax *= 2.0;
+    }
+    size_t ld = (size_t)n;
+    double* Dp = m->d;
+    int n_total = n;
+    void* args[] = {&Dp, &ld, &U, &u, &K, &PP, &psum, &pmax, &pub, &sel, &cb, &ps, &realID, &c0, &c1, &l0, &l1, &n_total, &dmax};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)nj_pruned_kernel, dim3(G), dim3(PT), args, 0, c->stream);
+    if (e != cudaSuccess) { set_error("nj_pruned: cooperative launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
+    c->launches++;
+    DIPB_CUDA(cudaStreamSynchronize(c->stream));
+    PShared hs;
+    DIPB_CUDA(cudaMemcpy(&hs, ps, sizeof(hs), cudaMemcpyDeviceToHost));
+    c->nj_rows_scanned = hs.rows_scanned;
+    c->nj_iterations = hs.iters;
+    cudaFree(K); cudaFree(PP); cudaFree(psum); cudaFree(pmax); cudaFree(pub); cudaFree(sel); cudaFree(cb); cudaFree(ps); cudaFree(dmax_d);
+    return 0;
+}
+
+}  // namespace dipb

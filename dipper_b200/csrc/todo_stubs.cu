@@ -4,9 +4,6 @@
 #include "nj.cuh"
 using namespace dipb;
 #define NOTYET(name) do { set_error(name ": not implemented in this build"); return DIPB_E_STATE; } while (0)
-namespace dipb {
-int nj_pruned_loop(dipb_matrix*, double*, double*, double*, NJState*, int*, int32_t*, int32_t*, double*, double*) { NOTYET("nj_pruned_loop"); }
-}
 extern "C" {
 int dipb_mash_upload(dipb_ctx*, const uint64_t* const*, const uint64_t*, size_t, int, int, dipb_mash**) { NOTYET("dipb_mash_upload"); }
 int dipb_mash_upload_flat(dipb_ctx*, const uint64_t*, const uint64_t*, const uint64_t*, size_t, int, int, dipb_mash**) { NOTYET("dipb_mash_upload_flat"); }

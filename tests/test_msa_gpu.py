@@ -27,7 +27,7 @@ def test_counts_bit_exact(ctx, oracle, n, L):
 def test_counts_with_lowercase_and_N(ctx, oracle):
     rng = np.random.default_rng(2)
     n, L = 20, 777
-    seqs = ["".join(rng.choice(list("ACGTUacgtN-RY"), L, p=[.2, .2, .2, .15, .05, .02, .02, .02, .02, .04, .04, .01, .01]))
+    seqs = ["".join(rng.choice(list("ACGTUacgtN-RY"), L, p=[.2, .2, .2, .15, .05, .02, .02, .02, .02, .05, .05, .01, .01]))
             for _ in range(n)]
     P = np.stack([oracle.pack4(s) for s in seqs])
     msa = upload(ctx, P, L)
