@@ -288,9 +288,11 @@ int nj_run(dipb_matrix* m, int algo, int32_t* child0, int32_t* child1, double* l
     if (rc) return rc;
     NJState hs;
     DIPB_CUDA(cudaMemcpy(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost));
-    c->nj_rows_scanned = hs.rows_scanned;
-    c->nj_iterations = hs.iters;
-    c->nj_bytes_scanned = 0;  // filled by callers that know the per-row size; see dipb_nj_stats
+    if (!done) {
+        c->nj_rows_scanned = hs.rows_scanned;
+        c->nj_iterations = hs.iters;
+        c->nj_bytes_scanned = 0;
+    }
     DIPB_CUDA(cudaMemcpy(child0, c0, sizeof(int32_t) * (n - 1), cudaMemcpyDeviceToHost));
     DIPB_CUDA(cudaMemcpy(child1, c1, sizeof(int32_t) * (n - 1), cudaMemcpyDeviceToHost));
     DIPB_CUDA(cudaMemcpy(len0, l0, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost));

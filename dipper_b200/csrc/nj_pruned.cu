@@ -25,6 +25,7 @@
 //   C1 select rows with lb <= ub into a work list
 //   C2 all CTAs scan (row, 4096-column chunk) items of the list
 //   D  every CTA reduces the per-CTA winners to the same (x, y); CTA 0 records the tree
+#include <cstdlib>
 #include <vector>
 #include "common.cuh"
 #include "nj.cuh"
@@ -48,6 +49,7 @@ struct PShared {
     unsigned int sel_count;
     unsigned int pad;
     unsigned long long rows_scanned, iters;
+    unsigned long long cyc[8];   // CTA 0 cycle counters per phase: A, bar, B, bar, C1, bar, C2+bar, D
 };
 
 __device__ __forceinline__ unsigned long long enc_f64(double v) {
@@ -80,19 +82,21 @@ __device__ __forceinline__ bool p_before(double ta, int ia, int ja, double tb, i
     return p_tie_key(ia, ja, n) < p_tie_key(ib, jb, n);
 }
 
-__device__ __forceinline__ void grid_barrier(PShared* ps, unsigned int nblocks) {
+// Grid barrier on one monotonically increasing counter: barrier k is complete when the
+// counter reaches k * nblocks.  One release-fence + atomic per CTA, relaxed polling by a
+// single thread (all-to-all flag polling was measured slower: it floods L2 while other
+// CTAs still work).  Requires all CTAs co-resident (cooperative launch).
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int nblocks, unsigned int& gen) {
+    gen++;
     __syncthreads();
     if (threadIdx.x == 0) {
-        volatile unsigned int* gen = &ps->bar_gen;
-        unsigned int g = *gen;
+        const unsigned int target = gen * nblocks;
         __threadfence();
-        if (atomicAdd(&ps->bar_count, 1u) == nblocks - 1) {
-            ps->bar_count = 0;
-            __threadfence();
-            atomicAdd(&ps->bar_gen, 1u);
-        } else {
-            while (*gen == g) { }
-        }
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while ((int)(v - target) < 0);
         __threadfence();
     }
     __syncthreads();
@@ -118,12 +122,12 @@ __global__ void __launch_bounds__(PT, 1)
 nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, double* __restrict__ u,
                  unsigned long long* __restrict__ K, unsigned long long* __restrict__ PP, double* __restrict__ partial_sum,
                  double* __restrict__ partial_max, double* __restrict__ partial_ub, int* __restrict__ sel_rows,
-                 PCand* __restrict__ cta_best, PShared* ps, int* __restrict__ realID, int32_t* __restrict__ child0,
-                 int32_t* __restrict__ child1, double* __restrict__ len0, double* __restrict__ len1, int n_total,
-                 double dmax) {
+                 PCand* __restrict__ cta_best, PShared* ps, unsigned int* __restrict__ bar_flags,
+                 int2* __restrict__ log_xy, double2* __restrict__ log_bl, int n_total, double dmax) {
     __shared__ double sh[32];
     __shared__ PCand shc[32];
     __shared__ double s_ux, s_C, s_ub;
+    __shared__ double s_part[PT];
     const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     int n = n_total;
     double C = 0.0;
@@ -132,10 +136,23 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
     double dxy = 0.0;
     bool first = true;
     unsigned long long my_rows = 0;
+    unsigned int bar_gen = 0;
+    int iter = 0;
+
+    long long tmark = clock64();
+#define PHASE_MARK(k)                                                   \
+    do {                                                                \
+        if (cta == 0 && tid == 0) {                                     \
+            long long now__ = clock64();                                \
+            ps->cyc[k] += (unsigned long long)(now__ - tmark);          \
+            tmark = now__;                                              \
+        }                                                               \
+    } while (0)
 
     while (n > 2) {
         double ub = 1e300;
         if (!first) {
+            PHASE_MARK(7);
             // ------------------------------------------------ Phase A: merge update
             const int last = n - 1;
             const double den_new = (double)(n - 3);
@@ -198,21 +215,25 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                 double mx = block_max(dlt, sh);
                 if (tid == 0) partial_max[blk] = mx;
             }
-            grid_barrier(ps, G);
+            PHASE_MARK(0);
+            grid_barrier(bar_flags, G, bar_gen);
+            PHASE_MARK(1);
 
             // ------------------------------------------------ Phase B: finalise U[x], fold column x, upper bound
             n = last;
             if (n <= 2) break;
-            if (tid == 0) {
-                double acc = 0.0, mx = -1e300;
-                int nb = (last + PT - 1) / PT;
-                for (int b = 0; b < nb; b++) {
-                    acc += __ldcg(&partial_sum[b]);
-                    mx = fmax(mx, __ldcg(&partial_max[b]));
+            {
+                const int nb = (last + PT - 1) / PT;   // <= 1024 blocks (n <= 2^20) fit one pass
+                double pm = tid < nb ? __ldcg(&partial_max[tid]) : -1e300;
+                if (tid < nb) s_part[tid] = __ldcg(&partial_sum[tid]);
+                double mx = block_max(pm, sh);
+                if (tid == 0) {
+                    double acc = 0.0;
+                    for (int b = 0; b < nb; b++) acc += s_part[b];   // ascending block order (canonical sum)
+                    s_ux = acc / (double)(n - 2);
+                    s_C = C + mx;
+                    if (cta == 0) { U[x] = acc; u[x] = s_ux; }
                 }
-                s_ux = acc / (double)(n - 2);
-                s_C = C + mx;
-                if (cta == 0) { U[x] = acc; u[x] = s_ux; }
             }
             __syncthreads();
             const double ux = s_ux;
@@ -245,14 +266,10 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                 double m = block_min(loc, sh);
                 if (tid == 0) partial_ub[cta] = m;
             }
-            grid_barrier(ps, G);
-            if (tid == 0) {
-                double m = 1e300;
-                for (int b = 0; b < G; b++) m = fmin(m, __ldcg(&partial_ub[b]));
-                s_ub = m;
-            }
-            __syncthreads();
-            ub = s_ub;
+            PHASE_MARK(2);
+            grid_barrier(bar_flags, G, bar_gen);
+            PHASE_MARK(3);
+            ub = block_min(tid < G ? __ldcg(&partial_ub[tid]) : 1e300, sh);
         }
 
         // ---------------------------------------------------- Phase C1: select rows
@@ -276,7 +293,9 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                 }
             }
         }
-        grid_barrier(ps, G);
+        PHASE_MARK(4);
+        grid_barrier(bar_flags, G, bar_gen);
+        PHASE_MARK(5);
 
         // ---------------------------------------------------- Phase C2: scan (row, chunk) items
         {
@@ -304,34 +323,34 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                         }
                     }
                 }
-                // block-reduce: min m; best (t, j) in the reference order within row r
-                double mm = block_min(lm, sh);
-                // pack per-thread candidate for a shuffle reduction
-                double rt = lt; int rj = lj; double rd = ld_, ruj = luj;
+                // block-reduce: min m, and best (t, j) in the reference order within row r
+                double rt = lt; int rj = lj; double rd = ld_, ruj = luj, rm = lm;
 #pragma unroll
                 for (int s = 16; s >= 1; s >>= 1) {
                     double ot = __shfl_xor_sync(0xffffffffu, rt, s);
                     int oj = __shfl_xor_sync(0xffffffffu, rj, s);
                     double od = __shfl_xor_sync(0xffffffffu, rd, s);
                     double ouj = __shfl_xor_sync(0xffffffffu, ruj, s);
+                    rm = fmin(rm, __shfl_xor_sync(0xffffffffu, rm, s));
                     bool take = oj >= 0 && (rj < 0 || ot < rt || (ot == rt && (((oj & 255) < (rj & 255)) || ((oj & 255) == (rj & 255) && oj < rj))));
                     if (take) { rt = ot; rj = oj; rd = od; ruj = ouj; }
                 }
-                if (lane == 0) { shc[w].t = rt; shc[w].j = rj; shc[w].d = rd; shc[w].uj = ruj; }
+                if (lane == 0) { shc[w].t = rt; shc[w].j = rj; shc[w].d = rd; shc[w].uj = ruj; shc[w].ui = rm; }
                 __syncthreads();
                 if (w == 0) {
-                    rt = shc[lane].t; rj = shc[lane].j; rd = shc[lane].d; ruj = shc[lane].uj;
+                    rt = shc[lane].t; rj = shc[lane].j; rd = shc[lane].d; ruj = shc[lane].uj; rm = shc[lane].ui;
 #pragma unroll
                     for (int s = 16; s >= 1; s >>= 1) {
                         double ot = __shfl_xor_sync(0xffffffffu, rt, s);
                         int oj = __shfl_xor_sync(0xffffffffu, rj, s);
                         double od = __shfl_xor_sync(0xffffffffu, rd, s);
                         double ouj = __shfl_xor_sync(0xffffffffu, ruj, s);
+                        rm = fmin(rm, __shfl_xor_sync(0xffffffffu, rm, s));
                         bool take = oj >= 0 && (rj < 0 || ot < rt || (ot == rt && (((oj & 255) < (rj & 255)) || ((oj & 255) == (rj & 255) && oj < rj))));
                         if (take) { rt = ot; rj = oj; rd = od; ruj = ouj; }
                     }
                     if (lane == 0) {
-                        if (mm < 1e299) atomicMin(&K[r], enc_f64(mm + C));
+                        if (rm < 1e299) atomicMin(&K[r], enc_f64(rm + C));
                         if (rj >= 0) {
                             atomicMin(&PP[r], ((unsigned long long)enc_f32((float)rt) << 32) | (unsigned int)rj);
                             if (p_before(rt, r, rj, bt, bi, bj, n)) { bt = rt; bi = r; bj = rj; bd = rd; bui = ur; buj = ruj; }
@@ -346,7 +365,8 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                 cta_best[cta] = c;
             }
         }
-        grid_barrier(ps, G);
+        grid_barrier(bar_flags, G, bar_gen);
+        PHASE_MARK(6);
 
         // ---------------------------------------------------- Phase D: pick (identical in every CTA)
         {
@@ -387,22 +407,23 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
             if (wi < wj) { x = wi; y = wj; uxo = wui; uyo = wuj; } else { x = wj; y = wi; uxo = wuj; uyo = wui; }
             dxy = wd;
             if (cta == 0 && tid == 0) {
-                // host step of the reference, src/neighborJoining.cu:219-237
+                // host step of the reference, src/neighborJoining.cu:219-237; realID bookkeeping
+                // (:233-237) is replayed on the host from this log after the kernel
                 double blX = (dxy + uxo - uyo) * 0.5;
                 double blY = dxy - blX;
                 if (blX < 0) { blY += blX; blX = 0; }
                 if (blY < 0) { blX += blY; blY = 0; }
-                child0[next_id - n_total] = realID[x]; len0[next_id - n_total] = blX;
-                child1[next_id - n_total] = realID[y]; len1[next_id - n_total] = blY;
-                realID[x] = next_id; realID[y] = realID[n - 1];
+                log_xy[iter] = make_int2(x, y);
+                log_bl[iter] = make_double2(blX, blY);
                 ps->sel_count = 0;   // next use is after two more grid barriers
-                ps->iters += 1;
             }
+            iter++;
             next_id++;
         }
         first = false;
     }
     if (tid == 0 && my_rows) atomicAdd(&ps->rows_scanned, my_rows);
+    if (cta == 0 && tid == 0) ps->iters = (unsigned long long)iter;
 }
 
 int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJState* st, int* realID, int32_t* c0,
@@ -445,15 +466,57 @@ int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJStat
     size_t ld = (size_t)n;
     double* Dp = m->d;
     int n_total = n;
-    void* args[] = {&Dp, &ld, &U, &u, &K, &PP, &psum, &pmax, &pub, &sel, &cb, &ps, &realID, &c0, &c1, &l0, &l1, &n_total, &dmax};
+    unsigned int* flags = nullptr;
+    int2* log_xy = nullptr;
+    double2* log_bl = nullptr;
+    DIPB_CUDA(cudaMalloc(&flags, sizeof(unsigned int) * 1024));
+    DIPB_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * 1024, c->stream));
+    DIPB_CUDA(cudaMalloc(&log_xy, sizeof(int2) * n));
+    DIPB_CUDA(cudaMalloc(&log_bl, sizeof(double2) * n));
+    void* args[] = {&Dp, &ld, &U, &u, &K, &PP, &psum, &pmax, &pub, &sel, &cb, &ps, &flags, &log_xy, &log_bl, &n_total, &dmax};
     cudaError_t e = cudaLaunchCooperativeKernel((void*)nj_pruned_kernel, dim3(G), dim3(PT), args, 0, c->stream);
     if (e != cudaSuccess) { set_error("nj_pruned: cooperative launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
     c->launches++;
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
+    {
+        // replay of realID / tree bookkeeping (src/neighborJoining.cu:233-237) from the device log
+        const int iters = n - 2;
+        std::vector<int2> hxy(iters);
+        std::vector<double2> hbl(iters);
+        std::vector<int> rid(n), hc0(n), hc1(n);
+        std::vector<double> hl0(n), hl1(n);
+        DIPB_CUDA(cudaMemcpy(hxy.data(), log_xy, sizeof(int2) * iters, cudaMemcpyDeviceToHost));
+        DIPB_CUDA(cudaMemcpy(hbl.data(), log_bl, sizeof(double2) * iters, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) rid[i] = i;
+        int id = n;
+        for (int it = 0; it < iters; it++) {
+            const int xx = hxy[it].x, yy = hxy[it].y, act = n - it;
+            hc0[it] = rid[xx]; hl0[it] = hbl[it].x;
+            hc1[it] = rid[yy]; hl1[it] = hbl[it].y;
+            rid[xx] = id++; rid[yy] = rid[act - 1];
+        }
+        DIPB_CUDA(cudaMemcpy(c0, hc0.data(), sizeof(int32_t) * iters, cudaMemcpyHostToDevice));
+        DIPB_CUDA(cudaMemcpy(c1, hc1.data(), sizeof(int32_t) * iters, cudaMemcpyHostToDevice));
+        DIPB_CUDA(cudaMemcpy(l0, hl0.data(), sizeof(double) * iters, cudaMemcpyHostToDevice));
+        DIPB_CUDA(cudaMemcpy(l1, hl1.data(), sizeof(double) * iters, cudaMemcpyHostToDevice));
+        DIPB_CUDA(cudaMemcpy(realID, rid.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    }
+    cudaFree(flags); cudaFree(log_xy); cudaFree(log_bl);
     PShared hs;
     DIPB_CUDA(cudaMemcpy(&hs, ps, sizeof(hs), cudaMemcpyDeviceToHost));
     c->nj_rows_scanned = hs.rows_scanned;
     c->nj_iterations = hs.iters;
+    c->nj_bytes_scanned = 0;
+    if (getenv("DIPB_NJ_PROFILE")) {
+        const char* nm[8] = {"A update", "barrier1", "B fold+ub", "barrier2", "C1 select", "barrier3", "C2 scan+barrier4", "D pick"};
+        double tot = 0;
+        for (int k = 0; k < 8; k++) tot += (double)hs.cyc[k];
+        fprintf(stderr, "[nj_pruned] n=%d iters=%llu rows_scanned=%llu (%.1f/iter)\n", n, hs.iters, hs.rows_scanned,
+                hs.iters ? (double)hs.rows_scanned / hs.iters : 0.0);
+        for (int k = 0; k < 8; k++)
+            fprintf(stderr, "[nj_pruned]   %-18s %10.0f cyc/iter  %5.1f%%\n", nm[k], hs.iters ? hs.cyc[k] / (double)hs.iters : 0.0,
+                    tot > 0 ? 100.0 * hs.cyc[k] / tot : 0.0);
+    }
     cudaFree(K); cudaFree(PP); cudaFree(psum); cudaFree(pmax); cudaFree(pub); cudaFree(sel); cudaFree(cb); cudaFree(ps); cudaFree(dmax_d);
     return 0;
 }
