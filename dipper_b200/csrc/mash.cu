@@ -1,0 +1,402 @@
+// K2/K3: MinHash sketches of unaligned sequences and sketch-vs-sketch Mash distance.
+//
+// Replaces MashDeviceArrays::{allocateDeviceArrays, sketchConstructionOnGpu,
+// distConstructionOnGpu} (reference src/mash.cu:14-122,260-471) and the D&C twins
+// (DC/mash.cu).  Not a port:
+//  * sketching: one CTA per sequence hashes every canonical k-mer (MurmurHash3_x64_128,
+//    seed 42, low 64 bits; canonical form chosen by comparing the 2-bit forward and
+//    reverse-complement words instead of byte strings) and keeps the bottom-s MULTISET
+//    with a threshold-filtered shared-memory buffer + bitonic sort (the reference re-sorts
+//    1536 keys per 512 k-mers); sketches stay on the device, row-major [n][s].
+//  * distance: 16 x 8 sketch tiles are staged in shared memory with 1-D TMA bulk copies
+//    and every thread walks one pair with the reference's merge rule, branch-free per
+//    step; p-value free Mash distance in fp64 with the reference's expression.
+#include <vector>
+#include "common.cuh"
+
+struct dipb_mash {
+    dipb_ctx* ctx = nullptr;
+    int n = 0, k = 15, s = 1000;
+    uint64_t* seqs = nullptr;      // flat 2-bit words (+1 pad word)
+    uint64_t* word_off = nullptr;  // [n]
+    uint64_t* lens = nullptr;      // [n] bases
+    uint64_t* sketches = nullptr;  // [n][s]
+    bool sketched = false;
+};
+
+namespace dipb {
+
+constexpr int SK_THREADS = 1024;
+constexpr int SK_BUF = 4096;
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return k;
+}
+
+// MurmurHash3_x64_128 (low 64 bits) of the k ASCII bytes of a k-mer given as 2-bit codes,
+// first base in the lowest bits of `codes` (k <= 32).  src/mash.cu:159-236.
+__device__ __forceinline__ uint64_t murmur_kmer(uint64_t codes, int k, uint32_t seed) {
+    // expand to ASCII, 8 bases per 64-bit word, byte t = base t (little endian like the char array)
+    uint64_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 32; t++) {
+        if (t < k) {
+            uint32_t c = (uint32_t)(codes >> (2 * t)) & 3u;
+            // A 0x41, C 0x43, G 0x47, T 0x54
+            uint64_t ch = c == 0 ? 0x41 : (c == 1 ? 0x43 : (c == 2 ? 0x47 : 0x54));
+            w[t >> 3] |= ch << (8 * (t & 7));
+        }
+    }
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    uint64_t h1 = seed, h2 = seed;
+    const int nblocks = k / 16;
+#define DIPB_MURMUR_BLOCK(K1, K2)                                              \
+    do {                                                                       \
+        uint64_t k1 = (K1), k2 = (K2);                                         \
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;                     \
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;               \
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;                     \
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;               \
+    } while (0)
+    if (nblocks >= 1) DIPB_MURMUR_BLOCK(w[0], w[1]);
+    if (nblocks >= 2) DIPB_MURMUR_BLOCK(w[2], w[3]);
+#undef DIPB_MURMUR_BLOCK
+    const int rem = k & 15;
+    if (rem) {
+        // bytes beyond k are zero in w[], so the switch fall-through of the reference is implicit
+        uint64_t k1 = nblocks == 0 ? w[0] : w[2], k2 = nblocks == 0 ? w[1] : w[3];
+        if (rem > 8) { k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    }
+    h1 ^= (uint64_t)k; h2 ^= (uint64_t)k;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2;
+    return h1;
+}
+
+// canonical k-mer (src/mash.cu:239-258,320-321): the lexicographically smaller of the
+// forward string and its reverse complement (A<C<G<T == code order), forward on ties.
+__device__ __forceinline__ uint64_t canonical_codes(uint64_t fwd, int k) {
+    // rc: complement (3 - c == ~c & 3) and reverse the order of the k 2-bit groups
+    uint64_t x = ~fwd;
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = __byte_perm((uint32_t)(x >> 32), 0, 0x0123) | ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32);
+    uint64_t rc = k == 32 ? x : (x >> (64 - 2 * k));
+    uint64_t mask = k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    fwd &= mask;
+    // lexicographic compare == integer compare with the FIRST base most significant
+    auto msb_first = [&](uint64_t v) {
+        uint64_t y = v;
+        y = ((y >> 2) & 0x3333333333333333ULL) | ((y & 0x3333333333333333ULL) << 2);
+        y = ((y >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((y & 0x0F0F0F0F0F0F0F0FULL) << 4);
+        y = __byte_perm((uint32_t)(y >> 32), 0, 0x0123) | ((uint64_t)__byte_perm((uint32_t)y, 0, 0x0123) << 32);
+        return k == 32 ? y : (y >> (64 - 2 * k));
+    };
+    return msb_first(fwd) <= msb_first(rc) ? fwd : rc;
+}
+
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* buf, int n_pow2) {
+    for (int size = 2; size <= n_pow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < n_pow2 / 2; t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = (lo & size) == 0;
+                uint64_t a = buf[lo], b = buf[hi];
+                if ((a > b) == up) { buf[lo] = b; buf[hi] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SK_THREADS, 1)
+sketch_kernel(const uint64_t* __restrict__ seqs, const uint64_t* __restrict__ word_off, const uint64_t* __restrict__ lens,
+              int n, int k, int s, uint64_t* __restrict__ out) {
+    __shared__ uint64_t buf[SK_BUF];
+    __shared__ int cnt;
+    __shared__ uint64_t thr;
+    const int tid = threadIdx.x;
+    for (int seq = blockIdx.x; seq < n; seq += gridDim.x) {
+        const uint64_t* w = seqs + word_off[seq];
+        const uint64_t len = lens[seq];
+        for (int t = tid; t < SK_BUF; t += SK_THREADS) buf[t] = ~0ULL;
+        if (tid == 0) { cnt = 0; thr = ~0ULL; }
+        __syncthreads();
+        const uint64_t nk = len >= (uint64_t)k ? len - k + 1 : 0;
+        for (uint64_t base = 0; base < nk; base += SK_THREADS) {
+            // make room: after a sort only the bottom s survive
+            if (cnt > SK_BUF - SK_THREADS) {
+                bitonic_sort_smem(buf, SK_BUF);
+                for (int t = s + tid; t < SK_BUF; t += SK_THREADS) buf[t] = ~0ULL;
+                __syncthreads();
+                if (tid == 0) { cnt = s; thr = buf[s - 1]; }
+                __syncthreads();
+            }
+            const uint64_t j = base + tid;
+            if (j < nk) {
+                const uint64_t idx = j >> 5;
+                const int sh = 2 * (int)(j & 31);
+                uint64_t kmer = w[idx] >> sh;
+                if (sh) kmer |= w[idx + 1] << (64 - sh);   // flat buffer carries one pad word (App. B18)
+                uint64_t h = murmur_kmer(canonical_codes(kmer, k), k, 42u);
+                if (h < thr) {
+                    int pos = atomicAdd(&cnt, 1);
+                    buf[pos] = h;
+                }
+            }
+            __syncthreads();
+        }
+        bitonic_sort_smem(buf, SK_BUF);
+        for (int t = tid; t < s; t += SK_THREADS) out[(size_t)seq * s + t] = buf[t];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Mash distance tiles
+// ---------------------------------------------------------------------------
+constexpr int MD_TA = 16;   // column sketches per tile (the "A" list of src/mash.cu:437)
+constexpr int MD_TB = 8;    // row sketches per tile (the "B" list, rowId)
+constexpr int MD_THREADS = MD_TA * MD_TB;
+
+struct MashTileParams {
+    const uint64_t* sk;
+    int n, s, k;
+    int tri;           // 1: lower triangle with mirror into an n x n matrix
+    int r0, r1, ncols; // rectangle: rows [r0,r1) x cols [0,ncols)
+    double* out;
+    size_t ld;
+    int row_off;
+};
+
+__global__ void __launch_bounds__(MD_THREADS, 1) mash_tile_kernel(MashTileParams p, long long num_tiles, int tiles_x) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* sA = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* sB = sA + (size_t)MD_TA * p.s;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sB + (size_t)MD_TB * p.s);
+    const int tid = threadIdx.x;
+    const int ia = tid % MD_TA, ib = tid / MD_TA;
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    uint32_t phase = 0;
+    const uint32_t sk_bytes = (uint32_t)p.s * 8u;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int tb, ta;
+        if (p.tri) {
+            // tile rows of MD_TB, tile cols of MD_TA over the lower triangle (col0 <= row_max)
+            tb = (int)(t / tiles_x); ta = (int)(t % tiles_x);
+        } else {
+            tb = (int)(t / tiles_x); ta = (int)(t % tiles_x);
+        }
+        const int row0 = p.r0 + tb * MD_TB, col0 = ta * MD_TA;
+        const int row_max = min(row0 + MD_TB, p.r1) - 1;
+        if (p.tri && col0 > row_max) continue;   // strictly above the diagonal: nothing to do (uniform per CTA)
+        if (tid == 0) {
+            int na = min(MD_TA, p.n - col0), nb = min(MD_TB, p.r1 - row0);
+            mbar_arrive_expect_tx(bar, (uint32_t)(na + nb) * sk_bytes);
+            for (int q = 0; q < na; q++) tma_bulk_g2s(sA + (size_t)q * p.s, p.sk + (size_t)(col0 + q) * p.s, sk_bytes, bar);
+            for (int q = 0; q < nb; q++) tma_bulk_g2s(sB + (size_t)q * p.s, p.sk + (size_t)(row0 + q) * p.s, sk_bytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        const int i = row0 + ib, j = col0 + ia;
+        const int jlim = p.tri ? i : p.ncols;
+        if (i < p.r1 && j < jlim && j < p.n) {
+            const uint64_t* A = sA + (size_t)ia * p.s;
+            const uint64_t* B = sB + (size_t)ib * p.s;
+            const int s = p.s;
+            int a = 0, b = 0, uni = 0, inter = 0;
+            uint64_t av = A[0], bv = B[0];
+            // src/mash.cu:439-450, one consumed element per step
+            while (uni < s) {
+                const bool bvalid = b < s;
+                const bool takeB = bvalid && bv <= av;
+                const bool eq = takeB && bv == av;
+                if (takeB) { b++; bv = B[b < s ? b : s - 1]; }
+                else { a++; av = A[a < s ? a : s - 1]; }
+                uni += eq ? 0 : 1;
+                inter += eq ? 1 : 0;
+            }
+            // :453-454
+            double jac = fmax(double(inter), 1.0) / uni;
+            double d = fmin(1.0, fabs(log(2.0 * jac / (1.0 + jac)) / p.k));
+            if (p.tri) {
+                p.out[(size_t)i * p.ld + j] = d;
+                p.out[(size_t)j * p.ld + i] = d;
+            } else {
+                p.out[(size_t)(i - p.row_off) * p.ld + j] = d;
+            }
+        }
+        __syncthreads();   // tile buffers are reused
+    }
+}
+
+__global__ void zero_diag_kernel(double* D, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) D[(size_t)i * n + i] = 0.0;
+}
+
+static int mash_launch(dipb_mash* m, MashTileParams p) {
+    dipb_ctx* c = m->ctx;
+    size_t smem = (size_t)(MD_TA + MD_TB) * m->s * 8 + 64;
+    if (smem > 227 * 1024) { set_error("mash distance: sketch size %d does not fit shared memory tiles", m->s); return DIPB_E_ARG; }
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        DIPB_CUDA(cudaFuncSetAttribute(mash_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    int rows = p.r1 - p.r0;
+    int ncols = p.tri ? p.r1 : p.ncols;
+    int tiles_y = (rows + MD_TB - 1) / MD_TB, tiles_x = (ncols + MD_TA - 1) / MD_TA;
+    long long tiles = (long long)tiles_y * tiles_x;
+    if (tiles <= 0) return 0;
+    int grid = (int)(tiles < (long long)c->num_sms * 8 ? tiles : (long long)c->num_sms * 8);
+    mash_tile_kernel<<<grid, MD_THREADS, smem, c->stream>>>(p, tiles, tiles_x);
+    DIPB_KERNEL_CHECK(c);
+    return 0;
+}
+
+}  // namespace dipb
+
+using namespace dipb;
+
+extern "C" {
+
+int dipb_mash_upload_flat(dipb_ctx* c, const uint64_t* flat, const uint64_t* word_off, const uint64_t* len, size_t n,
+                          int k, int s, dipb_mash** out) {
+    if (!c || !flat || !word_off || !len || !out || n == 0) { set_error("dipb_mash_upload_flat: bad argument"); return DIPB_E_ARG; }
+    if (k < 2 || k > 32) { set_error("dipb_mash_upload: k-mer size %d outside 2..32", k); return DIPB_E_ARG; }
+    if (s < 2 || s > SK_BUF - SK_THREADS || (s & 1)) { set_error("dipb_mash_upload: sketch size %d must be even and within 2..%d", s, SK_BUF - SK_THREADS); return DIPB_E_ARG; }
+    DIPB_CUDA(cudaSetDevice(c->device));
+    dipb_mash* m = new dipb_mash();
+    m->ctx = c; m->n = (int)n; m->k = k; m->s = s;
+    size_t words = word_off[n - 1] + (len[n - 1] + 31) / 32;
+    DIPB_CUDA(cudaMalloc(&m->seqs, (words + 1) * 8));
+    DIPB_CUDA(cudaMalloc(&m->word_off, n * 8));
+    DIPB_CUDA(cudaMalloc(&m->lens, n * 8));
+    DIPB_CUDA(cudaMalloc(&m->sketches, n * (size_t)s * 8));
+    DIPB_CUDA(cudaMemsetAsync(m->seqs + words, 0, 8, c->stream));
+    DIPB_CUDA(cudaMemcpyAsync(m->seqs, flat, words * 8, cudaMemcpyHostToDevice, c->stream));
+    DIPB_CUDA(cudaMemcpyAsync(m->word_off, word_off, n * 8, cudaMemcpyHostToDevice, c->stream));
+    DIPB_CUDA(cudaMemcpyAsync(m->lens, len, n * 8, cudaMemcpyHostToDevice, c->stream));
+    DIPB_CUDA(cudaStreamSynchronize(c->stream));
+    *out = m;
+    return 0;
+}
+
+int dipb_mash_upload(dipb_ctx* c, const uint64_t* const* seq2, const uint64_t* len, size_t n, int k, int s, dipb_mash** out) {
+    if (!c || !seq2 || !len || !out || n == 0) { set_error("dipb_mash_upload: bad argument"); return DIPB_E_ARG; }
+    std::vector<uint64_t> off(n);
+    size_t tot = 0;
+    for (size_t i = 0; i < n; i++) { off[i] = tot; tot += (len[i] + 31) / 32; }
+    std::vector<uint64_t> flat(tot ? tot : 1);
+    for (size_t i = 0; i < n; i++) memcpy(flat.data() + off[i], seq2[i], ((len[i] + 31) / 32) * 8);
+    return dipb_mash_upload_flat(c, flat.data(), off.data(), len, n, k, s, out);
+}
+
+int dipb_mash_set_sketches(dipb_ctx* c, const uint64_t* h_sk, size_t n, int k, int s, dipb_mash** out) {
+    if (!c || !h_sk || !out || n == 0 || s < 2 || (s & 1)) { set_error("dipb_mash_set_sketches: bad argument (sketch size must be even)"); return DIPB_E_ARG; }
+    DIPB_CUDA(cudaSetDevice(c->device));
+    dipb_mash* m = new dipb_mash();
+    m->ctx = c; m->n = (int)n; m->k = k; m->s = s;
+    DIPB_CUDA(cudaMalloc(&m->sketches, n * (size_t)s * 8));
+    DIPB_CUDA(cudaMemcpy(m->sketches, h_sk, n * (size_t)s * 8, cudaMemcpyHostToDevice));
+    m->sketched = true;
+    *out = m;
+    return 0;
+}
+
+void dipb_mash_free(dipb_mash* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    cudaFree(m->seqs); cudaFree(m->word_off); cudaFree(m->lens); cudaFree(m->sketches);
+    delete m;
+}
+
+int dipb_mash_sketch(dipb_mash* m) {
+    if (!m || !m->seqs) { set_error("dipb_mash_sketch: no sequences uploaded"); return DIPB_E_STATE; }
+    dipb_ctx* c = m->ctx;
+    DIPB_CUDA(cudaSetDevice(c->device));
+    int rc = timer_begin(c);
+    if (rc) return rc;
+    int grid = m->n < c->num_sms * 2 ? m->n : c->num_sms * 2;
+    sketch_kernel<<<grid, SK_THREADS, 0, c->stream>>>(m->seqs, m->word_off, m->lens, m->n, m->k, m->s, m->sketches);
+    DIPB_KERNEL_CHECK(c);
+    rc = timer_end(c, DIPB_T_SKETCH);
+    if (rc) return rc;
+    m->sketched = true;
+    return 0;
+}
+
+int dipb_mash_get_sketches(dipb_mash* m, uint64_t* h_out) {
+    if (!m || !h_out) { set_error("dipb_mash_get_sketches: bad argument"); return DIPB_E_ARG; }
+    if (!m->sketched) { set_error("dipb_mash_get_sketches: call dipb_mash_sketch first"); return DIPB_E_STATE; }
+    DIPB_CUDA(cudaSetDevice(m->ctx->device));
+    DIPB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    DIPB_CUDA(cudaMemcpy(h_out, m->sketches, (size_t)m->n * m->s * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dipb_mash_dist_block(dipb_mash* m, int r0, int r1, int ncols, double* d_out, size_t ld) {
+    if (!m || !d_out || r0 < 0 || r1 > m->n || r0 >= r1 || ncols < 0 || ncols > m->n) { set_error("dipb_mash_dist_block: bad argument"); return DIPB_E_ARG; }
+    if (!m->sketched) { set_error("dipb_mash_dist_block: sketches not built (call dipb_mash_sketch)"); return DIPB_E_STATE; }
+    if (ncols == 0) return 0;
+    DIPB_CUDA(cudaSetDevice(m->ctx->device));
+    MashTileParams p{};
+    p.sk = m->sketches; p.n = m->n; p.s = m->s; p.k = m->k; p.tri = 0; p.r0 = r0; p.r1 = r1; p.ncols = ncols;
+    p.out = d_out; p.ld = ld; p.row_off = r0;
+    return mash_launch(m, p);
+}
+
+int dipb_mash_dist_row(dipb_mash* m, int row, double* d_out) {
+    if (!m || !d_out || row < 0 || row >= m->n) { set_error("dipb_mash_dist_row: bad argument"); return DIPB_E_ARG; }
+    if (row == 0) return 0;
+    int rc = dipb_mash_dist_block(m, row, row + 1, row, d_out, (size_t)m->n);
+    if (rc) return rc;
+    DIPB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return 0;
+}
+
+int dipb_mash_dist_row_host(dipb_mash* m, int row, double* h_out) {
+    if (!m || !h_out || row < 0 || row >= m->n) { set_error("dipb_mash_dist_row_host: bad argument"); return DIPB_E_ARG; }
+    if (row == 0) return 0;
+    DIPB_CUDA(cudaSetDevice(m->ctx->device));
+    double* d = nullptr;
+    DIPB_CUDA(cudaMalloc(&d, sizeof(double) * m->n));
+    int rc = dipb_mash_dist_row(m, row, d);
+    if (!rc && cudaMemcpy(h_out, d, sizeof(double) * row, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("dipb_mash_dist_row_host: D2H failed"); rc = DIPB_E_CUDA; }
+    cudaFree(d);
+    return rc;
+}
+
+int dipb_mash_dist_matrix(dipb_mash* m, dipb_matrix** out) {
+    if (!m || !out) { set_error("dipb_mash_dist_matrix: bad argument"); return DIPB_E_ARG; }
+    if (!m->sketched) { set_error("dipb_mash_dist_matrix: sketches not built (call dipb_mash_sketch)"); return DIPB_E_STATE; }
+    dipb_ctx* c = m->ctx;
+    DIPB_CUDA(cudaSetDevice(c->device));
+    dipb_matrix* M = new dipb_matrix();
+    M->ctx = c; M->n = m->n;
+    size_t bytes = (size_t)m->n * m->n * sizeof(double);
+    if (cudaMalloc(&M->d, bytes) != cudaSuccess) { set_error("dipb_mash_dist_matrix: cudaMalloc(%zu) failed", bytes); delete M; return DIPB_E_NOMEM; }
+    int rc = timer_begin(c);
+    MashTileParams p{};
+    p.sk = m->sketches; p.n = m->n; p.s = m->s; p.k = m->k; p.tri = 1; p.r0 = 0; p.r1 = m->n; p.ncols = m->n;
+    p.out = M->d; p.ld = (size_t)m->n; p.row_off = 0;
+    if (!rc) rc = mash_launch(m, p);
+    if (!rc) {
+        zero_diag_kernel<<<(m->n + 255) / 256, 256, 0, c->stream>>>(M->d, m->n);
+        c->launches++;
+        rc = timer_end(c, DIPB_T_MASH_DIST);
+    }
+    if (rc) { cudaFree(M->d); delete M; return rc; }
+    *out = M;
+    return 0;
+}
+
+}  // extern "C"

@@ -5,16 +5,6 @@
 using namespace dipb;
 #define NOTYET(name) do { set_error(name ": not implemented in this build"); return DIPB_E_STATE; } while (0)
 extern "C" {
-int dipb_mash_upload(dipb_ctx*, const uint64_t* const*, const uint64_t*, size_t, int, int, dipb_mash**) { NOTYET("dipb_mash_upload"); }
-int dipb_mash_upload_flat(dipb_ctx*, const uint64_t*, const uint64_t*, const uint64_t*, size_t, int, int, dipb_mash**) { NOTYET("dipb_mash_upload_flat"); }
-void dipb_mash_free(dipb_mash*) {}
-int dipb_mash_sketch(dipb_mash*) { NOTYET("dipb_mash_sketch"); }
-int dipb_mash_get_sketches(dipb_mash*, uint64_t*) { NOTYET("dipb_mash_get_sketches"); }
-int dipb_mash_set_sketches(dipb_ctx*, const uint64_t*, size_t, int, int, dipb_mash**) { NOTYET("dipb_mash_set_sketches"); }
-int dipb_mash_dist_row(dipb_mash*, int, double*) { NOTYET("dipb_mash_dist_row"); }
-int dipb_mash_dist_row_host(dipb_mash*, int, double*) { NOTYET("dipb_mash_dist_row_host"); }
-int dipb_mash_dist_block(dipb_mash*, int, int, int, double*, size_t) { NOTYET("dipb_mash_dist_block"); }
-int dipb_mash_dist_matrix(dipb_mash*, dipb_matrix**) { NOTYET("dipb_mash_dist_matrix"); }
 int dipb_place_kclosest(dipb_ctx*, const dipb_dist_source*, int, dipb_tree**) { NOTYET("dipb_place_kclosest"); }
 int dipb_place_add(dipb_ctx*, const dipb_dist_source*, int, int, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const double*, dipb_tree**) { NOTYET("dipb_place_add"); }
 int dipb_tree_export(dipb_tree*, int32_t*, int32_t*, int32_t*, int32_t*, double*) { NOTYET("dipb_tree_export"); }

@@ -64,3 +64,25 @@ def test_msa_nj_tree_vs_reference_cuda(ctx, oracle, tmp_path):
     assert newick.max_branch_diff(nwk, ref_nwk) < 1e-5
     o = oracle.nj(oracle.msa_dist_matrix(P, L, 2))
     assert newick.rf_distance(oracle.nj_newick(*o, synth.names(n)), ref_nwk) == 0
+
+
+def test_mash_sketches_and_rows_vs_reference_cuda(ctx, oracle, tmp_path):
+    codes, _ = synth.evolve(64, 3000, seed=43, regime="tiefree", gap_cols=0.02)
+    seqs = synth.unaligned(codes)
+    packed = [synth.pack2_np(s) for s in seqs]
+    lens = np.array([len(s) for s in seqs], np.uint64)
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "o")
+    write_bin(inp, packed, lens, 2)
+    run_ref("mash_sketch", inp, out, 2, 15)
+    ref_sk = np.fromfile(out + ".sk", np.uint64).reshape(64, 1000)
+    m = api.MashDeviceArrays(ctx)
+    m.allocateDeviceArrays(packed, lens, 64, api.Param(kmerSize=15, sketchSize=1000, in_="r"))
+    m.sketchConstructionOnGpu()
+    assert np.array_equal(m.sketches(), ref_sk)                      # bit-exact vs the reference's kernel
+    flat, offs, ln = synth.flatten2(seqs)
+    assert np.array_equal(oracle.sketch_all(flat, offs, ln, 15, 1000), ref_sk)   # pins the oracle too
+    run_ref("mash_rows", inp, out, 2, 15)
+    ref_rows = np.fromfile(out + ".rows", np.float64)
+    D = m.distMatrix().to_host()
+    mine = np.concatenate([D[i, :i] for i in range(1, 64)])
+    assert np.array_equal(mine, ref_rows)
