@@ -86,3 +86,23 @@ def test_mash_sketches_and_rows_vs_reference_cuda(ctx, oracle, tmp_path):
     D = m.distMatrix().to_host()
     mine = np.concatenate([D[i, :i] for i in range(1, 64)])
     assert np.array_equal(mine, ref_rows)
+
+
+def test_msa_placement_tree_vs_reference_cuda(ctx, oracle, tmp_path):
+    """-m 1 k-closest placement: our tree vs the reference's own placement kernels."""
+    n, L = 300, 3000
+    codes, P, _ = make_msa(n, L, seed=44)
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "o")
+    write_bin(inp, P, [L] * n, 4)
+    run_ref("msa_place", inp, out, 2)
+    ref_nwk = open(out + ".nwk").read()
+    prm = api.Param(distanceType=2, in_="m")
+    msa = api.MSADeviceArrays(ctx)
+    msa.allocateDeviceArrays(P, np.full(n, L, np.uint64), n, prm)
+    kp = api.KPlacementDeviceArrays(ctx)
+    kp.allocateDeviceArrays(n)
+    kp.findPlacementTree(prm, msaDeviceArrays=msa)
+    nwk = kp.printTree(synth.names(n))
+    assert newick.rf_distance(nwk, ref_nwk) == 0
+    assert newick.max_branch_diff(nwk, ref_nwk) < 1e-5
+    assert nwk == ref_nwk      # same slots, same adjacency order, same %g text
