@@ -149,6 +149,16 @@ int dipb_place_kclosest(dipb_ctx *ctx, const dipb_dist_source *src, int n, dipb_
 int dipb_place_add(dipb_ctx *ctx, const dipb_dist_source *src, int n, int backbone, const int32_t *h_head,
                    const int32_t *h_e, const int32_t *h_nxt, const int32_t *h_belong, const double *h_len,
                    dipb_tree **out);
+/* divide and conquer (-m 3): KPlacementDeviceArraysDC::{findBackboneTreeDC, findClustersDC,
+ * findClusterTreeDC}, DC/placement_close_k.cu:731-1535.  Tips 0..backbone-1 form the
+ * backbone (placed as above, internal node ids offset by n), every other tip is assigned
+ * to its best backbone edge and the per-edge clusters are placed independently.
+ * The reference uses backbone = n / 20 (src/tree_generation.cu:425,545). */
+int dipb_dc(dipb_ctx *ctx, const dipb_dist_source *src, int n, int backbone, dipb_tree **out);
+/* test hook: cluster (backbone slot) of every tip after the last dipb_dc on this context;
+ * h_out[n], entries of backbone tips are -1 */
+int dipb_dc_cluster_ids(dipb_ctx *ctx, int32_t *h_out, int n);
+
 /* printTree's D2H half (src/placement_close_k.cu:595-618): head[2n], e/nxt/belong[8n], len[8n] */
 int dipb_tree_export(dipb_tree *t, int32_t *head, int32_t *e, int32_t *nxt, int32_t *belong, double *len);
 /* closest lists, for parity tests: cid[40n], cdis[40n] */
