@@ -332,6 +332,18 @@ class KPlacementDeviceArrays:
                                    ln, C.byref(h)))
         self.h = h
 
+    def findTreeDC(self, params, backboneSize=None, mashDeviceArrays=None, matrix=None, msaDeviceArrays=None):
+        """-m 3: findBackboneTreeDC + findClustersDC + findClusterTreeDC (DC/placement_close_k.cu:731-1535);
+        backbone = numSequences / 20 unless given (src/tree_generation.cu:425,545)."""
+        s = self._source(params, mashDeviceArrays, matrix, msaDeviceArrays)
+        B = self.numSequences // 20 if backboneSize is None else backboneSize
+        h = C.c_void_p()
+        check(lib().dipb_dc(self.ctx.h, C.byref(s), self.numSequences, B, C.byref(h)))
+        self.h = h
+        cl = np.zeros(self.numSequences, np.int32)
+        check(lib().dipb_dc_cluster_ids(self.ctx.h, cl, self.numSequences))
+        self.clusterID = cl
+
     def export(self):
         n = self.numSequences
         head = np.zeros(2 * n, np.int32)

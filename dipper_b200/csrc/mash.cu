@@ -14,15 +14,7 @@
 #include <vector>
 #include "common.cuh"
 
-struct dipb_mash {
-    dipb_ctx* ctx = nullptr;
-    int n = 0, k = 15, s = 1000;
-    uint64_t* seqs = nullptr;      // flat 2-bit words (+1 pad word)
-    uint64_t* word_off = nullptr;  // [n]
-    uint64_t* lens = nullptr;      // [n] bases
-    uint64_t* sketches = nullptr;  // [n][s]
-    bool sketched = false;
-};
+#include "mash.cuh"
 
 namespace dipb {
 

@@ -22,6 +22,7 @@
 //    loop with other boolean functors, accumulating int32 counters per pair.
 #include "common.cuh"
 #include "msa.cuh"
+#include "msa_pair.cuh"
 
 namespace dipb {
 
@@ -63,39 +64,6 @@ __global__ void msa_repack_kernel(const uint64_t* __restrict__ in, int n, int se
     planes[base + (2 * MSA_KC + kk) * MSA_TS + sl] = pv;
 }
 
-// ---------------------------------------------------------------------------
-// per-word boolean functors: two 32-bit masks whose popcounts are accumulated
-// ---------------------------------------------------------------------------
-template <int FN>
-__device__ __forceinline__ void pair_masks(uint32_t a0, uint32_t a1, uint32_t av, uint32_t b0, uint32_t b1,
-                                           uint32_t bv, uint32_t& m1, uint32_t& m2) {
-    uint32_t vv = av & bv;
-    uint32_t x0 = a0 ^ b0, x1 = a1 ^ b1;
-    if (FN == 0) {  // match, both-valid                       src/MSA.cu:96-97
-        m1 = vv & ~(x0 | x1);
-        m2 = vv;
-    } else if (FN == 1) {  // transitions, transversions         DC/msa.cu:161-162
-        m1 = vv & ~x0 & x1;
-        m2 = vv & x0;
-    } else if (FN == 2) {  // GC at mismatching sites: row seq, column seq   DC/msa.cu:195-196
-        uint32_t mm = vv & (x0 | x1);
-        m1 = mm & (a0 ^ a1);
-        m2 = mm & (b0 ^ b1);
-    } else if (FN >= 3 && FN <= 6) {  // occurrences of code FN-3 over both-valid sites  DC/msa.cu:115
-        const int c = FN - 3;
-        uint32_t ea = ((c & 1) ? a0 : ~a0) & ((c & 2) ? a1 : ~a1);
-        uint32_t eb = ((c & 1) ? b0 : ~b0) & ((c & 2) ? b1 : ~b1);
-        m1 = vv & ea;
-        m2 = vv & eb;
-    } else if (FN == 7) {  // unordered pairs {A,G}, {A,T}        DC/msa.cu:121-122
-        m1 = vv & x1 & ~a0 & ~b0;
-        m2 = vv & x0 & x1 & ~(a0 ^ a1);
-    } else {  // FN == 8: {C,G}, {C,T}                            DC/msa.cu:123-124
-        m1 = vv & x0 & x1 & (a0 ^ a1);
-        m2 = vv & x1 & a0 & b0;
-    }
-}
-
 struct TileParams {
     const uint32_t* planes;
     const int* nv;
@@ -132,13 +100,6 @@ __device__ __forceinline__ void tile_of(const TileParams& p, long long t, int& b
         bi = p.bi0 + (int)(t / p.nbj);
         bj = (int)(t % p.nbj);
     }
-}
-
-__device__ __forceinline__ double dist_p_jc(int match, int useful, int dist_type) {
-    // src/MSA.cu:233-235, same expression order
-    double uncor = 1 - double(match) / useful;
-    if (dist_type == DIPB_DIST_UNCORRECTED) return uncor;
-    return -0.75 * log(1.0 - uncor / 0.75);
 }
 
 template <int FN, bool FAST>
@@ -273,35 +234,6 @@ __global__ void __launch_bounds__(MSA_THREADS, 1) msa_tile_kernel(TileParams p, 
 struct StatPtrs {
     const int* c[18];  // FN f -> c[2f], c[2f+1]
 };
-
-__device__ double dist_from_counts(int type, int match, int both, int nvi, int nvj, int ts, int tv, int gcr, int gcc,
-                                   const int* frac, const int* pr) {
-    if (type == DIPB_DIST_UNCORRECTED || type == DIPB_DIST_JC) return dist_p_jc(match, nvi + nvj - both, type);
-    int tot = both;
-    if (type == DIPB_DIST_TAJIMANEI) {  // DC/msa.cu:239-250
-        double fr[4];
-        for (int i = 0; i < 4; i++) fr[i] = double(frac[i]) / tot / 2.0;
-        double h = 0;
-        h += 0.5 * pr[0] * fr[0] * fr[2];
-        h += 0.5 * pr[1] * fr[0] * fr[3];
-        h += 0.5 * pr[2] * fr[1] * fr[2];
-        h += 0.5 * pr[3] * fr[1] * fr[3];
-        double D = double(tot - match) / tot;
-        double b = 0.5 * (1.0 - fr[0] * fr[0] - fr[2] * fr[2] + D * D / h);
-        return -b * log(1.0 - D / b);
-    }
-    if (type == DIPB_DIST_K2P || type == DIPB_DIST_JINNEI) {  // DC/msa.cu:252-257
-        double pp = double(ts) / tot, qq = double(tv) / tot;
-        if (type == DIPB_DIST_K2P) return -0.5 * log((1 - 2 * pp - qq) * sqrt(1 - 2 * qq));
-        return 0.5 * (1.0 / (1 - 2 * pp - qq) + 0.5 / (1 - qq * 2) - 1.5);
-    }
-    if (type == DIPB_DIST_TAMURA) {  // DC/msa.cu:259-263
-        double pp = double(ts) / tot, qq = double(tv) / tot,
-               c = double(gcr) / tot + double(gcc) / tot - 2 * double(gcr) * double(gcc) / tot / tot;
-        return -c * log(1 - pp / c - qq) - 0.5 * (1 - c) * log(1 - 2 * qq);
-    }
-    return 0.0;
-}
 
 __global__ void msa_finalize_kernel(StatPtrs sp, const int* __restrict__ nv, int type, int r0, int r1, int ncols,
                                     size_t ld_cnt, double* out, size_t ld_out, int row_off, int mirror) {

@@ -16,71 +16,9 @@
 #include "common.cuh"
 #include "msa.cuh"
 
-struct dipb_mash;
-extern "C" int dipb_mash_dist_block(dipb_mash* m, int r0, int r1, int ncols, double* d_out, size_t ld);
-
-struct dipb_tree {
-    dipb_ctx* ctx = nullptr;
-    int n = 0;
-    int *head = nullptr, *e = nullptr, *nxt = nullptr, *belong = nullptr, *cid = nullptr, *rev = nullptr;
-    double *len = nullptr, *cdis = nullptr;
-};
+#include "placement_dev.cuh"
 
 namespace dipb {
-
-constexpr int KC5 = 5;
-constexpr int PL_THREADS = 256;
-
-struct PlCand {
-    double add;
-    double frac;
-    int slot;
-    int pad;
-};
-
-struct PlShared {
-    unsigned int bar_counter;
-    unsigned int q_tail;
-    int idx;   // next free slot
-    int pad;
-};
-
-__device__ __forceinline__ void pl_grid_barrier(unsigned int* counter, unsigned int nblocks, unsigned int& gen) {
-    gen++;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int target = gen * nblocks;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned int v;
-        do {
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while ((int)(v - target) < 0);
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void link_slot(int* head, int* e, int* nxt, int* belong, double* len, int slot, int from,
-                                          int to, double l) {
-    e[slot] = to; len[slot] = l; nxt[slot] = head[from]; head[from] = slot; belong[slot] = from;
-}
-
-// insert (d, x) into the 5-entry list of slot s before the first entry with dis > d; true if inserted
-__device__ __forceinline__ bool list_insert(double* cdis, int* cid, int s, double d, int x) {
-    for (int j = 0; j < KC5; j++) {
-        if (cdis[s * KC5 + j] > d) {
-            for (int k = KC5 - 1; k > j; k--) {
-                cdis[s * KC5 + k] = cdis[s * KC5 + k - 1];
-                cid[s * KC5 + k] = cid[s * KC5 + k - 1];
-            }
-            cdis[s * KC5 + j] = d;
-            cid[s * KC5 + j] = x;
-            return true;
-        }
-    }
-    return false;
-}
 
 // updateClosestNodes (:86-124) as a level-synchronous BFS run by one CTA.  Every slot is
 // reached at most once (tree), so processing a level in parallel gives the serial result.
@@ -111,61 +49,6 @@ __device__ void bfs_closest(const int* head, const int* nxt, const int* e, const
         __syncthreads();
     }
     __syncthreads();
-}
-
-// updateTreeStructure (:446-528), one thread
-__device__ void split_edge(int* head, int* nxt, int* e, double* len, double* cdis, int* cid, int* belong, int* rev,
-                           int eid, double fracLen, double addLen, int placeId, int edgeCount, int node_off) {
-    const int middle = placeId + node_off - 1, outside = placeId;
-    const int x = belong[eid], y = e[eid];
-    const double orig = len[eid];
-    const int xe = eid, ye = rev[eid];
-    e[xe] = middle; len[xe] = fracLen;
-    e[ye] = middle; len[ye] -= fracLen;
-    const int c0 = edgeCount, c1 = edgeCount + 1, c2 = edgeCount + 2, c3 = edgeCount + 3;
-    link_slot(head, e, nxt, belong, len, c0, middle, x, fracLen);
-    for (int k = 0; k < KC5; k++)
-        if (cid[ye * KC5 + k] != -1) { cid[c0 * KC5 + k] = cid[ye * KC5 + k]; cdis[c0 * KC5 + k] = cdis[ye * KC5 + k] + orig - fracLen; }
-    link_slot(head, e, nxt, belong, len, c1, middle, y, orig - fracLen);
-    for (int k = 0; k < KC5; k++)
-        if (cid[xe * KC5 + k] != -1) { cid[c1 * KC5 + k] = cid[xe * KC5 + k]; cdis[c1 * KC5 + k] = cdis[xe * KC5 + k] + fracLen; }
-    link_slot(head, e, nxt, belong, len, c2, outside, middle, addLen);
-    link_slot(head, e, nxt, belong, len, c3, middle, outside, addLen);
-    const int src[2] = {c1, c0};
-    for (int w = 0; w < 2; w++)
-        for (int i = 0; i < KC5; i++) {
-            if (cid[src[w] * KC5 + i] == -1) break;
-            list_insert(cdis, cid, c3, cdis[src[w] * KC5 + i], cid[src[w] * KC5 + i]);
-        }
-    rev[xe] = c0; rev[c0] = xe; rev[ye] = c1; rev[c1] = ye; rev[c2] = c3; rev[c3] = c2;
-}
-
-// calculateBranchLength (:309-358) for one candidate slot
-__device__ __forceinline__ void score_slot(const double* __restrict__ dis, const int* cid, const double* cdis,
-                                           const double* len, const int* rev, int q, double& frac, double& add) {
-    const int r = __ldcg(&rev[q]);
-    double d1 = 0, d2 = 0;
-#pragma unroll
-    for (int k = 0; k < KC5; k++) {
-        int id = __ldcg(&cid[q * KC5 + k]);
-        if (id != -1) { double v = dis[id] - __ldcg(&cdis[q * KC5 + k]); if (v > d1) d1 = v; }
-    }
-#pragma unroll
-    for (int k = 0; k < KC5; k++) {
-        int id = __ldcg(&cid[r * KC5 + k]);
-        if (id != -1) { double v = dis[id] - __ldcg(&cdis[r * KC5 + k]); if (v > d2) d2 = v; }
-    }
-    const double L = __ldcg(&len[q]);
-    double a = (d1 + d2 - L) / 2;
-    if (a < 0) a = 0;
-    d1 -= a; d2 -= a;
-    if (d1 < 0) d1 = 0;
-    if (d2 < 0) d2 = 0;
-    if (d1 > L) { a += d1 - L; d1 = L; }
-    if (d2 > L) { a += d2 - L; d2 = L; }
-    const double rest = L - d1 - d2;
-    d1 += rest / 2;
-    frac = d1; add = a;
 }
 
 // Places tips [i0, i1).  dist row of tip i: rows + (i - row_base) * ld.
@@ -283,7 +166,7 @@ __global__ void place_backbone_kernel(int* head, int* e, int* nxt, int* belong, 
     for (int i = 0; i < B; i++) bfs_closest(head, nxt, e, len, cdis, cid, i, q_node, q_from, q_dis, &s_tail);
 }
 
-static int tree_alloc(dipb_ctx* c, int n, dipb_tree** out) {
+int tree_alloc(dipb_ctx* c, int n, dipb_tree** out) {
     dipb_tree* t = new dipb_tree();
     t->ctx = c; t->n = n;
     size_t N = (size_t)n;
@@ -302,31 +185,39 @@ static int tree_alloc(dipb_ctx* c, int n, dipb_tree** out) {
     return 0;
 }
 
-struct RowSource {
-    const dipb_dist_source* src;
-    int n;
-    double* buf = nullptr;
-    size_t ld = 0;
-    int batch = 0;
-    // fill rows [r0, r1) (columns < r1) and return base pointer / row_base
-    int fetch(int r0, int r1, const double** rows, int* row_base) {
-        if (src->matrix) { *rows = src->matrix->d; *row_base = 0; ld = (size_t)src->matrix->n; return 0; }
-        *rows = buf; *row_base = r0;
-        if (src->msa) return msa_block(src->msa, src->dist_type, r0, r1, r1, buf, ld);
-        return dipb_mash_dist_block(src->mash, r0, r1, r1, buf, ld);
-    }
-};
+int place_scratch_alloc(dipb_ctx* c, int n, PlaceScratch* s) {
+    DIPB_CUDA(cudaMalloc(&s->ps, sizeof(PlShared)));
+    DIPB_CUDA(cudaMemsetAsync(s->ps, 0, sizeof(PlShared), c->stream));
+    DIPB_CUDA(cudaMalloc(&s->q_node, sizeof(int) * (2 * (size_t)n + 8)));
+    DIPB_CUDA(cudaMalloc(&s->q_from, sizeof(int) * (2 * (size_t)n + 8)));
+    DIPB_CUDA(cudaMalloc(&s->q_dis, sizeof(double) * (2 * (size_t)n + 8)));
+    return 0;
+}
+void place_scratch_free(PlaceScratch* s) {
+    cudaFree(s->ps); cudaFree(s->q_node); cudaFree(s->q_from); cudaFree(s->q_dis);
+    *s = PlaceScratch();
+}
 
-static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n, int first_tip, dipb_tree* t, PlShared* ps,
-                     int* q_node, int* q_from, double* q_dis) {
-    RowSource rs{src, n};
-    rs.ld = (size_t)n;
-    rs.batch = 512;
+// rows [r0, r1) x cols [0, r1) of the selected provider into buf (or the matrix itself)
+static int fetch_rows(const dipb_dist_source* src, int r0, int r1, double* buf, size_t ld, const double** rows, int* row_base,
+                      size_t* ld_out) {
+    if (src->matrix) { *rows = src->matrix->d; *row_base = 0; *ld_out = (size_t)src->matrix->n; return 0; }
+    *rows = buf; *row_base = r0; *ld_out = ld;
+    if (src->msa) return msa_block(src->msa, src->dist_type, r0, r1, r1, buf, ld);
+    return dipb_mash_dist_block(src->mash, r0, r1, r1, buf, ld);
+}
+
+// places tips [first_tip, end) onto the tree held in t (arrays sized for n_alloc leaves, internal ids offset by n_alloc)
+static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int first_tip, int end, dipb_tree* t,
+                     PlaceScratch* sc) {
+    int batch = 512;
+    double* buf = nullptr;
+    const size_t ld = (size_t)end;
     if (!src->matrix) {
         // keep the row buffer around 256 MB
-        size_t want = (size_t)rs.batch * n * sizeof(double);
-        while (want > (1ull << 28) && rs.batch > 128) { rs.batch /= 2; want /= 2; }
-        DIPB_CUDA(cudaMalloc(&rs.buf, (size_t)rs.batch * n * sizeof(double)));
+        size_t want = (size_t)batch * ld * sizeof(double);
+        while (want > (1ull << 28) && batch > 128) { batch /= 2; want /= 2; }
+        DIPB_CUDA(cudaMalloc(&buf, (size_t)batch * ld * sizeof(double)));
     }
     int G = c->num_sms;
     int per_sm = 0;
@@ -336,15 +227,15 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n, int first_
     DIPB_CUDA(cudaMalloc(&cb, sizeof(PlCand) * G));
     int rc = 0;
     unsigned int gen0 = 0;
-    for (int i0 = first_tip; i0 < n && !rc; i0 += rs.batch) {
-        int i1 = i0 + rs.batch < n ? i0 + rs.batch : n;
-        const double* rows; int row_base;
-        rc = rs.fetch(i0, i1, &rows, &row_base);
+    DIPB_CUDA(cudaMemsetAsync(&sc->ps->bar_counter, 0, sizeof(unsigned int), c->stream));
+    for (int i0 = first_tip; i0 < end && !rc; i0 += batch) {
+        int i1 = i0 + batch < end ? i0 + batch : end;
+        const double* rows; int row_base; size_t ldr;
+        rc = fetch_rows(src, i0, i1, buf, ld, &rows, &row_base, &ldr);
         if (rc) break;
-        size_t ld = rs.ld;
-        int node_off = n;
-        void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &t->cid, &t->cdis, &t->rev, &rows, &ld, &row_base,
-                        &i0, &i1, &node_off, &ps, &cb, &q_node, &q_from, &q_dis, &gen0};
+        int node_off = n_alloc;
+        void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &t->cid, &t->cdis, &t->rev, &rows, &ldr, &row_base,
+                        &i0, &i1, &node_off, &sc->ps, &cb, &sc->q_node, &sc->q_from, &sc->q_dis, &gen0};
         cudaError_t e = cudaLaunchCooperativeKernel((void*)place_batch_kernel, dim3(G), dim3(PL_THREADS), args, 0, c->stream);
         if (e != cudaSuccess) { set_error("placement: cooperative launch failed: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; break; }
         c->launches++;
@@ -353,11 +244,30 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n, int first_
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (!rc && e != cudaSuccess) { set_error("placement: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; }
     cudaFree(cb);
-    if (rs.buf) cudaFree(rs.buf);
+    if (buf) cudaFree(buf);
     return rc;
 }
 
-static int check_source(const dipb_dist_source* s, int n) {
+int place_from_scratch(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int end, dipb_tree* t, PlaceScratch* sc) {
+    // d(1,0)
+    const double* d01 = nullptr;
+    double* row1 = nullptr;
+    int rc = 0;
+    if (src->matrix) d01 = src->matrix->d + (size_t)src->matrix->n;   // row 1, column 0
+    else {
+        DIPB_CUDA(cudaMalloc(&row1, sizeof(double) * 8));
+        rc = src->msa ? msa_block(src->msa, src->dist_type, 1, 2, 1, row1, 8) : dipb_mash_dist_block(src->mash, 1, 2, 1, row1, 8);
+        if (rc) { cudaFree(row1); return rc; }
+        d01 = row1;
+    }
+    place_first_two_kernel<<<1, PL_THREADS, 0, c->stream>>>(t->head, t->e, t->nxt, t->belong, t->len, t->cid, t->cdis, t->rev, d01, n_alloc, sc->ps, sc->q_node, sc->q_from, sc->q_dis);
+    DIPB_KERNEL_CHECK(c);
+    rc = place_run(c, src, n_alloc, 2, end, t, sc);
+    if (row1) cudaFree(row1);
+    return rc;
+}
+
+int check_source(const dipb_dist_source* s, int n) {
     int cnt = (s->msa != nullptr) + (s->mash != nullptr) + (s->matrix != nullptr);
     if (cnt != 1) { set_error("placement: exactly one distance source must be set"); return DIPB_E_ARG; }
     if (s->msa && s->msa->n != n) { set_error("placement: msa holds %d sequences, n = %d", s->msa->n, n); return DIPB_E_ARG; }
@@ -381,28 +291,10 @@ int dipb_place_kclosest(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tr
     dipb_tree* t = nullptr;
     rc = tree_alloc(c, n, &t);
     if (rc) return rc;
-    PlShared* ps = nullptr;
-    int *q_node = nullptr, *q_from = nullptr;
-    double *q_dis = nullptr, *row1 = nullptr;
-    DIPB_CUDA(cudaMalloc(&ps, sizeof(PlShared)));
-    DIPB_CUDA(cudaMemsetAsync(ps, 0, sizeof(PlShared), c->stream));
-    DIPB_CUDA(cudaMalloc(&q_node, sizeof(int) * (2 * (size_t)n + 8)));
-    DIPB_CUDA(cudaMalloc(&q_from, sizeof(int) * (2 * (size_t)n + 8)));
-    DIPB_CUDA(cudaMalloc(&q_dis, sizeof(double) * (2 * (size_t)n + 8)));
-    // d(1,0)
-    const double* d01 = nullptr;
-    if (src->matrix) d01 = src->matrix->d + (size_t)n;   // row 1, column 0
-    else {
-        DIPB_CUDA(cudaMalloc(&row1, sizeof(double) * n));
-        rc = src->msa ? msa_block(src->msa, src->dist_type, 1, 2, 1, row1, (size_t)n) : dipb_mash_dist_block(src->mash, 1, 2, 1, row1, (size_t)n);
-        if (rc) return rc;
-        d01 = row1;
-    }
-    place_first_two_kernel<<<1, PL_THREADS, 0, c->stream>>>(t->head, t->e, t->nxt, t->belong, t->len, t->cid, t->cdis, t->rev, d01, n, ps, q_node, q_from, q_dis);
-    DIPB_KERNEL_CHECK(c);
-    rc = place_run(c, src, n, 2, t, ps, q_node, q_from, q_dis);
-    cudaFree(ps); cudaFree(q_node); cudaFree(q_from); cudaFree(q_dis);
-    if (row1) cudaFree(row1);
+    PlaceScratch sc;
+    rc = place_scratch_alloc(c, n, &sc);
+    if (!rc) rc = place_from_scratch(c, src, n, n, t, &sc);
+    place_scratch_free(&sc);
     if (rc) { dipb_tree_free(t); return rc; }
     rc = timer_end(c, DIPB_T_PLACE);
     if (rc) return rc;
@@ -430,19 +322,14 @@ int dipb_place_add(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone
     DIPB_CUDA(cudaMemcpyAsync(t->nxt, h_nxt, 8 * N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     DIPB_CUDA(cudaMemcpyAsync(t->belong, h_belong, 8 * N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     DIPB_CUDA(cudaMemcpyAsync(t->len, h_len, 8 * N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    PlShared* ps = nullptr;
-    int *q_node = nullptr, *q_from = nullptr;
-    double* q_dis = nullptr;
-    DIPB_CUDA(cudaMalloc(&ps, sizeof(PlShared)));
-    DIPB_CUDA(cudaMemsetAsync(ps, 0, sizeof(PlShared), c->stream));
-    DIPB_CUDA(cudaMalloc(&q_node, sizeof(int) * (2 * N + 8)));
-    DIPB_CUDA(cudaMalloc(&q_from, sizeof(int) * (2 * N + 8)));
-    DIPB_CUDA(cudaMalloc(&q_dis, sizeof(double) * (2 * N + 8)));
+    PlaceScratch sc;
+    rc = place_scratch_alloc(c, n, &sc);
+    if (rc) return rc;
     // rooted binary backbone: 4B-4 slots (src/placement_close_k.cu:887)
-    place_backbone_kernel<<<1, PL_THREADS, 0, c->stream>>>(t->head, t->e, t->nxt, t->belong, t->len, t->cid, t->cdis, t->rev, 4 * backbone - 4, backbone, ps, q_node, q_from, q_dis);
+    place_backbone_kernel<<<1, PL_THREADS, 0, c->stream>>>(t->head, t->e, t->nxt, t->belong, t->len, t->cid, t->cdis, t->rev, 4 * backbone - 4, backbone, sc.ps, sc.q_node, sc.q_from, sc.q_dis);
     DIPB_KERNEL_CHECK(c);
-    rc = place_run(c, src, n, backbone, t, ps, q_node, q_from, q_dis);
-    cudaFree(ps); cudaFree(q_node); cudaFree(q_from); cudaFree(q_dis);
+    rc = place_run(c, src, n, backbone, n, t, &sc);
+    place_scratch_free(&sc);
     if (rc) { dipb_tree_free(t); return rc; }
     rc = timer_end(c, DIPB_T_PLACE);
     if (rc) return rc;

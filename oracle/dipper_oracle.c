@@ -818,3 +818,139 @@ ORC_API int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------- */
+/* A.7 divide and conquer                                                    */
+/* ------------------------------------------------------------------------- */
+
+/* d(row, col): row is the tip being placed / assigned, col the leaf it is compared with
+ * (the roles matter for Mash: A = col, B = row). */
+typedef double (*orc_pair_fn)(void *ctx, int row, int col);
+
+/* calculateBranchLengthSpecialIDDC DC/placement_close_k.cu:180-233 over mask positions:
+ * first minimum by POSITION in edge_mask; non-candidates emit (0,0,2). */
+static void best_edge_masked(const orc_ptree *t, const double *dis, const int *edge_mask, int cnt, int *slot,
+                             double *frac, double *add) {
+    orc_place_cand best = {0, 0, 2};
+    int have = 0;
+    for (int p = 0; p < cnt; p++) {
+        orc_place_cand c = {0, 0, 2};
+        edge_candidate(t, dis, edge_mask[p], &c);
+        if (!have || c.add < best.add) { best = c; have = 1; }
+    }
+    *slot = best.slot; *frac = best.frac; *add = best.add;
+}
+
+/* updateTreeStructureInClusterDC :442-525: like orc_ptree_insert but the internal node id
+ * comes from the running count of inserted leaves */
+static void insert_in_cluster(orc_ptree *t, int eid, double fracLen, double addLen, int leaf, int edgeCount,
+                              int placeCount) {
+    int save = t->node_off;
+    /* middle = placeCount + totalN - 1, outside = leaf */
+    t->node_off = save + placeCount - leaf;
+    orc_ptree_insert(t, eid, fracLen, addLen, leaf, edgeCount);
+    t->node_off = save;
+}
+
+/* updateClosestNodesInClusterDC :312-356 */
+static void bfs_in_cluster(orc_ptree *t, int x, int cluster_eid, const int *mask_index) {
+    int l = 0, r = 0;
+    t->q_id[0] = x; t->q_dis[0] = 0; t->q_from[0] = -1;
+    int ed1 = t->e[cluster_eid], ed2 = t->belong[cluster_eid];
+    while (l <= r) {
+        int node = t->q_id[l], fb = t->q_from[l];
+        double d = t->q_dis[l];
+        l++;
+        if (node == ed1 || node == ed2) continue;
+        for (int s = t->head[node]; s != -1; s = t->nxt[s]) {
+            if (mask_index[s] != s) continue;
+            if (t->e[s] == fb) continue;
+            for (int j = 0; j < KC; j++) {
+                if (t->cdis[s * KC + j] > d) {
+                    for (int k = KC - 1; k > j; k--) {
+                        t->cdis[s * KC + k] = t->cdis[s * KC + k - 1];
+                        t->cid[s * KC + k] = t->cid[s * KC + k - 1];
+                    }
+                    t->cdis[s * KC + j] = d; t->cid[s * KC + j] = x;
+                    r++;
+                    t->q_id[r] = t->e[s]; t->q_dis[r] = d + t->len[s]; t->q_from[r] = node;
+                    break;
+                }
+            }
+        }
+    }
+}
+
+/* findBackboneTreeDC + findClustersDC + findClusterTreeDC, DC/placement_close_k.cu:731-1535.
+ * cluster_out[n]: winning backbone slot of every tip >= B (-1 for backbone tips). */
+ORC_API orc_ptree *orc_dc(int n, int B, orc_pair_fn pair, void *ctx, int32_t *cluster_out) {
+    orc_ptree *t = orc_ptree_new(n);   /* node_off = n = totalNumSequences */
+    double *dis = (double *)calloc((size_t)n, sizeof(double));
+    /* stage 1: backbone = tips 0..B-1 */
+    dis[0] = pair(ctx, 1, 0);
+    orc_ptree_init2(t, dis[0]);
+    int idx = 4;
+    orc_ptree_bfs(t, 0);
+    orc_ptree_bfs(t, 1);
+    for (int i = 2; i < B; i++) {
+        for (int j = 0; j < i; j++) dis[j] = pair(ctx, i, j);
+        int slot; double frac, add;
+        orc_ptree_best_edge(t, dis, 4 * i - 4, &slot, &frac, &add);
+        orc_ptree_insert(t, slot, frac, add, i, idx);
+        idx += 4;
+        orc_ptree_bfs(t, i);
+    }
+    /* stage 2: cluster of every remaining tip = its best backbone slot (:1014-1029) */
+    int nslots = 4 * B - 4;
+    for (int j = 0; j < n; j++) cluster_out[j] = -1;
+    for (int j = B; j < n; j++) {
+        for (int q = 0; q < B; q++) dis[q] = pair(ctx, j, q);
+        int slot; double frac, add;
+        orc_ptree_best_edge(t, dis, nslots, &slot, &frac, &add);
+        cluster_out[j] = slot;
+    }
+    /* stage 3: clusters in ascending slot order, tips ascending (:1283-1285,1357,1375) */
+    int *mask_index = (int *)malloc((size_t)8 * n * sizeof(int));
+    int *edge_mask = (int *)malloc((size_t)(4 * n + 8) * sizeof(int));
+    int *leaf_mask = (int *)malloc((size_t)(n + 16) * sizeof(int));
+    int insertLeafCount = B;
+    for (int c = 0; c < nslots; c++) {
+        int any = 0;
+        for (int j = B; j < n; j++) if (cluster_out[j] == c) { any = 1; break; }
+        if (!any) continue;
+        for (int s = 0; s < 8 * n; s++) mask_index[s] = -1;            /* resetEdgeMaskIndexDC */
+        /* initializeClusterDC :604-628 */
+        int x = t->belong[c], y = t->e[c];
+        int oth = t->head[y];
+        while (t->e[oth] != x) oth = t->nxt[oth];
+        int leafCount = 0, edgeCount = 0;
+        for (int k = 0; k < KC; k++) leaf_mask[leafCount++] = t->cid[c * KC + k];
+        for (int k = 0; k < KC; k++) leaf_mask[leafCount++] = t->cid[oth * KC + k];
+        edge_mask[edgeCount++] = c; edge_mask[edgeCount++] = oth;
+        mask_index[c] = c; mask_index[oth] = oth;
+        for (int leaf = B; leaf < n; leaf++) {
+            if (cluster_out[leaf] != c) continue;
+            for (int p = 0; p < leafCount; p++)
+                if (leaf_mask[p] != -1) dis[leaf_mask[p]] = pair(ctx, leaf, leaf_mask[p]);
+            int slot; double frac, add;
+            best_edge_masked(t, dis, edge_mask, edgeCount, &slot, &frac, &add);
+            insert_in_cluster(t, slot, frac, add, leaf, idx, insertLeafCount);
+            idx += 4; insertLeafCount++;
+            /* updateClusterInfoDC :553-572 */
+            leaf_mask[leafCount++] = leaf;
+            for (int k = 1; k <= 4; k++) { edge_mask[edgeCount++] = idx - k; mask_index[idx - k] = idx - k; }
+            bfs_in_cluster(t, leaf, c, mask_index);
+        }
+    }
+    free(mask_index); free(edge_mask); free(leaf_mask); free(dis);
+    return t;
+}
+
+static double mat_pair(void *c, int row, int col) {
+    mat_ctx *m = (mat_ctx *)c;
+    return m->D[(size_t)row * m->n + col];
+}
+ORC_API orc_ptree *orc_dc_matrix(const double *D, int n, int B, int32_t *cluster_out) {
+    mat_ctx c = {D, n};
+    return orc_dc(n, B, mat_pair, &c, cluster_out);
+}

@@ -65,6 +65,8 @@ def lib():
         L.orc_place_all_matrix.restype = C.c_void_p
         L.orc_place_add_matrix.argtypes = [C.c_void_p, f64p, C.c_int, C.c_int]
         L.orc_ptree_load_backbone.argtypes = [C.c_void_p, C.c_int, i32p, i32p, i32p, f64p, C.c_int]
+        L.orc_dc_matrix.argtypes = [f64p, C.c_int, C.c_int, i32p]
+        L.orc_dc_matrix.restype = C.c_void_p
         L.orc_ptree_newick.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
         L.orc_ptree_newick.restype = C.c_void_p
         for nm, ty in (("head", C.c_int), ("e", C.c_int), ("nxt", C.c_int), ("belong", C.c_int),
@@ -244,3 +246,11 @@ def place_add(D, B, root, child_off, child_idx, parent, bl):
                                   np.ascontiguousarray(bl, np.float64), B)
     lib().orc_place_add_matrix(t.h, D, n, B)
     return t
+
+
+def dc(D, B):
+    """Divide-and-conquer tree (DC/placement_close_k.cu:731-1535); returns (PTree, cluster ids)."""
+    D = np.ascontiguousarray(D, np.float64)
+    n = D.shape[0]
+    cl = np.zeros(n, np.int32)
+    return PTree(lib().orc_dc_matrix(D, n, B, cl), n), cl
