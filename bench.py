@@ -216,11 +216,10 @@ def main():
     prm = api.Param(distanceType=2, in_="m")
     pairs = n * (n - 1) / 2
 
-    # row-block shard of the lower triangle, balanced by area, aligned to 128-row tiles
+    from dipper_b200 import sharding
+
     def shard(r):
-        cuts = [int(round(n * np.sqrt(k / world) / 128.0)) * 128 for k in range(world + 1)]
-        cuts[0], cuts[-1] = 0, n
-        return cuts[r], cuts[r + 1]
+        return sharding.row_block_shards(n, world)[r]
 
     class DevView:   # __cuda_array_interface__ over the library's matrix for NCCL
         def __init__(self, ptr, count):
