@@ -35,7 +35,8 @@ namespace dipb {
 namespace {
 
 constexpr int PT = 1024;        // threads per CTA
-constexpr int CHUNK = 4 * PT;   // columns per scan item
+constexpr int EPT = 8;          // columns per thread per scan item
+constexpr int CHUNK = EPT * PT; // columns per scan item
 
 struct PCand {
     double t;   // candidate value, 1e300 = empty
@@ -203,17 +204,21 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                         PP[y] = pp;
                     }
                 }
-                // canonical block sum (same order as nj.cu / the oracle) and max drift
+                // canonical block sum (same order as nj.cu / the oracle) and max drift, one exchange
                 double v = warp_tree_sum(slot);
-                if (lane == 0) sh[w] = v;
+                double mxw = dlt;
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) mxw = fmax(mxw, __shfl_xor_sync(0xffffffffu, mxw, s));
+                if (lane == 0) { sh[w] = v; s_part[w] = mxw; }
                 __syncthreads();
                 if (w == 0) {
                     double g = warp_tree_sum(sh[lane]);
-                    if (lane == 0) partial_sum[blk] = g;
+                    double mx = s_part[lane];
+#pragma unroll
+                    for (int s = 16; s >= 1; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+                    if (lane == 0) { partial_sum[blk] = g; partial_max[blk] = mx; }
                 }
                 __syncthreads();
-                double mx = block_max(dlt, sh);
-                if (tid == 0) partial_max[blk] = mx;
             }
             PHASE_MARK(0);
             grid_barrier(bar_flags, G, bar_gen);
@@ -309,12 +314,20 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                 const double ur = __ldcg(&u[r]);
                 const double* row = D + (size_t)r * ld;
                 double lt = 1e300, lm = 1e300, ld_ = 0, luj = 0; int lj = -1;
+                double dv[EPT], uv[EPT];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int q = 0; q < EPT; q++) {
+                    int j = c0 + q * PT + tid;
+                    bool ok = j < n && j != r;
+                    dv[q] = ok ? __ldcg(&row[j]) : 0.0;
+                    uv[q] = ok ? __ldcg(&u[j]) : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < EPT; q++) {
                     int j = c0 + q * PT + tid;
                     if (j < n && j != r) {
-                        double d = __ldcg(&row[j]);
-                        double uj = __ldcg(&u[j]);
+                        double d = dv[q];
+                        double uj = uv[q];
                         double t = (d - ur) - uj;
                         double m = d - uj;
                         lm = fmin(lm, m);
