@@ -37,6 +37,7 @@ namespace {
 constexpr int PT = 1024;        // threads per CTA
 constexpr int EPT = 8;          // columns per thread per scan item
 constexpr int CHUNK = EPT * PT; // columns per scan item
+constexpr int POOL = 512;       // carried candidate pairs (upper bound of the minimum without a grid reduction)
 
 struct PCand {
     double t;   // candidate value, 1e300 = empty
@@ -121,14 +122,16 @@ __device__ __forceinline__ double block_max(double v, double* sh) { return -bloc
 
 __global__ void __launch_bounds__(PT, 1)
 nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, double* __restrict__ u,
-                 unsigned long long* __restrict__ K, unsigned long long* __restrict__ PP, double* __restrict__ partial_sum,
-                 double* __restrict__ partial_max, double* __restrict__ partial_ub, int* __restrict__ sel_rows,
+                 unsigned long long* __restrict__ K, double* __restrict__ partial_sum,
+                 double* __restrict__ partial_max, int* __restrict__ sel_rows,
                  PCand* __restrict__ cta_best, PShared* ps, unsigned int* __restrict__ bar_flags,
                  int2* __restrict__ log_xy, double2* __restrict__ log_bl, int n_total, double dmax) {
     __shared__ double sh[32];
     __shared__ PCand shc[32];
     __shared__ double s_ux, s_C, s_ub;
     __shared__ double s_part[PT];
+    __shared__ int pool_i[POOL], pool_j[POOL];
+    __shared__ int s_pool_head;
     const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     int n = n_total;
     double C = 0.0;
@@ -140,6 +143,9 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
     unsigned int bar_gen = 0;
     int iter = 0;
 
+    for (int p = tid; p < POOL; p += PT) { pool_i[p] = -1; pool_j[p] = -1; }
+    if (tid == 0) s_pool_head = 0;
+    __syncthreads();
     long long tmark = clock64();
 #define PHASE_MARK(k)                                                   \
     do {                                                                \
@@ -178,11 +184,6 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                             dlt = un - __ldcg(&u[i]);
                             u[i] = un;
                         }
-                        // partner remap: merged rows vanish, the last row now lives at y
-                        unsigned long long pp = __ldcg(&PP[i]);
-                        int p = (int)(unsigned int)(pp & 0xffffffffull);
-                        if (p == x || p == y) PP[i] = pp | 0xffffffffull;
-                        else if (p == last) PP[i] = (pp & 0xffffffff00000000ull) | (unsigned int)y;
                     } else {
                         double a = __ldcg(&D[(size_t)x * ld + last]), b = __ldcg(&D[(size_t)y * ld + last]);
                         double val = (a + b - dxy) * 0.5;
@@ -198,10 +199,6 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                             u[y] = un;
                         }
                         K[y] = __ldcg(&K[last]);
-                        unsigned long long pp = __ldcg(&PP[last]);
-                        int p = (int)(unsigned int)(pp & 0xffffffffull);
-                        if (p == x || p == y) pp |= 0xffffffffull;
-                        PP[y] = pp;
                     }
                 }
                 // canonical block sum (same order as nj.cu / the oracle) and max drift, one exchange
@@ -243,59 +240,50 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
             __syncthreads();
             const double ux = s_ux;
             C = s_C;
+            // upper bound of the minimum: carried pairs re-evaluated exactly with the post-merge u
+            // (no pair touches x or y; every u[] entry was rewritten in phase A)
             {
+                double pv = 1e300;
+                if (tid < POOL && pool_i[tid] >= 0) {
+                    const int pi = pool_i[tid], pj = pool_j[tid];
+                    pv = (__ldcg(&D[(size_t)pi * ld + pj]) - __ldcg(&u[pi])) - __ldcg(&u[pj]);
+                }
+                ub = block_min(pv, sh);
+            }
+            // fold the new column into K and select the rows of this CTA's segment
+            {
+                const double margin = 1e-9 * (4.0 * dmax + fabs(C));
                 const int seg = (n + G - 1) / G;
-                double loc = 1e300;
                 for (int k = tid; k < seg; k += PT) {
                     int i = cta * seg + k;
                     if (i >= n) break;
-                    if (i == x) {
-                        K[x] = 0ull;  // encoded value below every double: forces a rescan of the new row
-                        PP[x] = 0xffffffffffffffffull;
-                        continue;
+                    bool take = (i == x);   // the new row is always rescanned
+                    if (!take) {
+                        double ui = __ldcg(&u[i]);
+                        double dix = __ldcg(&D[(size_t)i * ld + x]);
+                        unsigned long long kc = enc_f64((dix - ux) + C);
+                        unsigned long long ko = __ldcg(&K[i]);
+                        if (kc < ko) { ko = kc; K[i] = kc; }
+                        double lb = (dec_f64(ko) - C) - ui - margin;
+                        take = (ko == 0ull) || !(lb > ub);
                     }
-                    double ui = __ldcg(&u[i]);
-                    double dix = __ldcg(&D[(size_t)i * ld + x]);
-                    unsigned long long kc = enc_f64((dix - ux) + C);
-                    unsigned long long ko = __ldcg(&K[i]);
-                    if (kc < ko) K[i] = kc;
-                    double t = (dix - ui) - ux;
-                    loc = fmin(loc, t);
-                    int p = (int)(unsigned int)(__ldcg(&PP[i]) & 0xffffffffull);
-                    if (p >= 0 && p < n && p != i) {
-                        double up = (p == x) ? ux : __ldcg(&u[p]);
-                        double tp = (__ldcg(&D[(size_t)i * ld + p]) - ui) - up;
-                        loc = fmin(loc, tp);
+                    if (take) {
+                        unsigned int pos = atomicAdd(&ps->sel_count, 1u);
+                        sel_rows[pos] = i;
+                        K[i] = 0xffffffffffffffffull;   // reset, the scan atomically lowers it
                     }
                 }
-                double m = block_min(loc, sh);
-                if (tid == 0) partial_ub[cta] = m;
             }
             PHASE_MARK(2);
-            grid_barrier(bar_flags, G, bar_gen);
-            PHASE_MARK(3);
-            ub = block_min(tid < G ? __ldcg(&partial_ub[tid]) : 1e300, sh);
-        }
-
-        // ---------------------------------------------------- Phase C1: select rows
-        {
-            const double margin = 1e-9 * (4.0 * dmax + fabs(C));
+        } else {
+            // first search: every row
             const int seg = (n + G - 1) / G;
             for (int k = tid; k < seg; k += PT) {
                 int i = cta * seg + k;
                 if (i >= n) break;
-                unsigned long long ke = __ldcg(&K[i]);
-                bool take = (ke == 0ull);
-                if (!take) {
-                    double lb = (dec_f64(ke) - C) - __ldcg(&u[i]) - margin;
-                    take = !(lb > ub);
-                }
-                if (take) {
-                    unsigned int pos = atomicAdd(&ps->sel_count, 1u);
-                    sel_rows[pos] = i;
-                    K[i] = 0xffffffffffffffffull;   // reset, the scan atomically lowers it
-                    PP[i] = 0xffffffffffffffffull;
-                }
+                unsigned int pos = atomicAdd(&ps->sel_count, 1u);
+                sel_rows[pos] = i;
+                K[i] = 0xffffffffffffffffull;
             }
         }
         PHASE_MARK(4);
@@ -365,7 +353,6 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                     if (lane == 0) {
                         if (rm < 1e299) atomicMin(&K[r], enc_f64(rm + C));
                         if (rj >= 0) {
-                            atomicMin(&PP[r], ((unsigned long long)enc_f32((float)rt) << 32) | (unsigned int)rj);
                             if (p_before(rt, r, rj, bt, bi, bj, n)) { bt = rt; bi = r; bj = rj; bd = rd; bui = ur; buj = ruj; }
                         }
                     }
@@ -389,6 +376,7 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
                 t = __ldcg(&cb->t); ci = __ldcg(&cb->i); cj = __ldcg(&cb->j);
                 cd = __ldcg(&cb->d); cui = __ldcg(&cb->ui); cuj = __ldcg(&cb->uj);
             }
+            const double mt = t; const int mi = ci, mj = cj;   // this CTA-winner record goes into the candidate pool
             // reduce over the first ceil(G/32) warps
 #pragma unroll
             for (int s = 16; s >= 1; s >>= 1) {
@@ -419,6 +407,28 @@ nj_pruned_kernel(double* __restrict__ D, size_t ld, double* __restrict__ U, doub
             double uxo, uyo;
             if (wi < wj) { x = wi; y = wj; uxo = wui; uyo = wuj; } else { x = wj; y = wi; uxo = wuj; uyo = wui; }
             dxy = wd;
+            // candidate pool: drop pairs touching x or y, move `last` to y, append this scan's per-CTA winners
+            {
+                const int last_ = n - 1;
+                for (int p = tid; p < POOL; p += PT) {
+                    int pi = pool_i[p], pj = pool_j[p];
+                    if (pi >= 0) {
+                        if (pi == x || pi == y || pj == x || pj == y) pool_i[p] = -1;
+                        else {
+                            if (pi == last_) pool_i[p] = y;
+                            if (pj == last_) pool_j[p] = y;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (tid < G && mt < 1e299 && mi != x && mi != y && mj != x && mj != y) {
+                    const int slot = (s_pool_head + tid) % POOL;
+                    pool_i[slot] = mi == last_ ? y : mi;
+                    pool_j[slot] = mj == last_ ? y : mj;
+                }
+                __syncthreads();
+                if (tid == 0) s_pool_head = (s_pool_head + G) % POOL;
+            }
             if (cta == 0 && tid == 0) {
                 // host step of the reference, src/neighborJoining.cu:219-237; realID bookkeeping
                 // (:233-237) is replayed on the host from this log after the kernel
@@ -448,24 +458,21 @@ int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJStat
     int max_blocks = 0;
     DIPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, nj_pruned_kernel, PT, 0));
     if (max_blocks < 1) { set_error("nj_pruned: kernel does not fit an SM"); return DIPB_E_CUDA; }
-    unsigned long long *K = nullptr, *PP = nullptr;
-    double *psum = nullptr, *pmax = nullptr, *pub = nullptr, *dmax_d = nullptr;
+    unsigned long long* K = nullptr;
+    double *psum = nullptr, *pmax = nullptr, *dmax_d = nullptr;
     int* sel = nullptr;
     PCand* cb = nullptr;
     PShared* ps = nullptr;
     const int nblk = (n + PT - 1) / PT + 1;
     DIPB_CUDA(cudaMalloc(&K, sizeof(unsigned long long) * n));
-    DIPB_CUDA(cudaMalloc(&PP, sizeof(unsigned long long) * n));
     DIPB_CUDA(cudaMalloc(&psum, sizeof(double) * nblk));
     DIPB_CUDA(cudaMalloc(&pmax, sizeof(double) * nblk));
-    DIPB_CUDA(cudaMalloc(&pub, sizeof(double) * G));
     DIPB_CUDA(cudaMalloc(&sel, sizeof(int) * n));
     DIPB_CUDA(cudaMalloc(&cb, sizeof(PCand) * G));
     DIPB_CUDA(cudaMalloc(&ps, sizeof(PShared)));
     DIPB_CUDA(cudaMalloc(&dmax_d, sizeof(double)));
     DIPB_CUDA(cudaMemsetAsync(ps, 0, sizeof(PShared), c->stream));
     DIPB_CUDA(cudaMemsetAsync(K, 0, sizeof(unsigned long long) * n, c->stream));       // 0 = "rescan me"
-    DIPB_CUDA(cudaMemsetAsync(PP, 0xff, sizeof(unsigned long long) * n, c->stream));   // no partner
     // scale for the safety margin: the initial row sums bound every later |d| and |u|
     double dmax = 0.0;
     {
@@ -486,7 +493,7 @@ int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJStat
     DIPB_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * 1024, c->stream));
     DIPB_CUDA(cudaMalloc(&log_xy, sizeof(int2) * n));
     DIPB_CUDA(cudaMalloc(&log_bl, sizeof(double2) * n));
-    void* args[] = {&Dp, &ld, &U, &u, &K, &PP, &psum, &pmax, &pub, &sel, &cb, &ps, &flags, &log_xy, &log_bl, &n_total, &dmax};
+    void* args[] = {&Dp, &ld, &U, &u, &K, &psum, &pmax, &sel, &cb, &ps, &flags, &log_xy, &log_bl, &n_total, &dmax};
     cudaError_t e = cudaLaunchCooperativeKernel((void*)nj_pruned_kernel, dim3(G), dim3(PT), args, 0, c->stream);
     if (e != cudaSuccess) { set_error("nj_pruned: cooperative launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
     c->launches++;
@@ -521,7 +528,7 @@ int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJStat
     c->nj_iterations = hs.iters;
     c->nj_bytes_scanned = 0;
     if (getenv("DIPB_NJ_PROFILE")) {
-        const char* nm[8] = {"A update", "barrier1", "B fold+ub", "barrier2", "C1 select", "barrier3", "C2 scan+barrier4", "D pick"};
+        const char* nm[8] = {"A update", "barrier1", "B fold+ub+select", "-", "-", "barrier3", "C2 scan+barrier4", "D pick+pool"};
         double tot = 0;
         for (int k = 0; k < 8; k++) tot += (double)hs.cyc[k];
         fprintf(stderr, "[nj_pruned] n=%d iters=%llu rows_scanned=%llu (%.1f/iter)\n", n, hs.iters, hs.rows_scanned,
@@ -530,7 +537,7 @@ int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJStat
             fprintf(stderr, "[nj_pruned]   %-18s %10.0f cyc/iter  %5.1f%%\n", nm[k], hs.iters ? hs.cyc[k] / (double)hs.iters : 0.0,
                     tot > 0 ? 100.0 * hs.cyc[k] / tot : 0.0);
     }
-    cudaFree(K); cudaFree(PP); cudaFree(psum); cudaFree(pmax); cudaFree(pub); cudaFree(sel); cudaFree(cb); cudaFree(ps); cudaFree(dmax_d);
+    cudaFree(K); cudaFree(psum); cudaFree(pmax); cudaFree(sel); cudaFree(cb); cudaFree(ps); cudaFree(dmax_d);
     return 0;
 }
 
