@@ -68,6 +68,14 @@ SIGNATURES = {
     "dipb_place_add": (C.c_int, [vp, C.POINTER(DistSource), C.c_int, C.c_int, i32p, i32p, i32p, i32p, f64p, vpp]),
     "dipb_dc": (C.c_int, [vp, C.POINTER(DistSource), C.c_int, C.c_int, vpp]),
     "dipb_dc_cluster_ids": (C.c_int, [vp, i32p, C.c_int]),
+    "dipb_dc_begin": (C.c_int, [vp, C.POINTER(DistSource), C.c_int, C.c_int, vpp]),
+    "dipb_dc_assign": (C.c_int, [vp, C.c_int, C.c_int, i32p]),
+    "dipb_dc_set_clusters": (C.c_int, [vp, i32p, C.POINTER(C.c_int)]),
+    "dipb_dc_cluster_sizes": (C.c_int, [vp, i32p]),
+    "dipb_dc_run_clusters": (C.c_int, [vp, C.c_int, C.c_int]),
+    "dipb_dc_export_slice": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "dipb_dc_import_slice": (C.c_int, [vp, vp, C.c_size_t]),
+    "dipb_dc_finish": (C.c_int, [vp, vpp]),
     "dipb_tree_export": (C.c_int, [vp, i32p, i32p, i32p, i32p, f64p]),
     "dipb_tree_export_closest": (C.c_int, [vp, i32p, f64p]),
     "dipb_tree_n": (C.c_int, [vp]),

@@ -344,6 +344,50 @@ class KPlacementDeviceArrays:
         check(lib().dipb_dc_cluster_ids(self.ctx.h, cl, self.numSequences))
         self.clusterID = cl
 
+    def findTreeDC_sharded(self, params, rank, world, all_gather, gather_to_root, backboneSize=None,
+                           mashDeviceArrays=None, matrix=None, msaDeviceArrays=None):
+        """-m 3 with stage 2 (queries) and stage 3 (clusters) sharded over `world` ranks, one process
+        per GPU.  `all_gather(np.int32 array)` must return the list of every rank's array;
+        `gather_to_root(bytes)` must return the list of every rank's blob on rank 0 (None elsewhere).
+        With torch.distributed these are all_gather_object / gather_object on a gloo group.
+        Only rank 0 ends up holding the merged tree (self.h); other ranks get self.h = None."""
+        from . import sharding
+        L = lib()
+        s = self._source(params, mashDeviceArrays, matrix, msaDeviceArrays)
+        n = self.numSequences
+        B = n // 20 if backboneSize is None else backboneSize
+        st = C.c_void_p()
+        check(L.dipb_dc_begin(self.ctx.h, C.byref(s), n, B, C.byref(st)))
+        q0, q1 = sharding.split_units(n - B, world)[rank]
+        mine = np.zeros(max(q1 - q0, 1), np.int32)
+        check(L.dipb_dc_assign(st, B + q0, B + q1, mine))
+        parts = all_gather(mine[: q1 - q0])
+        cl = np.concatenate([np.full(B, -1, np.int32)] + [np.asarray(p, np.int32) for p in parts])
+        nc = C.c_int()
+        check(L.dipb_dc_set_clusters(st, np.ascontiguousarray(cl), C.byref(nc)))
+        sizes = np.zeros(max(nc.value, 1), np.int32)
+        check(L.dipb_dc_cluster_sizes(st, sizes))
+        ranges = sharding.balance_clusters(sizes[: nc.value], world)
+        c0, c1 = ranges[rank]
+        check(L.dipb_dc_run_clusters(st, c0, c1))
+        nbytes = C.c_size_t()
+        check(L.dipb_dc_export_slice(st, c0, c1, None, 0, C.byref(nbytes)))
+        buf = (C.c_char * max(nbytes.value, 1))()
+        check(L.dipb_dc_export_slice(st, c0, c1, buf, nbytes.value, C.byref(nbytes)))
+        blobs = gather_to_root(bytes(buf[: nbytes.value]))
+        self.clusterID = cl
+        if rank == 0:
+            for r, blob in enumerate(blobs):
+                if r == 0:
+                    continue
+                check(L.dipb_dc_import_slice(st, blob, len(blob)))
+            h = C.c_void_p()
+            check(L.dipb_dc_finish(st, C.byref(h)))
+            self.h = h
+        else:
+            check(L.dipb_dc_finish(st, None))
+            self.h = None
+
     def export(self):
         n = self.numSequences
         head = np.zeros(2 * n, np.int32)

@@ -243,82 +243,121 @@ using namespace dipb;
 
 static std::vector<int32_t> g_last_clusters;   // test hook storage (dipb_dc_cluster_ids)
 
+// Staged divide-and-conquer state: lets one process per GPU shard stage 2 (queries) and
+// stage 3 (clusters) and merge the per-rank tree slices on rank 0.
+struct dipb_dc_state {
+    dipb_ctx* ctx = nullptr;
+    dipb_dist_source src{};
+    int n = 0, B = 0;
+    dipb_tree* tree = nullptr;
+    std::vector<int32_t> cl;            // cluster (backbone slot) per tip, -1 for backbone tips
+    std::vector<int> order, cl_slot, cl_off;
+    // device copies for stage 3
+    int *d_slot = nullptr, *d_off = nullptr, *d_tips = nullptr;
+    DcArgs a{};
+    bool stage3_ready = false;
+};
+
+static void dc_free_stage3(dipb_dc_state* st) {
+    if (!st->stage3_ready) return;
+    cudaFree(st->d_slot); cudaFree(st->d_off); cudaFree(st->d_tips);
+    cudaFree(st->a.leaf_mask); cudaFree(st->a.distm); cudaFree(st->a.edge_mask);
+    cudaFree(st->a.q_node); cudaFree(st->a.q_from); cudaFree(st->a.q_dis); cudaFree(st->a.pos_of); cudaFree(st->a.owner);
+    cudaFree(st->a.next_cluster);
+    st->stage3_ready = false;
+}
+
 extern "C" {
 
-int dipb_dc(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone, dipb_tree** out) {
-    if (!c || !src || !out || n < 4) { set_error("dipb_dc: bad argument"); return DIPB_E_ARG; }
-    const int B = backbone;
-    if (B < 2 || B >= n) { set_error("dipb_dc: backbone size %d must be in [2, n)", B); return DIPB_E_ARG; }
+// stage 1: backbone placement of tips [0, B) (findBackboneTreeDC, DC/placement_close_k.cu:731-935)
+int dipb_dc_begin(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone, dipb_dc_state** out) {
+    if (!c || !src || !out || n < 4) { set_error("dipb_dc_begin: bad argument"); return DIPB_E_ARG; }
+    if (backbone < 2 || backbone >= n) { set_error("dipb_dc: backbone size %d must be in [2, n)", backbone); return DIPB_E_ARG; }
     int rc = check_source(src, n);
     if (rc) return rc;
     DIPB_CUDA(cudaSetDevice(c->device));
-    rc = timer_begin(c);
-    if (rc) return rc;
-    dipb_tree* t = nullptr;
-    rc = tree_alloc(c, n, &t);
-    if (rc) return rc;
+    dipb_dc_state* st = new dipb_dc_state();
+    st->ctx = c; st->src = *src; st->n = n; st->B = backbone;
+    rc = tree_alloc(c, n, &st->tree);
+    if (rc) { delete st; return rc; }
     PlaceScratch sc;
     rc = place_scratch_alloc(c, n, &sc);
-    // ---- stage 1: backbone tree over tips [0, B), internal ids offset by n
-    if (!rc) rc = place_from_scratch(c, src, n, B, t, &sc);
+    if (!rc) rc = place_from_scratch(c, src, n, backbone, st->tree, &sc);
     place_scratch_free(&sc);
-    if (rc) { dipb_tree_free(t); return rc; }
+    if (rc) { dipb_tree_free(st->tree); delete st; return rc; }
+    st->cl.assign(n, -1);
+    *out = st;
+    return 0;
+}
 
-    // ---- stage 2: cluster of every tip >= B
-    const int nslots = 4 * B - 4;
+// stage 2 for queries [q0, q1): winning backbone slot of each (findClustersDC :937-1037)
+int dipb_dc_assign(dipb_dc_state* st, int q0, int q1, int32_t* h_cluster) {
+    if (!st || !h_cluster || q0 < st->B || q1 > st->n || q0 > q1) { set_error("dipb_dc_assign: bad range"); return DIPB_E_ARG; }
+    if (q0 == q1) return 0;
+    dipb_ctx* c = st->ctx;
+    const dipb_dist_source* src = &st->src;
+    dipb_tree* t = st->tree;
+    const int B = st->B, nslots = 4 * B - 4;
+    DIPB_CUDA(cudaSetDevice(c->device));
     int* d_cluster = nullptr;
-    DIPB_CUDA(cudaMalloc(&d_cluster, sizeof(int) * n));
-    DIPB_CUDA(cudaMemsetAsync(d_cluster, 0xff, sizeof(int) * n, c->stream));
-    {
-        int qb = 1024;
-        const size_t ld = (size_t)((B + 127) / 128 * 128);
-        while ((size_t)qb * ld * sizeof(double) > (1ull << 30) && qb > 128) qb /= 2;
-        double* buf = nullptr;
-        if (!src->matrix) DIPB_CUDA(cudaMalloc(&buf, (size_t)qb * ld * sizeof(double)));
-        for (int q0 = B; q0 < n && !rc; q0 += qb) {
-            int q1 = q0 + qb < n ? q0 + qb : n;
-            const double* rows; size_t ldr;
-            if (src->matrix) { rows = src->matrix->d + (size_t)q0 * src->matrix->n; ldr = (size_t)src->matrix->n; }
-            else {
-                rows = buf; ldr = ld;
-                rc = src->msa ? msa_block(src->msa, src->dist_type, q0, q1, B, buf, ld) : dipb_mash_dist_block(src->mash, q0, q1, B, buf, ld);
-                if (rc) break;
-            }
-            int grid = q1 - q0 < c->num_sms * 8 ? q1 - q0 : c->num_sms * 8;
-            dc_assign_kernel<<<grid, 256, 0, c->stream>>>(t->e, t->belong, t->len, t->cid, t->cdis, t->rev, nslots, rows, ldr, q0, q1 - q0, d_cluster);
-            c->launches++;
+    DIPB_CUDA(cudaMalloc(&d_cluster, sizeof(int) * (q1 - q0)));
+    int qb = 1024;
+    const size_t ld = (size_t)((B + 127) / 128 * 128);
+    while ((size_t)qb * ld * sizeof(double) > (1ull << 30) && qb > 128) qb /= 2;
+    double* buf = nullptr;
+    if (!src->matrix) DIPB_CUDA(cudaMalloc(&buf, (size_t)qb * ld * sizeof(double)));
+    int rc = 0;
+    for (int a0 = q0; a0 < q1 && !rc; a0 += qb) {
+        int a1 = a0 + qb < q1 ? a0 + qb : q1;
+        const double* rows; size_t ldr;
+        if (src->matrix) { rows = src->matrix->d + (size_t)a0 * src->matrix->n; ldr = (size_t)src->matrix->n; }
+        else {
+            rows = buf; ldr = ld;
+            rc = src->msa ? msa_block(src->msa, src->dist_type, a0, a1, B, buf, ld) : dipb_mash_dist_block(src->mash, a0, a1, B, buf, ld);
+            if (rc) break;
         }
-        cudaError_t e = cudaStreamSynchronize(c->stream);
-        if (buf) cudaFree(buf);
-        if (!rc && e != cudaSuccess) { set_error("dipb_dc stage 2: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; }
-        if (rc) { cudaFree(d_cluster); dipb_tree_free(t); return rc; }
+        int grid = a1 - a0 < c->num_sms * 8 ? a1 - a0 : c->num_sms * 8;
+        dc_assign_kernel<<<grid, 256, 0, c->stream>>>(t->e, t->belong, t->len, t->cid, t->cdis, t->rev, nslots, rows, ldr, a0 - q0, a1 - a0, d_cluster);
+        c->launches++;
     }
-    std::vector<int32_t> cl(n);
-    DIPB_CUDA(cudaMemcpy(cl.data(), d_cluster, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (buf) cudaFree(buf);
+    if (!rc && e != cudaSuccess) { set_error("dipb_dc_assign: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; }
+    if (!rc && cudaMemcpy(h_cluster, d_cluster, sizeof(int) * (q1 - q0), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("dipb_dc_assign: D2H failed"); rc = DIPB_E_CUDA; }
     cudaFree(d_cluster);
-    g_last_clusters = cl;
+    return rc;
+}
 
-    // ---- cluster lists: ascending slot, tips ascending (contains[], :1283-1285)
-    const int ntips = n - B;
-    std::vector<int> order(ntips);
-    for (int i = 0; i < ntips; i++) order[i] = B + i;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cl[x] < cl[y]; });
-    std::vector<int> cl_slot, cl_off;
-    for (int i = 0; i < ntips; i++) {
-        if (i == 0 || cl[order[i]] != cl[order[i - 1]]) { cl_slot.push_back(cl[order[i]]); cl_off.push_back(i); }
-    }
-    cl_off.push_back(ntips);
-    const int nc = (int)cl_slot.size();
-
-    // ---- stage 3
-    DcArgs a{};
+// all cluster ids known (after an all-gather across ranks): build the cluster lists
+// (contains[], :1283-1285: ascending slot, tips ascending) and the stage-3 device state
+int dipb_dc_set_clusters(dipb_dc_state* st, const int32_t* h_cluster_all, int* num_clusters) {
+    if (!st || !h_cluster_all) { set_error("dipb_dc_set_clusters: bad argument"); return DIPB_E_ARG; }
+    dipb_ctx* c = st->ctx;
+    const int n = st->n, B = st->B, ntips = n - B;
+    DIPB_CUDA(cudaSetDevice(c->device));
+    dc_free_stage3(st);
+    st->cl.assign(h_cluster_all, h_cluster_all + n);
+    for (int i = 0; i < B; i++) st->cl[i] = -1;
+    for (int i = B; i < n; i++)
+        if (st->cl[i] < 0 || st->cl[i] >= 4 * B - 4) { set_error("dipb_dc_set_clusters: tip %d has cluster %d", i, st->cl[i]); return DIPB_E_ARG; }
+    g_last_clusters = st->cl;
+    st->order.resize(ntips);
+    for (int i = 0; i < ntips; i++) st->order[i] = B + i;
+    std::stable_sort(st->order.begin(), st->order.end(), [&](int x, int y) { return st->cl[x] < st->cl[y]; });
+    st->cl_slot.clear(); st->cl_off.clear();
+    for (int i = 0; i < ntips; i++)
+        if (i == 0 || st->cl[st->order[i]] != st->cl[st->order[i - 1]]) { st->cl_slot.push_back(st->cl[st->order[i]]); st->cl_off.push_back(i); }
+    st->cl_off.push_back(ntips);
+    const int nc = (int)st->cl_slot.size();
+    dipb_tree* t = st->tree;
+    DcArgs& a = st->a;
+    a = DcArgs{};
     a.head = t->head; a.e = t->e; a.nxt = t->nxt; a.belong = t->belong; a.cid = t->cid; a.rev = t->rev; a.len = t->len; a.cdis = t->cdis;
     a.n = n; a.B = B; a.num_clusters = nc;
-    int *d_slot = nullptr, *d_off = nullptr, *d_tips = nullptr;
     const size_t lm_sz = (size_t)10 * nc + ntips, em_sz = (size_t)4 * nc + 4 * (size_t)ntips + 8;
-    DIPB_CUDA(cudaMalloc(&d_slot, sizeof(int) * (nc + 1)));
-    DIPB_CUDA(cudaMalloc(&d_off, sizeof(int) * (nc + 1)));
-    DIPB_CUDA(cudaMalloc(&d_tips, sizeof(int) * (ntips + 1)));
+    DIPB_CUDA(cudaMalloc(&st->d_slot, sizeof(int) * (nc + 1)));
+    DIPB_CUDA(cudaMalloc(&st->d_off, sizeof(int) * (nc + 1)));
+    DIPB_CUDA(cudaMalloc(&st->d_tips, sizeof(int) * (ntips + 1)));
     DIPB_CUDA(cudaMalloc(&a.leaf_mask, sizeof(int) * lm_sz));
     DIPB_CUDA(cudaMalloc(&a.distm, sizeof(double) * lm_sz));
     DIPB_CUDA(cudaMalloc(&a.edge_mask, sizeof(int) * em_sz));
@@ -328,34 +367,193 @@ int dipb_dc(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone, dipb_
     DIPB_CUDA(cudaMalloc(&a.pos_of, sizeof(int) * n));
     DIPB_CUDA(cudaMalloc(&a.owner, sizeof(int) * 8 * (size_t)n));
     DIPB_CUDA(cudaMalloc(&a.next_cluster, sizeof(unsigned int)));
-    DIPB_CUDA(cudaMemsetAsync(a.next_cluster, 0, sizeof(unsigned int), c->stream));
-    DIPB_CUDA(cudaMemcpyAsync(d_slot, cl_slot.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, c->stream));
-    DIPB_CUDA(cudaMemcpyAsync(d_off, cl_off.data(), sizeof(int) * (nc + 1), cudaMemcpyHostToDevice, c->stream));
-    DIPB_CUDA(cudaMemcpyAsync(d_tips, order.data(), sizeof(int) * ntips, cudaMemcpyHostToDevice, c->stream));
-    a.cl_slot = d_slot; a.cl_off = d_off; a.cl_tips = d_tips;
-    {
-        long long tot = 8LL * n;
-        fill_int_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(a.owner, tot, -1);
-        c->launches++;
-    }
+    st->stage3_ready = true;
+    DIPB_CUDA(cudaMemcpyAsync(st->d_slot, st->cl_slot.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, c->stream));
+    DIPB_CUDA(cudaMemcpyAsync(st->d_off, st->cl_off.data(), sizeof(int) * (nc + 1), cudaMemcpyHostToDevice, c->stream));
+    DIPB_CUDA(cudaMemcpyAsync(st->d_tips, st->order.data(), sizeof(int) * ntips, cudaMemcpyHostToDevice, c->stream));
+    a.cl_slot = st->d_slot; a.cl_off = st->d_off; a.cl_tips = st->d_tips;
+    long long tot = 8LL * n;
+    fill_int_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(a.owner, tot, -1);
+    DIPB_KERNEL_CHECK(c);
+    DIPB_CUDA(cudaStreamSynchronize(c->stream));
+    if (num_clusters) *num_clusters = nc;
+    return 0;
+}
+
+// sizes of the clusters in processing order (for balancing cluster ranges over ranks)
+int dipb_dc_cluster_sizes(dipb_dc_state* st, int32_t* h_sizes) {
+    if (!st || !h_sizes || !st->stage3_ready) { set_error("dipb_dc_cluster_sizes: call dipb_dc_set_clusters first"); return DIPB_E_STATE; }
+    for (size_t k = 0; k + 1 < st->cl_off.size(); k++) h_sizes[k] = st->cl_off[k + 1] - st->cl_off[k];
+    return 0;
+}
+
+// stage 3 for clusters [c0, c1) (findClusterTreeDC :1251-1535); slot / node numbers are global
+int dipb_dc_run_clusters(dipb_dc_state* st, int c0, int c1) {
+    if (!st || !st->stage3_ready) { set_error("dipb_dc_run_clusters: call dipb_dc_set_clusters first"); return DIPB_E_STATE; }
+    const int nc = st->a.num_clusters;
+    if (c0 < 0 || c1 > nc || c0 > c1) { set_error("dipb_dc_run_clusters: bad cluster range"); return DIPB_E_ARG; }
+    if (c0 == c1) return 0;
+    dipb_ctx* c = st->ctx;
+    DIPB_CUDA(cudaSetDevice(c->device));
+    unsigned int start = (unsigned int)c0;
+    DIPB_CUDA(cudaMemcpyAsync(st->a.next_cluster, &start, sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
+    DcArgs a = st->a;
+    a.num_clusters = c1;   // the work counter starts at c0
     DcSource ds{};
+    const dipb_dist_source* src = &st->src;
     if (src->msa) { ds.planes = src->msa->planes; ds.nv = src->msa->nv; ds.nkc = src->msa->nkc; ds.dist_type = src->dist_type; }
     else if (src->mash) { ds.sketches = src->mash->sketches; ds.s = src->mash->s; ds.k = src->mash->k; }
     else { ds.matrix = src->matrix->d; ds.mld = (size_t)src->matrix->n; }
-    {
-        int grid = nc < c->num_sms * 8 ? nc : c->num_sms * 8;
-        if (grid < 1) grid = 1;
-        dc_cluster_kernel<<<grid, DC_THREADS, 0, c->stream>>>(a, ds);
-        c->launches++;
-    }
-    cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_slot); cudaFree(d_off); cudaFree(d_tips); cudaFree(a.leaf_mask); cudaFree(a.distm); cudaFree(a.edge_mask);
-    cudaFree(a.q_node); cudaFree(a.q_from); cudaFree(a.q_dis); cudaFree(a.pos_of); cudaFree(a.owner); cudaFree(a.next_cluster);
-    if (e != cudaSuccess) { set_error("dipb_dc stage 3: %s", cudaGetErrorString(e)); dipb_tree_free(t); return DIPB_E_CUDA; }
-    rc = timer_end(c, DIPB_T_PLACE);
-    if (rc) return rc;
-    *out = t;
+    int grid = (c1 - c0) < c->num_sms * 8 ? (c1 - c0) : c->num_sms * 8;
+    dc_cluster_kernel<<<grid, DC_THREADS, 0, c->stream>>>(a, ds);
+    DIPB_KERNEL_CHECK(c);
+    DIPB_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+// Everything clusters [c0, c1) changed in the tree, as one byte blob: header {c0,c1,T0,T1},
+// the new slot slice (e, nxt, belong, rev, len, closest lists), head[] of the new internal
+// nodes and of the placed tips, and the two patched backbone slots of every cluster.
+int dipb_dc_export_slice(dipb_dc_state* st, int c0, int c1, void* h_buf, size_t cap, size_t* bytes) {
+    if (!st || !st->stage3_ready || !bytes) { set_error("dipb_dc_export_slice: bad state"); return DIPB_E_STATE; }
+    const int nc = (int)st->cl_slot.size();
+    if (c0 < 0 || c1 > nc || c0 > c1) { set_error("dipb_dc_export_slice: bad cluster range"); return DIPB_E_ARG; }
+    const int n = st->n, B = st->B;
+    const int T0 = st->cl_off[c0], T1 = st->cl_off[c1], nt = T1 - T0, ncl = c1 - c0;
+    const size_t ns = (size_t)4 * nt;
+    const size_t per_bb = 2 * sizeof(int32_t) + sizeof(double) + 5 * sizeof(int32_t) + 5 * sizeof(double);
+    size_t need = 4 * sizeof(int32_t) + ns * (4 * sizeof(int32_t) + sizeof(double) + 5 * sizeof(int32_t) + 5 * sizeof(double)) +
+                  (size_t)nt * 2 * sizeof(int32_t) + (size_t)ncl * 2 * per_bb;
+    *bytes = need;
+    if (!h_buf) return 0;
+    if (cap < need) { set_error("dipb_dc_export_slice: buffer too small (%zu < %zu)", cap, need); return DIPB_E_ARG; }
+    dipb_tree* t = st->tree;
+    DIPB_CUDA(cudaSetDevice(st->ctx->device));
+    char* p = (char*)h_buf;
+    int32_t hdr[4] = {c0, c1, T0, T1};
+    memcpy(p, hdr, sizeof hdr); p += sizeof hdr;
+    const size_t s0 = (size_t)4 * B - 4 + 4 * (size_t)T0;
+    auto pull = [&](const void* dptr, size_t elem, size_t off, size_t cnt) -> int {
+        if (cnt && cudaMemcpy(p, (const char*)dptr + off * elem, cnt * elem, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("dipb_dc_export_slice: D2H failed"); return DIPB_E_CUDA; }
+        p += cnt * elem;
+        return 0;
+    };
+    int rc = 0;
+    // the new slots of these clusters are one contiguous range
+    if ((rc = pull(t->e, 4, s0, ns)) || (rc = pull(t->nxt, 4, s0, ns)) || (rc = pull(t->belong, 4, s0, ns)) || (rc = pull(t->rev, 4, s0, ns)) ||
+        (rc = pull(t->len, 8, s0, ns)) || (rc = pull(t->cid, 4, s0 * 5, ns * 5)) || (rc = pull(t->cdis, 8, s0 * 5, ns * 5))) return rc;
+    // head of the new internal nodes (ids n + B - 1 + T0 .., contiguous), then head of the placed tips (scattered)
+    if ((rc = pull(t->head, 4, (size_t)n + B - 1 + T0, nt))) return rc;
+    {
+        std::vector<int32_t> hh((size_t)n);
+        DIPB_CUDA(cudaMemcpy(hh.data(), t->head, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+        for (int k = T0; k < T1; k++) { memcpy(p, &hh[st->order[k]], 4); p += 4; }
+    }
+    // patched backbone slots of every cluster (its slot and the reverse slot), found through the owner table
+    const size_t nbb = (size_t)4 * B - 4;
+    std::vector<int32_t> owner_bb(nbb), be(nbb), bcid(nbb * 5);
+    std::vector<double> blen(nbb), bcdis(nbb * 5);
+    DIPB_CUDA(cudaMemcpy(owner_bb.data(), st->a.owner, nbb * 4, cudaMemcpyDeviceToHost));
+    DIPB_CUDA(cudaMemcpy(be.data(), t->e, nbb * 4, cudaMemcpyDeviceToHost));
+    DIPB_CUDA(cudaMemcpy(blen.data(), t->len, nbb * 8, cudaMemcpyDeviceToHost));
+    DIPB_CUDA(cudaMemcpy(bcid.data(), t->cid, nbb * 20, cudaMemcpyDeviceToHost));
+    DIPB_CUDA(cudaMemcpy(bcdis.data(), t->cdis, nbb * 40, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> slot_of((size_t)ncl * 2, -1);
+    for (size_t q = 0; q < nbb; q++) {
+        int o = owner_bb[q];
+        if (o >= c0 && o < c1) { int k = o - c0; if (slot_of[2 * k] < 0) slot_of[2 * k] = (int32_t)q; else slot_of[2 * k + 1] = (int32_t)q; }
+    }
+    for (int k = 0; k < 2 * ncl; k++) {
+        int32_t q = slot_of[k];
+        memcpy(p, &q, 4); p += 4;
+        if (q < 0) { memset(p, 0, per_bb - 4); p += per_bb - 4; continue; }
+        memcpy(p, &be[q], 4); p += 4;
+        memcpy(p, &blen[q], 8); p += 8;
+        memcpy(p, &bcid[(size_t)q * 5], 20); p += 20;
+        memcpy(p, &bcdis[(size_t)q * 5], 40); p += 40;
+    }
+    return 0;
+}
+
+int dipb_dc_import_slice(dipb_dc_state* st, const void* h_buf, size_t bytes) {
+    if (!st || !h_buf || bytes < 16 || !st->stage3_ready) { set_error("dipb_dc_import_slice: bad argument"); return DIPB_E_ARG; }
+    const int n = st->n, B = st->B;
+    const char* p = (const char*)h_buf;
+    int32_t hdr[4];
+    memcpy(hdr, p, sizeof hdr); p += sizeof hdr;
+    const int c0 = hdr[0], c1 = hdr[1], T0 = hdr[2], T1 = hdr[3], nt = T1 - T0, ncl = c1 - c0;
+    if (c0 < 0 || c1 > (int)st->cl_slot.size() || c0 > c1 || T0 != st->cl_off[c0] || T1 != st->cl_off[c1]) { set_error("dipb_dc_import_slice: slice does not match this run's clusters"); return DIPB_E_ARG; }
+    dipb_tree* t = st->tree;
+    DIPB_CUDA(cudaSetDevice(st->ctx->device));
+    const size_t ns = (size_t)4 * nt, s0 = (size_t)4 * B - 4 + 4 * (size_t)T0;
+    const size_t per_bb = 2 * sizeof(int32_t) + sizeof(double) + 5 * sizeof(int32_t) + 5 * sizeof(double);
+    auto push = [&](void* dptr, size_t elem, size_t off, size_t cnt) -> int {
+        if (cnt && cudaMemcpy((char*)dptr + off * elem, p, cnt * elem, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("dipb_dc_import_slice: H2D failed"); return DIPB_E_CUDA; }
+        p += cnt * elem;
+        return 0;
+    };
+    int rc = 0;
+    if ((rc = push(t->e, 4, s0, ns)) || (rc = push(t->nxt, 4, s0, ns)) || (rc = push(t->belong, 4, s0, ns)) || (rc = push(t->rev, 4, s0, ns)) ||
+        (rc = push(t->len, 8, s0, ns)) || (rc = push(t->cid, 4, s0 * 5, ns * 5)) || (rc = push(t->cdis, 8, s0 * 5, ns * 5))) return rc;
+    if ((rc = push(t->head, 4, (size_t)n + B - 1 + T0, nt))) return rc;
+    {
+        std::vector<int32_t> hh((size_t)n);
+        DIPB_CUDA(cudaMemcpy(hh.data(), t->head, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+        for (int k = T0; k < T1; k++) { memcpy(&hh[st->order[k]], p, 4); p += 4; }
+        DIPB_CUDA(cudaMemcpy(t->head, hh.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    }
+    const size_t nbb = (size_t)4 * B - 4;
+    std::vector<int32_t> be(nbb), bcid(nbb * 5);
+    std::vector<double> blen(nbb), bcdis(nbb * 5);
+    DIPB_CUDA(cudaMemcpy(be.data(), t->e, nbb * 4, cudaMemcpyDeviceToHost));
+    DIPB_CUDA(cudaMemcpy(blen.data(), t->len, nbb * 8, cudaMemcpyDeviceToHost));
+    DIPB_CUDA(cudaMemcpy(bcid.data(), t->cid, nbb * 20, cudaMemcpyDeviceToHost));
+    DIPB_CUDA(cudaMemcpy(bcdis.data(), t->cdis, nbb * 40, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 2 * ncl; k++) {
+        int32_t q;
+        memcpy(&q, p, 4); p += 4;
+        if (q < 0 || (size_t)q >= nbb) { p += per_bb - 4; continue; }
+        memcpy(&be[q], p, 4); p += 4;
+        memcpy(&blen[q], p, 8); p += 8;
+        memcpy(&bcid[(size_t)q * 5], p, 20); p += 20;
+        memcpy(&bcdis[(size_t)q * 5], p, 40); p += 40;
+    }
+    DIPB_CUDA(cudaMemcpy(t->e, be.data(), nbb * 4, cudaMemcpyHostToDevice));
+    DIPB_CUDA(cudaMemcpy(t->len, blen.data(), nbb * 8, cudaMemcpyHostToDevice));
+    DIPB_CUDA(cudaMemcpy(t->cid, bcid.data(), nbb * 20, cudaMemcpyHostToDevice));
+    DIPB_CUDA(cudaMemcpy(t->cdis, bcdis.data(), nbb * 40, cudaMemcpyHostToDevice));
+    if ((size_t)(p - (const char*)h_buf) != bytes) { set_error("dipb_dc_import_slice: size mismatch"); return DIPB_E_ARG; }
+    return 0;
+}
+
+// hands the tree over (rank 0 after importing every other rank's slices) and frees the state
+int dipb_dc_finish(dipb_dc_state* st, dipb_tree** out) {
+    if (!st) return DIPB_E_ARG;
+    cudaSetDevice(st->ctx->device);
+    dc_free_stage3(st);
+    if (out) { *out = st->tree; st->tree = nullptr; }
+    if (st->tree) dipb_tree_free(st->tree);
+    delete st;
+    return 0;
+}
+
+int dipb_dc(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone, dipb_tree** out) {
+    if (!out) { set_error("dipb_dc: bad argument"); return DIPB_E_ARG; }
+    if (!c) { set_error("dipb_dc: bad argument"); return DIPB_E_ARG; }
+    int rc = timer_begin(c);
+    if (rc) return rc;
+    dipb_dc_state* st = nullptr;
+    rc = dipb_dc_begin(c, src, n, backbone, &st);
+    if (rc) return rc;
+    std::vector<int32_t> cl(n, -1);
+    rc = dipb_dc_assign(st, backbone, n, cl.data() + backbone);
+    int nc = 0;
+    if (!rc) rc = dipb_dc_set_clusters(st, cl.data(), &nc);
+    if (!rc) rc = dipb_dc_run_clusters(st, 0, nc);
+    if (rc) { dipb_dc_finish(st, nullptr); return rc; }
+    rc = dipb_dc_finish(st, out);
+    if (rc) return rc;
+    return timer_end(c, DIPB_T_PLACE);
 }
 
 int dipb_dc_cluster_ids(dipb_ctx* c, int32_t* h_out, int n) {

@@ -26,3 +26,19 @@ def split_units(num_units, world):
         out.append((s, e))
         s = e
     return out
+
+
+def balance_clusters(sizes, world):
+    """Contiguous cluster ranges [c0, c1) per rank balanced by the in-cluster work
+    ~ 10*s + s^2/2 pair distances for a cluster of s tips."""
+    sizes = np.asarray(sizes, np.float64)
+    cost = 10.0 * sizes + 0.5 * sizes * sizes + 8.0
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * r / world)))
+    cuts.append(len(sizes))
+    for k in range(1, len(cuts)):
+        cuts[k] = max(cuts[k], cuts[k - 1])
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]

@@ -155,6 +155,23 @@ int dipb_place_add(dipb_ctx *ctx, const dipb_dist_source *src, int n, int backbo
  * to its best backbone edge and the per-edge clusters are placed independently.
  * The reference uses backbone = n / 20 (src/tree_generation.cu:425,545). */
 int dipb_dc(dipb_ctx *ctx, const dipb_dist_source *src, int n, int backbone, dipb_tree **out);
+/* The same three stages as separate calls, so that one process per GPU can shard stage 2
+ * (queries are independent) and stage 3 (clusters touch disjoint slots) and merge on rank 0
+ * (SURVEY.md §8e).  Every rank: dipb_dc_begin (backbone; deterministic, so identical on all
+ * ranks) -> dipb_dc_assign(own query range) -> all-gather the cluster ids ->
+ * dipb_dc_set_clusters -> dipb_dc_run_clusters(own cluster range) -> dipb_dc_export_slice;
+ * rank 0 imports the other ranks' slices and calls dipb_dc_finish.  Slot and node numbers are
+ * global prefix sums, identical to the single-GPU run. */
+typedef struct dipb_dc_state dipb_dc_state;
+int dipb_dc_begin(dipb_ctx *ctx, const dipb_dist_source *src, int n, int backbone, dipb_dc_state **out);
+int dipb_dc_assign(dipb_dc_state *st, int q0, int q1, int32_t *h_cluster /* q1-q0 */);
+int dipb_dc_set_clusters(dipb_dc_state *st, const int32_t *h_cluster_all /* n */, int *num_clusters);
+int dipb_dc_cluster_sizes(dipb_dc_state *st, int32_t *h_sizes /* num_clusters */);
+int dipb_dc_run_clusters(dipb_dc_state *st, int c0, int c1);
+/* h_buf == NULL: only report the size in *bytes */
+int dipb_dc_export_slice(dipb_dc_state *st, int c0, int c1, void *h_buf, size_t cap, size_t *bytes);
+int dipb_dc_import_slice(dipb_dc_state *st, const void *h_buf, size_t bytes);
+int dipb_dc_finish(dipb_dc_state *st, dipb_tree **out /* may be NULL */);
 /* test hook: cluster (backbone slot) of every tip after the last dipb_dc on this context;
  * h_out[n], entries of backbone tips are -1 */
 int dipb_dc_cluster_ids(dipb_ctx *ctx, int32_t *h_out, int n);
