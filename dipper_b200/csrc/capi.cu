@@ -126,6 +126,8 @@ void dipb_msa_free(dipb_msa* m) {
     cudaSetDevice(m->ctx->device);
     cudaFree(m->planes);
     cudaFree(m->nv);
+    cudaFree(m->tc_S);
+    cudaFree(m->tc_V);
     delete m;
 }
 

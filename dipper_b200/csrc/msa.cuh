@@ -18,6 +18,10 @@ struct dipb_msa {
     int n = 0, npad = 0, seq_len = 0, nkc = 0;
     uint32_t* planes = nullptr;  // [npad/128][nkc][3][16][128]
     int* nv = nullptr;           // valid sites per sequence [npad]
+    // tensor-core operands (msa_tc.cu), built on first use: simplex int8 [tc_rows][tc_ks], validity int8 [tc_rows][tc_kv]
+    int8_t* tc_S = nullptr;
+    int8_t* tc_V = nullptr;
+    size_t tc_ks = 0, tc_kv = 0, tc_rows = 0;
 };
 
 namespace dipb {
@@ -25,4 +29,6 @@ int msa_repack(dipb_msa* m, const uint64_t* d_in, int comp64);
 int msa_block(dipb_msa* m, int type, int r0, int r1, int ncols, double* d_out, size_t ld);
 int msa_matrix(dipb_msa* m, int type, int row_begin, int row_end, double* d_out);
 int msa_counts_dev(dipb_msa* m, int i0, int i1, int j1, int* d_match, int* d_both, size_t ld);
+bool msa_tc_supported(const dipb_msa* m, int type);
+int msa_tc_matrix(dipb_msa* m, int type, double* d_out);
 }  // namespace dipb

@@ -1,0 +1,319 @@
+// K1-TC: aligned-MSA all-pairs distances on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// Same outputs as msa_tile_kernel<0,true> (bit-identical counts, same fp64 epilogue) for the p / JC
+// models; replaces the POPC-bound SIMT counting (XU pipe 92 % busy, profiles/r1_ncu_summary.json)
+// with two int8 GEMMs accumulated in TMEM:
+//   every site of a sequence becomes a vector s in {-1,0,1}^3 (simplex corners: <s_a,s_b> = 3 if the
+//   bases are equal, -1 if they differ, 0 if either is not ACGT) and a validity flag v in {0,1}:
+//       D1(i,j) = sum_sites <s_i, s_j> = 4 * match - both        (K = 3L int8)
+//       D2(i,j) = sum_sites  v_i * v_j  = both                   (K =  L int8)
+//   => match = (D1 + D2) / 4,  useful = nv[i] + nv[j] - D2        (exact in s32)
+// Structure (one CTA per SM, persistent over 128 x 256 tiles of the lower triangle):
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) of a 128 x 128 B A slab and a
+//            256 x 128 B B slab per stage, 4-stage mbarrier ring
+//   warp 1   MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::i8 (M128 N256 K32), four per
+//            stage, D1 in TMEM columns [0,256), D2 in [256,512); tcgen05.commit frees the stage
+//   warps 2-5 epilogue: tcgen05.ld 32x32b, fp64 p / JC in the reference's expression order, D[i][j] + mirror
+// The GEMM is L2-bandwidth bound (384 operand bytes per 32 768 outputs per K byte), see DESIGN.md §4.1.
+#include <cuda.h>
+#include <vector>
+#include "common.cuh"
+#include "msa.cuh"
+#include "msa_pair.cuh"
+
+namespace dipb {
+
+constexpr int TC_M = 128, TC_N = 256, TC_KB = 128;          // tile rows, tile cols, K bytes per stage
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_M * TC_KB, TC_B_BYTES = TC_N * TC_KB;
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;     // 48 KB
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+
+// ---- operand expansion: planes -> simplex int8 (S) and validity int8 (V), K-major rows ----------
+__global__ void msa_tc_expand_kernel(const uint32_t* __restrict__ planes, int n, int nkc, int w32, int8_t* __restrict__ S,
+                                     size_t ks, int8_t* __restrict__ V, size_t kv) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n * w32) return;
+    const int s = (int)(gid / w32), w = (int)(gid % w32);
+    const int sb = s / MSA_TS, sl = s % MSA_TS, kc = w / MSA_KC, kk = w % MSA_KC;
+    const size_t base = ((size_t)sb * nkc + kc) * MSA_SLAB_WORDS + (size_t)kk * MSA_TS + sl;
+    const uint32_t b0 = planes[base], b1 = planes[base + MSA_KC * MSA_TS], v = planes[base + 2 * MSA_KC * MSA_TS];
+    int8_t* so = S + (size_t)s * ks + (size_t)w * 96;
+    int8_t* vo = V + (size_t)s * kv + (size_t)w * 32;
+#pragma unroll 4
+    for (int q = 0; q < 8; q++) {
+        uint32_t e0 = 0, e1 = 0, e2 = 0, vv = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int bit = 4 * q + t;
+            const int ok = (v >> bit) & 1, x0 = (b0 >> bit) & 1, x1 = (b1 >> bit) & 1;
+            const int c0 = ok ? 1 - 2 * x1 : 0, c1 = ok ? 1 - 2 * x0 : 0, c2 = ok ? 1 - 2 * (x0 ^ x1) : 0;
+            e0 |= (uint32_t)(uint8_t)c0 << (8 * t);
+            e1 |= (uint32_t)(uint8_t)c1 << (8 * t);
+            e2 |= (uint32_t)(uint8_t)c2 << (8 * t);
+            vv |= (uint32_t)ok << (8 * t);
+        }
+        reinterpret_cast<uint32_t*>(so)[q] = e0;
+        reinterpret_cast<uint32_t*>(so + 32)[q] = e1;
+        reinterpret_cast<uint32_t*>(so + 64)[q] = e2;
+        reinterpret_cast<uint32_t*>(vo)[q] = vv;
+    }
+}
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO), LBO unused, descriptor version 1 (sm_100)
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+struct TcParams {
+    const int2* tiles;      // (row block of 128, col block of 256)
+    int num_tiles;
+    int ns_chunks, nv_chunks;   // 128-byte K chunks of the S and V operands
+    const int* nv;
+    int n;
+    double* out;
+    size_t ld;
+    int dist_type;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__ CUtensorMap mapSB,
+              const __grid_constant__ CUtensorMap mapVA, const __grid_constant__ CUtensorMap mapVB, TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte alignment
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full = bars;                    // [TC_STAGES]
+    uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]
+    uint64_t* tmem_full = bars + 2 * TC_STAGES;
+    uint64_t* tmem_empty = bars + 2 * TC_STAGES + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);   // one arrival per epilogue warp
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int nchunks = p.ns_chunks + p.nv_chunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int2 tl = p.tiles[t];
+                for (int c = 0; c < nchunks; c++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* a = smem + (size_t)stage * TC_STAGE_BYTES;
+                    unsigned char* b = a + TC_A_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+                    if (c < p.ns_chunks) {
+                        tma_load_2d(a, &mapSA, c * TC_KB, tl.x * TC_M, &full[stage]);
+                        tma_load_2d(b, &mapSB, c * TC_KB, tl.y * TC_N, &full[stage]);
+                    } else {
+                        const int cv = c - p.ns_chunks;
+                        tma_load_2d(a, &mapVA, cv * TC_KB, tl.x * TC_M, &full[stage]);
+                        tma_load_2d(b, &mapVB, cv * TC_KB, tl.y * TC_N, &full[stage]);
+                    }
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 256, M = 128
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            uint32_t stage = 0, phase = 0, tphase = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                mbar_wait(tmem_empty, tphase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int c = 0; c < nchunks; c++) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * TC_STAGE_BYTES);
+                    const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(a_addr + TC_A_BYTES);
+                    const bool second = c >= p.ns_chunks;
+                    const uint32_t d = tmem_base + (second ? 256u : 0u);
+                    const bool first_of_acc = (c == 0) || (c == p.ns_chunks);
+#pragma unroll
+                    for (int k = 0; k < TC_KB / 32; k++)   // UMMA_K = 32 int8 = 32 B: advance the start address by 2 (x16 B)
+                        umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first_of_acc && k == 0) ? 0u : 1u);
+                    umma_commit(&empty[stage]);            // stage is free when these MMAs have read it
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tmem_full);                    // both accumulators complete
+                tphase ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                            // TMEM lane quarter this warp may read
+        uint32_t tphase = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            const int2 tl = p.tiles[t];
+            mbar_wait(tmem_full, tphase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int i = tl.x * TC_M + 32 * q + lane;
+            const int nvi = i < p.n ? p.nv[i] : 0;
+            for (int cb = 0; cb < TC_N / 32; cb++) {
+                uint32_t r1[32], r2[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cb * 32);
+                tmem_ld32(taddr, r1);
+                tmem_ld32(taddr + 256u, r2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int j0 = tl.y * TC_N + cb * 32;
+                if (i < p.n && j0 <= i) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int j = j0 + c;
+                        if (j < i) {
+                            const int both = (int)r2[c];
+                            const int match = ((int)r1[c] + both) >> 2;
+                            const double d = dist_p_jc(match, nvi + p.nv[j] - both, p.dist_type);
+                            p.out[(size_t)i * p.ld + j] = d;
+                            p.out[(size_t)j * p.ld + i] = d;
+                        } else if (j == i) {
+                            p.out[(size_t)i * p.ld + i] = 0.0;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            tphase ^= 1;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(EncodeTiledFn fn, CUtensorMap* m, void* base, size_t kbytes, size_t rows, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kbytes};
+    cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DIPB_E_CUDA; }
+    return 0;
+}
+
+bool msa_tc_supported(const dipb_msa* m, int type) {
+    return (type == DIPB_DIST_UNCORRECTED || type == DIPB_DIST_JC) && m->n >= 2;
+}
+
+int msa_tc_prepare(dipb_msa* m) {
+    if (m->tc_S) return 0;
+    dipb_ctx* c = m->ctx;
+    const int w32 = (m->seq_len + 31) / 32;
+    m->tc_ks = ((size_t)w32 * 96 + TC_KB - 1) / TC_KB * TC_KB;
+    m->tc_kv = ((size_t)w32 * 32 + TC_KB - 1) / TC_KB * TC_KB;
+    m->tc_rows = ((size_t)m->n + TC_N - 1) / TC_N * TC_N;
+    DIPB_CUDA(cudaMalloc(&m->tc_S, m->tc_rows * m->tc_ks));
+    DIPB_CUDA(cudaMalloc(&m->tc_V, m->tc_rows * m->tc_kv));
+    DIPB_CUDA(cudaMemsetAsync(m->tc_S, 0, m->tc_rows * m->tc_ks, c->stream));
+    DIPB_CUDA(cudaMemsetAsync(m->tc_V, 0, m->tc_rows * m->tc_kv, c->stream));
+    long long total = (long long)m->n * w32;
+    msa_tc_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(m->planes, m->n, m->nkc, w32, m->tc_S, m->tc_ks, m->tc_V, m->tc_kv);
+    DIPB_KERNEL_CHECK(c);
+    return 0;
+}
+
+// full symmetric matrix (all rows), p or JC
+int msa_tc_matrix(dipb_msa* m, int type, double* d_out) {
+    dipb_ctx* c = m->ctx;
+    int rc = msa_tc_prepare(m);
+    if (rc) return rc;
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DIPB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return DIPB_E_CUDA; }
+        encode = (EncodeTiledFn)fn;
+    }
+    CUtensorMap mSA, mSB, mVA, mVB;
+    if ((rc = make_map(encode, &mSA, m->tc_S, m->tc_ks, m->tc_rows, TC_M)) || (rc = make_map(encode, &mSB, m->tc_S, m->tc_ks, m->tc_rows, TC_N)) ||
+        (rc = make_map(encode, &mVA, m->tc_V, m->tc_kv, m->tc_rows, TC_M)) || (rc = make_map(encode, &mVB, m->tc_V, m->tc_kv, m->tc_rows, TC_N)))
+        return rc;
+    // tiles of the lower triangle: column block nj intersects rows of block mi when nj*256 <= mi*128 + 127
+    const int mb = (m->n + TC_M - 1) / TC_M;
+    std::vector<int2> tiles;
+    for (int mi = mb - 1; mi >= 0; mi--)
+        for (int nj = 0; nj * TC_N <= mi * TC_M + TC_M - 1; nj++) tiles.push_back(make_int2(mi, nj));
+    int2* d_tiles = nullptr;
+    DIPB_CUDA(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
+    DIPB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
+    TcParams p{};
+    p.tiles = d_tiles; p.num_tiles = (int)tiles.size();
+    p.ns_chunks = (int)(m->tc_ks / TC_KB); p.nv_chunks = (int)(m->tc_kv / TC_KB);
+    p.nv = m->nv; p.n = m->n; p.out = d_out; p.ld = (size_t)m->n; p.dist_type = type;
+    static bool attr = false;
+    if (!attr) { DIPB_CUDA(cudaFuncSetAttribute(msa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); attr = true; }
+    int grid = p.num_tiles < c->num_sms ? p.num_tiles : c->num_sms;
+    msa_tc_kernel<<<grid, TC_THREADS, TC_SMEM, c->stream>>>(mSA, mSB, mVA, mVB, p);
+    DIPB_KERNEL_CHECK(c);
+    DIPB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_tiles);
+    return 0;
+}
+
+}  // namespace dipb

@@ -119,3 +119,19 @@ def test_row_sharded_matrix_sums_to_full(ctx, oracle):
     a = msa.distMatrix(prm, 0, 256).to_host()
     b = msa.distMatrix(prm, 256, n).to_host()
     assert np.array_equal(a + b, full)
+
+
+@pytest.mark.parametrize("n,L", [(2, 40), (129, 1000), (300, 515), (700, 4000)])
+@pytest.mark.parametrize("dist_type", [1, 2])
+def test_tensor_core_path_is_bit_identical(ctx, oracle, n, L, dist_type, monkeypatch):
+    """msa_tc.cu (tcgen05 int8 GEMMs) must give exactly the matrix of the popcount kernel."""
+    codes, P, _ = make_msa(n, L, seed=900 + n, gap_cols=0.05)
+    msa = upload(ctx, P, L)
+    prm = api.Param(distanceType=dist_type, in_="m")
+    monkeypatch.setenv("DIPB_MSA_TC", "0")
+    ref = msa.distMatrix(prm).to_host()          # popcount kernel
+    monkeypatch.setenv("DIPB_MSA_TC", "1")
+    got = msa.distMatrix(prm).to_host()          # tcgen05 kernel (the default)
+    monkeypatch.delenv("DIPB_MSA_TC")
+    assert np.array_equal(got, ref, equal_nan=True)
+    assert np.allclose(got, oracle.msa_dist_matrix(P, L, dist_type), rtol=1e-6, atol=0, equal_nan=True)
