@@ -134,6 +134,16 @@ class MSADeviceArrays:
         check(lib().dipb_msa_dist_row_host(self.h, params.distanceType, rowId, out))
         return out[:rowId]
 
+    def distBlock(self, params, r0, r1, ncols):
+        """d(i, j) for i in [r0, r1), j in [0, ncols): the batched rows placement and the divide-and-conquer
+        stages consume (DC/msa.cu:269-372).  Returned as a host array [r1 - r0, ncols]."""
+        import torch
+        ld = (ncols + 127) // 128 * 128
+        buf = torch.empty((r1 - r0, ld), dtype=torch.float64, device=f"cuda:{self.ctx.device}")
+        check(lib().dipb_msa_dist_block(self.h, params.distanceType, r0, r1, ncols, buf.data_ptr(), ld))
+        self.ctx.sync()
+        return buf[:, :ncols].cpu().numpy()
+
     def counts(self, i0, i1, j0, j1):
         m = np.zeros((i1 - i0, j1 - j0), np.int32)
         u = np.zeros((i1 - i0, j1 - j0), np.int32)

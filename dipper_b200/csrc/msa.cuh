@@ -30,5 +30,6 @@ int msa_block(dipb_msa* m, int type, int r0, int r1, int ncols, double* d_out, s
 int msa_matrix(dipb_msa* m, int type, int row_begin, int row_end, double* d_out);
 int msa_counts_dev(dipb_msa* m, int i0, int i1, int j1, int* d_match, int* d_both, size_t ld);
 bool msa_tc_supported(const dipb_msa* m, int type);
-int msa_tc_matrix(dipb_msa* m, int type, double* d_out);
+int msa_tc_matrix(dipb_msa* m, int type, int row_begin, int row_end, double* d_out);
+int msa_tc_block(dipb_msa* m, int type, int r0, int r1, int ncols, double* d_out, size_t ld);
 }  // namespace dipb

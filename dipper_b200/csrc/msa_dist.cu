@@ -372,6 +372,11 @@ static bool fast_ok(const dipb_msa* m, int type) {
 int msa_block(dipb_msa* m, int type, int r0, int r1, int ncols, double* d_out, size_t ld) {
     if (r0 < 0 || r1 > m->n || r0 >= r1 || ncols < 0 || ncols > m->n) { set_error("msa_block: bad range"); return DIPB_E_ARG; }
     if (ncols == 0) return 0;
+    if (r1 - r0 >= 64 && msa_tc_supported(m, type)) {
+        // enough rows to fill 128-row tensor-core tiles (placement row blocks, D&C query batches)
+        const char* e = getenv("DIPB_MSA_TC");
+        if (!(e && e[0] == '0')) return msa_tc_block(m, type, r0, r1, ncols, d_out, ld);
+    }
     if (!fast_ok(m, type)) return generic_block(m, type, r0, r1, ncols, d_out, ld, r0, 0);
     TileParams p{};
     p.planes = m->planes; p.nv = m->nv; p.nkc = m->nkc; p.kc0 = 0; p.kc1 = m->nkc; p.tri = 0; p.n = m->n;
@@ -383,11 +388,11 @@ int msa_block(dipb_msa* m, int type, int r0, int r1, int ncols, double* d_out, s
 int msa_matrix(dipb_msa* m, int type, int row_begin, int row_end, double* d_out) {
     // lower-triangle tiles whose row block intersects [row_begin,row_end); mirrored
     if (row_begin < 0 || row_end > m->n || row_begin >= row_end) { set_error("msa_matrix: bad rows"); return DIPB_E_ARG; }
-    if (row_begin == 0 && row_end == m->n && msa_tc_supported(m, type)) {
+    if (msa_tc_supported(m, type)) {
         // tensor-core path (msa_tc.cu): 4.4x the popcount kernel on B200 (3.4 ms vs 15.0 ms at 8000 x 30000),
         // bit-identical output.  DIPB_MSA_TC=0 forces the popcount kernel.
         const char* e = getenv("DIPB_MSA_TC");
-        if (!(e && e[0] == '0')) return msa_tc_matrix(m, type, d_out);
+        if (!(e && e[0] == '0')) return msa_tc_matrix(m, type, row_begin, row_end, d_out);
     }
     if (!fast_ok(m, type)) return generic_block(m, type, row_begin, row_end, 0, d_out, (size_t)m->n, 0, 1);
     TileParams p{};

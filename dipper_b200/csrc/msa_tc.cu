@@ -16,6 +16,7 @@
 //   warps 2-5 epilogue: tcgen05.ld 32x32b, fp64 p / JC in the reference's expression order, D[i][j] + mirror
 // The GEMM is L2-bandwidth bound (384 operand bytes per 32 768 outputs per K byte), see DESIGN.md §4.1.
 #include <cuda.h>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 #include "msa.cuh"
@@ -114,6 +115,8 @@ struct TcParams {
     double* out;
     size_t ld;
     int dist_type;
+    int rect;                   // 0: lower triangle + mirror into an n x n matrix; 1: rows [r0,r1) x cols [0,ncols)
+    int r0, r1, ncols;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -213,7 +216,19 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
                 tmem_ld32(taddr + 256u, r2);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int j0 = tl.y * TC_N + cb * 32;
-                if (i < p.n && j0 <= i) {
+                if (p.rect) {
+                    if (i >= p.r0 && i < p.r1 && j0 < p.ncols) {
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            const int j = j0 + c;
+                            if (j < p.ncols) {
+                                const int both = (int)r2[c];
+                                const int match = ((int)r1[c] + both) >> 2;
+                                p.out[(size_t)(i - p.r0) * p.ld + j] = dist_p_jc(match, nvi + p.nv[j] - both, p.dist_type);
+                            }
+                        }
+                    }
+                } else if (i >= p.r0 && i < p.r1 && j0 <= i) {
 #pragma unroll
                     for (int c = 0; c < 32; c++) {
                         const int j = j0 + c;
@@ -277,11 +292,11 @@ int msa_tc_prepare(dipb_msa* m) {
     return 0;
 }
 
-// full symmetric matrix (all rows), p or JC
-int msa_tc_matrix(dipb_msa* m, int type, double* d_out) {
+static int tc_launch(dipb_msa* m, const std::vector<int2>& tiles, TcParams p) {
     dipb_ctx* c = m->ctx;
     int rc = msa_tc_prepare(m);
     if (rc) return rc;
+    if (tiles.empty()) return 0;
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -294,18 +309,12 @@ int msa_tc_matrix(dipb_msa* m, int type, double* d_out) {
     if ((rc = make_map(encode, &mSA, m->tc_S, m->tc_ks, m->tc_rows, TC_M)) || (rc = make_map(encode, &mSB, m->tc_S, m->tc_ks, m->tc_rows, TC_N)) ||
         (rc = make_map(encode, &mVA, m->tc_V, m->tc_kv, m->tc_rows, TC_M)) || (rc = make_map(encode, &mVB, m->tc_V, m->tc_kv, m->tc_rows, TC_N)))
         return rc;
-    // tiles of the lower triangle: column block nj intersects rows of block mi when nj*256 <= mi*128 + 127
-    const int mb = (m->n + TC_M - 1) / TC_M;
-    std::vector<int2> tiles;
-    for (int mi = mb - 1; mi >= 0; mi--)
-        for (int nj = 0; nj * TC_N <= mi * TC_M + TC_M - 1; nj++) tiles.push_back(make_int2(mi, nj));
     int2* d_tiles = nullptr;
     DIPB_CUDA(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
     DIPB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
-    TcParams p{};
     p.tiles = d_tiles; p.num_tiles = (int)tiles.size();
     p.ns_chunks = (int)(m->tc_ks / TC_KB); p.nv_chunks = (int)(m->tc_kv / TC_KB);
-    p.nv = m->nv; p.n = m->n; p.out = d_out; p.ld = (size_t)m->n; p.dist_type = type;
+    p.nv = m->nv; p.n = m->n;
     static bool attr = false;
     if (!attr) { DIPB_CUDA(cudaFuncSetAttribute(msa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); attr = true; }
     int grid = p.num_tiles < c->num_sms ? p.num_tiles : c->num_sms;
@@ -314,6 +323,41 @@ int msa_tc_matrix(dipb_msa* m, int type, double* d_out) {
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_tiles);
     return 0;
+}
+
+// Tiles are ordered so that the ~148 tiles running concurrently form a compact 16 x 9 super-tile: they stream
+// only 16 + 9 distinct operand slabs through L2 instead of 1 + 148 (the GEMM is bandwidth bound, not MMA bound).
+static const int SM_ROWS = 16, SM_COLS = 9;
+
+// symmetric matrix entries (i, j) and (j, i) for i in [row_begin, row_end), j < i, plus the diagonal; p or JC
+int msa_tc_matrix(dipb_msa* m, int type, int row_begin, int row_end, double* d_out) {
+    // lower triangle: column block nj intersects row block mi when nj*256 <= mi*128 + 127
+    const int mb0 = row_begin / TC_M, mb = (row_end + TC_M - 1) / TC_M;
+    std::vector<int2> tiles;
+    for (int sm = (mb + SM_ROWS - 1) / SM_ROWS - 1; sm >= mb0 / SM_ROWS; sm--) {
+        const int mi_hi = std::min(mb, (sm + 1) * SM_ROWS) - 1;
+        const int nj_max = (mi_hi * TC_M + TC_M - 1) / TC_N;
+        for (int sn = 0; sn * SM_COLS <= nj_max; sn++)
+            for (int mi = std::max(mb0, sm * SM_ROWS); mi <= mi_hi; mi++)
+                for (int nj = sn * SM_COLS; nj < (sn + 1) * SM_COLS; nj++)
+                    if (nj * TC_N <= mi * TC_M + TC_M - 1) tiles.push_back(make_int2(mi, nj));
+    }
+    TcParams p{};
+    p.out = d_out; p.ld = (size_t)m->n; p.dist_type = type; p.rect = 0; p.r0 = row_begin; p.r1 = row_end;
+    return tc_launch(m, tiles, p);
+}
+
+// rows [r0, r1) x columns [0, ncols) into out[(i - r0) * ld + j]  (placement row blocks, D&C stage 2)
+int msa_tc_block(dipb_msa* m, int type, int r0, int r1, int ncols, double* d_out, size_t ld) {
+    const int mi0 = r0 / TC_M, mi1 = (r1 - 1) / TC_M, nb = (ncols + TC_N - 1) / TC_N;
+    std::vector<int2> tiles;
+    for (int sm = mi0; sm <= mi1; sm += SM_ROWS)
+        for (int sn = 0; sn < nb; sn += SM_COLS)
+            for (int mi = sm; mi <= std::min(mi1, sm + SM_ROWS - 1); mi++)
+                for (int nj = sn; nj < std::min(nb, sn + SM_COLS); nj++) tiles.push_back(make_int2(mi, nj));
+    TcParams p{};
+    p.out = d_out; p.ld = ld; p.dist_type = type; p.rect = 1; p.r0 = r0; p.r1 = r1; p.ncols = ncols;
+    return tc_launch(m, tiles, p);
 }
 
 }  // namespace dipb

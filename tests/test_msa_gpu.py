@@ -135,3 +135,37 @@ def test_tensor_core_path_is_bit_identical(ctx, oracle, n, L, dist_type, monkeyp
     monkeypatch.delenv("DIPB_MSA_TC")
     assert np.array_equal(got, ref, equal_nan=True)
     assert np.allclose(got, oracle.msa_dist_matrix(P, L, dist_type), rtol=1e-6, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("dist_type", [1, 2])
+@pytest.mark.parametrize("r0,r1,ncols", [(0, 64, 700), (100, 700, 100), (130, 515, 515), (511, 700, 257)])
+def test_tensor_core_block_rows(ctx, oracle, dist_type, r0, r1, ncols, monkeypatch):
+    """Row blocks of >= 64 rows (placement batches, D&C stage 2) go through the tcgen05 kernel too."""
+    n, L = 700, 2100
+    codes, P, _ = make_msa(n, L, seed=77, gap_cols=0.05)
+    msa = upload(ctx, P, L)
+    prm = api.Param(distanceType=dist_type, in_="m")
+    monkeypatch.setenv("DIPB_MSA_TC", "0")
+    ref = msa.distBlock(prm, r0, r1, ncols)
+    monkeypatch.setenv("DIPB_MSA_TC", "1")
+    got = msa.distBlock(prm, r0, r1, ncols)
+    monkeypatch.delenv("DIPB_MSA_TC")
+    full = oracle.msa_dist_matrix(P, L, dist_type)
+    off = np.arange(r0, r1)[:, None] != np.arange(ncols)[None, :]      # the diagonal is unspecified in block mode
+    assert np.array_equal(got[off], ref[off], equal_nan=True)
+    assert np.allclose(got[off], full[r0:r1, :ncols][off], rtol=1e-6, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("cut", [1, 128, 300, 699])
+def test_tensor_core_row_sharded_matrix(ctx, oracle, cut, monkeypatch):
+    n, L = 700, 1300
+    codes, P, _ = make_msa(n, L, seed=78)
+    msa = upload(ctx, P, L)
+    prm = api.Param(distanceType=2, in_="m")
+    monkeypatch.setenv("DIPB_MSA_TC", "0")
+    full = msa.distMatrix(prm).to_host()
+    monkeypatch.setenv("DIPB_MSA_TC", "1")
+    a = msa.distMatrix(prm, 0, cut).to_host()
+    b = msa.distMatrix(prm, cut, n).to_host()
+    monkeypatch.delenv("DIPB_MSA_TC")
+    assert np.array_equal(a + b, full)
