@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import DipperError, DistSource, check, lib
 
 DIST_UNCORRECTED, DIST_JUKESCANTOR, DIST_TAJIMANEI, DIST_KIMURA2P, DIST_TAMURA, DIST_JINNEI = 1, 2, 3, 4, 5, 6
-NJ_AUTO, NJ_FULLSCAN, NJ_PRUNED = 0, 1, 2
+NJ_AUTO, NJ_FULLSCAN, NJ_PRUNED, NJ_CLUSTER = 0, 1, 2, 3
 T_MSA_UPLOAD, T_MSA_DIST, T_NJ, T_SKETCH, T_MASH_DIST, T_PLACE = 0, 1, 2, 3, 4, 5
 
 

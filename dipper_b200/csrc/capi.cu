@@ -290,7 +290,7 @@ void dipb_matrix_free(dipb_matrix* m) {
 // ---- NJ ------------------------------------------------------------------------
 int dipb_nj(dipb_matrix* m, int algo, int32_t* child0, int32_t* child1, double* len0, double* len1) {
     if (!m || !child0 || !child1 || !len0 || !len1) { set_error("dipb_nj: bad argument"); return DIPB_E_ARG; }
-    if (algo < 0 || algo > 2) { set_error("dipb_nj: unknown algorithm %d", algo); return DIPB_E_ARG; }
+    if (algo < 0 || algo > DIPB_NJ_CLUSTER) { set_error("dipb_nj: unknown algorithm %d", algo); return DIPB_E_ARG; }
     DIPB_CUDA(cudaSetDevice(m->ctx->device));
     return nj_run(m, algo, child0, child1, len0, len1);
 }

@@ -29,6 +29,7 @@
 #include <vector>
 #include "common.cuh"
 #include "nj.cuh"
+#include "nj_bound.cuh"
 
 namespace dipb {
 
@@ -53,36 +54,6 @@ struct PShared {
     unsigned long long rows_scanned, iters;
     unsigned long long cyc[8];   // CTA 0 cycle counters per phase: A, bar, B, bar, C1, bar, C2+bar, D
 };
-
-__device__ __forceinline__ unsigned long long enc_f64(double v) {
-    unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double dec_f64(unsigned long long e) {
-    unsigned long long b = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
-    return __longlong_as_double((long long)b);
-}
-__device__ __forceinline__ unsigned int enc_f32(float v) {
-    unsigned int b = __float_as_uint(v);
-    return (b >> 31) ? ~b : (b | 0x80000000u);
-}
-
-__device__ __forceinline__ int p_rowblock_of(int i, int n) {
-    int sz = n / 256, rem = n % 256;
-    long long split = (long long)(sz + 1) * rem;
-    if (i < split) return i / (sz + 1);
-    return rem + (int)((i - split) / sz);
-}
-__device__ __forceinline__ unsigned long long p_tie_key(int i, int j, int n) {
-    return ((unsigned long long)p_rowblock_of(i, n) << 56) | ((unsigned long long)(j & 255) << 48) |
-           ((unsigned long long)j << 24) | (unsigned long long)i;
-}
-__device__ __forceinline__ bool p_before(double ta, int ia, int ja, double tb, int ib, int jb, int n) {
-    if (ta < tb) return true;
-    if (ta > tb) return false;
-    if (ta >= 10000.0) return false;
-    return p_tie_key(ia, ja, n) < p_tie_key(ib, jb, n);
-}
 
 // Grid barrier on one monotonically increasing counter: barrier k is complete when the
 // counter reaches k * nblocks.  One release-fence + atomic per CTA, relaxed polling by a

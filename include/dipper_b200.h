@@ -37,7 +37,8 @@ extern "C" {
 /* NJ search strategies; every one returns the reference's argmin (same tie-break) */
 #define DIPB_NJ_AUTO 0
 #define DIPB_NJ_FULLSCAN 1  /* scans all n^2 candidates each iteration (reference cost model) */
-#define DIPB_NJ_PRUNED 2    /* exact lower-bound pruning, rescans only rows that can hold the minimum */
+#define DIPB_NJ_PRUNED 2    /* exact lower-bound pruning, rescans only rows that can hold the minimum (whole-grid kernel) */
+#define DIPB_NJ_CLUSTER 3   /* the same pruned search run by one 16-CTA thread-block cluster (default when it fits) */
 
 typedef struct dipb_ctx dipb_ctx;
 typedef struct dipb_msa dipb_msa;

@@ -7,7 +7,7 @@ from conftest import make_msa
 
 pytestmark = pytest.mark.gpu
 
-ALGOS = [api.NJ_FULLSCAN, api.NJ_PRUNED]
+ALGOS = [api.NJ_FULLSCAN, api.NJ_PRUNED, api.NJ_CLUSTER]
 
 
 def run_nj(ctx, D, algo):
@@ -73,8 +73,9 @@ def test_pruned_equals_fullscan_at_scale(ctx):
         nj.findNeighbourJoiningTree(synth.names(n), algo)
         res.append(nj.result)
         nj.deallocateDeviceArrays()
-    for a, b in zip(res[0], res[1]):
-        assert np.array_equal(a, b)
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert np.array_equal(a, b)
 
 
 def test_msa_to_tree_end_to_end_rf_zero(ctx, oracle):

@@ -14,6 +14,6 @@ msa.allocateDeviceArrays(P, np.full(n, L, np.uint64), n, prm)
 for rep in range(2):
     nj = api.NJDeviceArrays(ctx)
     nj.getDismatrix(n, prm, msaDeviceArrays=msa)
-    nj.findNeighbourJoiningTree(["T%d" % i for i in range(n)], 2)
+    nj.findNeighbourJoiningTree(["T%d" % i for i in range(n)], int(os.environ.get("NJ_ALGO", "0")))
     print("n=%d dist %.2f ms  nj %.2f ms  (%.2f us/iter)" % (n, ctx.elapsed_ms(api.T_MSA_DIST), ctx.elapsed_ms(api.T_NJ), 1e3 * ctx.elapsed_ms(api.T_NJ) / n), ctx.nj_stats())
     nj.deallocateDeviceArrays()
