@@ -19,6 +19,11 @@ __device__ __forceinline__ unsigned int enc_f32(float v) {
     return (b >> 31) ? ~b : (b | 0x80000000u);
 }
 
+__device__ __forceinline__ float dec_f32(unsigned int e) {
+    unsigned int b = (e >> 31) ? (e & 0x7fffffffu) : ~e;
+    return __uint_as_float(b);
+}
+
 __device__ __forceinline__ int p_rowblock_of(int i, int n) {
     const int sz = n / 256, rem = n % 256;
     const int split = (sz + 1) * rem;   // <= n

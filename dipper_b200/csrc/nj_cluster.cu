@@ -1,28 +1,31 @@
 // K4 (cluster): the bound-pruned exact NJ search of nj_pruned.cu, run by ONE thread-block cluster.
 //
 // Why one cluster and not the whole GPU.  After pruning an NJ iteration touches little data (~34 rows
-// rescanned + 5 row/column updates: ~8 MB at 30 000 tips, shrinking linearly), but it is a chain of four
-// dependent steps.  Spread over 148 CTAs each step ends in a software grid barrier through L2 (~2 us) and
-// every exchanged scalar is another L2 round trip: 25 us per iteration, the same at 4 000 tips as at
-// 30 000 (profiles/r1_nj_phase_cycles.txt).  A 16-CTA cluster synchronises in hardware
-// (barrier.cluster, ~0.2 us), exchanges scalars through distributed shared memory, and keeps the per-row
-// state (U, u, the new column) in shared memory; 16 SMs still pull ~1.5 TB/s, enough for the scan.
+// rescanned + 5 row/column updates: ~8 MB at 30 000 tips, shrinking linearly), but it is a chain of
+// dependent steps.  Spread over 148 CTAs each step ends in a software grid barrier through L2 and every
+// exchanged scalar is another L2 round trip: 25 us per iteration, the same at 4 000 tips as at 30 000.
+// A 16-CTA cluster synchronises in hardware (barrier.cluster), exchanges scalars by pushing them into the
+// peers' shared memory, and keeps the per-row state (U, u, lower-bound keys, the new column) in shared
+// memory.  What the one GPC of the main cluster is bad at -- the 2n scattered 8-byte column stores of every
+// merge -- is handed to helper clusters on the other GPCs through a doorbell in global memory.
 //
 // Same algorithm and result as nj_pruned.cu (see its header for the bound): replaces the loop of
 // NJDeviceArrays::findNeighbourJoiningTree (src/neighborJoining.cu:196-246) with findMinDist (:117-148),
 // thrust::min_element (:214) and updateDisMatrix (:161-194), tie order and U summation order included.
 //
 // Layout.  Rows are dealt to the CTAs in chunks of 32: chunk w = i / 32 belongs to CTA w % CS, local slot
-// (w / CS) * 32 + i % 32.  A CTA owns U, u, the folded new-column value of its rows, and scans its own
-// column chunks of every selected row (u of those columns is local).  K (row lower-bound keys) and D live in
-// global memory, read with ld.global.cg.
+// (w / CS) * 32 + i % 32.  A CTA owns U, u, K and the distances of its rows to the two slots the last merge
+// rewrote (v: new node x, f: the node moved into y), and scans its own column chunks of every selected row
+// (u of those columns is local).  D lives in global memory and is read with ld.global.cg.
 //
-// Iteration (4 cluster barriers):
-//   D  every CTA reduces the 16 published CTA winners to the same (x, y); rank 0 logs the merge
-//   A  owners update rows/columns x, y (move `last` into y), U, u, chunk sums, max u-drift      | barrier
-//   B1 U[x] (canonical sum order), C += drift; each CTA re-evaluates its carried candidate pairs  | barrier
-//   B2 ub = min over CTAs; owners fold the new column into K and select rows with lb <= ub        | barrier
-//   C  every CTA scans its column chunks of the selected rows; publishes its winner to all CTAs   | barrier
+// Iteration (4 cluster barriers; everything a peer needs after a barrier was pushed into its shared memory
+// before it -- measured: pulling the same word from one CTA by 512 warps serialises for ~1500 cycles):
+//   D  every CTA reduces the published CTA winners to the same (x, y); rank 0 logs the merge
+//   A  owners update rows x, y (move `last` into y), U, u; push chunk sums and max u-drift           | barrier
+//   B1 U[x] (canonical sum order), C += drift; ring the helpers; re-evaluate carried candidates      | barrier
+//   B2 ub = min over CTAs; owners fold the new column into K and select rows with lb <= ub           | barrier
+//   C  every CTA stages the selected rows (index, u, v, f) in shared memory, scans its column chunks of them,
+//      combines per-row minima in shared memory, pushes them to the row owners' K; publishes its winner  | barrier
 #include <cooperative_groups.h>
 #include <cstdlib>
 #include <vector>
@@ -37,9 +40,13 @@ namespace dipb {
 namespace {
 
 constexpr int MAXW = 32;      // warps per CTA at most
-constexpr int UC = 8;         // column chunks per scan unit (loads in flight per lane)
 constexpr int CPOOL = 128;    // carried candidate pairs per CTA
 constexpr int MAXCS = 16;
+constexpr int TILE = 512;     // selected rows staged in shared memory at a time
+constexpr unsigned long long KMAX = 0xffffffffffffffffull;
+constexpr unsigned int K32MAX = 0xffffffffu;   // row keys are order-preserving fp32, rounded DOWN (a lower bound stays one);
+                                               // 32-bit min is a native shared-memory atomic, local and remote
+                                               // (red.shared::cluster.min.u64 assembles but does not take effect on sm_100a)
 
 struct CRec {                 // a CTA's best candidate of one scan
     double t, d, ui, uj;
@@ -65,55 +72,71 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
     const unsigned int ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
     return ((unsigned long long)mh << 32) | ml;
 }
-
-// distributed-shared-memory load: the same variable in CTA `rank` of the cluster (mapa + ld.shared::cluster)
-__device__ __forceinline__ double ld_peer_f64(const double* p, int rank) {
-    const unsigned int a = (unsigned int)__cvta_generic_to_shared(p);
-    unsigned int ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-    double v;
-    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
-    return v;
-}
-
 __device__ __forceinline__ double warp_min_f64(double v) { return dec_f64(warp_min_u64(enc_f64(v))); }
 __device__ __forceinline__ double warp_max_f64(double v) { return -warp_min_f64(-v); }
 
-// ---- candidate order (reference scan order, nj_bound.cuh) kept OUT of line: exact ties are rare, and the
-// kernel must stay small -- every warp walks the whole iteration body once per merge, so a body that
-// overflows the 32 KB instruction cache pays an L2 fetch every few instructions.
+// ---- distributed shared memory: the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ unsigned int peer_addr(const void* p, int rank) {
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(p);
+    unsigned int ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ double ld_peer_f64(const double* p, int rank) {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(peer_addr(p, rank)) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_peer_u32(const unsigned int* p, int rank) {
+    unsigned int v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(peer_addr(p, rank)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_peer_f64(double* p, int rank, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(peer_addr(p, rank)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_peer_min_u32(unsigned int* p, int rank, unsigned int v) {
+    asm volatile("red.shared::cluster.min.u32 [%0], %1;" ::"r"(peer_addr(p, rank)), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int key_of(double v) { return enc_f32(__double2float_rd(v)); }
+
+// ---- candidate order (reference scan order, nj_bound.cuh), out of line: exact ties are rare
 __device__ __noinline__ bool tie_before(int ia, int ja, int ib, int jb, int n) {
     if (ia == ib) return ((ja & 255) < (jb & 255)) || ((ja & 255) == (jb & 255) && ja < jb);
     return p_tie_key(ia, ja, n) < p_tie_key(ib, jb, n);
 }
 __device__ __noinline__ int tie_lane(unsigned int tied, int i, int j, int n) {
     const bool in = (tied >> (threadIdx.x & 31)) & 1u;
-    const unsigned long long key = in ? p_tie_key(i, j, n) : 0xffffffffffffffffull;
+    const unsigned long long key = in ? p_tie_key(i, j, n) : KMAX;
     const unsigned long long km = warp_min_u64(key);
     return __ffs(__ballot_sync(0xffffffffu, key == km)) - 1;
 }
 // lane holding the best candidate of the warp (t ascending, then reference order), -1 when no lane has one
 __device__ __forceinline__ int warp_best_lane(double t, int i, int j, int n) {
-    const unsigned long long e = i >= 0 ? enc_f64(t) : 0xffffffffffffffffull;
+    const unsigned long long e = i >= 0 ? enc_f64(t) : KMAX;
     const unsigned long long m = warp_min_u64(e);
-    if (m == 0xffffffffffffffffull) return -1;
+    if (m == KMAX) return -1;
     const unsigned int tied = __ballot_sync(0xffffffffu, e == m);
     if ((tied & (tied - 1u)) == 0u) return __ffs(tied) - 1;
     return tie_lane(tied, i, j, n);
 }
 
+// bytes of dynamic shared memory for LS owned rows per CTA and `chunks` 32-row chunks in total
+inline size_t cluster_smem_bytes(int LS, int chunks) {
+    return sizeof(double) * ((size_t)4 * LS + chunks + 2) + sizeof(unsigned int) * (size_t)LS + (size_t)TILE * (3 * 8 + 4 + 4);
+}
+
 }  // namespace
 
-template <int CS, int CT, bool PROF>
+template <int CS, int CT, int UC, bool PROF>   // UC: column chunks per scan unit (loads in flight per lane)
 __global__ void __launch_bounds__(CT, 1)
 nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ U0, const double* __restrict__ u0,
-                  unsigned long long* __restrict__ K, int* __restrict__ sel_rows, CStats* stats,
-                  int2* __restrict__ log_xy, double2* __restrict__ log_bl, int n_total, int LS, double dmax,
-                  NJCtl* ctl, int HC) {
+                  int* __restrict__ sel_rows, CStats* stats, int2* __restrict__ log_xy, double2* __restrict__ log_bl,
+                  int n_total, int LS, double dmax, NJCtl* ctl, int HC) {
     if (blockIdx.x >= CS) {
         // ---- helper clusters (the other GPCs): transpose rows x and y of each published merge into columns x and
         // y.  These 2n scattered 8-byte stores per merge are request-rate bound on one GPC's L2 port when the
-        // main cluster issues them itself (1 us per 1000 tips); spread over the other GPCs they are off the
+        // main cluster issues them itself (~1 us per 1000 tips); spread over the other GPCs they are off the
         // critical path.
         const int hc = (int)blockIdx.x - CS, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
         __shared__ int s_msg[4];
@@ -151,36 +174,43 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     const int rank = (int)cluster.block_rank();
     constexpr int NW = CT / 32;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int chunks_total = (n_total + 31) >> 5;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* U_s = reinterpret_cast<double*>(smem_raw);   // [LS] row sums of owned rows
     double* u_s = U_s + LS;                              // [LS] U / (n - 2)
-    double* v_s = u_s + LS;                              // [LS] distance of owned rows to the newest node x
-    double* f_s = v_s + LS;                              // [LS] distance of owned rows to the node moved into slot y
-    double* cs_s = f_s + LS;                             // [LS / 32] chunk sums of the new column (canonical order)
-    // (+ UC * 32 doubles of padding: the scan reads u_s up to UC - 1 chunks past the last owned one)
+    double* v_s = u_s + LS;                              // [LS] distance to the newest node x
+    double* f_s = v_s + LS;                              // [LS] distance to the node moved into slot y
+    double* cs_all = f_s + LS;                           // [chunks_total] chunk sums of the new column, pushed by the owners
+    double* t_u = cs_all + chunks_total + 2;             // staged selected rows: u, v, f, combined minimum, index
+    double* t_v = t_u + TILE;
+    double* t_f = t_v + TILE;
+    unsigned int* t_min = reinterpret_cast<unsigned int*>(t_f + TILE);
+    int* t_row = reinterpret_cast<int*>(t_min + TILE);
+    unsigned int* K_s = reinterpret_cast<unsigned int*>(t_row + TILE);   // [LS] lower-bound keys of owned rows
 
     __shared__ CRec recs[MAXCS];            // winners published by every CTA of the cluster
     __shared__ CRec wrec[MAXW];
-    __shared__ double s_drift, s_ubmin;     // this CTA's max u-drift / best carried candidate (read by peers)
-    __shared__ double s_red[MAXW], s_blk[128 + 16];   // s_blk: one sum per 1024-row block (n <= 131 072)
-    __shared__ double s_total, s_C, s_ub;
+    __shared__ double drift_all[MAXCS], ubmin_all[MAXCS];   // pushed by the peers
+    __shared__ double s_red[MAXW], s_blk[128 + 16];         // s_blk: one sum per 1024-row block (n <= 131 072)
+    __shared__ double s_total, s_C;
     __shared__ unsigned int s_sel;          // selected-row counter (rank 0's copy is the live one)
     __shared__ int pool_i[CPOOL], pool_j[CPOOL];
     __shared__ double pool_d[CPOOL];        // d of a carried pair never changes while both ends survive
     __shared__ int s_pool_head, s_nsel;
     __shared__ unsigned long long s_cyc[24];   // rank 0, thread 0: cycles per phase (DIPB_NJ_PROFILE)
 
-
     // ---- load owned state
     for (int s = tid; s < LS; s += CT) {
         const int i = ((s >> 5) * CS + rank) * 32 + (s & 31);
         U_s[s] = i < n_total ? U0[i] : 0.0;
         u_s[s] = i < n_total ? u0[i] : 0.0;
-        v_s[s] = 0.0;
+        v_s[s] = 0.0; f_s[s] = 0.0;
+        K_s[s] = K32MAX;
     }
+    if (tid == 0) t_row[0] = 0;
     for (int p = tid; p < CPOOL; p += CT) { pool_i[p] = -1; pool_j[p] = -1; }
-    if (tid == 0) { s_pool_head = 0; s_sel = 0; s_drift = -1e300; s_ubmin = 1e300; }
+    if (tid == 0) { s_pool_head = 0; s_sel = 0; }
     if (tid < 24) s_cyc[tid] = 0;
     __syncthreads();
     cluster.sync();
@@ -208,7 +238,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
         double ub = 1e300;
         if (!first) {
             // ------------------------------------------------------------ A: merge update by row owners
-            CL_MARK(1);
+            CL_MARK(0);
             const int last = n - 1;
             const double den_new = (double)(n - 3);
             const int nchunk = (last + 31) >> 5;               // chunks holding rows < last
@@ -228,7 +258,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         const int lo = (last >> 5) % CS, ls = ((last >> 5) / CS) * 32 + (last & 31);
                         Ui = ld_peer_f64(&U_s[ls], lo);
                         uo = ld_peer_f64(&u_s[ls], lo);
-                        K[y] = __ldcg(&K[last]);
+                        K_s[s] = ld_peer_u32(&K_s[ls], lo);
                     }
                     const double val = (a + b - dxy) * 0.5;
                     Ui += -a - b + val;
@@ -236,7 +266,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     D[(size_t)x * ld + i] = val;         // rows x and y: coalesced, visible after the next barrier
                     if (isy) D[(size_t)y * ld + x] = val;
                     else D[(size_t)y * ld + i] = far;
-                    f_s[s] = far;                        // columns x and y of row i are written during phase C
+                    f_s[s] = far;                        // columns x and y of row i are written by the helper clusters
                     slot = val;
                     if (n > 3) {
                         const double un = Ui / den_new;
@@ -245,25 +275,25 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     }
                 }
                 v_s[s] = slot;
-                const double csum = warp_tree_sum(slot);
-                if (lane == 0) cs_s[lw] = csum;
+                // canonical block sum, level 1: this chunk's stride-halving tree, pushed to every CTA
+                const double csum = __shfl_sync(0xffffffffu, warp_tree_sum(slot), 0);
+                if (lane < CS) st_peer_f64(&cs_all[lw * CS + rank], lane, csum);
             }
-            CL_MARK(2);
             dmx = warp_max_f64(dmx);
             if (lane == 0) s_red[w] = dmx;
             __syncthreads();
             if (w == 0) {
                 const double m = warp_max_f64(lane < NW ? s_red[lane] : -1e300);
-                if (lane == 0) s_drift = m;
+                if (lane < CS) st_peer_f64(&drift_all[rank], lane, m);
             }
-            CL_MARK(3);
+            CL_MARK(1);
             cluster.sync();
-            CL_MARK(4);
+            CL_MARK(2);
 
             // ------------------------------------------------------------ B1: U[x], drift, carried candidates
             n = last;
             if (n <= 2) {
-                // last merge: its column writes are not deferred (nj_finish_kernel reads D[0][1])
+                // last merge: nj_finish_kernel reads D[0][1], a column entry when x == 1
                 if (rank == 0 && tid < n && tid != x && tid != y) D[(size_t)tid * ld + x] = v_s[tid];
                 break;
             }
@@ -274,18 +304,13 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->seq), "r"((unsigned int)iter) : "memory");
             }
             {
-                // canonical sum: 1024-row blocks (32 chunk sums, stride-halving tree), blocks ascending
+                // canonical sum, level 2: 1024-row blocks (32 chunk sums, stride-halving tree), then blocks ascending
                 const int nblk = (last + 1023) >> 10;
                 for (int b = w; b < nblk; b += NW) {
                     const int cw = b * 32 + lane;
-                    double v = 0.0;
-                    if (cw < nchunk) v = ld_peer_f64(&cs_s[cw / CS], cw % CS);
-                    v = warp_tree_sum(v);
+                    const double v = warp_tree_sum(cw < nchunk ? cs_all[cw] : 0.0);
                     if (lane == 0) s_blk[b] = v;
                 }
-                double drift = -1e300;
-                if (tid < CS) drift = ld_peer_f64(&s_drift, tid);
-                if (w == 0) drift = warp_max_f64(drift);
                 __syncthreads();
                 if (tid == 0) {
                     double acc = 0.0;
@@ -296,12 +321,14 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
 #pragma unroll
                         for (int q = 0; q < 16; q++) if (b0 + q < nblk) acc += v[q];
                     }
+                    double drift = drift_all[0];
+                    for (int q = 1; q < CS; q++) drift = fmax(drift, drift_all[q]);
                     s_total = acc;
                     s_C = C + drift;
                 }
                 __syncthreads();
             }
-            CL_MARK(5);
+            CL_MARK(3);
             const double total = s_total;
             const double ux = total / (double)(n - 2);
             C = s_C;
@@ -311,38 +338,32 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 u_s[sx] = ux;
             }
             // carried candidates of this CTA, re-evaluated exactly with the post-merge u (none touches x or y)
-            {
+            if (tid < CPOOL) {
                 double pv = 1e300;
-                if (tid < CPOOL && pool_i[tid] >= 0) {
+                if (pool_i[tid] >= 0) {
                     const int pi = pool_i[tid], pj = pool_j[tid];
-                    const double d = pool_d[tid];
                     const double upi = ld_peer_f64(&u_s[((pi >> 5) / CS) * 32 + (pi & 31)], (pi >> 5) % CS);
                     const double upj = ld_peer_f64(&u_s[((pj >> 5) / CS) * 32 + (pj & 31)], (pj >> 5) % CS);
-                    pv = (d - upi) - upj;
+                    pv = (pool_d[tid] - upi) - upj;
                 }
-                if (tid < CPOOL) {
-                    pv = warp_min_f64(pv);
-                    if (lane == 0) s_red[w] = pv;
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    double m = s_red[0];
-                    for (int q = 1; q < CPOOL / 32; q++) m = fmin(m, s_red[q]);
-                    s_ubmin = m;
-                }
-            }
-            CL_MARK(7);
-            cluster.sync();
-            CL_MARK(8);
-
-            // ------------------------------------------------------------ B2: upper bound, fold column x, select
-            if (w == 0) {
-                const double m = warp_min_f64(lane < CS ? ld_peer_f64(&s_ubmin, lane) : 1e300);
-                if (lane == 0) s_ub = m;
+                pv = warp_min_f64(pv);
+                if (lane == 0) s_red[w] = pv;
             }
             __syncthreads();
-            ub = s_ub;
-            CL_MARK(9);
+            if (w == 0) {
+                double m = s_red[0];
+#pragma unroll
+                for (int q = 1; q < CPOOL / 32; q++) m = fmin(m, s_red[q]);
+                if (lane < CS) st_peer_f64(&ubmin_all[rank], lane, m);
+            }
+            CL_MARK(4);
+            cluster.sync();
+            CL_MARK(5);
+
+            // ------------------------------------------------------------ B2: upper bound, fold column x, select
+            ub = ubmin_all[0];
+#pragma unroll
+            for (int q = 1; q < CS; q++) ub = fmin(ub, ubmin_all[q]);
             {
                 const double margin = 1e-9 * (4.0 * dmax + fabs(C));
                 const int nch = (n + 31) >> 5;
@@ -353,11 +374,11 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     if (i < n) {
                         take = (i == x);                          // the new row is always rescanned
                         if (!take) {
-                            const unsigned long long kc = enc_f64((v_s[s] - ux) + C);
-                            unsigned long long ko = __ldcg(&K[i]);
-                            if (kc < ko) { ko = kc; K[i] = kc; }
-                            const double lb = (dec_f64(ko) - C) - u_s[s] - margin;
-                            take = (ko == 0ull) || !(lb > ub);
+                            const unsigned int kc = key_of((v_s[s] - ux) + C);
+                            unsigned int ko = K_s[s];
+                            if (kc < ko) { ko = kc; K_s[s] = kc; }
+                            const double lb = ((double)dec_f32(ko) - C) - u_s[s] - margin;
+                            take = !(lb > ub);
                         }
                     }
                     const unsigned int bal = __ballot_sync(0xffffffffu, take);
@@ -367,7 +388,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         base = __shfl_sync(0xffffffffu, base, 0);
                         if (take) {
                             sel_rows[base + __popc(bal & ((1u << lane) - 1u))] = i;
-                            K[i] = 0xffffffffffffffffull;         // reset, the scan lowers it atomically
+                            K_s[s] = K32MAX;                      // reset, the scan lowers it
                         }
                     }
                 }
@@ -382,106 +403,106 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 unsigned int base = 0;
                 if (lane == 0) base = atomicAdd(sel0, (unsigned int)__popc(bal));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (take) {
-                    sel_rows[base + __popc(bal & ((1u << lane) - 1u))] = i;
-                    K[i] = 0xffffffffffffffffull;
-                }
+                if (take) sel_rows[base + __popc(bal & ((1u << lane) - 1u))] = i;
             }
         }
-        CL_MARK(10);
+        CL_MARK(6);
         cluster.sync();
-        CL_MARK(11);
+        CL_MARK(7);
 
         // ---------------------------------------------------------------- C: scan own column chunks of the selected rows
         {
             if (tid == 0) s_nsel = (int)*sel0;
             const bool merged = !first;
             const bool ymoved = merged && y < n;               // false when y was the last slot: nothing moved into it
-            // Deferred column writes of this merge (D[i][x], D[i][y] for owned rows) are scattered 8-byte stores:
-            // ~2 cycles each per SM, and loads queue behind them (a single L2 load took 1600 cycles right after
-            // a burst; tools/cluster_microbench.cu).  So each warp slips one chunk (64 stores) behind the loads of
-            // each scan unit, and the scan takes columns x and y from v_s / f_s instead of D.
-            const int st_nch = (merged && HC == 0) ? (n + 31) >> 5 : 0;   // with helper clusters the main cluster stores no columns
+            // Without helper clusters the main cluster writes columns x and y itself; the stores ride behind the
+            // loads of the scan units, one chunk (64 scattered stores) per warp and unit.
+            const int st_nch = (merged && HC == 0) ? (n + 31) >> 5 : 0;
             int st_lw = w;
-            auto column_stores = [&]() {
-                const int i = (st_lw * CS + rank) * 32 + lane;
-                if (i < n && i != x && i != y) {
-                    D[(size_t)i * ld + x] = v_s[st_lw * 32 + lane];
-                    if (ymoved) D[(size_t)i * ld + y] = f_s[st_lw * 32 + lane];
-                }
-                st_lw += NW;
-            };
             __syncthreads();
-            CL_MARK(12);
             const int nsel = s_nsel;
             const int nch = (n + 31) >> 5;
             const int lch = nch > rank ? (nch - rank + CS - 1) / CS : 0;      // local chunks holding columns < n
             const int parts = (lch + UC - 1) / UC;
-            const int units = nsel * parts;                                   // <= 131 072 * 32
-            // local chunk / lane of columns x and y when this CTA owns them
+            const int pdiv = parts > 0 ? parts : 1;
+            // local chunk / lane of columns x and y when this CTA owns them: the scan takes those two columns from
+            // v / f of the row, not from D (the helpers may still be writing them)
             const int xlw = (merged && ((x >> 5) % CS) == rank) ? (x >> 5) / CS : -1000000;
             const int ylw = (ymoved && ((y >> 5) % CS) == rank) ? (y >> 5) / CS : -1000000;
             double bt = 1e300, bd = 0.0, bui = 0.0, buj = 0.0;
             int bi = -1, bj = -1;
-            int un = w;
-            const int pdiv = parts > 0 ? parts : 1;
-            int r_next = un < units ? __ldcg(&sel_rows[un / pdiv]) : 0;
-            if (PROF && r_next >= 0) CL_MARK(18);
-            // one pass = one scan unit (8 column chunks of one selected row) + one chunk of column stores; a warp
-            // that has run out of one of the two keeps going with the other (a dead unit loads nothing)
-            for (; un < units || st_lw * CS + rank < st_nch; un += NW) {
-                const bool live = un < units;
-                const int r = live ? r_next : 0;
-                const int lw0 = live ? (un % pdiv) * UC : lch;
-                if (un + NW < units) r_next = __ldcg(&sel_rows[(un + NW) / pdiv]);
-                const double* row = D + (size_t)r * ld;
-                double dv[UC];
+            for (int t0 = 0; t0 < nsel || (t0 == 0 && st_nch > 0); t0 += TILE) {
+                const int tn = nsel - t0 < TILE ? nsel - t0 : TILE;
+                // stage the tile: row index, u, v, f of the row (owner's shared memory), empty combined minimum
+                for (int k = tid; k < tn; k += CT) {
+                    const int r = __ldcg(&sel_rows[t0 + k]);
+                    const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
+                    t_row[k] = r;
+                    t_u[k] = ld_peer_f64(&u_s[rs], ro);
+                    t_v[k] = ld_peer_f64(&v_s[rs], ro);
+                    t_f[k] = ld_peer_f64(&f_s[rs], ro);
+                    t_min[k] = K32MAX;
+                }
+                __syncthreads();
+                CL_MARK(8);
+                const int units = tn > 0 ? tn * parts : 0;
+                // one pass = one scan unit (UC column chunks of one selected row) + one chunk of column stores; a warp
+                // that has run out of one of the two keeps going with the other (a dead unit loads nothing)
+                for (int un = w; un < units || st_lw * CS + rank < st_nch; un += NW) {
+                    const bool live = un < units;
+                    const int k = live ? un / pdiv : 0;
+                    const int r = t_row[k];
+                    const int lw0 = live ? (un % pdiv) * UC : lch;
+                    const double* row = D + (size_t)r * ld;
+                    double dv[UC];
 #pragma unroll
-                for (int q = 0; q < UC; q++) {
-                    const int j = ((lw0 + q) * CS + rank) * 32 + lane;
-                    dv[q] = (live && j < n && j != r) ? __ldcg(&row[j]) : 1e300;   // 1e300: never a candidate
-                }
-                CL_MARK(6);
-                if (st_lw * CS + rank < st_nch) column_stores();
-                CL_MARK(14);
-                // u[r] and, for rows other than x and y, their fresh distances to x and y (owner's shared memory)
-                double rv = 0.0;
-                if (lane < 3) {
-                    double* src = lane == 0 ? u_s : (lane == 1 ? v_s : f_s);
-                    rv = ld_peer_f64(&src[((r >> 5) / CS) * 32 + (r & 31)], (r >> 5) % CS);
-                }
-                if (PROF && rv > -1.0) CL_MARK(22);
-                const double ur = __shfl_sync(0xffffffffu, rv, 0);
-                const double vr = __shfl_sync(0xffffffffu, rv, 1);
-                const double fr = __shfl_sync(0xffffffffu, rv, 2);
-                if (PROF && fr > -1.0) CL_MARK(19);
-                const bool patch = merged && r != x && r != y;
-                const int xq = (patch && lane == (x & 31)) ? xlw - lw0 : -1;
-                const int yq = (patch && lane == (y & 31)) ? ylw - lw0 : -1;
-                // A lane's columns of one row differ by multiples of 32 * CS (a multiple of 256), so the reference
-                // order within the row is plain ascending j: the first strict minimum is the right one.
-                double lm = 1e300, ut = 1e300, ud = 0.0, uuj = 0.0;
-                int uq = 0;
+                    for (int q = 0; q < UC; q++) {
+                        const int j = ((lw0 + q) * CS + rank) * 32 + lane;
+                        dv[q] = (live && j < n && j != r) ? __ldcg(&row[j]) : 1e300;   // 1e300: never a candidate
+                    }
+                    if (st_lw * CS + rank < st_nch) {
+                        const int i = (st_lw * CS + rank) * 32 + lane;
+                        if (i < n && i != x && i != y) {
+                            D[(size_t)i * ld + x] = v_s[st_lw * 32 + lane];
+                            if (ymoved) D[(size_t)i * ld + y] = f_s[st_lw * 32 + lane];
+                        }
+                        st_lw += NW;
+                    }
+                    const double ur = t_u[k];
+                    const bool patch = merged && r != x && r != y;
+                    const int xq = (patch && lane == (x & 31)) ? xlw - lw0 : -1;
+                    const int yq = (patch && lane == (y & 31)) ? ylw - lw0 : -1;
+                    // A lane's columns of one row differ by multiples of 32 * CS (a multiple of 256), so the reference
+                    // order within the row is plain ascending j: the first strict minimum is the right one.
+                    double lm = 1e300, ut = 1e300, ud = 0.0, uuj = 0.0;
+                    int uq = 0;
 #pragma unroll
-                for (int q = 0; q < UC; q++) {
-                    double d = dv[q];
-                    if (q == xq) d = vr;
-                    if (q == yq) d = fr;
-                    const double uj = u_s[(lw0 + q) * 32 + lane];
-                    const double t = (d - ur) - uj;
-                    lm = fmin(lm, d - uj);
-                    if (t < ut) { ut = t; ud = d; uuj = uj; uq = q; }
+                    for (int q = 0; q < UC; q++) {
+                        double d = dv[q];
+                        if (q == xq) d = t_v[k];
+                        if (q == yq) d = t_f[k];
+                        const double uj = u_s[(lw0 + q < lch ? lw0 + q : 0) * 32 + lane];   // (dead columns carry d = 1e300)
+                        const double t = (d - ur) - uj;
+                        lm = fmin(lm, d - uj);
+                        if (t < ut) { ut = t; ud = d; uuj = uj; uq = q; }
+                    }
+                    if (ut < 10000.0 && (ut < bt || (ut == bt && bi != r && tie_before(r, ((lw0 + uq) * CS + rank) * 32 + lane, bi, bj, n)))) {
+                        bt = ut; bi = r; bj = ((lw0 + uq) * CS + rank) * 32 + lane; bd = ud; bui = ur; buj = uuj;
+                    }
+                    const unsigned int km = __reduce_min_sync(0xffffffffu, lm < 1e299 ? key_of(lm + C) : K32MAX);
+                    if (lane == 0 && km != K32MAX) atomicMin(&t_min[k], km);
+                    if (lane == 0 && live && lw0 == 0 && rank == 0) my_rows++;
                 }
-                if (ut < 10000.0 && (ut < bt || (ut == bt && bi != r && tie_before(r, ((lw0 + uq) * CS + rank) * 32 + lane, bi, bj, n)))) {
-                    bt = ut; bi = r; bj = ((lw0 + uq) * CS + rank) * 32 + lane; bd = ud; bui = ur; buj = uuj;
+                __syncthreads();
+                CL_MARK(9);
+                // this CTA's minimum of each staged row goes to the row owner's key
+                for (int k = tid; k < tn; k += CT) {
+                    const unsigned int km = t_min[k];
+                    const int r = t_row[k];
+                    if (km != K32MAX) red_peer_min_u32(&K_s[((r >> 5) / CS) * 32 + (r & 31)], (r >> 5) % CS, km);
                 }
-                if (PROF && bt > -1e300) CL_MARK(20);
-                const unsigned long long km = warp_min_u64(lm < 1e299 ? enc_f64(lm + C) : 0xffffffffffffffffull);
-                if (lane == 0 && km != 0xffffffffffffffffull) atomicMin(&K[r], km);
-                if (lane == 0 && lw0 == 0 && rank == 0) my_rows++;
-                if (PROF && km != 1ull) CL_MARK(21);
+                __syncthreads();
             }
-            CL_MARK(13);
             // warp winner -> CTA winner (reference order), every warp winner also feeds the candidate pool
             {
                 const int wl = warp_best_lane(bt, bi, bj, n);
@@ -498,9 +519,9 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 }
             }
         }
-        CL_MARK(15);
+        CL_MARK(10);
         cluster.sync();
-        CL_MARK(16);
+        CL_MARK(11);
 
         // ---------------------------------------------------------------- D: pick (identical in every CTA)
         {
@@ -510,11 +531,10 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 const int wl = warp_best_lane(recs[src].t, ci, recs[src].j, n);
                 if (lane == 0) wrec[0] = recs[wl < 0 ? 0 : wl];
             }
-            // this scan's warp winners (still in wrec[1..], and lane 0's registers for warp 0) go to the pool below
+            // this scan's warp winners (still in wrec[1..]) go to the pool below
             const int mi = (tid < NW && tid > 0) ? wrec[tid].i : -1, mj = (tid < NW && tid > 0) ? wrec[tid].j : -1;
             const double md = (tid < NW && tid > 0) ? wrec[tid].d : 0.0;
             __syncthreads();
-            CL_MARK(17);
             const int wi = wrec[0].i, wj = wrec[0].j;
             const double wd = wrec[0].d, wui = wrec[0].ui, wuj = wrec[0].uj;
             double uxo, uyo;
@@ -574,11 +594,15 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     cluster.sync();   // no CTA may exit while peers can still read its shared memory
 }
 
-template <int CS, int CT, bool PROF>
-static int launch_cluster(dipb_ctx* c, int LS, void** args, int* HC, int max_helper_clusters, bool* ok) {
-    const size_t smem = sizeof(double) * ((size_t)4 * LS + LS / 32 + 2 + UC * 32);
-    auto kern = nj_cluster_kernel<CS, CT, PROF>;
+template <int CS, int CT, int UC, bool PROF>
+static int launch_cluster(dipb_ctx* c, int n, void** args, int* LS_out, int* HC, int max_helper_clusters, bool* ok) {
+    const int chunks = (n + 31) / 32;
+    const int LS = ((chunks + CS - 1) / CS) * 32;
+    const size_t smem = cluster_smem_bytes(LS, chunks);
+    auto kern = nj_cluster_kernel<CS, CT, UC, PROF>;
     *ok = false;
+    *LS_out = LS;
+    if (smem > 220u * 1024u) return 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     if (CS > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
     cudaLaunchConfig_t cfg = {};
@@ -601,30 +625,27 @@ static int launch_cluster(dipb_ctx* c, int LS, void** args, int* HC, int max_hel
 }
 
 bool nj_cluster_fits(int n) {
-    // 3 doubles of state per owned row (+ chunk sums) within 200 KB of shared memory per CTA, 8 CTAs at worst
+    // shared memory of the 8-CTA fallback layout (per-row state of n / 8 rows + the staging tile) within 200 KB
     const int chunks = (n + 31) / 32;
     const int LS = ((chunks + 7) / 8) * 32;
-    return n <= 131072 && sizeof(double) * ((size_t)4 * LS + LS / 32 + 2 + UC * 32) <= 200u * 1024u;
+    return n <= 131072 && cluster_smem_bytes(LS, chunks) <= 200u * 1024u;
 }
 
 int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* c0, int32_t* c1, double* l0, double* l1) {
     dipb_ctx* c = m->ctx;
     const int n = m->n;
-    unsigned long long* K = nullptr;
     int* sel = nullptr;
     CStats* stats = nullptr;
+    NJCtl* ctl = nullptr;
     int2* log_xy = nullptr;
     double2* log_bl = nullptr;
-    DIPB_CUDA(cudaMalloc(&K, sizeof(unsigned long long) * n));
     DIPB_CUDA(cudaMalloc(&sel, sizeof(int) * n));
     DIPB_CUDA(cudaMalloc(&stats, sizeof(CStats)));
-    NJCtl* ctl = nullptr;
     DIPB_CUDA(cudaMalloc(&ctl, sizeof(NJCtl)));
-    DIPB_CUDA(cudaMemsetAsync(ctl, 0, sizeof(NJCtl), c->stream));
     DIPB_CUDA(cudaMalloc(&log_xy, sizeof(int2) * n));
     DIPB_CUDA(cudaMalloc(&log_bl, sizeof(double2) * n));
     DIPB_CUDA(cudaMemsetAsync(stats, 0, sizeof(CStats), c->stream));
-    DIPB_CUDA(cudaMemsetAsync(K, 0, sizeof(unsigned long long) * n, c->stream));
+    DIPB_CUDA(cudaMemsetAsync(ctl, 0, sizeof(NJCtl), c->stream));
     // scale of the safety margin: twice the largest |u| of the input (as nj_pruned.cu)
     double dmax = 0.0;
     {
@@ -637,26 +658,22 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     size_t ld = (size_t)n;
     double* Dp = m->d;
     int n_total = n;
-    int profile = getenv("DIPB_NJ_PROFILE") ? 1 : 0;
-    const int chunks = (n + 31) / 32;
+    const int profile = getenv("DIPB_NJ_PROFILE") ? 1 : 0;
+    const char* force = getenv("DIPB_NJ_CLUSTER");   // 8 or 16; default: 16 when the device can co-schedule it
+    const int want = force ? atoi(force) : 16;
+    const char* hp = getenv("DIPB_NJ_HELPERS");      // helper clusters for the column stores (default: all that fit, at most 7)
+    const int max_helpers = hp ? atoi(hp) : 7;
+    int used = 0, HC = 0, LS = 0;
     bool ok = false;
     int rc = 0;
-    const char* force = getenv("DIPB_NJ_CLUSTER");   // 8 or 16; default: 16 when the device can co-schedule it
-    int want = force ? atoi(force) : 16;
-    int used = 0;
-    int HC = 0;
-    const char* hp = getenv("DIPB_NJ_HELPERS");   // helper clusters for the column stores (default: all that fit, at most 7)
-    const int max_helpers = hp ? atoi(hp) : 7;
+    void* args[] = {&Dp, &ld, &U, &u, &sel, &stats, &log_xy, &log_bl, &n_total, &LS, &dmax, &ctl, &HC};
+    // 1024 threads, 8 loads in flight per lane: measured best of {512, 1024} x {8, 16} (profiles/r1_nj_cluster_tuning.json)
     if (want >= 16) {
-        int LS = ((chunks + 15) / 16) * 32;
-        void* args[] = {&Dp, &ld, &U, &u, &K, &sel, &stats, &log_xy, &log_bl, &n_total, &LS, &dmax, &ctl, &HC};
-        rc = profile ? launch_cluster<16, 1024, true>(c, LS, args, &HC, max_helpers, &ok) : launch_cluster<16, 1024, false>(c, LS, args, &HC, max_helpers, &ok);
+        rc = profile ? launch_cluster<16, 1024, 8, true>(c, n, args, &LS, &HC, max_helpers, &ok) : launch_cluster<16, 1024, 8, false>(c, n, args, &LS, &HC, max_helpers, &ok);
         used = 16;
     }
     if (!rc && !ok) {
-        int LS = ((chunks + 7) / 8) * 32;
-        void* args[] = {&Dp, &ld, &U, &u, &K, &sel, &stats, &log_xy, &log_bl, &n_total, &LS, &dmax, &ctl, &HC};
-        rc = profile ? launch_cluster<8, 1024, true>(c, LS, args, &HC, max_helpers, &ok) : launch_cluster<8, 1024, false>(c, LS, args, &HC, max_helpers, &ok);
+        rc = profile ? launch_cluster<8, 1024, 8, true>(c, n, args, &LS, &HC, max_helpers, &ok) : launch_cluster<8, 1024, 8, false>(c, n, args, &LS, &HC, max_helpers, &ok);
         used = 8;
     }
     if (!rc && !ok) { set_error("nj_cluster: no cluster configuration fits this device"); rc = DIPB_E_CUDA; }
@@ -692,18 +709,17 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     c->nj_iterations = hs.iters;
     c->nj_bytes_scanned = 0;
     if (profile) {
-        const char* nm[24] = {"-", "D rest (pool, log)", "A row loop", "A drift reduce", "barrier 1", "B1 canonical sum", "C unit: issue loads", "B1 pool eval",
-                              "barrier 2", "B2 ub", "B2 fold+select", "barrier 3", "C col stores+nsel", "C unit loop", "C unit: issue col stores", "C reduce+publish",
-                              "barrier 4", "D pick", "C first row index", "C unit: shfl", "C unit: loads+min", "C unit: redux+atomic", "C unit: wait DSMEM", "-"};
+        const char* nm[12] = {"D pick + pool", "A update + push", "barrier 1", "B1 canonical sum", "B1 pool eval + push", "barrier 2",
+                              "B2 fold + select", "barrier 3", "C stage tile", "C scan units", "C keys + reduce + publish", "barrier 4"};
         double tot = 0;
-        for (int k = 0; k < 24; k++) tot += (double)hs.cyc[k];
-        fprintf(stderr, "[nj_cluster] n=%d cluster=%d helper_ctas=%d iters=%llu rows_scanned=%llu (%.1f/iter)\n", n, used, HC, hs.iters, hs.rows_scanned,
-                hs.iters ? (double)hs.rows_scanned / hs.iters : 0.0);
-        for (int k = 0; k < 24; k++)
-            if (hs.cyc[k]) fprintf(stderr, "[nj_cluster]   %-18s %10.0f cyc/iter  %5.1f%%\n", nm[k], hs.iters ? hs.cyc[k] / (double)hs.iters : 0.0,
+        for (int k = 0; k < 12; k++) tot += (double)hs.cyc[k];
+        fprintf(stderr, "[nj_cluster] n=%d cluster=%d helper_ctas=%d iters=%llu rows_scanned=%llu (%.1f/iter)\n", n, used, HC, hs.iters,
+                hs.rows_scanned, hs.iters ? (double)hs.rows_scanned / hs.iters : 0.0);
+        for (int k = 0; k < 12; k++)
+            fprintf(stderr, "[nj_cluster]   %-26s %8.0f cyc/iter  %5.1f%%\n", nm[k], hs.iters ? hs.cyc[k] / (double)hs.iters : 0.0,
                     tot > 0 ? 100.0 * hs.cyc[k] / tot : 0.0);
     }
-    cudaFree(K); cudaFree(sel); cudaFree(stats); cudaFree(ctl); cudaFree(log_xy); cudaFree(log_bl);
+    cudaFree(sel); cudaFree(stats); cudaFree(ctl); cudaFree(log_xy); cudaFree(log_bl);
     return 0;
 }
 
