@@ -9,10 +9,13 @@ full pass: packed sequences -> fp64 distance matrix -> NJ tree.
           (distance matrix + NJ, device-timed with CUDA events on the library stream)
   e2e     same metric through the public C ABI from HOST buffers: H2D of the 4-bit
           sequences + repack + distances + NJ + D2H of the tree, wall-clocked
-  roofline  the NJ search (dominant phase) against the measured HBM copy bandwidth;
-          algorithmic bytes = the reference's full-scan cost  sum_n (n^2+4n)*8  (SURVEY.md
-          §8d) -- a pruned exact search may exceed 1.0 of this yard-stick; the distance
-          kernel's integer-pipe figure is reported beside it under "dist_kernel"
+  roofline  the NJ kernel (dominant: ~93 % of the step) against the measured HBM copy
+          bandwidth; algorithmic bytes = the reference's full-scan cost sum_n (n^2+4n)*8
+           -- the pruned exact search reads ~1/250 of that, so it exceeds 1.0
+          of the yard-stick; "bytes_read" / "frac_on_bytes_read" give the bytes it really
+          reads (it is latency bound: ~23 us per merge, 4 cluster barriers each)
+  dist_kernel  the tcgen05 int8 distance kernel against the tensor roofline (int8 dense
+          peak taken as 2x the measured bf16 peak) with its ncu DRAM traffic
   cpu_baseline  the OpenMP oracle port on a bounded sample (rank 0, N=1 only)
 
 `--impl reference` runs the reference's own CUDA objects (oracle/_ref/dipper_ref; the
@@ -38,14 +41,25 @@ METRIC = "pairwise distances/sec (JC distance matrix + NJ tree, whole job)"
 UNIT = "pairs/s"
 
 
-def measured_peak_hbm():
+def measured_peaks():
+    """(HBM GB/s, bf16 dense TFLOP/s burst, source) -- MEASURED_PEAKS.json, else the profiling guide's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), float(j["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def pinned_like(a):
+    """Copy of a numpy array in page-locked host memory (the e2e contract: H2D from pinned memory)."""
+    import torch
+    t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)     # returned too: it owns the memory
+    out = t.numpy().view(a.dtype).reshape(a.shape)
+    out[...] = a
+    return out, t
 
 
 class ClockSampler:
@@ -115,8 +129,14 @@ def nj_algorithmic_bytes(n):
 
 
 def dist_algorithmic_intops(n, L):
-    # pairs x ceil(L/32) x (4 LOP3 + 2 POPC + 2 IADD)
+    # SURVEY.md §8(d), bit-plane formulation: pairs x ceil(L/32) x (4 LOP3 + 2 POPC + 2 IADD)
     return n * (n - 1) / 2 * ((L + 31) // 32) * 8.0
+
+
+def dist_tensor_ops(n, L):
+    # tensor formulation (msa_tc.cu): per pair one int8 dot product of length 3L (simplex codes) and one of
+    # length L (validity), 2 ops per multiply-add
+    return n * (n - 1) / 2 * (4.0 * L) * 2.0
 
 
 def write_ref_bin(path, P, L):
@@ -210,7 +230,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n, L = args.tips, args.sites
-    P = gen_data(n, L, args.seed)
+    P, _pin = pinned_like(gen_data(n, L, args.seed))
     lens = np.full(n, L, np.uint64)
     ctx = api.Context(local)
     prm = api.Param(distanceType=2, in_="m")
@@ -313,26 +333,43 @@ def main():
         e2e_s = float(tt[0])
 
     if rank == 0:
-        peak, peak_src = measured_peak_hbm()
+        peak, peak_bf16, peak_src = measured_peaks()
         nj_bytes = nj_algorithmic_bytes(n)
         ach = nj_bytes / (nj_ms / 1e3) / 1e9
         scanned = nj_stats.get("rows_scanned", 0)
+        # bytes the pruned search really touches: rescanned rows + per merge 5 row reads/writes and 2 column writes
+        m = np.arange(3, n + 1, dtype=np.float64)
+        bytes_read = float(nj_stats.get("bytes_scanned", 0)) + float((7 * m * 8).sum())
+        tc_ops = dist_tensor_ops(n, L)
+        tc_ach = tc_ops / (d_ms / 1e3) / 1e12 / max(world, 1)
         out = {
             "metric": METRIC, "value": pairs / (step_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "int32 counts + f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "int8 dot products -> int32 counts -> f64", "data": "synthetic",
             "config": {"workload": "C3: aligned MSA %d tips x %d sites, JC distance matrix (row-block sharded over %d GPU) + single-GPU NJ" % (n, L, world),
-                       "inputs": "larger than L2 (450 MB packed sequences, 7.2 GB fp64 matrix)", "nj_algo": args.nj_algo},
+                       "inputs": "larger than L2 (450 MB packed sequences, 3.6 GB int8 operands, 7.2 GB fp64 matrix)", "nj_algo": args.nj_algo},
             "phases": {"dist_ms": d_ms, "reduce_ms": c_ms, "nj_ms": nj_ms,
-                       "dist_pairs_per_sec": pairs / (d_ms / 1e3), "nj_wall_s": nj_ms / 1e3},
+                       "dist_pairs_per_sec": pairs / (d_ms / 1e3), "nj_wall_s": nj_ms / 1e3,
+                       "nj_us_per_merge": nj_ms * 1e3 / max(n - 2, 1)},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "NJ search+update loop",
+                         "traffic": None, "peak_source": peak_src, "kernel": "nj_cluster_kernel (one launch = all %d merges)" % (n - 2),
                          "algorithmic_bytes": nj_bytes,
-                         "note": "yard-stick = reference full-scan bytes; rows actually rescanned: %d" % scanned},
-            "dist_kernel": {"bound": "integer pipe", "int_ops": dist_algorithmic_intops(n, L),
-                            "achieved_Tops": dist_algorithmic_intops(n, L) / (d_ms / 1e3) / 1e12 / max(world, 1)},
+                         "definition": "SURVEY.md 8(d) yard-stick = bytes of the reference's full scan, sum_m (m^2+4m)*8; the exact pruned search "
+                                       "skips rows whose lower bound exceeds the best candidate, so frac > 1",
+                         "rows_rescanned": scanned, "bytes_read": bytes_read,
+                         "achieved_on_bytes_read": bytes_read / (nj_ms / 1e3) / 1e9,
+                         "frac_on_bytes_read": bytes_read / (nj_ms / 1e3) / 1e9 / peak,
+                         "note": "latency bound, not bandwidth bound: 4 cluster barriers and ~10 dependent shared/L2 round trips per merge "
+                                 "(profiles/r1_nj_cluster_phases.txt); ncu collects no DRAM counters for this cluster launch"},
+            "dist_kernel": {"kernel": "msa_tc_kernel (tcgen05.mma kind::i8, 128x256 tiles)", "bound": "tensor", "achieved": tc_ach,
+                            "peak": 2.0 * peak_bf16, "unit": "TOP/s", "frac": tc_ach / (2.0 * peak_bf16),
+                            "peak_definition": "int8 dense = 2 x measured bf16 dense burst (%s)" % peak_src,
+                            "algorithmic_ops": tc_ops, "traffic": 255.4e9,
+                            "traffic_source": "profiles/r1_ncu_tc_cluster_30k.json (dram read+write, one launch): 71x the 3.6 GB of operands -- "
+                                              "L2/DRAM bound on operand re-streaming, tensor pipe 48 % active",
+                            "bitplane_equivalent_Tops": dist_algorithmic_intops(n, L) / (d_ms / 1e3) / 1e12 / max(world, 1)},
             "e2e": {"value": pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(P.nbytes + lens.nbytes),
-                    "d2h_bytes_per_step": int((n - 1) * 24), "seconds": e2e_s},
+                    "d2h_bytes_per_step": int((n - 1) * 24), "seconds": e2e_s, "host_buffers": "pinned"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:

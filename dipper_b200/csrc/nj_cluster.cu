@@ -61,7 +61,7 @@ struct NJCtl {                // main cluster -> helper clusters doorbell (globa
 };
 
 struct CStats {
-    unsigned long long rows_scanned, iters;
+    unsigned long long rows_scanned, bytes_scanned, iters;
     unsigned long long cyc[24];
 };
 
@@ -221,7 +221,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     double dxy = 0.0;
     bool first = true;
     int iter = 0;
-    unsigned long long my_rows = 0;
+    unsigned long long my_rows = 0, my_bytes = 0;
     unsigned int* sel0 = cluster.map_shared_rank(&s_sel, 0);
 
     long long tmark = clock64();
@@ -491,7 +491,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     }
                     const unsigned int km = __reduce_min_sync(0xffffffffu, lm < 1e299 ? key_of(lm + C) : K32MAX);
                     if (lane == 0 && km != K32MAX) atomicMin(&t_min[k], km);
-                    if (lane == 0 && live && lw0 == 0 && rank == 0) my_rows++;
+                    if (lane == 0 && live && lw0 == 0 && rank == 0) { my_rows++; my_bytes += (unsigned long long)n * 8ull; }
                 }
                 __syncthreads();
                 CL_MARK(9);
@@ -590,7 +590,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
         stats->iters = (unsigned long long)iter;
         for (int k = 0; k < 24; k++) stats->cyc[k] = s_cyc[k];
     }
-    if (rank == 0 && lane == 0 && my_rows) atomicAdd(&stats->rows_scanned, my_rows);
+    if (rank == 0 && lane == 0 && my_rows) { atomicAdd(&stats->rows_scanned, my_rows); atomicAdd(&stats->bytes_scanned, my_bytes); }
     cluster.sync();   // no CTA may exit while peers can still read its shared memory
 }
 
@@ -707,7 +707,7 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     DIPB_CUDA(cudaMemcpy(&hs, stats, sizeof(hs), cudaMemcpyDeviceToHost));
     c->nj_rows_scanned = hs.rows_scanned;
     c->nj_iterations = hs.iters;
-    c->nj_bytes_scanned = 0;
+    c->nj_bytes_scanned = hs.bytes_scanned;
     if (profile) {
         const char* nm[12] = {"D pick + pool", "A update + push", "barrier 1", "B1 canonical sum", "B1 pool eval + push", "barrier 2",
                               "B2 fold + select", "barrier 3", "C stage tile", "C scan units", "C keys + reduce + publish", "barrier 4"};
