@@ -372,10 +372,15 @@ static bool fast_ok(const dipb_msa* m, int type) {
 int msa_block(dipb_msa* m, int type, int r0, int r1, int ncols, double* d_out, size_t ld) {
     if (r0 < 0 || r1 > m->n || r0 >= r1 || ncols < 0 || ncols > m->n) { set_error("msa_block: bad range"); return DIPB_E_ARG; }
     if (ncols == 0) return 0;
-    if (r1 - r0 >= 64 && msa_tc_supported(m, type)) {
-        // enough rows to fill 128-row tensor-core tiles (placement row blocks, D&C query batches)
+    if (msa_tc_supported(m, type)) {
+        // Tensor-core kernel when there are enough rows to fill 128-row tiles and enough pairs to amortise the
+        // launch set-up (tensor maps, tile list) and, on first use, the int8 operand expansion: placement row
+        // blocks, D&C query batches against large backbones.  Small blocks stay on the popcount kernel (measured:
+        // D&C of 30 000 tips with a 1 500-tip backbone 158 ms vs 340 ms).  DIPB_MSA_TC=0 never, =2 always (tests).
         const char* e = getenv("DIPB_MSA_TC");
-        if (!(e && e[0] == '0')) return msa_tc_block(m, type, r0, r1, ncols, d_out, ld);
+        const bool never = e && e[0] == '0', always = e && e[0] == '2';
+        if (!never && (always || (r1 - r0 >= 64 && (long long)(r1 - r0) * ncols >= (1ll << 22))))
+            return msa_tc_block(m, type, r0, r1, ncols, d_out, ld);
     }
     if (!fast_ok(m, type)) return generic_block(m, type, r0, r1, ncols, d_out, ld, r0, 0);
     TileParams p{};
@@ -389,10 +394,13 @@ int msa_matrix(dipb_msa* m, int type, int row_begin, int row_end, double* d_out)
     // lower-triangle tiles whose row block intersects [row_begin,row_end); mirrored
     if (row_begin < 0 || row_end > m->n || row_begin >= row_end) { set_error("msa_matrix: bad rows"); return DIPB_E_ARG; }
     if (msa_tc_supported(m, type)) {
-        // tensor-core path (msa_tc.cu): 4.4x the popcount kernel on B200 (3.4 ms vs 15.0 ms at 8000 x 30000),
-        // bit-identical output.  DIPB_MSA_TC=0 forces the popcount kernel.
+        // tensor-core path (msa_tc.cu): 3.8x the popcount kernel at 30 000 x 30 000 (53 ms vs 201 ms), bit-identical
+        // output; below ~4 M pairs its set-up costs more than it saves (2 000 x 10 000: 1.0 ms vs 0.4 ms).
+        // DIPB_MSA_TC=0 never, =2 always.
         const char* e = getenv("DIPB_MSA_TC");
-        if (!(e && e[0] == '0')) return msa_tc_matrix(m, type, row_begin, row_end, d_out);
+        const bool never = e && e[0] == '0', always = e && e[0] == '2';
+        const long long pairs = ((long long)row_end * row_end - (long long)row_begin * row_begin) / 2;
+        if (!never && (always || pairs >= (1ll << 22))) return msa_tc_matrix(m, type, row_begin, row_end, d_out);
     }
     if (!fast_ok(m, type)) return generic_block(m, type, row_begin, row_end, 0, d_out, (size_t)m->n, 0, 1);
     TileParams p{};

@@ -130,7 +130,7 @@ def test_tensor_core_path_is_bit_identical(ctx, oracle, n, L, dist_type, monkeyp
     prm = api.Param(distanceType=dist_type, in_="m")
     monkeypatch.setenv("DIPB_MSA_TC", "0")
     ref = msa.distMatrix(prm).to_host()          # popcount kernel
-    monkeypatch.setenv("DIPB_MSA_TC", "1")
+    monkeypatch.setenv("DIPB_MSA_TC", "2")
     got = msa.distMatrix(prm).to_host()          # tcgen05 kernel (the default)
     monkeypatch.delenv("DIPB_MSA_TC")
     assert np.array_equal(got, ref, equal_nan=True)
@@ -147,7 +147,7 @@ def test_tensor_core_block_rows(ctx, oracle, dist_type, r0, r1, ncols, monkeypat
     prm = api.Param(distanceType=dist_type, in_="m")
     monkeypatch.setenv("DIPB_MSA_TC", "0")
     ref = msa.distBlock(prm, r0, r1, ncols)
-    monkeypatch.setenv("DIPB_MSA_TC", "1")
+    monkeypatch.setenv("DIPB_MSA_TC", "2")       # force: blocks this small normally stay on the popcount kernel
     got = msa.distBlock(prm, r0, r1, ncols)
     monkeypatch.delenv("DIPB_MSA_TC")
     full = oracle.msa_dist_matrix(P, L, dist_type)
@@ -164,7 +164,7 @@ def test_tensor_core_row_sharded_matrix(ctx, oracle, cut, monkeypatch):
     prm = api.Param(distanceType=2, in_="m")
     monkeypatch.setenv("DIPB_MSA_TC", "0")
     full = msa.distMatrix(prm).to_host()
-    monkeypatch.setenv("DIPB_MSA_TC", "1")
+    monkeypatch.setenv("DIPB_MSA_TC", "2")
     a = msa.distMatrix(prm, 0, cut).to_host()
     b = msa.distMatrix(prm, cut, n).to_host()
     monkeypatch.delenv("DIPB_MSA_TC")
