@@ -240,7 +240,8 @@ int nj_run(dipb_matrix* m, int algo, int32_t* child0, int32_t* child1, double* l
     dipb_ctx* c = m->ctx;
     const int n = m->n;
     if (n < 2) { set_error("dipb_nj: need at least 2 sequences"); return DIPB_E_ARG; }
-    if (algo == DIPB_NJ_AUTO) algo = nj_cluster_fits(n) ? DIPB_NJ_CLUSTER : DIPB_NJ_PRUNED;
+    const bool auto_algo = algo == DIPB_NJ_AUTO;
+    if (auto_algo) algo = nj_cluster_fits(n) ? DIPB_NJ_CLUSTER : DIPB_NJ_PRUNED;
     if (algo == DIPB_NJ_CLUSTER && !nj_cluster_fits(n)) { set_error("dipb_nj: %d tips do not fit the cluster kernel's shared memory", n); return DIPB_E_ARG; }
     const size_t ld = (size_t)n;
     double *U = nullptr, *u = nullptr, *partial = nullptr, *l0 = nullptr, *l1 = nullptr;
@@ -270,8 +271,9 @@ int nj_run(dipb_matrix* m, int algo, int32_t* child0, int32_t* child1, double* l
         DIPB_KERNEL_CHECK(c);
         if (algo == DIPB_NJ_CLUSTER) {
             rc = nj_cluster_loop(m, U, u, realID, c0, c1, l0, l1);
-            if (rc) return rc;
-            done = 1;
+            if (rc == DIPB_E_UNSUPPORTED && auto_algo) algo = DIPB_NJ_PRUNED;   // no cluster shape fits this device
+            else if (rc) return rc;
+            else done = 1;
         }
         if (algo == DIPB_NJ_PRUNED) {
             rc = nj_pruned_loop(m, U, u, partial, st, realID, c0, c1, l0, l1);

@@ -53,11 +53,11 @@ struct CRec {                 // a CTA's best candidate of one scan
     int i, j;
 };
 
-struct NJCtl {                // main cluster -> helper clusters doorbell (global memory)
-    unsigned int seq;         // number of merges published; 0xffffffff = quit
-    int x, y, n;              // the published merge: new node x, slot y (received the old last row when y < n)
-    unsigned int done;        // helper CTAs that finished, cumulative
-    unsigned int pad[3];
+struct NJCtl {                     // main cluster -> helper clusters doorbell (global memory)
+    unsigned long long bell;       // one word, one plain store: [seq:13 | x:17 | y:17 | n:17]; all ones = quit.
+                                   // x: new node, y: slot that received the old last row when y < n, seq: merge number
+    unsigned int done;             // helper CTAs that finished, cumulative
+    unsigned int pad;
 };
 
 struct CStats {
@@ -98,6 +98,19 @@ __device__ __forceinline__ void st_peer_f64(double* p, int rank, double v) {
 __device__ __forceinline__ void red_peer_min_u32(unsigned int* p, int rank, unsigned int v) {
     asm volatile("red.shared::cluster.min.u32 [%0], %1;" ::"r"(peer_addr(p, rank)), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned int atom_peer_min_u32(unsigned int* p, int rank, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.shared::cluster.min.u32 %0, [%1], %2;" : "=r"(old) : "r"(peer_addr(p, rank)), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void st_peer_s32(int* p, int rank, int v) {
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(peer_addr(p, rank)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_peer_s32(const int* p, int rank) {
+    int v;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(peer_addr(p, rank)) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned int key_of(double v) { return enc_f32(__double2float_rd(v)); }
 
 // ---- candidate order (reference scan order, nj_bound.cuh), out of line: exact ties are rare
@@ -123,7 +136,7 @@ __device__ __forceinline__ int warp_best_lane(double t, int i, int j, int n) {
 
 // bytes of dynamic shared memory for LS owned rows per CTA and `chunks` 32-row chunks in total
 inline size_t cluster_smem_bytes(int LS, int chunks) {
-    return sizeof(double) * ((size_t)4 * LS + chunks + 2) + sizeof(unsigned int) * (size_t)LS + (size_t)TILE * (3 * 8 + 4 + 4);
+    return sizeof(double) * ((size_t)5 * LS + chunks + 2) + sizeof(unsigned int) * (size_t)3 * LS + (size_t)TILE * (3 * 8 + 8 + 4 + 4);
 }
 
 }  // namespace
@@ -139,24 +152,24 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
         // main cluster issues them itself (~1 us per 1000 tips); spread over the other GPCs they are off the
         // critical path.
         const int hc = (int)blockIdx.x - CS, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-        __shared__ int s_msg[4];
-        unsigned int seen = 0;
+        __shared__ unsigned long long s_msg;
+        unsigned long long seen = 0;
         for (;;) {
             if (tid == 0) {
-                unsigned int q;
+                unsigned long long q;
                 for (;;) {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(q) : "l"(&ctl->seq) : "memory");
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(q) : "l"(&ctl->bell) : "memory");
                     if (q != seen) break;
                     __nanosleep(64);
                 }
-                s_msg[0] = (int)q; s_msg[1] = __ldcg(&ctl->x); s_msg[2] = __ldcg(&ctl->y); s_msg[3] = __ldcg(&ctl->n);
+                s_msg = q;
             }
             __syncthreads();
-            const unsigned int q = (unsigned int)s_msg[0];
-            const int x = s_msg[1], y = s_msg[2], n = s_msg[3];
+            const unsigned long long q = s_msg;
             __syncthreads();
-            if (q == 0xffffffffu) return;
+            if (q == KMAX) return;
             seen = q;
+            const int x = (int)((q >> 34) & 0x1ffffu), y = (int)((q >> 17) & 0x1ffffu), n = (int)(q & 0x1ffffu);
             const int nch = (n + 31) >> 5;
             for (int c = hc + w * HC; c < nch; c += HC * (CT / 32)) {
                 const int i = c * 32 + lane;
@@ -181,13 +194,20 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     double* u_s = U_s + LS;                              // [LS] U / (n - 2)
     double* v_s = u_s + LS;                              // [LS] distance to the newest node x
     double* f_s = v_s + LS;                              // [LS] distance to the node moved into slot y
-    double* cs_all = f_s + LS;                           // [chunks_total] chunk sums of the new column, pushed by the owners
+    double* da_s = f_s + LS;                             // [LS] distance to the tracked best partner a (exact, constant while both live)
+    double* cs_all = da_s + LS;                          // [chunks_total] chunk sums of the new column, pushed by the owners
     double* t_u = cs_all + chunks_total + 2;             // staged selected rows: u, v, f, combined minimum, index
     double* t_v = t_u + TILE;
     double* t_f = t_v + TILE;
-    unsigned int* t_min = reinterpret_cast<unsigned int*>(t_f + TILE);
-    int* t_row = reinterpret_cast<int*>(t_min + TILE);
-    unsigned int* K_s = reinterpret_cast<unsigned int*>(t_row + TILE);   // [LS] lower-bound keys of owned rows
+    unsigned long long* t_best = reinterpret_cast<unsigned long long*>(t_f + TILE);   // (key of the row minimum << 32) | its column
+    unsigned int* t_k2 = reinterpret_cast<unsigned int*>(t_best + TILE);              // key of the runner-up
+    int* t_row = reinterpret_cast<int*>(t_k2 + TILE);
+    // Lower-bound keys of owned rows.  K1 bounds the tracked best partner a_s (whose exact value can be re-evaluated
+    // from da_s and u[a]), K2 every other column; both are (value + C) at evaluation time, so `dec(K) - C` stays a
+    // lower bound while u drifts.
+    unsigned int* K1_s = reinterpret_cast<unsigned int*>(t_row + TILE);
+    unsigned int* K2_s = K1_s + LS;
+    int* a_s = reinterpret_cast<int*>(K2_s + LS);
 
     __shared__ CRec recs[MAXCS];            // winners published by every CTA of the cluster
     __shared__ CRec wrec[MAXW];
@@ -197,6 +217,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     __shared__ unsigned int s_sel;          // selected-row counter (rank 0's copy is the live one)
     __shared__ int pool_i[CPOOL], pool_j[CPOOL];
     __shared__ double pool_d[CPOOL];        // d of a carried pair never changes while both ends survive
+    __shared__ double pool_t[CPOOL];        // its value at the last re-evaluation: new candidates replace worse ones only
     __shared__ int s_pool_head, s_nsel;
     __shared__ unsigned long long s_cyc[24];   // rank 0, thread 0: cycles per phase (DIPB_NJ_PROFILE)
 
@@ -206,7 +227,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
         U_s[s] = i < n_total ? U0[i] : 0.0;
         u_s[s] = i < n_total ? u0[i] : 0.0;
         v_s[s] = 0.0; f_s[s] = 0.0;
-        K_s[s] = K32MAX;
+        K1_s[s] = K32MAX; K2_s[s] = K32MAX; a_s[s] = -1; da_s[s] = 0.0;
     }
     if (tid == 0) t_row[0] = 0;
     for (int p = tid; p < CPOOL; p += CT) { pool_i[p] = -1; pool_j[p] = -1; }
@@ -223,6 +244,27 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     int iter = 0;
     unsigned long long my_rows = 0, my_bytes = 0;
     unsigned int* sel0 = cluster.map_shared_rank(&s_sel, 0);
+
+    // Partner records: the CTA whose slice holds a scanned row's minimum (its key equals the combined K1) tells the
+    // owner the column and the exact distance, so that the owner can re-evaluate that pair exactly instead of
+    // rescanning the row while only the bound has drifted.  Runs after a cluster barrier that follows the key flush.
+    auto partner_records = [&](int tn, bool merged, int x, int y, int n) {
+        for (int k = tid; k < tn; k += CT) {
+            const unsigned long long best = t_best[k];
+            const unsigned int k1 = (unsigned int)(best >> 32);
+            if (k1 == K32MAX) continue;
+            const int r = t_row[k];
+            const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
+            if (ld_peer_u32(&K1_s[rs], ro) != k1) continue;
+            const int j1 = (int)(unsigned int)best;
+            double da;
+            if (merged && r != x && r != y && j1 == x) da = t_v[k];
+            else if (merged && r != x && r != y && j1 == y && y < n) da = t_f[k];
+            else da = __ldcg(&D[(size_t)r * ld + j1]);
+            st_peer_s32(&a_s[rs], ro, j1);
+            st_peer_f64(&da_s[rs], ro, da);
+        }
+    };
 
     long long tmark = clock64();
 #define CL_MARK(k)                                                      \
@@ -258,7 +300,6 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         const int lo = (last >> 5) % CS, ls = ((last >> 5) / CS) * 32 + (last & 31);
                         Ui = ld_peer_f64(&U_s[ls], lo);
                         uo = ld_peer_f64(&u_s[ls], lo);
-                        K_s[s] = ld_peer_u32(&K_s[ls], lo);
                     }
                     const double val = (a + b - dxy) * 0.5;
                     Ui += -a - b + val;
@@ -298,10 +339,11 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 break;
             }
             if (HC > 0 && rank == 0 && tid == 0) {
-                // rows x and y are complete and fenced (every thread ran MEMBAR.GPU before the barrier): ring the helpers
-                ctl->x = x; ctl->y = y; ctl->n = n;
-                __threadfence();
-                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->seq), "r"((unsigned int)iter) : "memory");
+                // rows x and y are complete and fenced (every thread ran MEMBAR.GPU before the barrier), so the bell is
+                // one relaxed store; merge numbers differ in the low 13 bits between consecutive merges
+                const unsigned long long q = ((unsigned long long)(iter & 0x1fff) << 51) | ((unsigned long long)x << 34) |
+                                             ((unsigned long long)y << 17) | (unsigned long long)n;
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->bell), "l"(q) : "memory");
             }
             {
                 // canonical sum, level 2: 1024-row blocks (32 chunk sums, stride-halving tree), then blocks ascending
@@ -346,6 +388,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     const double upj = ld_peer_f64(&u_s[((pj >> 5) / CS) * 32 + (pj & 31)], (pj >> 5) % CS);
                     pv = (pool_d[tid] - upi) - upj;
                 }
+                pool_t[tid] = pv;
                 pv = warp_min_f64(pv);
                 if (lane == 0) s_red[w] = pv;
             }
@@ -374,11 +417,41 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     if (i < n) {
                         take = (i == x);                          // the new row is always rescanned
                         if (!take) {
+                            unsigned int k1 = K1_s[s], k2 = K2_s[s];
+                            int a = a_s[s];
+                            if (i == y && y < n) {
+                                // slot y now holds the row that lived in `last` (= n): take over its keys and partner
+                                const int lo = (n >> 5) % CS, ls = ((n >> 5) / CS) * 32 + (n & 31);
+                                k1 = ld_peer_u32(&K1_s[ls], lo); k2 = ld_peer_u32(&K2_s[ls], lo);
+                                a = ld_peer_s32(&a_s[ls], lo);
+                                da_s[s] = ld_peer_f64(&da_s[ls], lo);
+                            }
+                            // the tracked partner may have been merged away (x, old y) or moved (last -> y)
+                            if (a == x || a == y) { a = -1; k1 = K32MAX; }
+                            else if (a == n) a = y;
+                            // the new column x joins the untracked columns
                             const unsigned int kc = key_of((v_s[s] - ux) + C);
-                            unsigned int ko = K_s[s];
-                            if (kc < ko) { ko = kc; K_s[s] = kc; }
-                            const double lb = ((double)dec_f32(ko) - C) - u_s[s] - margin;
-                            take = !(lb > ub);
+                            if (kc < k2) k2 = kc;
+                            // stage 1: both keys as drifting lower bounds (no memory traffic)
+                            const unsigned int km = k1 < k2 ? k1 : k2;
+                            take = !(((double)dec_f32(km) - C) - u_s[s] - margin > ub);
+                            if (take && a >= 0) {
+                                // stage 2: the tracked partner exactly (its d never changes, u[a] from its owner)
+                                const double e1 = da_s[s] - ld_peer_f64(&u_s[((a >> 5) / CS) * 32 + (a & 31)], (a >> 5) % CS);
+                                k1 = key_of(e1 + C);
+                                const double rest = (double)dec_f32(k2) - C;
+                                take = !((e1 < rest ? e1 : rest) - u_s[s] - margin > ub);
+                            }
+                            if (PROF && rank == 0 && take) {
+                                // why rows are rescanned (rank 0's rows only): 12 no tracked partner, 13 partner itself is
+                                // a contender, 14 the runner-up bound has drifted down to the upper bound
+                                const int why = a < 0 ? 12 : ((da_s[s] - ld_peer_f64(&u_s[((a >> 5) / CS) * 32 + (a & 31)], (a >> 5) % CS)) - u_s[s] - margin > ub ? 14 : 13);
+                                atomicAdd(&s_cyc[why], 1ull);
+                            }
+                            if (take) { k1 = K32MAX; k2 = K32MAX; a = -1; }   // reset, the scan lowers them
+                            K1_s[s] = k1; K2_s[s] = k2; a_s[s] = a;
+                        } else {
+                            K1_s[s] = K32MAX; K2_s[s] = K32MAX; a_s[s] = -1;
                         }
                     }
                     const unsigned int bal = __ballot_sync(0xffffffffu, take);
@@ -388,7 +461,6 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         base = __shfl_sync(0xffffffffu, base, 0);
                         if (take) {
                             sel_rows[base + __popc(bal & ((1u << lane) - 1u))] = i;
-                            K_s[s] = K32MAX;                      // reset, the scan lowers it
                         }
                     }
                 }
@@ -441,7 +513,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     t_u[k] = ld_peer_f64(&u_s[rs], ro);
                     t_v[k] = ld_peer_f64(&v_s[rs], ro);
                     t_f[k] = ld_peer_f64(&f_s[rs], ro);
-                    t_min[k] = K32MAX;
+                    t_best[k] = KMAX;
+                    t_k2[k] = K32MAX;
                 }
                 __syncthreads();
                 CL_MARK(8);
@@ -474,8 +547,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     const int yq = (patch && lane == (y & 31)) ? ylw - lw0 : -1;
                     // A lane's columns of one row differ by multiples of 32 * CS (a multiple of 256), so the reference
                     // order within the row is plain ascending j: the first strict minimum is the right one.
-                    double lm = 1e300, ut = 1e300, ud = 0.0, uuj = 0.0;
-                    int uq = 0;
+                    double lm1 = 1e300, lm2 = 1e300, ut = 1e300, ud = 0.0, uuj = 0.0;   // lm1/lm2: two smallest d - u_j
+                    int uq = 0, lq = 0;
 #pragma unroll
                     for (int q = 0; q < UC; q++) {
                         double d = dv[q];
@@ -483,25 +556,51 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         if (q == yq) d = t_f[k];
                         const double uj = u_s[(lw0 + q < lch ? lw0 + q : 0) * 32 + lane];   // (dead columns carry d = 1e300)
                         const double t = (d - ur) - uj;
-                        lm = fmin(lm, d - uj);
+                        const double mv = d - uj;
+                        if (mv < lm1) { lm2 = lm1; lm1 = mv; lq = q; } else lm2 = fmin(lm2, mv);
                         if (t < ut) { ut = t; ud = d; uuj = uj; uq = q; }
                     }
                     if (ut < 10000.0 && (ut < bt || (ut == bt && bi != r && tie_before(r, ((lw0 + uq) * CS + rank) * 32 + lane, bi, bj, n)))) {
                         bt = ut; bi = r; bj = ((lw0 + uq) * CS + rank) * 32 + lane; bd = ud; bui = ur; buj = uuj;
                     }
-                    const unsigned int km = __reduce_min_sync(0xffffffffu, lm < 1e299 ? key_of(lm + C) : K32MAX);
-                    if (lane == 0 && km != K32MAX) atomicMin(&t_min[k], km);
+                    // row minimum and runner-up of this unit -> the CTA's (minimum, column) and runner-up of the row.  An
+                    // atomic that loses to (or displaces) the standing minimum demotes the loser to the runner-up.
+                    const unsigned int key1 = lm1 < 1e299 ? key_of(lm1 + C) : K32MAX;
+                    const unsigned int k1w = __reduce_min_sync(0xffffffffu, key1);
+                    if (k1w != K32MAX) {
+                        const int wl = __ffs(__ballot_sync(0xffffffffu, key1 == k1w)) - 1;
+                        const int jw = __shfl_sync(0xffffffffu, ((lw0 + lq) * CS + rank) * 32 + lane, wl);
+                        const unsigned int key2 = lane == wl ? (lm2 < 1e299 ? key_of(lm2 + C) : K32MAX) : key1;
+                        const unsigned int k2w = __reduce_min_sync(0xffffffffu, key2);
+                        if (lane == 0) {
+                            const unsigned long long mine = ((unsigned long long)k1w << 32) | (unsigned int)jw;
+                            const unsigned long long old = atomicMin(&t_best[k], mine);
+                            const unsigned int demoted = mine < old ? (unsigned int)(old >> 32) : k1w;
+                            atomicMin(&t_k2[k], demoted < k2w ? demoted : k2w);
+                        }
+                    }
                     if (lane == 0 && live && lw0 == 0 && rank == 0) { my_rows++; my_bytes += (unsigned long long)n * 8ull; }
                 }
                 __syncthreads();
                 CL_MARK(9);
                 // this CTA's minimum of each staged row goes to the row owner's key
                 for (int k = tid; k < tn; k += CT) {
-                    const unsigned int km = t_min[k];
-                    const int r = t_row[k];
-                    if (km != K32MAX) red_peer_min_u32(&K_s[((r >> 5) / CS) * 32 + (r & 31)], (r >> 5) % CS, km);
+                    const unsigned int k1 = (unsigned int)(t_best[k] >> 32);
+                    if (k1 != K32MAX) {
+                        const int r = t_row[k];
+                        const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
+                        const unsigned int old = atom_peer_min_u32(&K1_s[rs], ro, k1);
+                        const unsigned int demoted = k1 < old ? old : k1;
+                        const unsigned int k2 = t_k2[k];
+                        red_peer_min_u32(&K2_s[rs], ro, demoted < k2 ? demoted : k2);
+                    }
                 }
-                __syncthreads();
+                if (nsel > TILE) {
+                    // rare (first search, bursts): one extra cluster barrier per tile so that every tile gets its records
+                    cluster.sync();
+                    partner_records(tn, merged, x, y, n);
+                    __syncthreads();
+                }
             }
             // warp winner -> CTA winner (reference order), every warp winner also feeds the candidate pool
             {
@@ -525,6 +624,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
 
         // ---------------------------------------------------------------- D: pick (identical in every CTA)
         {
+            // partner records of a selection that fitted one tile (larger selections did this per tile in phase C)
+            if (s_nsel <= TILE) partner_records(s_nsel, !first, x, y, n);
             if (w == 0) {
                 const int src = lane < CS ? lane : 0;
                 const int ci = lane < CS ? recs[src].i : -1;
@@ -533,7 +634,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             }
             // this scan's warp winners (still in wrec[1..]) go to the pool below
             const int mi = (tid < NW && tid > 0) ? wrec[tid].i : -1, mj = (tid < NW && tid > 0) ? wrec[tid].j : -1;
-            const double md = (tid < NW && tid > 0) ? wrec[tid].d : 0.0;
+            const double md = (tid < NW && tid > 0) ? wrec[tid].d : 0.0, mt = (tid < NW && tid > 0) ? wrec[tid].t : 1e300;
             __syncthreads();
             const int wi = wrec[0].i, wj = wrec[0].j;
             const double wd = wrec[0].d, wui = wrec[0].ui, wuj = wrec[0].uj;
@@ -553,10 +654,14 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             }
             __syncthreads();
             if (tid > 0 && tid < NW && mi >= 0 && mi != x && mi != y && mj != x && mj != y) {
+                // keep the best: a slot is overwritten only by a candidate that is better than its last evaluation
                 const int slot = (s_pool_head + tid) % CPOOL;
-                pool_i[slot] = mi == last_ ? y : mi;
-                pool_j[slot] = mj == last_ ? y : mj;
-                pool_d[slot] = md;
+                if (pool_i[slot] < 0 || mt < pool_t[slot]) {
+                    pool_i[slot] = mi == last_ ? y : mi;
+                    pool_j[slot] = mj == last_ ? y : mj;
+                    pool_d[slot] = md;
+                    pool_t[slot] = mt;
+                }
             }
             if (HC > 0 && tid == 0 && iter > 0) {
                 // the next update reads whole rows: the helpers must have finished the columns of the previous merge
@@ -586,7 +691,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
         first = false;
     }
     if (rank == 0 && tid == 0) {
-        if (HC > 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->seq), "r"(0xffffffffu) : "memory");
+        if (HC > 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->bell), "l"(KMAX) : "memory");
         stats->iters = (unsigned long long)iter;
         for (int k = 0; k < 24; k++) stats->cyc[k] = s_cyc[k];
     }
@@ -625,10 +730,11 @@ static int launch_cluster(dipb_ctx* c, int n, void** args, int* LS_out, int* HC,
 }
 
 bool nj_cluster_fits(int n) {
-    // shared memory of the 8-CTA fallback layout (per-row state of n / 8 rows + the staging tile) within 200 KB
+    // shared memory of the 16-CTA layout (per-row state of n / 16 rows + the staging tile) within 200 KB; when the
+    // device cannot co-schedule 16 CTAs and the 8-CTA layout is too large, nj_cluster_loop reports DIPB_E_UNSUPPORTED
     const int chunks = (n + 31) / 32;
-    const int LS = ((chunks + 7) / 8) * 32;
-    return n <= 131072 && cluster_smem_bytes(LS, chunks) <= 200u * 1024u;
+    const int LS = ((chunks + 15) / 16) * 32;
+    return n < 131072 && cluster_smem_bytes(LS, chunks) <= 200u * 1024u;   // (the doorbell packs indices in 17 bits)
 }
 
 int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* c0, int32_t* c1, double* l0, double* l1) {
@@ -676,8 +782,8 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
         rc = profile ? launch_cluster<8, 1024, 8, true>(c, n, args, &LS, &HC, max_helpers, &ok) : launch_cluster<8, 1024, 8, false>(c, n, args, &LS, &HC, max_helpers, &ok);
         used = 8;
     }
-    if (!rc && !ok) { set_error("nj_cluster: no cluster configuration fits this device"); rc = DIPB_E_CUDA; }
-    if (rc) return rc;
+    if (!rc && !ok) { set_error("nj_cluster: no cluster configuration fits this device"); rc = DIPB_E_UNSUPPORTED; }
+    if (rc) { cudaFree(sel); cudaFree(stats); cudaFree(ctl); cudaFree(log_xy); cudaFree(log_bl); return rc; }
     c->launches++;
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
     {
@@ -711,6 +817,8 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     if (profile) {
         const char* nm[12] = {"D pick + pool", "A update + push", "barrier 1", "B1 canonical sum", "B1 pool eval + push", "barrier 2",
                               "B2 fold + select", "barrier 3", "C stage tile", "C scan units", "C keys + reduce + publish", "barrier 4"};
+        fprintf(stderr, "[nj_cluster] rescans of rank 0's rows: %llu without a tracked partner, %llu partner is a contender, %llu runner-up bound reached ub\n",
+                hs.cyc[12], hs.cyc[13], hs.cyc[14]);
         double tot = 0;
         for (int k = 0; k < 12; k++) tot += (double)hs.cyc[k];
         fprintf(stderr, "[nj_cluster] n=%d cluster=%d helper_ctas=%d iters=%llu rows_scanned=%llu (%.1f/iter)\n", n, used, HC, hs.iters,

@@ -25,6 +25,7 @@ extern "C" {
 #define DIPB_E_ARG -2       /* invalid argument */
 #define DIPB_E_NOMEM -3     /* host or device allocation failed */
 #define DIPB_E_STATE -4     /* call order violated (e.g. distances before sketching) */
+#define DIPB_E_UNSUPPORTED -5 /* the requested kernel variant does not fit this device / input size */
 
 /* distance models, same numbering as -d / Param::distanceType (src/MSA.cu:81-86) */
 #define DIPB_DIST_UNCORRECTED 1
