@@ -94,6 +94,20 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// multicast forms: the TMA box lands at the same shared-memory offset in every CTA of `mask` and completes bytes on
+// the barrier at the same offset there; the commit arrives on that barrier in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -119,9 +133,67 @@ struct TcParams {
     int r0, r1, ncols;
 };
 
+// Epilogue of one 128 x 256 tile: thread (q, lane) owns row 32 q + lane of the tile; D1 in TMEM columns [0,256), D2 in
+// [256,512).  match = (D1 + D2) / 4, useful = nv_i + nv_j - D2, then p / JC in fp64 in the reference's expression order.
+__device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tmem_base, int tile_row, int tile_col, int q, int lane) {
+    const int2 tl = make_int2(tile_row, tile_col);
+    const int i = tl.x * TC_M + 32 * q + lane;
+    const int nvi = i < p.n ? p.nv[i] : 0;
+    for (int cb = 0; cb < TC_N / 32; cb++) {
+        uint32_t r1[32], r2[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cb * 32);
+        tmem_ld32(taddr, r1);
+        tmem_ld32(taddr + 256u, r2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int j0 = tl.y * TC_N + cb * 32;
+        if (p.rect) {
+            if (i >= p.r0 && i < p.r1 && j0 < p.ncols) {
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const int j = j0 + c;
+                    if (j < p.ncols) {
+                        const int both = (int)r2[c];
+                        const int match = ((int)r1[c] + both) >> 2;
+                        p.out[(size_t)(i - p.r0) * p.ld + j] = dist_p_jc(match, nvi + p.nv[j] - both, p.dist_type);
+                    }
+                }
+            }
+        } else if (i >= p.r0 && i < p.r1 && j0 <= i) {
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const int j = j0 + c;
+                if (j < i) {
+                    const int both = (int)r2[c];
+                    const int match = ((int)r1[c] + both) >> 2;
+                    const double d = dist_p_jc(match, nvi + p.nv[j] - both, p.dist_type);
+                    p.out[(size_t)i * p.ld + j] = d;
+                    p.out[(size_t)j * p.ld + i] = d;
+                } else if (j == i) {
+                    p.out[(size_t)i * p.ld + i] = 0.0;
+                }
+            }
+        }
+    }
+}
+
+// CM x CN CTAs form a cluster that computes a (CM * 128) x (CN * 256) tile: the A slab of a tile row is needed by the CN
+// CTAs of that row and the B slab of a tile column by the CM CTAs of that column, so every CTA loads 1/CN of its A
+// slab and 1/CM of its B slab and TMA-multicasts them to the peers: (1/CN + 2/CM) / 3 of the L2 -> SM traffic of
+// independent CTAs, and sharing no longer depends on L2 residency (ncu, 1 x 1: 248 GB of DRAM reads for 3.6 GB of operands).
+template <int CM, int CN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__ CUtensorMap mapSB,
               const __grid_constant__ CUtensorMap mapVA, const __grid_constant__ CUtensorMap mapVB, TcParams p) {
+    constexpr int CSZ = CM * CN;
+    uint32_t crank = 0;
+    if (CSZ > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int cr = (int)crank / CN, cc = (int)crank % CN;
+    const int cluster_id = (int)blockIdx.x / CSZ, num_clusters = (int)gridDim.x / CSZ;
+    const uint16_t mask_row = (uint16_t)(((1u << CN) - 1u) << (cr * CN));      // CTAs that need my part of the A slab
+    uint16_t mask_col = 0;                                                      // CTAs that need my part of the B slab
+#pragma unroll
+    for (int r = 0; r < CM; r++) mask_col |= (uint16_t)(1u << (r * CN + cc));
+    constexpr int A_PART = TC_A_BYTES / CN, B_PART = TC_B_BYTES / CM;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operands need 1024-byte alignment
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -134,7 +206,8 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        // a stage is free when every CTA that reads what this CTA writes into it has consumed it
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CM + CN - 1); }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 4);   // one arrival per epilogue warp
         mbar_fence_init();
@@ -145,6 +218,10 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CSZ > 1) {   // barriers of every CTA initialised before any peer multicasts into them
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int nchunks = p.ns_chunks + p.nv_chunks;
@@ -153,20 +230,23 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
                 const int2 tl = p.tiles[t];
+                const int arow = (tl.x * CM + cr) * TC_M + cc * (TC_M / CN);   // my part of my tile row's A slab
+                const int brow = (tl.y * CN + cc) * TC_N + cr * (TC_N / CM);   // my part of my tile column's B slab
                 for (int c = 0; c < nchunks; c++) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    unsigned char* a = smem + (size_t)stage * TC_STAGE_BYTES;
-                    unsigned char* b = a + TC_A_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
-                    if (c < p.ns_chunks) {
-                        tma_load_2d(a, &mapSA, c * TC_KB, tl.x * TC_M, &full[stage]);
-                        tma_load_2d(b, &mapSB, c * TC_KB, tl.y * TC_N, &full[stage]);
+                    unsigned char* a = smem + (size_t)stage * TC_STAGE_BYTES + cc * A_PART;
+                    unsigned char* b = smem + (size_t)stage * TC_STAGE_BYTES + TC_A_BYTES + cr * B_PART;
+                    mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);   // own parts + the peers' multicasts
+                    const bool sv = c >= p.ns_chunks;
+                    const int kc = (sv ? c - p.ns_chunks : c) * TC_KB;
+                    if (CSZ == 1) {
+                        tma_load_2d(a, sv ? &mapVA : &mapSA, kc, arow, &full[stage]);
+                        tma_load_2d(b, sv ? &mapVB : &mapSB, kc, brow, &full[stage]);
                     } else {
-                        const int cv = c - p.ns_chunks;
-                        tma_load_2d(a, &mapVA, cv * TC_KB, tl.x * TC_M, &full[stage]);
-                        tma_load_2d(b, &mapVB, cv * TC_KB, tl.y * TC_N, &full[stage]);
+                        tma_load_2d_mc(a, sv ? &mapVA : &mapSA, kc, arow, &full[stage], mask_row);
+                        tma_load_2d_mc(b, sv ? &mapVB : &mapSB, kc, brow, &full[stage], mask_col);
                     }
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -178,7 +258,7 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
             // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 256, M = 128
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
             uint32_t stage = 0, phase = 0, tphase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
                 mbar_wait(tmem_empty, tphase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int c = 0; c < nchunks; c++) {
@@ -192,7 +272,9 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < TC_KB / 32; k++)   // UMMA_K = 32 int8 = 32 B: advance the start address by 2 (x16 B)
                         umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first_of_acc && k == 0) ? 0u : 1u);
-                    umma_commit(&empty[stage]);            // stage is free when these MMAs have read it
+                    // the stage is free when these MMAs have read it: tell every CTA that writes into it
+                    if (CSZ == 1) umma_commit(&empty[stage]);
+                    else umma_commit_mc(&empty[stage], (uint16_t)(mask_row | mask_col));
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tmem_full);                    // both accumulators complete
@@ -203,47 +285,11 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                            // TMEM lane quarter this warp may read
         uint32_t tphase = 0;
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-            const int2 tl = p.tiles[t];
+        for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
+            const int2 tl = make_int2(p.tiles[t].x * CM + cr, p.tiles[t].y * CN + cc);   // this CTA's 128 x 256 tile
             mbar_wait(tmem_full, tphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int i = tl.x * TC_M + 32 * q + lane;
-            const int nvi = i < p.n ? p.nv[i] : 0;
-            for (int cb = 0; cb < TC_N / 32; cb++) {
-                uint32_t r1[32], r2[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cb * 32);
-                tmem_ld32(taddr, r1);
-                tmem_ld32(taddr + 256u, r2);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int j0 = tl.y * TC_N + cb * 32;
-                if (p.rect) {
-                    if (i >= p.r0 && i < p.r1 && j0 < p.ncols) {
-#pragma unroll
-                        for (int c = 0; c < 32; c++) {
-                            const int j = j0 + c;
-                            if (j < p.ncols) {
-                                const int both = (int)r2[c];
-                                const int match = ((int)r1[c] + both) >> 2;
-                                p.out[(size_t)(i - p.r0) * p.ld + j] = dist_p_jc(match, nvi + p.nv[j] - both, p.dist_type);
-                            }
-                        }
-                    }
-                } else if (i >= p.r0 && i < p.r1 && j0 <= i) {
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const int j = j0 + c;
-                        if (j < i) {
-                            const int both = (int)r2[c];
-                            const int match = ((int)r1[c] + both) >> 2;
-                            const double d = dist_p_jc(match, nvi + p.nv[j] - both, p.dist_type);
-                            p.out[(size_t)i * p.ld + j] = d;
-                            p.out[(size_t)j * p.ld + i] = d;
-                        } else if (j == i) {
-                            p.out[(size_t)i * p.ld + i] = 0.0;
-                        }
-                    }
-                }
-            }
+            tc_epilogue_tile(p, tmem_base, tl.x, tl.y, q, lane);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
@@ -252,6 +298,10 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CSZ > 1) {   // no CTA exits while a peer may still multicast into it or arrive on its barriers
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
@@ -292,11 +342,12 @@ int msa_tc_prepare(dipb_msa* m) {
     return 0;
 }
 
-static int tc_launch(dipb_msa* m, const std::vector<int2>& tiles, TcParams p) {
+typedef std::vector<int2> (*TileListFn)(int tile_m, int tile_n, int sm_rows, int sm_cols, const void* arg);
+
+template <int CM, int CN>
+static int tc_launch_c(dipb_msa* m, TileListFn make_tiles, const void* arg, TcParams p, bool* launched) {
     dipb_ctx* c = m->ctx;
-    int rc = msa_tc_prepare(m);
-    if (rc) return rc;
-    if (tiles.empty()) return 0;
+    *launched = false;
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -305,9 +356,29 @@ static int tc_launch(dipb_msa* m, const std::vector<int2>& tiles, TcParams p) {
         if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return DIPB_E_CUDA; }
         encode = (EncodeTiledFn)fn;
     }
+    auto kern = msa_tc_kernel<CM, CN>;
+    constexpr int CSZ = CM * CN;
+    DIPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    if (CSZ > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CSZ); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CSZ; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = c->num_sms;
+    if (CSZ > 1 && (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1)) { cudaGetLastError(); return 0; }
+    // the clusters that run concurrently form one super-tile (rows x cols of cluster tiles) that shares operand slabs in L2
+    int sm_cols = 1;
+    while ((sm_cols + 1) * (sm_cols + 1) * CM * 2 <= nclusters * CN) sm_cols++;   // keep the super-tile about square in elements
+    int sm_rows = nclusters / sm_cols;
+    if (sm_rows < 1) sm_rows = 1;
+    std::vector<int2> tiles = make_tiles(CM * TC_M, CN * TC_N, sm_rows, sm_cols, arg);
+    if (tiles.empty()) { *launched = true; return 0; }
+    int rc;
     CUtensorMap mSA, mSB, mVA, mVB;
-    if ((rc = make_map(encode, &mSA, m->tc_S, m->tc_ks, m->tc_rows, TC_M)) || (rc = make_map(encode, &mSB, m->tc_S, m->tc_ks, m->tc_rows, TC_N)) ||
-        (rc = make_map(encode, &mVA, m->tc_V, m->tc_kv, m->tc_rows, TC_M)) || (rc = make_map(encode, &mVB, m->tc_V, m->tc_kv, m->tc_rows, TC_N)))
+    if ((rc = make_map(encode, &mSA, m->tc_S, m->tc_ks, m->tc_rows, TC_M / CN)) || (rc = make_map(encode, &mSB, m->tc_S, m->tc_ks, m->tc_rows, TC_N / CM)) ||
+        (rc = make_map(encode, &mVA, m->tc_V, m->tc_kv, m->tc_rows, TC_M / CN)) || (rc = make_map(encode, &mVB, m->tc_V, m->tc_kv, m->tc_rows, TC_N / CM)))
         return rc;
     int2* d_tiles = nullptr;
     DIPB_CUDA(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
@@ -315,49 +386,79 @@ static int tc_launch(dipb_msa* m, const std::vector<int2>& tiles, TcParams p) {
     p.tiles = d_tiles; p.num_tiles = (int)tiles.size();
     p.ns_chunks = (int)(m->tc_ks / TC_KB); p.nv_chunks = (int)(m->tc_kv / TC_KB);
     p.nv = m->nv; p.n = m->n;
-    static bool attr = false;
-    if (!attr) { DIPB_CUDA(cudaFuncSetAttribute(msa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); attr = true; }
-    int grid = p.num_tiles < c->num_sms ? p.num_tiles : c->num_sms;
-    msa_tc_kernel<<<grid, TC_THREADS, TC_SMEM, c->stream>>>(mSA, mSB, mVA, mVB, p);
-    DIPB_KERNEL_CHECK(c);
+    const int use = p.num_tiles < nclusters ? p.num_tiles : nclusters;
+    cfg.gridDim = dim3(use * CSZ);
+    void* args[] = {&mSA, &mSB, &mVA, &mVB, &p};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
+    if (e != cudaSuccess) { cudaFree(d_tiles); set_error("msa_tc: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
+    c->launches++;
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_tiles);
+    *launched = true;
     return 0;
 }
 
-// Tiles are ordered so that the ~148 tiles running concurrently form a compact 16 x 9 super-tile: they stream
-// only 16 + 9 distinct operand slabs through L2 instead of 1 + 148 (the GEMM is bandwidth bound, not MMA bound).
-static const int SM_ROWS = 16, SM_COLS = 9;
+static int tc_launch(dipb_msa* m, TileListFn make_tiles, const void* arg, TcParams p) {
+    int rc = msa_tc_prepare(m);
+    if (rc) return rc;
+    // cluster shape: DIPB_MSA_TC_CLUSTER=RxC (1x1, 2x2, 2x4, 4x2, 4x4).  Multicast clusters cut the DRAM traffic (4x4: 87 GB
+    // instead of 248 GB at C3) but not the run time -- the kernel is bound by each SM's 48 KB per stage of operand
+    // ingest, not by L2 or DRAM (profiles/r1_ncu_tc_multicast.json) -- so independent CTAs on all 148 SMs stay the default.
+    const char* e = getenv("DIPB_MSA_TC_CLUSTER");
+    int cm = 1, cn = 1;
+    if (e && e[0] >= '1' && e[0] <= '4' && e[1] == 'x' && e[2] >= '1' && e[2] <= '4') { cm = e[0] - '0'; cn = e[2] - '0'; }
+    bool ok = false;
+    if (cm == 4 && cn == 4) rc = tc_launch_c<4, 4>(m, make_tiles, arg, p, &ok);
+    else if (cm == 2 && cn == 4) rc = tc_launch_c<2, 4>(m, make_tiles, arg, p, &ok);
+    else if (cm == 4 && cn == 2) rc = tc_launch_c<4, 2>(m, make_tiles, arg, p, &ok);
+    else if (cm == 2 && cn == 2) rc = tc_launch_c<2, 2>(m, make_tiles, arg, p, &ok);
+    if (rc || ok) return rc;
+    return tc_launch_c<1, 1>(m, make_tiles, arg, p, &ok);
+}
+
+struct TriArg { int row_begin, row_end; };
+// lower-triangle tiles of rows [row_begin, row_end), super-tile by super-tile from the bottom (longest rows first)
+static std::vector<int2> tri_tiles(int tm, int tn, int sm_rows, int sm_cols, const void* arg) {
+    const TriArg* a = static_cast<const TriArg*>(arg);
+    const int mb0 = a->row_begin / tm, mb = (a->row_end + tm - 1) / tm;
+    std::vector<int2> tiles;
+    for (int sm = (mb + sm_rows - 1) / sm_rows - 1; sm >= mb0 / sm_rows; sm--) {
+        const int mi_hi = std::min(mb, (sm + 1) * sm_rows) - 1;
+        const int nj_max = (mi_hi * tm + tm - 1) / tn;
+        for (int sn = 0; sn * sm_cols <= nj_max; sn++)
+            for (int mi = std::max(mb0, sm * sm_rows); mi <= mi_hi; mi++)
+                for (int nj = sn * sm_cols; nj < (sn + 1) * sm_cols; nj++)
+                    if ((long long)nj * tn <= (long long)mi * tm + tm - 1) tiles.push_back(make_int2(mi, nj));   // touches the triangle
+    }
+    return tiles;
+}
+
+struct RectArg { int r0, r1, ncols; };
+static std::vector<int2> rect_tiles(int tm, int tn, int sm_rows, int sm_cols, const void* arg) {
+    const RectArg* a = static_cast<const RectArg*>(arg);
+    const int mi0 = a->r0 / tm, mi1 = (a->r1 - 1) / tm, nb = (a->ncols + tn - 1) / tn;
+    std::vector<int2> tiles;
+    for (int sm = mi0; sm <= mi1; sm += sm_rows)
+        for (int sn = 0; sn < nb; sn += sm_cols)
+            for (int mi = sm; mi <= std::min(mi1, sm + sm_rows - 1); mi++)
+                for (int nj = sn; nj < std::min(nb, sn + sm_cols); nj++) tiles.push_back(make_int2(mi, nj));
+    return tiles;
+}
 
 // symmetric matrix entries (i, j) and (j, i) for i in [row_begin, row_end), j < i, plus the diagonal; p or JC
 int msa_tc_matrix(dipb_msa* m, int type, int row_begin, int row_end, double* d_out) {
-    // lower triangle: column block nj intersects row block mi when nj*256 <= mi*128 + 127
-    const int mb0 = row_begin / TC_M, mb = (row_end + TC_M - 1) / TC_M;
-    std::vector<int2> tiles;
-    for (int sm = (mb + SM_ROWS - 1) / SM_ROWS - 1; sm >= mb0 / SM_ROWS; sm--) {
-        const int mi_hi = std::min(mb, (sm + 1) * SM_ROWS) - 1;
-        const int nj_max = (mi_hi * TC_M + TC_M - 1) / TC_N;
-        for (int sn = 0; sn * SM_COLS <= nj_max; sn++)
-            for (int mi = std::max(mb0, sm * SM_ROWS); mi <= mi_hi; mi++)
-                for (int nj = sn * SM_COLS; nj < (sn + 1) * SM_COLS; nj++)
-                    if (nj * TC_N <= mi * TC_M + TC_M - 1) tiles.push_back(make_int2(mi, nj));
-    }
+    TriArg a{row_begin, row_end};
     TcParams p{};
     p.out = d_out; p.ld = (size_t)m->n; p.dist_type = type; p.rect = 0; p.r0 = row_begin; p.r1 = row_end;
-    return tc_launch(m, tiles, p);
+    return tc_launch(m, tri_tiles, &a, p);
 }
 
 // rows [r0, r1) x columns [0, ncols) into out[(i - r0) * ld + j]  (placement row blocks, D&C stage 2)
 int msa_tc_block(dipb_msa* m, int type, int r0, int r1, int ncols, double* d_out, size_t ld) {
-    const int mi0 = r0 / TC_M, mi1 = (r1 - 1) / TC_M, nb = (ncols + TC_N - 1) / TC_N;
-    std::vector<int2> tiles;
-    for (int sm = mi0; sm <= mi1; sm += SM_ROWS)
-        for (int sn = 0; sn < nb; sn += SM_COLS)
-            for (int mi = sm; mi <= std::min(mi1, sm + SM_ROWS - 1); mi++)
-                for (int nj = sn; nj < std::min(nb, sn + SM_COLS); nj++) tiles.push_back(make_int2(mi, nj));
+    RectArg a{r0, r1, ncols};
     TcParams p{};
     p.out = d_out; p.ld = ld; p.dist_type = type; p.rect = 1; p.r0 = r0; p.r1 = r1; p.ncols = ncols;
-    return tc_launch(m, tiles, p);
+    return tc_launch(m, rect_tiles, &a, p);
 }
 
 }  // namespace dipb
