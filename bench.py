@@ -361,7 +361,7 @@ def main():
                          "frac_on_bytes_read": bytes_read / (nj_ms / 1e3) / 1e9 / peak,
                          "note": "latency bound, not bandwidth bound: 4 cluster barriers and ~10 dependent shared/L2 round trips per merge "
                                  "(profiles/r1_nj_cluster_phases.txt); ncu collects no DRAM counters for this cluster launch"},
-            "dist_kernel": {"kernel": "msa_tc_kernel (tcgen05.mma kind::i8, 128x256 tiles)", "bound": "tensor", "achieved": tc_ach,
+            "dist_kernel": {"kernel": "msa_tc2_kernel (tcgen05.mma.cta_group::2.kind::i8, 256x256 tiles per CTA pair)", "bound": "tensor", "achieved": tc_ach,
                             "peak": 2.0 * peak_bf16, "unit": "TOP/s", "frac": tc_ach / (2.0 * peak_bf16),
                             "peak_definition": "int8 dense = 2 x measured bf16 dense burst (%s)" % peak_src,
                             "algorithmic_ops": tc_ops, "traffic": 255.4e9,

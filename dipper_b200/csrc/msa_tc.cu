@@ -305,6 +305,159 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+// =====================================================================================================
+// 2-CTA variant (tcgen05 cta_group::2).  ncu on the 1-CTA kernel: the tensor pipe is ~50 % active because every
+// SM has to take in 48 KB of operands per 128-byte K step (~1060 cycles) against 541 cycles of MMA.  A CTA pair
+// computes a 256 x 256 tile with ONE MMA stream: each CTA stages only its own 128 A rows and its own half of the
+// 256 B rows (32 KB per step, 7 stages instead of 4); the leader's MMA reads both halves from both shared memories
+// and writes each CTA's 128 accumulator rows into that CTA's TMEM.  Both CTAs run a TMA producer (completing bytes on
+// the LEADER's full barrier) and an epilogue; only the leader issues MMAs and multicasts its commits to both CTAs.
+// =====================================================================================================
+constexpr int T2_STAGES = 7;
+constexpr int T2_HALF_BYTES = 128 * TC_KB;                  // 128 rows x 128 B
+constexpr int T2_STAGE_BYTES = 2 * T2_HALF_BYTES;           // A rows + half of B: 32 KB
+constexpr int T2_SMEM = T2_STAGES * T2_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t cluster_addr(const void* p, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+    // relaxed: the bytes are ordered by the TMA completion itself; a release at cluster scope is a MEMBAR.GPU (~1000 cycles,
+    // once per stage in the producer: measured 1970 instead of ~700 cycles per stage)
+    asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory that completes its bytes on a barrier of the pair's leader
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+msa_tc2_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapV, TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE_BYTES);
+    uint64_t* full = bars;                      // [T2_STAGES]  used in the leader: both producers arm it and complete bytes on it
+    uint64_t* empty = bars + T2_STAGES;         // [T2_STAGES]  in each CTA: the leader's commit frees the stage in both
+    uint64_t* tmem_full = bars + 2 * T2_STAGES;       // in each CTA: accumulators of the tile complete
+    uint64_t* tmem_empty = bars + 2 * T2_STAGES + 1;  // in the leader: 4 + 4 epilogue warps of the pair have drained TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T2_STAGES + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int pair_id = (int)blockIdx.x >> 1, num_pairs = (int)gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T2_STAGES; s++) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 8);
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int nchunks = p.ns_chunks + p.nv_chunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = pair_id; t < p.num_tiles; t += num_pairs) {
+                const int2 tl = p.tiles[t];                                  // 256-row block, 256-column block
+                const int arow = tl.x * 256 + (int)crank * 128;              // my 128 A rows
+                const int brow = tl.y * 256 + (int)crank * 128;              // my half of the B rows
+                for (int c = 0; c < nchunks; c++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* a = smem + (size_t)stage * T2_STAGE_BYTES;
+                    const uint32_t lfull = cluster_addr(&full[stage], 0);
+                    mbar_arrive_expect_tx_cluster(lfull, T2_STAGE_BYTES);
+                    const bool sv = c >= p.ns_chunks;
+                    const int kc = (sv ? c - p.ns_chunks : c) * TC_KB;
+                    tma_load_2d_pair(a, sv ? &mapV : &mapS, kc, arow, lfull);
+                    tma_load_2d_pair(a + T2_HALF_BYTES, sv ? &mapV : &mapS, kc, brow, lfull);
+                    if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader only) =====================
+        if (lane == 0 && crank == 0) {
+            // D = s32, A = B = signed 8-bit, both K-major, N = 256, M = 256 (128 rows in each CTA's TMEM)
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            uint32_t stage = 0, phase = 0, tphase = 0;
+            for (int t = pair_id; t < p.num_tiles; t += num_pairs) {
+                mbar_wait(tmem_empty, tphase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int c = 0; c < nchunks; c++) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * T2_STAGE_BYTES);
+                    const uint64_t adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(a_addr + T2_HALF_BYTES);
+                    const bool second = c >= p.ns_chunks;
+                    const uint32_t d = tmem_base + (second ? 256u : 0u);
+                    const bool first_of_acc = (c == 0) || (c == p.ns_chunks);
+#pragma unroll
+                    for (int k = 0; k < TC_KB / 32; k++)
+                        umma2_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first_of_acc && k == 0) ? 0u : 1u);
+                    umma2_commit(&empty[stage]);
+                    if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma2_commit(tmem_full);
+                tphase ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5, both CTAs) =====================
+        const int q = warp & 3;
+        uint32_t tphase = 0;
+        const uint32_t l_tmem_empty = cluster_addr(tmem_empty, 0);
+        for (int t = pair_id; t < p.num_tiles; t += num_pairs) {
+            const int2 tl = p.tiles[t];
+            mbar_wait(tmem_full, tphase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc_epilogue_tile(p, tmem_base, tl.x * 2 + (int)crank, tl.y, q, lane);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(l_tmem_empty);
+            tphase ^= 1;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -398,9 +551,66 @@ static int tc_launch_c(dipb_msa* m, TileListFn make_tiles, const void* arg, TcPa
     return 0;
 }
 
+// 2-CTA kernel: 256 x 256 tiles, one CTA pair (cluster of 2) each
+static int tc_launch_pair(dipb_msa* m, TileListFn make_tiles, const void* arg, TcParams p, bool force, bool* launched) {
+    dipb_ctx* c = m->ctx;
+    *launched = false;
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DIPB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return DIPB_E_CUDA; }
+        encode = (EncodeTiledFn)fn;
+    }
+    if (cudaFuncSetAttribute(msa_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = T2_SMEM; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int npairs = 0;
+    if (cudaOccupancyMaxActiveClusters(&npairs, msa_tc2_kernel, &cfg) != cudaSuccess || npairs < 1) { cudaGetLastError(); return 0; }
+    int sm_cols = 1;
+    while ((sm_cols + 1) * (sm_cols + 1) <= npairs) sm_cols++;      // square tiles: square super-tile
+    const int sm_rows = npairs / sm_cols;
+    std::vector<int2> tiles = make_tiles(256, 256, sm_rows, sm_cols, arg);
+    if (tiles.empty()) { *launched = true; return 0; }
+    if (!force && (int)tiles.size() < 4 * npairs) return 0;      // too few 256 x 256 tiles to balance: 128 x 256 tiles of the 1-CTA kernel
+    int rc;
+    CUtensorMap mS, mV;
+    if ((rc = make_map(encode, &mS, m->tc_S, m->tc_ks, m->tc_rows, 128)) || (rc = make_map(encode, &mV, m->tc_V, m->tc_kv, m->tc_rows, 128))) return rc;
+    int2* d_tiles = nullptr;
+    DIPB_CUDA(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
+    DIPB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
+    p.tiles = d_tiles; p.num_tiles = (int)tiles.size();
+    p.ns_chunks = (int)(m->tc_ks / TC_KB); p.nv_chunks = (int)(m->tc_kv / TC_KB);
+    p.nv = m->nv; p.n = m->n;
+    const int use = p.num_tiles < npairs ? p.num_tiles : npairs;
+    cfg.gridDim = dim3(use * 2);
+    void* args[] = {&mS, &mV, &p};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)msa_tc2_kernel, args);
+    if (e != cudaSuccess) { cudaFree(d_tiles); set_error("msa_tc2: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
+    c->launches++;
+    DIPB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_tiles);
+    *launched = true;
+    return 0;
+}
+
 static int tc_launch(dipb_msa* m, TileListFn make_tiles, const void* arg, TcParams p) {
     int rc = msa_tc_prepare(m);
     if (rc) return rc;
+    {
+        // 2-CTA kernel (39.9 ms vs 56.7 ms at C3) whenever there are enough 256 x 256 tiles; DIPB_MSA_TC2=0 never, =1 always
+        const char* e2 = getenv("DIPB_MSA_TC2");
+        if (!(e2 && e2[0] == '0')) {
+            bool ok2 = false;
+            rc = tc_launch_pair(m, make_tiles, arg, p, e2 && e2[0] == '1', &ok2);
+            if (rc || ok2) return rc;
+        }
+    }
     // cluster shape: DIPB_MSA_TC_CLUSTER=RxC (1x1, 2x2, 2x4, 4x2, 4x4).  Multicast clusters cut the DRAM traffic (4x4: 87 GB
     // instead of 248 GB at C3) but not the run time -- the kernel is bound by each SM's 48 KB per stage of operand
     // ingest, not by L2 or DRAM (profiles/r1_ncu_tc_multicast.json) -- so independent CTAs on all 148 SMs stay the default.

@@ -123,8 +123,10 @@ def test_row_sharded_matrix_sums_to_full(ctx, oracle):
 
 @pytest.mark.parametrize("n,L", [(2, 40), (129, 1000), (300, 515), (700, 4000)])
 @pytest.mark.parametrize("dist_type", [1, 2])
-def test_tensor_core_path_is_bit_identical(ctx, oracle, n, L, dist_type, monkeypatch):
-    """msa_tc.cu (tcgen05 int8 GEMMs) must give exactly the matrix of the popcount kernel."""
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_tensor_core_path_is_bit_identical(ctx, oracle, n, L, dist_type, pair, monkeypatch):
+    """msa_tc.cu (tcgen05 int8 GEMMs; pair = 2-CTA cta_group::2 kernel) must give exactly the matrix of the popcount kernel."""
+    monkeypatch.setenv("DIPB_MSA_TC2", pair)
     codes, P, _ = make_msa(n, L, seed=900 + n, gap_cols=0.05)
     msa = upload(ctx, P, L)
     prm = api.Param(distanceType=dist_type, in_="m")
@@ -139,8 +141,10 @@ def test_tensor_core_path_is_bit_identical(ctx, oracle, n, L, dist_type, monkeyp
 
 @pytest.mark.parametrize("dist_type", [1, 2])
 @pytest.mark.parametrize("r0,r1,ncols", [(0, 64, 700), (100, 700, 100), (130, 515, 515), (511, 700, 257)])
-def test_tensor_core_block_rows(ctx, oracle, dist_type, r0, r1, ncols, monkeypatch):
-    """Row blocks of >= 64 rows (placement batches, D&C stage 2) go through the tcgen05 kernel too."""
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_tensor_core_block_rows(ctx, oracle, dist_type, r0, r1, ncols, pair, monkeypatch):
+    """Row blocks of >= 64 rows (placement batches, D&C stage 2) go through the tcgen05 kernels too."""
+    monkeypatch.setenv("DIPB_MSA_TC2", pair)
     n, L = 700, 2100
     codes, P, _ = make_msa(n, L, seed=77, gap_cols=0.05)
     msa = upload(ctx, P, L)
@@ -157,7 +161,9 @@ def test_tensor_core_block_rows(ctx, oracle, dist_type, r0, r1, ncols, monkeypat
 
 
 @pytest.mark.parametrize("cut", [1, 128, 300, 699])
-def test_tensor_core_row_sharded_matrix(ctx, oracle, cut, monkeypatch):
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_tensor_core_row_sharded_matrix(ctx, oracle, cut, pair, monkeypatch):
+    monkeypatch.setenv("DIPB_MSA_TC2", pair)
     n, L = 700, 1300
     codes, P, _ = make_msa(n, L, seed=78)
     msa = upload(ctx, P, L)
