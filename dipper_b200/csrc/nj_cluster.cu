@@ -602,6 +602,12 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     __syncthreads();
                 }
             }
+            // the next merge reads row n - 1 (it moves into the freed slot): pull my chunks of it into L2 now
+            if (n > 3 && lane < 2) {
+                const int pch = (n - 1 + 31) >> 5;
+                for (int lw = w; lw * CS + rank < pch; lw += NW)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(D + (size_t)(n - 1) * ld + (size_t)(lw * CS + rank) * 32 + lane * 16));
+            }
             // warp winner -> CTA winner (reference order), every warp winner also feeds the candidate pool
             {
                 const int wl = warp_best_lane(bt, bi, bj, n);
@@ -712,18 +718,26 @@ static int launch_cluster(dipb_ctx* c, int n, void** args, int* LS_out, int* HC,
     if (CS > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS); cfg.blockDim = dim3(CT); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;     // helpers spin on the main cluster: all clusters resident or no launch
+    at[1].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int nclusters = 0;
     if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return 0; }
     // helper clusters spin on a doorbell of the main cluster: only as many as are co-resident with it
     int helpers = nclusters - 1 < max_helper_clusters ? nclusters - 1 : max_helper_clusters;
     if (helpers < 0) helpers = 0;
-    *HC = helpers * CS;
-    cfg.gridDim = dim3(CS * (1 + helpers));
-    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
+    cudaError_t e = cudaErrorUnknown;
+    for (; helpers >= 0; helpers = helpers > 0 ? 0 : -1) {
+        *HC = helpers * CS;
+        cfg.gridDim = dim3(CS * (1 + helpers));
+        cfg.numAttrs = helpers > 0 ? 2 : 1;
+        e = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
+        if (e == cudaSuccess) break;
+        cudaGetLastError();                        // e.g. the GPU is shared right now: retry without helpers
+    }
     if (e != cudaSuccess) { set_error("nj_cluster: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
     *ok = true;
     return 0;
