@@ -605,8 +605,10 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             // the next merge reads row n - 1 (it moves into the freed slot): pull my chunks of it into L2 now
             if (n > 3 && lane < 2) {
                 const int pch = (n - 1 + 31) >> 5;
-                for (int lw = w; lw * CS + rank < pch; lw += NW)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(D + (size_t)(n - 1) * ld + (size_t)(lw * CS + rank) * 32 + lane * 16));
+                for (int lw = w; lw * CS + rank < pch; lw += NW) {
+                    const int col = (lw * CS + rank) * 32 + lane * 16;
+                    if (col < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(D + (size_t)(n - 1) * ld + col));
+                }
             }
             // warp winner -> CTA winner (reference order), every warp winner also feeds the candidate pool
             {
