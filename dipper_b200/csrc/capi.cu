@@ -43,6 +43,15 @@ int dipb_init(int device, dipb_ctx** out) {
         return DIPB_E_CUDA;
     }
     DIPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        // keep freed pool pages for re-use (see pool_alloc in common.cuh)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     DIPB_CUDA(cudaEventCreate(&c->ev0));
     DIPB_CUDA(cudaEventCreate(&c->ev1));
     for (int i = 0; i < DIPB_T_COUNT; i++) c->elapsed[i] = -1.0;
@@ -81,7 +90,7 @@ static int msa_create(dipb_ctx* c, const uint64_t* d_in, size_t n, uint64_t seq_
     m->nkc = (w32 + MSA_KC - 1) / MSA_KC;
     if (m->nkc < 1) m->nkc = 1;
     size_t words = (size_t)(m->npad / MSA_TS) * m->nkc * MSA_SLAB_WORDS;
-    DIPB_CUDA(cudaMalloc(&m->planes, words * sizeof(uint32_t)));
+    DIPB_CUDA(pool_alloc(c, (void**)&m->planes, words * sizeof(uint32_t)));
     DIPB_CUDA(cudaMalloc(&m->nv, sizeof(int) * m->npad));
     DIPB_CUDA(cudaMemsetAsync(m->nv, 0, sizeof(int) * m->npad, c->stream));
     int rc = msa_repack(m, d_in, (int)((seq_len + 15) / 16));
@@ -124,10 +133,10 @@ int dipb_msa_upload(dipb_ctx* c, const uint64_t* const* seq4, const uint64_t* le
 void dipb_msa_free(dipb_msa* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
-    cudaFree(m->planes);
+    pool_free(m->ctx, m->planes);
     cudaFree(m->nv);
-    cudaFree(m->tc_S);
-    cudaFree(m->tc_V);
+    pool_free(m->ctx, m->tc_S);
+    pool_free(m->ctx, m->tc_V);
     delete m;
 }
 
@@ -208,13 +217,13 @@ int dipb_msa_dist_matrix_rows(dipb_msa* m, int dist_type, int row_begin, int row
     M->ctx = m->ctx;
     M->n = m->n;
     size_t bytes = (size_t)m->n * m->n * sizeof(double);
-    cudaError_t e = cudaMalloc(&M->d, bytes);
-    if (e != cudaSuccess) { set_error("dipb_msa_dist_matrix: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); delete M; return DIPB_E_NOMEM; }
+    cudaError_t e = pool_alloc(m->ctx, (void**)&M->d, bytes);
+    if (e != cudaSuccess) { set_error("dipb_msa_dist_matrix: allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); delete M; return DIPB_E_NOMEM; }
     if (row_begin != 0 || row_end != m->n) DIPB_CUDA(cudaMemsetAsync(M->d, 0, bytes, m->ctx->stream));
     int rc = timer_begin(m->ctx);
     if (!rc) rc = msa_matrix(m, dist_type, row_begin, row_end, M->d);
     if (!rc) rc = timer_end(m->ctx, DIPB_T_MSA_DIST);
-    if (rc) { cudaFree(M->d); delete M; return rc; }
+    if (rc) { pool_free(M->ctx, M->d); delete M; return rc; }
     *out = M;
     return 0;
 }
@@ -249,8 +258,8 @@ int dipb_matrix_from_host(dipb_ctx* c, const double* h, int n, int full, dipb_ma
     M->ctx = c;
     M->n = n;
     size_t bytes = (size_t)n * n * sizeof(double);
-    cudaError_t e = cudaMalloc(&M->d, bytes);
-    if (e != cudaSuccess) { set_error("dipb_matrix_from_host: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); delete M; return DIPB_E_NOMEM; }
+    cudaError_t e = pool_alloc(c, (void**)&M->d, bytes);
+    if (e != cudaSuccess) { set_error("dipb_matrix_from_host: allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); delete M; return DIPB_E_NOMEM; }
     dim3 grid((n + 255) / 256, n);
     if (full) {
         DIPB_CUDA(cudaMemcpyAsync(M->d, h, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -283,7 +292,7 @@ int dipb_matrix_to_host(dipb_matrix* m, double* h_out) {
 void dipb_matrix_free(dipb_matrix* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
-    cudaFree(m->d);
+    pool_free(m->ctx, m->d);
     delete m;
 }
 

@@ -375,7 +375,7 @@ int dipb_mash_dist_matrix(dipb_mash* m, dipb_matrix** out) {
     dipb_matrix* M = new dipb_matrix();
     M->ctx = c; M->n = m->n;
     size_t bytes = (size_t)m->n * m->n * sizeof(double);
-    if (cudaMalloc(&M->d, bytes) != cudaSuccess) { set_error("dipb_mash_dist_matrix: cudaMalloc(%zu) failed", bytes); delete M; return DIPB_E_NOMEM; }
+    if (pool_alloc(c, (void**)&M->d, bytes) != cudaSuccess) { set_error("dipb_mash_dist_matrix: allocation of %zu bytes failed", bytes); delete M; return DIPB_E_NOMEM; }
     int rc = timer_begin(c);
     MashTileParams p{};
     p.sk = m->sketches; p.n = m->n; p.s = m->s; p.k = m->k; p.tri = 1; p.r0 = 0; p.r1 = m->n; p.ncols = m->n;
@@ -386,7 +386,7 @@ int dipb_mash_dist_matrix(dipb_mash* m, dipb_matrix** out) {
         c->launches++;
         rc = timer_end(c, DIPB_T_MASH_DIST);
     }
-    if (rc) { cudaFree(M->d); delete M; return rc; }
+    if (rc) { pool_free(c, M->d); delete M; return rc; }
     *out = M;
     return 0;
 }

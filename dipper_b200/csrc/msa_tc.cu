@@ -485,8 +485,8 @@ int msa_tc_prepare(dipb_msa* m) {
     m->tc_ks = ((size_t)w32 * 96 + TC_KB - 1) / TC_KB * TC_KB;
     m->tc_kv = ((size_t)w32 * 32 + TC_KB - 1) / TC_KB * TC_KB;
     m->tc_rows = ((size_t)m->n + TC_N - 1) / TC_N * TC_N;
-    DIPB_CUDA(cudaMalloc(&m->tc_S, m->tc_rows * m->tc_ks));
-    DIPB_CUDA(cudaMalloc(&m->tc_V, m->tc_rows * m->tc_kv));
+    DIPB_CUDA(pool_alloc(c, (void**)&m->tc_S, m->tc_rows * m->tc_ks));
+    DIPB_CUDA(pool_alloc(c, (void**)&m->tc_V, m->tc_rows * m->tc_kv));
     DIPB_CUDA(cudaMemsetAsync(m->tc_S, 0, m->tc_rows * m->tc_ks, c->stream));
     DIPB_CUDA(cudaMemsetAsync(m->tc_V, 0, m->tc_rows * m->tc_kv, c->stream));
     long long total = (long long)m->n * w32;
