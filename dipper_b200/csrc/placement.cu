@@ -22,32 +22,66 @@ namespace dipb {
 
 // updateClosestNodes (:86-124) as a level-synchronous BFS run by one CTA.  Every slot is
 // reached at most once (tree), so processing a level in parallel gives the serial result.
+// The frontier is tiny (15 queue entries and 6.6 levels per tip at 30 000 tips) and every level is a chain of
+// dependent L2 round trips, so the level is kept short: the queue lives in shared memory (global arrays only
+// for entries beyond PL_QCAP), the up-to-three slots of a node are handled by three threads (thread k skips k
+// links of the adjacency list) instead of one after the other, and the head of a node is prefetched when the
+// node is queued.
+constexpr int PL_QCAP = 1024;
+struct PlQueue {
+    int node[PL_QCAP], from[PL_QCAP];
+    double dis[PL_QCAP];
+};
 __device__ void bfs_closest(const int* head, const int* nxt, const int* e, const double* len, double* cdis, int* cid,
-                            int x, int* q_node, int* q_from, double* q_dis, unsigned int* s_tail) {
+                            int x, int* q_node, int* q_from, double* q_dis, unsigned int* s_tail, PlShared* prof) {
     __shared__ unsigned int lo, hi;
+    __shared__ PlQueue q;
     if (threadIdx.x == 0) {
-        q_node[0] = x; q_from[0] = -1; q_dis[0] = 0.0;   // intended seed
+        q.node[0] = x; q.from[0] = -1; q.dis[0] = 0.0;   // intended seed
         lo = 0; hi = 1; *s_tail = 1;
     }
     __syncthreads();
     while (true) {
         const unsigned int l = lo, h = hi;
         if (l >= h) break;
-        for (unsigned int t = l + threadIdx.x; t < h; t += blockDim.x) {
-            const int node = q_node[t], fb = q_from[t];
-            const double d = q_dis[t];
-            for (int s = head[node]; s != -1; s = nxt[s]) {
-                if (e[s] == fb) continue;
-                if (list_insert(cdis, cid, s, d, x)) {
-                    unsigned int pos = atomicAdd(s_tail, 1u);
-                    q_node[pos] = e[s]; q_from[pos] = node; q_dis[pos] = d + len[s];
+        for (unsigned int w = threadIdx.x; w < 3u * (h - l); w += blockDim.x) {
+            const unsigned int t = l + w / 3u;
+            const int k = (int)(w % 3u);
+            const int node = t < PL_QCAP ? q.node[t] : q_node[t], fb = t < PL_QCAP ? q.from[t] : q_from[t];
+            const double d = t < PL_QCAP ? q.dis[t] : q_dis[t];
+            int s = head[node];
+            for (int j = 0; j < k && s != -1; j++) s = nxt[s];
+            if (s == -1) continue;
+            // one round trip for everything the slot needs: target node, length, the 5-entry list
+            const int to = e[s];
+            const double ls = len[s];
+            double cd[KC5];
+            int ci[KC5];
+#pragma unroll
+            for (int j = 0; j < KC5; j++) { cd[j] = cdis[s * KC5 + j]; ci[j] = cid[s * KC5 + j]; }
+            if (to == fb) continue;
+            // list_insert: before the first entry with dis > d
+            int at = KC5;
+#pragma unroll
+            for (int j = KC5 - 1; j >= 0; j--) if (cd[j] > d) at = j;
+            if (at < KC5) {
+#pragma unroll
+                for (int j = KC5 - 1; j >= 0; j--) {
+                    if (j > at) { cdis[s * KC5 + j] = cd[j - 1]; cid[s * KC5 + j] = ci[j - 1]; }
+                    else if (j == at) { cdis[s * KC5 + j] = d; cid[s * KC5 + j] = x; }
                 }
+                const unsigned int pos = atomicAdd(s_tail, 1u);
+                const double nd = d + ls;
+                if (pos < PL_QCAP) { q.node[pos] = to; q.from[pos] = node; q.dis[pos] = nd; }
+                else { q_node[pos] = to; q_from[pos] = node; q_dis[pos] = nd; }
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(head + to));
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) { lo = h; hi = *s_tail; }
+        if (threadIdx.x == 0) { lo = h; hi = *s_tail; if (prof) prof->bfs_levels++; }
         __syncthreads();
     }
+    if (prof && threadIdx.x == 0) prof->bfs_nodes += *s_tail;
     __syncthreads();
 }
 
@@ -55,11 +89,20 @@ __device__ void bfs_closest(const int* head, const int* nxt, const int* e, const
 __global__ void __launch_bounds__(PL_THREADS)
 place_batch_kernel(int* head, int* e, int* nxt, int* belong, double* len, int* cid, double* cdis, int* rev,
                    const double* __restrict__ rows, size_t ld, int row_base, int i0, int i1, int node_off, PlShared* ps,
-                   PlCand* cta_best, int* q_node, int* q_from, double* q_dis, unsigned int gen0) {
+                   PlCand* cta_best, int* q_node, int* q_from, double* q_dis, unsigned int gen0, int profile) {
     __shared__ PlCand sb[PL_THREADS / 32];
     __shared__ unsigned int s_tail;
     const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     unsigned int gen = gen0;   // the barrier counter keeps counting across launches of one placement run
+    long long tm = clock64();
+#define PL_MARK(k)                                                                  \
+    do {                                                                            \
+        if (profile && blockIdx.x == 0 && tid == 0) {                               \
+            const long long now__ = clock64();                                      \
+            ps->cyc[k] += (unsigned long long)(now__ - tm);                         \
+            tm = now__;                                                             \
+        }                                                                           \
+    } while (0)
     for (int i = i0; i < i1; i++) {
         const double* dis = rows + (size_t)(i - row_base) * ld;
         const int nslots = 4 * i - 4;
@@ -87,7 +130,9 @@ place_batch_kernel(int* head, int* e, int* nxt, int* belong, double* len, int* c
                 if (sb[k].add < b.add || (sb[k].add == b.add && sb[k].slot < b.slot)) b = sb[k];
             cta_best[blockIdx.x] = b;
         }
+        PL_MARK(0);
         pl_grid_barrier(&ps->bar_counter, G, gen);
+        PL_MARK(1);
         // ---- CTA 0: global argmin, split the edge, update the closest lists
         if (blockIdx.x == 0) {
             double a = 1e300, f = 0; int sl = 0x7fffffff;
@@ -104,20 +149,24 @@ place_batch_kernel(int* head, int* e, int* nxt, int* belong, double* len, int* c
             }
             if (lane == 0) { sb[w].add = a; sb[w].frac = f; sb[w].slot = sl; }
             __syncthreads();
-            if (tid == 0) {
+            PL_MARK(4);
+            if (w == 0) {
                 PlCand b = sb[0];
                 for (int k = 1; k < PL_THREADS / 32; k++)
                     if (sb[k].add < b.add || (sb[k].add == b.add && sb[k].slot < b.slot)) b = sb[k];
                 if (!(b.add < 2.0)) { b.add = 2.0; b.frac = 0.0; b.slot = 0; }   // the (0,0,2) tuple at position 0 wins
                 const int idx = ps->idx;
-                split_edge(head, nxt, e, len, cdis, cid, belong, rev, b.slot, b.frac, b.add, i, idx, node_off);
-                ps->idx = idx + 4;
+                split_edge_warp(head, nxt, e, len, cdis, cid, belong, rev, b.slot, b.frac, b.add, i, idx, node_off);
+                if (lane == 0) ps->idx = idx + 4;
                 __threadfence_block();
             }
             __syncthreads();
-            bfs_closest(head, nxt, e, len, cdis, cid, i, q_node, q_from, q_dis, &s_tail);
+            PL_MARK(5);
+            bfs_closest(head, nxt, e, len, cdis, cid, i, q_node, q_from, q_dis, &s_tail, profile ? ps : nullptr);
         }
+        PL_MARK(2);
         pl_grid_barrier(&ps->bar_counter, G, gen);
+        PL_MARK(3);
     }
 }
 
@@ -148,8 +197,8 @@ __global__ void place_first_two_kernel(int* head, int* e, int* nxt, int* belong,
         ps->idx = 4;
     }
     __syncthreads();
-    bfs_closest(head, nxt, e, len, cdis, cid, 0, q_node, q_from, q_dis, &s_tail);
-    bfs_closest(head, nxt, e, len, cdis, cid, 1, q_node, q_from, q_dis, &s_tail);
+    bfs_closest(head, nxt, e, len, cdis, cid, 0, q_node, q_from, q_dis, &s_tail, nullptr);
+    bfs_closest(head, nxt, e, len, cdis, cid, 1, q_node, q_from, q_dis, &s_tail, nullptr);
 }
 
 // backbone: reverse-slot table + closest lists of leaves 0..B-1 in order (:241-260)
@@ -163,7 +212,7 @@ __global__ void place_backbone_kernel(int* head, int* e, int* nxt, int* belong, 
     }
     if (threadIdx.x == 0) ps->idx = nslots;
     __syncthreads();
-    for (int i = 0; i < B; i++) bfs_closest(head, nxt, e, len, cdis, cid, i, q_node, q_from, q_dis, &s_tail);
+    for (int i = 0; i < B; i++) bfs_closest(head, nxt, e, len, cdis, cid, i, q_node, q_from, q_dis, &s_tail, nullptr);
 }
 
 int tree_alloc(dipb_ctx* c, int n, dipb_tree** out) {
@@ -227,7 +276,9 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int 
     DIPB_CUDA(cudaMalloc(&cb, sizeof(PlCand) * G));
     int rc = 0;
     unsigned int gen0 = 0;
+    int profile = getenv("DIPB_PLACE_PROFILE") ? 1 : 0;
     DIPB_CUDA(cudaMemsetAsync(&sc->ps->bar_counter, 0, sizeof(unsigned int), c->stream));
+    DIPB_CUDA(cudaMemsetAsync(sc->ps->cyc, 0, sizeof(unsigned long long) * 8, c->stream));
     for (int i0 = first_tip; i0 < end && !rc; i0 += batch) {
         int i1 = i0 + batch < end ? i0 + batch : end;
         const double* rows; int row_base; size_t ldr;
@@ -235,7 +286,7 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int 
         if (rc) break;
         int node_off = n_alloc;
         void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &t->cid, &t->cdis, &t->rev, &rows, &ldr, &row_base,
-                        &i0, &i1, &node_off, &sc->ps, &cb, &sc->q_node, &sc->q_from, &sc->q_dis, &gen0};
+                        &i0, &i1, &node_off, &sc->ps, &cb, &sc->q_node, &sc->q_from, &sc->q_dis, &gen0, &profile};
         cudaError_t e = cudaLaunchCooperativeKernel((void*)place_batch_kernel, dim3(G), dim3(PL_THREADS), args, 0, c->stream);
         if (e != cudaSuccess) { set_error("placement: cooperative launch failed: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; break; }
         c->launches++;
@@ -243,6 +294,14 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int 
     }
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (!rc && e != cudaSuccess) { set_error("placement: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; }
+    if (!rc && profile) {
+        PlShared hs;
+        if (cudaMemcpy(&hs, sc->ps, sizeof(hs), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            const double tips = (double)(end - first_tip);
+            fprintf(stderr, "[placement] tips %d..%d: cycles per tip (CTA 0): score %.0f, barrier 1 %.0f, argmin %.0f, split %.0f, BFS %.0f, barrier 2 %.0f; BFS levels %.1f, queue entries %.1f per tip\n",
+                    first_tip, end, hs.cyc[0] / tips, hs.cyc[1] / tips, hs.cyc[4] / tips, hs.cyc[5] / tips, hs.cyc[2] / tips, hs.cyc[3] / tips, hs.bfs_levels / tips, hs.bfs_nodes / tips);
+        }
+    }
     cudaFree(cb);
     if (buf) cudaFree(buf);
     return rc;

@@ -30,6 +30,8 @@ struct PlShared {
     unsigned int q_tail;
     int idx;   // next free slot
     int pad;
+    unsigned long long cyc[6];     // DIPB_PLACE_PROFILE: CTA 0 cycles in scoring, barrier 1, BFS, barrier 2, argmin, split
+    unsigned long long bfs_levels, bfs_nodes;
 };
 
 __device__ __forceinline__ void pl_grid_barrier(unsigned int* counter, unsigned int nblocks, unsigned int& gen) {
@@ -94,6 +96,71 @@ __device__ __forceinline__ void split_edge(int* head, int* nxt, int* e, double* 
             list_insert(cdis, cid, c3, cdis[src[w] * KC5 + i], cid[src[w] * KC5 + i]);
         }
     rev[xe] = c0; rev[c0] = xe; rev[ye] = c1; rev[c1] = ye; rev[c2] = c3; rev[c3] = c2;
+}
+
+// updateTreeStructure (:446-528) by one WARP: the single-thread version above is a chain of ~25 dependent L2 round
+// trips (12 500 cycles per tip at 30 000 tips); here the two 5-entry lists are loaded by five lanes at once, the scalars
+// once, and the merge of the new leaf's list runs in lane 0's registers.  Same writes, same values.
+__device__ __forceinline__ void split_edge_warp(int* head, int* nxt, int* e, double* len, double* cdis, int* cid, int* belong, int* rev,
+                                                int eid, double fracLen, double addLen, int placeId, int edgeCount, int node_off) {
+    const int lane = threadIdx.x & 31;
+    const int middle = placeId + node_off - 1, outside = placeId;
+    const int xe = eid, ye = rev[eid];                       // (all lanes read the same words: one transaction each)
+    const int x = belong[eid], y = e[eid];
+    const double orig = len[eid], len_ye = len[ye];
+    const int h_mid = head[middle], h_out = head[outside];
+    const int c0 = edgeCount, c1 = edgeCount + 1, c2 = edgeCount + 2, c3 = edgeCount + 3;
+    int iy = -1, ix = -1;
+    double dy = 2.0, dx = 2.0;
+    if (lane < KC5) { iy = cid[ye * KC5 + lane]; dy = cdis[ye * KC5 + lane]; ix = cid[xe * KC5 + lane]; dx = cdis[xe * KC5 + lane]; }
+    // lists of the two halves of the split edge seen from the new inner node (entries without a leaf keep the initial (2, -1))
+    const int c0i = iy, c1i = ix;
+    const double c0d = iy != -1 ? dy + orig - fracLen : 2.0, c1d = ix != -1 ? dx + fracLen : 2.0;
+    if (lane < KC5) {
+        cid[c0 * KC5 + lane] = c0i; cdis[c0 * KC5 + lane] = c0d;
+        cid[c1 * KC5 + lane] = c1i; cdis[c1 * KC5 + lane] = c1d;
+    }
+    // list of the slot that leaves the new leaf: c1's entries, then c0's, inserted in order (list_insert semantics)
+    double ld[KC5];
+    int li[KC5];
+#pragma unroll
+    for (int k = 0; k < KC5; k++) { ld[k] = 2.0; li[k] = -1; }
+    bool open = true;
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        open = true;
+#pragma unroll
+        for (int k = 0; k < KC5; k++) {
+            const double d = __shfl_sync(0xffffffffu, pass == 0 ? c1d : c0d, k);
+            const int id = __shfl_sync(0xffffffffu, pass == 0 ? c1i : c0i, k);
+            if (id == -1) open = false;
+            if (open) {
+                bool done = false;
+#pragma unroll
+                for (int j = 0; j < KC5; j++) {
+                    if (!done && ld[j] > d) {
+#pragma unroll
+                        for (int q = KC5 - 1; q > j; q--) { ld[q] = ld[q - 1]; li[q] = li[q - 1]; }
+                        ld[j] = d; li[j] = id;
+                        done = true;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        e[xe] = middle; len[xe] = fracLen;
+        e[ye] = middle; len[ye] = len_ye - fracLen;
+        // link_slot x 4 with the list heads kept in registers
+        e[c0] = x; len[c0] = fracLen; nxt[c0] = h_mid; belong[c0] = middle;
+        e[c1] = y; len[c1] = orig - fracLen; nxt[c1] = c0; belong[c1] = middle;
+        e[c2] = middle; len[c2] = addLen; nxt[c2] = h_out; belong[c2] = outside; head[outside] = c2;
+        e[c3] = outside; len[c3] = addLen; nxt[c3] = c1; belong[c3] = middle; head[middle] = c3;
+#pragma unroll
+        for (int k = 0; k < KC5; k++) { cdis[c3 * KC5 + k] = ld[k]; cid[c3 * KC5 + k] = li[k]; }
+        rev[xe] = c0; rev[c0] = xe; rev[ye] = c1; rev[c1] = ye; rev[c2] = c3; rev[c3] = c2;
+    }
+    __syncwarp();
 }
 
 // calculateBranchLength (:309-358) for one candidate slot
