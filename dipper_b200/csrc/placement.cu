@@ -33,7 +33,8 @@ struct PlQueue {
     double dis[PL_QCAP];
 };
 __device__ void bfs_closest(const int* head, const int* nxt, const int* e, const double* len, double* cdis, int* cid,
-                            int x, int* q_node, int* q_from, double* q_dis, unsigned int* s_tail, PlShared* prof) {
+                            int x, int* q_node, int* q_from, double* q_dis, unsigned int* s_tail, PlShared* prof,
+                            int leaf_limit, int split_node_min) {
     __shared__ unsigned int lo, hi;
     __shared__ PlQueue q;
     if (threadIdx.x == 0) {
@@ -49,8 +50,13 @@ __device__ void bfs_closest(const int* head, const int* nxt, const int* e, const
             const int k = (int)(w % 3u);
             const int node = t < PL_QCAP ? q.node[t] : q_node[t], fb = t < PL_QCAP ? q.from[t] : q_from[t];
             const double d = t < PL_QCAP ? q.dis[t] : q_dis[t];
+            // The slots of a node never change after it is created: a leaf (id < leaf_limit) has one, an inner node made
+            // by split_edge (id >= split_node_min) has head, head - 2, head - 3 (c3, c1, c0); only nodes of a loaded
+            // backbone need the linked list.
             int s = head[node];
-            for (int j = 0; j < k && s != -1; j++) s = nxt[s];
+            if (node < leaf_limit) { if (k > 0) continue; }
+            else if (node >= split_node_min) s -= (k == 0 ? 0 : k + 1);
+            else for (int j = 0; j < k && s != -1; j++) s = nxt[s];
             if (s == -1) continue;
             // one round trip for everything the slot needs: target node, length, the 5-entry list
             const int to = e[s];
@@ -89,7 +95,7 @@ __device__ void bfs_closest(const int* head, const int* nxt, const int* e, const
 __global__ void __launch_bounds__(PL_THREADS)
 place_batch_kernel(int* head, int* e, int* nxt, int* belong, double* len, int* cid, double* cdis, int* rev,
                    const double* __restrict__ rows, size_t ld, int row_base, int i0, int i1, int node_off, PlShared* ps,
-                   PlCand* cta_best, int* q_node, int* q_from, double* q_dis, unsigned int gen0, int profile) {
+                   PlCand* cta_best, int* q_node, int* q_from, double* q_dis, unsigned int gen0, int profile, int first_split_tip) {
     __shared__ PlCand sb[PL_THREADS / 32];
     __shared__ unsigned int s_tail;
     const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -162,7 +168,7 @@ place_batch_kernel(int* head, int* e, int* nxt, int* belong, double* len, int* c
             }
             __syncthreads();
             PL_MARK(5);
-            bfs_closest(head, nxt, e, len, cdis, cid, i, q_node, q_from, q_dis, &s_tail, profile ? ps : nullptr);
+            bfs_closest(head, nxt, e, len, cdis, cid, i, q_node, q_from, q_dis, &s_tail, profile ? ps : nullptr, node_off, first_split_tip + node_off - 1);
         }
         PL_MARK(2);
         pl_grid_barrier(&ps->bar_counter, G, gen);
@@ -197,8 +203,8 @@ __global__ void place_first_two_kernel(int* head, int* e, int* nxt, int* belong,
         ps->idx = 4;
     }
     __syncthreads();
-    bfs_closest(head, nxt, e, len, cdis, cid, 0, q_node, q_from, q_dis, &s_tail, nullptr);
-    bfs_closest(head, nxt, e, len, cdis, cid, 1, q_node, q_from, q_dis, &s_tail, nullptr);
+    bfs_closest(head, nxt, e, len, cdis, cid, 0, q_node, q_from, q_dis, &s_tail, nullptr, 0, 0x7fffffff);
+    bfs_closest(head, nxt, e, len, cdis, cid, 1, q_node, q_from, q_dis, &s_tail, nullptr, 0, 0x7fffffff);
 }
 
 // backbone: reverse-slot table + closest lists of leaves 0..B-1 in order (:241-260)
@@ -212,7 +218,7 @@ __global__ void place_backbone_kernel(int* head, int* e, int* nxt, int* belong, 
     }
     if (threadIdx.x == 0) ps->idx = nslots;
     __syncthreads();
-    for (int i = 0; i < B; i++) bfs_closest(head, nxt, e, len, cdis, cid, i, q_node, q_from, q_dis, &s_tail, nullptr);
+    for (int i = 0; i < B; i++) bfs_closest(head, nxt, e, len, cdis, cid, i, q_node, q_from, q_dis, &s_tail, nullptr, 0, 0x7fffffff);
 }
 
 int tree_alloc(dipb_ctx* c, int n, dipb_tree** out) {
@@ -286,7 +292,7 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int 
         if (rc) break;
         int node_off = n_alloc;
         void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &t->cid, &t->cdis, &t->rev, &rows, &ldr, &row_base,
-                        &i0, &i1, &node_off, &sc->ps, &cb, &sc->q_node, &sc->q_from, &sc->q_dis, &gen0, &profile};
+                        &i0, &i1, &node_off, &sc->ps, &cb, &sc->q_node, &sc->q_from, &sc->q_dis, &gen0, &profile, &first_tip};
         cudaError_t e = cudaLaunchCooperativeKernel((void*)place_batch_kernel, dim3(G), dim3(PL_THREADS), args, 0, c->stream);
         if (e != cudaSuccess) { set_error("placement: cooperative launch failed: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; break; }
         c->launches++;
