@@ -534,7 +534,7 @@ static int tc_launch_c(dipb_msa* m, TileListFn make_tiles, const void* arg, TcPa
         (rc = make_map(encode, &mVA, m->tc_V, m->tc_kv, m->tc_rows, TC_M / CN)) || (rc = make_map(encode, &mVB, m->tc_V, m->tc_kv, m->tc_rows, TC_N / CM)))
         return rc;
     int2* d_tiles = nullptr;
-    DIPB_CUDA(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
+    DIPB_CUDA(pool_alloc(c, (void**)&d_tiles, sizeof(int2) * tiles.size()));
     DIPB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
     p.tiles = d_tiles; p.num_tiles = (int)tiles.size();
     p.ns_chunks = (int)(m->tc_ks / TC_KB); p.nv_chunks = (int)(m->tc_kv / TC_KB);
@@ -543,10 +543,10 @@ static int tc_launch_c(dipb_msa* m, TileListFn make_tiles, const void* arg, TcPa
     cfg.gridDim = dim3(use * CSZ);
     void* args[] = {&mSA, &mSB, &mVA, &mVB, &p};
     cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
-    if (e != cudaSuccess) { cudaFree(d_tiles); set_error("msa_tc: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
+    if (e != cudaSuccess) { pool_free(c, d_tiles); set_error("msa_tc: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
     c->launches++;
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d_tiles);
+    pool_free(c, d_tiles);
     *launched = true;
     return 0;
 }
@@ -582,7 +582,7 @@ static int tc_launch_pair(dipb_msa* m, TileListFn make_tiles, const void* arg, T
     CUtensorMap mS, mV;
     if ((rc = make_map(encode, &mS, m->tc_S, m->tc_ks, m->tc_rows, 128)) || (rc = make_map(encode, &mV, m->tc_V, m->tc_kv, m->tc_rows, 128))) return rc;
     int2* d_tiles = nullptr;
-    DIPB_CUDA(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
+    DIPB_CUDA(pool_alloc(c, (void**)&d_tiles, sizeof(int2) * tiles.size()));
     DIPB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
     p.tiles = d_tiles; p.num_tiles = (int)tiles.size();
     p.ns_chunks = (int)(m->tc_ks / TC_KB); p.nv_chunks = (int)(m->tc_kv / TC_KB);
@@ -591,10 +591,10 @@ static int tc_launch_pair(dipb_msa* m, TileListFn make_tiles, const void* arg, T
     cfg.gridDim = dim3(use * 2);
     void* args[] = {&mS, &mV, &p};
     cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)msa_tc2_kernel, args);
-    if (e != cudaSuccess) { cudaFree(d_tiles); set_error("msa_tc2: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
+    if (e != cudaSuccess) { pool_free(c, d_tiles); set_error("msa_tc2: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
     c->launches++;
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d_tiles);
+    pool_free(c, d_tiles);
     *launched = true;
     return 0;
 }

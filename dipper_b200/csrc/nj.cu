@@ -251,16 +251,16 @@ int nj_run(dipb_matrix* m, int algo, int32_t* child0, int32_t* child1, double* l
     Cand* bb = nullptr;
     const int scan_grid = c->num_sms * 4;
     const int upd_grid = (n + 1023) / 1024;
-    DIPB_CUDA(cudaMalloc(&U, sizeof(double) * n));
-    DIPB_CUDA(cudaMalloc(&u, sizeof(double) * n));
-    DIPB_CUDA(cudaMalloc(&partial, sizeof(double) * (upd_grid + 1)));
-    DIPB_CUDA(cudaMalloc(&l0, sizeof(double) * n));
-    DIPB_CUDA(cudaMalloc(&l1, sizeof(double) * n));
-    DIPB_CUDA(cudaMalloc(&c0, sizeof(int32_t) * n));
-    DIPB_CUDA(cudaMalloc(&c1, sizeof(int32_t) * n));
-    DIPB_CUDA(cudaMalloc(&realID, sizeof(int) * n));
-    DIPB_CUDA(cudaMalloc(&st, sizeof(NJState)));
-    DIPB_CUDA(cudaMalloc(&bb, sizeof(Cand) * scan_grid));
+    DIPB_CUDA(pool_alloc(c, (void**)&U, sizeof(double) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&u, sizeof(double) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&partial, sizeof(double) * (upd_grid + 1)));
+    DIPB_CUDA(pool_alloc(c, (void**)&l0, sizeof(double) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&l1, sizeof(double) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&c0, sizeof(int32_t) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&c1, sizeof(int32_t) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&realID, sizeof(int) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&st, sizeof(NJState)));
+    DIPB_CUDA(pool_alloc(c, (void**)&bb, sizeof(Cand) * scan_grid));
     int rc = timer_begin(c);
     if (rc) return rc;
     nj_init_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(st, realID, n);
@@ -305,8 +305,8 @@ int nj_run(dipb_matrix* m, int algo, int32_t* child0, int32_t* child1, double* l
     DIPB_CUDA(cudaMemcpy(child1, c1, sizeof(int32_t) * (n - 1), cudaMemcpyDeviceToHost));
     DIPB_CUDA(cudaMemcpy(len0, l0, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost));
     DIPB_CUDA(cudaMemcpy(len1, l1, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost));
-    cudaFree(U); cudaFree(u); cudaFree(partial); cudaFree(l0); cudaFree(l1); cudaFree(c0); cudaFree(c1);
-    cudaFree(realID); cudaFree(st); cudaFree(bb);
+    pool_free(c, U); pool_free(c, u); pool_free(c, partial); pool_free(c, l0); pool_free(c, l1); pool_free(c, c0); pool_free(c, c1);
+    pool_free(c, realID); pool_free(c, st); pool_free(c, bb);
     return 0;
 }
 

@@ -27,6 +27,7 @@
 //   C  every CTA stages the selected rows (index, u, v, f) in shared memory, scans its column chunks of them,
 //      combines per-row minima in shared memory, pushes them to the row owners' K; publishes its winner  | barrier
 #include <cooperative_groups.h>
+#include <chrono>
 #include <cstdlib>
 #include <vector>
 #include "common.cuh"
@@ -63,6 +64,7 @@ struct NJCtl {                     // main cluster -> helper clusters doorbell (
 struct CStats {
     unsigned long long rows_scanned, bytes_scanned, iters;
     unsigned long long cyc[24];
+    unsigned long long t_ns, t_cycles;   // whole main loop: globaltimer ns and SM cycles (their ratio is the SM clock)
 };
 
 // lexicographic warp minimum of a u64 through two 32-bit redux ops
@@ -267,6 +269,9 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     };
 
     long long tmark = clock64();
+    const long long cyc_begin = tmark;
+    unsigned long long ns_begin;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
 #define CL_MARK(k)                                                      \
     do {                                                                \
         if (PROF && rank == 0 && tid == 0) {                            \
@@ -702,6 +707,10 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
         if (HC > 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->bell), "l"(KMAX) : "memory");
         stats->iters = (unsigned long long)iter;
         for (int k = 0; k < 24; k++) stats->cyc[k] = s_cyc[k];
+        unsigned long long ns_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+        stats->t_ns = ns_end - ns_begin;
+        stats->t_cycles = (unsigned long long)(clock64() - cyc_begin);
     }
     if (rank == 0 && lane == 0 && my_rows) { atomicAdd(&stats->rows_scanned, my_rows); atomicAdd(&stats->bytes_scanned, my_bytes); }
     cluster.sync();   // no CTA may exit while peers can still read its shared memory
@@ -756,16 +765,23 @@ bool nj_cluster_fits(int n) {
 int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* c0, int32_t* c1, double* l0, double* l1) {
     dipb_ctx* c = m->ctx;
     const int n = m->n;
+    auto t_host0 = std::chrono::steady_clock::now();
+    double t_host[5] = {0, 0, 0, 0, 0};   // DIPB_NJ_PROFILE: allocations + margin scale, launch, kernel, replay, frees (ms)
+    auto lap = [&](int k) {
+        auto now = std::chrono::steady_clock::now();
+        t_host[k] += std::chrono::duration<double, std::milli>(now - t_host0).count();
+        t_host0 = now;
+    };
     int* sel = nullptr;
     CStats* stats = nullptr;
     NJCtl* ctl = nullptr;
     int2* log_xy = nullptr;
     double2* log_bl = nullptr;
-    DIPB_CUDA(cudaMalloc(&sel, sizeof(int) * n));
-    DIPB_CUDA(cudaMalloc(&stats, sizeof(CStats)));
-    DIPB_CUDA(cudaMalloc(&ctl, sizeof(NJCtl)));
-    DIPB_CUDA(cudaMalloc(&log_xy, sizeof(int2) * n));
-    DIPB_CUDA(cudaMalloc(&log_bl, sizeof(double2) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&sel, sizeof(int) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&stats, sizeof(CStats)));
+    DIPB_CUDA(pool_alloc(c, (void**)&ctl, sizeof(NJCtl)));
+    DIPB_CUDA(pool_alloc(c, (void**)&log_xy, sizeof(int2) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&log_bl, sizeof(double2) * n));
     DIPB_CUDA(cudaMemsetAsync(stats, 0, sizeof(CStats), c->stream));
     DIPB_CUDA(cudaMemsetAsync(ctl, 0, sizeof(NJCtl), c->stream));
     // scale of the safety margin: twice the largest |u| of the input (as nj_pruned.cu)
@@ -781,6 +797,7 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     double* Dp = m->d;
     int n_total = n;
     const int profile = getenv("DIPB_NJ_PROFILE") ? 1 : 0;
+    lap(0);
     const char* force = getenv("DIPB_NJ_CLUSTER");   // 8 or 16; default: 16 when the device can co-schedule it
     const int want = force ? atoi(force) : 16;
     const char* hp = getenv("DIPB_NJ_HELPERS");      // helper clusters for the column stores (default: all that fit, at most 7)
@@ -790,8 +807,12 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     int rc = 0;
     void* args[] = {&Dp, &ld, &U, &u, &sel, &stats, &log_xy, &log_bl, &n_total, &LS, &dmax, &ctl, &HC};
     // 1024 threads, 8 loads in flight per lane: measured best of {512, 1024} x {8, 16} (profiles/r1_nj_cluster_tuning.json)
+    const char* e_uc = getenv("DIPB_NJ_UC");
+    const int uc = e_uc ? atoi(e_uc) : 8;
     if (want >= 16) {
-        rc = profile ? launch_cluster<16, 1024, 8, true>(c, n, args, &LS, &HC, max_helpers, &ok) : launch_cluster<16, 1024, 8, false>(c, n, args, &LS, &HC, max_helpers, &ok);
+        if (profile) rc = launch_cluster<16, 1024, 8, true>(c, n, args, &LS, &HC, max_helpers, &ok);
+        else if (uc == 4) rc = launch_cluster<16, 1024, 4, false>(c, n, args, &LS, &HC, max_helpers, &ok);
+        else rc = launch_cluster<16, 1024, 8, false>(c, n, args, &LS, &HC, max_helpers, &ok);
         used = 16;
     }
     if (!rc && !ok) {
@@ -799,9 +820,11 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
         used = 8;
     }
     if (!rc && !ok) { set_error("nj_cluster: no cluster configuration fits this device"); rc = DIPB_E_UNSUPPORTED; }
-    if (rc) { cudaFree(sel); cudaFree(stats); cudaFree(ctl); cudaFree(log_xy); cudaFree(log_bl); return rc; }
+    if (rc) { pool_free(c, sel); pool_free(c, stats); pool_free(c, ctl); pool_free(c, log_xy); pool_free(c, log_bl); return rc; }
     c->launches++;
+    lap(1);
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
+    lap(2);
     {
         // replay of realID / tree bookkeeping (src/neighborJoining.cu:233-237) from the device log
         const int iters = n - 2;
@@ -825,6 +848,7 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
         DIPB_CUDA(cudaMemcpy(l1, hl1.data(), sizeof(double) * iters, cudaMemcpyHostToDevice));
         DIPB_CUDA(cudaMemcpy(realID, rid.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     }
+    lap(3);
     CStats hs;
     DIPB_CUDA(cudaMemcpy(&hs, stats, sizeof(hs), cudaMemcpyDeviceToHost));
     c->nj_rows_scanned = hs.rows_scanned;
@@ -833,6 +857,8 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     if (profile) {
         const char* nm[12] = {"D pick + pool", "A update + push", "barrier 1", "B1 canonical sum", "B1 pool eval + push", "barrier 2",
                               "B2 fold + select", "barrier 3", "C stage tile", "C scan units", "C keys + reduce + publish", "barrier 4"};
+        fprintf(stderr, "[nj_cluster] main loop: %.1f ms, %.3f G cycles -> SM clock %.0f MHz while it ran\n", hs.t_ns * 1e-6, hs.t_cycles * 1e-9,
+                hs.t_ns ? 1e3 * (double)hs.t_cycles / (double)hs.t_ns : 0.0);
         fprintf(stderr, "[nj_cluster] rescans of rank 0's rows: %llu without a tracked partner, %llu partner is a contender, %llu runner-up bound reached ub\n",
                 hs.cyc[12], hs.cyc[13], hs.cyc[14]);
         double tot = 0;
@@ -843,7 +869,9 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
             fprintf(stderr, "[nj_cluster]   %-26s %8.0f cyc/iter  %5.1f%%\n", nm[k], hs.iters ? hs.cyc[k] / (double)hs.iters : 0.0,
                     tot > 0 ? 100.0 * hs.cyc[k] / tot : 0.0);
     }
-    cudaFree(sel); cudaFree(stats); cudaFree(ctl); cudaFree(log_xy); cudaFree(log_bl);
+    pool_free(c, sel); pool_free(c, stats); pool_free(c, ctl); pool_free(c, log_xy); pool_free(c, log_bl);
+    lap(4);
+    if (profile) fprintf(stderr, "[nj_cluster] host ms: alloc+scale %.1f, launch %.1f, kernel wait %.1f, replay %.1f, profile print + frees %.1f\n", t_host[0], t_host[1], t_host[2], t_host[3], t_host[4]);
     return 0;
 }
 

@@ -435,13 +435,13 @@ int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJStat
     PCand* cb = nullptr;
     PShared* ps = nullptr;
     const int nblk = (n + PT - 1) / PT + 1;
-    DIPB_CUDA(cudaMalloc(&K, sizeof(unsigned long long) * n));
-    DIPB_CUDA(cudaMalloc(&psum, sizeof(double) * nblk));
-    DIPB_CUDA(cudaMalloc(&pmax, sizeof(double) * nblk));
-    DIPB_CUDA(cudaMalloc(&sel, sizeof(int) * n));
-    DIPB_CUDA(cudaMalloc(&cb, sizeof(PCand) * G));
-    DIPB_CUDA(cudaMalloc(&ps, sizeof(PShared)));
-    DIPB_CUDA(cudaMalloc(&dmax_d, sizeof(double)));
+    DIPB_CUDA(pool_alloc(c, (void**)&K, sizeof(unsigned long long) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&psum, sizeof(double) * nblk));
+    DIPB_CUDA(pool_alloc(c, (void**)&pmax, sizeof(double) * nblk));
+    DIPB_CUDA(pool_alloc(c, (void**)&sel, sizeof(int) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&cb, sizeof(PCand) * G));
+    DIPB_CUDA(pool_alloc(c, (void**)&ps, sizeof(PShared)));
+    DIPB_CUDA(pool_alloc(c, (void**)&dmax_d, sizeof(double)));
     DIPB_CUDA(cudaMemsetAsync(ps, 0, sizeof(PShared), c->stream));
     DIPB_CUDA(cudaMemsetAsync(K, 0, sizeof(unsigned long long) * n, c->stream));       // 0 = "rescan me"
     // scale for the safety margin: the initial row sums bound every later |d| and |u|
@@ -460,10 +460,10 @@ int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJStat
     unsigned int* flags = nullptr;
     int2* log_xy = nullptr;
     double2* log_bl = nullptr;
-    DIPB_CUDA(cudaMalloc(&flags, sizeof(unsigned int) * 1024));
+    DIPB_CUDA(pool_alloc(c, (void**)&flags, sizeof(unsigned int) * 1024));
     DIPB_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * 1024, c->stream));
-    DIPB_CUDA(cudaMalloc(&log_xy, sizeof(int2) * n));
-    DIPB_CUDA(cudaMalloc(&log_bl, sizeof(double2) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&log_xy, sizeof(int2) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&log_bl, sizeof(double2) * n));
     void* args[] = {&Dp, &ld, &U, &u, &K, &psum, &pmax, &sel, &cb, &ps, &flags, &log_xy, &log_bl, &n_total, &dmax};
     cudaError_t e = cudaLaunchCooperativeKernel((void*)nj_pruned_kernel, dim3(G), dim3(PT), args, 0, c->stream);
     if (e != cudaSuccess) { set_error("nj_pruned: cooperative launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
@@ -492,7 +492,7 @@ int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJStat
         DIPB_CUDA(cudaMemcpy(l1, hl1.data(), sizeof(double) * iters, cudaMemcpyHostToDevice));
         DIPB_CUDA(cudaMemcpy(realID, rid.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     }
-    cudaFree(flags); cudaFree(log_xy); cudaFree(log_bl);
+    pool_free(c, flags); pool_free(c, log_xy); pool_free(c, log_bl);
     PShared hs;
     DIPB_CUDA(cudaMemcpy(&hs, ps, sizeof(hs), cudaMemcpyDeviceToHost));
     c->nj_rows_scanned = hs.rows_scanned;
@@ -508,7 +508,7 @@ int nj_pruned_loop(dipb_matrix* m, double* U, double* u, double* partial, NJStat
             fprintf(stderr, "[nj_pruned]   %-18s %10.0f cyc/iter  %5.1f%%\n", nm[k], hs.iters ? hs.cyc[k] / (double)hs.iters : 0.0,
                     tot > 0 ? 100.0 * hs.cyc[k] / tot : 0.0);
     }
-    cudaFree(K); cudaFree(psum); cudaFree(pmax); cudaFree(sel); cudaFree(cb); cudaFree(ps); cudaFree(dmax_d);
+    pool_free(c, K); pool_free(c, psum); pool_free(c, pmax); pool_free(c, sel); pool_free(c, cb); pool_free(c, ps); pool_free(c, dmax_d);
     return 0;
 }
 

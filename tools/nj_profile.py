@@ -11,7 +11,7 @@ ctx = api.Context(0)
 prm = api.Param(distanceType=2, in_="m")
 msa = api.MSADeviceArrays(ctx)
 msa.allocateDeviceArrays(P, np.full(n, L, np.uint64), n, prm)
-for rep in range(2):
+for rep in range(int(os.environ.get("NJ_REPS", "2"))):
     nj = api.NJDeviceArrays(ctx)
     nj.getDismatrix(n, prm, msaDeviceArrays=msa)
     nj.findNeighbourJoiningTree(["T%d" % i for i in range(n)], int(os.environ.get("NJ_ALGO", "0")))
