@@ -260,10 +260,11 @@ struct dipb_dc_state {
 
 static void dc_free_stage3(dipb_dc_state* st) {
     if (!st->stage3_ready) return;
-    cudaFree(st->d_slot); cudaFree(st->d_off); cudaFree(st->d_tips);
-    cudaFree(st->a.leaf_mask); cudaFree(st->a.distm); cudaFree(st->a.edge_mask);
-    cudaFree(st->a.q_node); cudaFree(st->a.q_from); cudaFree(st->a.q_dis); cudaFree(st->a.pos_of); cudaFree(st->a.owner);
-    cudaFree(st->a.next_cluster);
+    dipb_ctx* c = st->ctx;
+    pool_free(c, st->d_slot); pool_free(c, st->d_off); pool_free(c, st->d_tips);
+    pool_free(c, st->a.leaf_mask); pool_free(c, st->a.distm); pool_free(c, st->a.edge_mask);
+    pool_free(c, st->a.q_node); pool_free(c, st->a.q_from); pool_free(c, st->a.q_dis); pool_free(c, st->a.pos_of); pool_free(c, st->a.owner);
+    pool_free(c, st->a.next_cluster);
     st->stage3_ready = false;
 }
 
@@ -283,7 +284,7 @@ int dipb_dc_begin(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone,
     PlaceScratch sc;
     rc = place_scratch_alloc(c, n, &sc);
     if (!rc) rc = place_from_scratch(c, src, n, backbone, st->tree, &sc);
-    place_scratch_free(&sc);
+    place_scratch_free(c, &sc);
     if (rc) { dipb_tree_free(st->tree); delete st; return rc; }
     st->cl.assign(n, -1);
     *out = st;
@@ -300,12 +301,12 @@ int dipb_dc_assign(dipb_dc_state* st, int q0, int q1, int32_t* h_cluster) {
     const int B = st->B, nslots = 4 * B - 4;
     DIPB_CUDA(cudaSetDevice(c->device));
     int* d_cluster = nullptr;
-    DIPB_CUDA(cudaMalloc(&d_cluster, sizeof(int) * (q1 - q0)));
+    DIPB_CUDA(pool_alloc(c, (void**)&d_cluster, sizeof(int) * (q1 - q0)));
     int qb = 1024;
     const size_t ld = (size_t)((B + 127) / 128 * 128);
     while ((size_t)qb * ld * sizeof(double) > (1ull << 30) && qb > 128) qb /= 2;
     double* buf = nullptr;
-    if (!src->matrix) DIPB_CUDA(cudaMalloc(&buf, (size_t)qb * ld * sizeof(double)));
+    if (!src->matrix) DIPB_CUDA(pool_alloc(c, (void**)&buf, (size_t)qb * ld * sizeof(double)));
     int rc = 0;
     for (int a0 = q0; a0 < q1 && !rc; a0 += qb) {
         int a1 = a0 + qb < q1 ? a0 + qb : q1;
@@ -321,10 +322,10 @@ int dipb_dc_assign(dipb_dc_state* st, int q0, int q1, int32_t* h_cluster) {
         c->launches++;
     }
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    if (buf) cudaFree(buf);
+    if (buf) pool_free(c, buf);
     if (!rc && e != cudaSuccess) { set_error("dipb_dc_assign: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; }
     if (!rc && cudaMemcpy(h_cluster, d_cluster, sizeof(int) * (q1 - q0), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("dipb_dc_assign: D2H failed"); rc = DIPB_E_CUDA; }
-    cudaFree(d_cluster);
+    pool_free(c, d_cluster);
     return rc;
 }
 
@@ -355,18 +356,18 @@ int dipb_dc_set_clusters(dipb_dc_state* st, const int32_t* h_cluster_all, int* n
     a.head = t->head; a.e = t->e; a.nxt = t->nxt; a.belong = t->belong; a.cid = t->cid; a.rev = t->rev; a.len = t->len; a.cdis = t->cdis;
     a.n = n; a.B = B; a.num_clusters = nc;
     const size_t lm_sz = (size_t)10 * nc + ntips, em_sz = (size_t)4 * nc + 4 * (size_t)ntips + 8;
-    DIPB_CUDA(cudaMalloc(&st->d_slot, sizeof(int) * (nc + 1)));
-    DIPB_CUDA(cudaMalloc(&st->d_off, sizeof(int) * (nc + 1)));
-    DIPB_CUDA(cudaMalloc(&st->d_tips, sizeof(int) * (ntips + 1)));
-    DIPB_CUDA(cudaMalloc(&a.leaf_mask, sizeof(int) * lm_sz));
-    DIPB_CUDA(cudaMalloc(&a.distm, sizeof(double) * lm_sz));
-    DIPB_CUDA(cudaMalloc(&a.edge_mask, sizeof(int) * em_sz));
-    DIPB_CUDA(cudaMalloc(&a.q_node, sizeof(int) * em_sz));
-    DIPB_CUDA(cudaMalloc(&a.q_from, sizeof(int) * em_sz));
-    DIPB_CUDA(cudaMalloc(&a.q_dis, sizeof(double) * em_sz));
-    DIPB_CUDA(cudaMalloc(&a.pos_of, sizeof(int) * n));
-    DIPB_CUDA(cudaMalloc(&a.owner, sizeof(int) * 8 * (size_t)n));
-    DIPB_CUDA(cudaMalloc(&a.next_cluster, sizeof(unsigned int)));
+    DIPB_CUDA(pool_alloc(c, (void**)&st->d_slot, sizeof(int) * (nc + 1)));
+    DIPB_CUDA(pool_alloc(c, (void**)&st->d_off, sizeof(int) * (nc + 1)));
+    DIPB_CUDA(pool_alloc(c, (void**)&st->d_tips, sizeof(int) * (ntips + 1)));
+    DIPB_CUDA(pool_alloc(c, (void**)&a.leaf_mask, sizeof(int) * lm_sz));
+    DIPB_CUDA(pool_alloc(c, (void**)&a.distm, sizeof(double) * lm_sz));
+    DIPB_CUDA(pool_alloc(c, (void**)&a.edge_mask, sizeof(int) * em_sz));
+    DIPB_CUDA(pool_alloc(c, (void**)&a.q_node, sizeof(int) * em_sz));
+    DIPB_CUDA(pool_alloc(c, (void**)&a.q_from, sizeof(int) * em_sz));
+    DIPB_CUDA(pool_alloc(c, (void**)&a.q_dis, sizeof(double) * em_sz));
+    DIPB_CUDA(pool_alloc(c, (void**)&a.pos_of, sizeof(int) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&a.owner, sizeof(int) * 8 * (size_t)n));
+    DIPB_CUDA(pool_alloc(c, (void**)&a.next_cluster, sizeof(unsigned int)));
     st->stage3_ready = true;
     DIPB_CUDA(cudaMemcpyAsync(st->d_slot, st->cl_slot.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, c->stream));
     DIPB_CUDA(cudaMemcpyAsync(st->d_off, st->cl_off.data(), sizeof(int) * (nc + 1), cudaMemcpyHostToDevice, c->stream));

@@ -241,15 +241,15 @@ int tree_alloc(dipb_ctx* c, int n, dipb_tree** out) {
 }
 
 int place_scratch_alloc(dipb_ctx* c, int n, PlaceScratch* s) {
-    DIPB_CUDA(cudaMalloc(&s->ps, sizeof(PlShared)));
+    DIPB_CUDA(pool_alloc(c, (void**)&s->ps, sizeof(PlShared)));
     DIPB_CUDA(cudaMemsetAsync(s->ps, 0, sizeof(PlShared), c->stream));
-    DIPB_CUDA(cudaMalloc(&s->q_node, sizeof(int) * (2 * (size_t)n + 8)));
-    DIPB_CUDA(cudaMalloc(&s->q_from, sizeof(int) * (2 * (size_t)n + 8)));
-    DIPB_CUDA(cudaMalloc(&s->q_dis, sizeof(double) * (2 * (size_t)n + 8)));
+    DIPB_CUDA(pool_alloc(c, (void**)&s->q_node, sizeof(int) * (2 * (size_t)n + 8)));
+    DIPB_CUDA(pool_alloc(c, (void**)&s->q_from, sizeof(int) * (2 * (size_t)n + 8)));
+    DIPB_CUDA(pool_alloc(c, (void**)&s->q_dis, sizeof(double) * (2 * (size_t)n + 8)));
     return 0;
 }
-void place_scratch_free(PlaceScratch* s) {
-    cudaFree(s->ps); cudaFree(s->q_node); cudaFree(s->q_from); cudaFree(s->q_dis);
+void place_scratch_free(dipb_ctx* c, PlaceScratch* s) {
+    pool_free(c, s->ps); pool_free(c, s->q_node); pool_free(c, s->q_from); pool_free(c, s->q_dis);
     *s = PlaceScratch();
 }
 
@@ -272,14 +272,14 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int 
         // keep the row buffer around 256 MB
         size_t want = (size_t)batch * ld * sizeof(double);
         while (want > (1ull << 28) && batch > 128) { batch /= 2; want /= 2; }
-        DIPB_CUDA(cudaMalloc(&buf, (size_t)batch * ld * sizeof(double)));
+        DIPB_CUDA(pool_alloc(c, (void**)&buf, (size_t)batch * ld * sizeof(double)));
     }
     int G = c->num_sms;
     int per_sm = 0;
     DIPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_batch_kernel, PL_THREADS, 0));
     if (per_sm < 1) { set_error("placement kernel does not fit"); return DIPB_E_CUDA; }
     PlCand* cb = nullptr;
-    DIPB_CUDA(cudaMalloc(&cb, sizeof(PlCand) * G));
+    DIPB_CUDA(pool_alloc(c, (void**)&cb, sizeof(PlCand) * G));
     int rc = 0;
     unsigned int gen0 = 0;
     int profile = getenv("DIPB_PLACE_PROFILE") ? 1 : 0;
@@ -308,8 +308,8 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int 
                     first_tip, end, hs.cyc[0] / tips, hs.cyc[1] / tips, hs.cyc[4] / tips, hs.cyc[5] / tips, hs.cyc[2] / tips, hs.cyc[3] / tips, hs.bfs_levels / tips, hs.bfs_nodes / tips);
         }
     }
-    cudaFree(cb);
-    if (buf) cudaFree(buf);
+    pool_free(c, cb);
+    if (buf) pool_free(c, buf);
     return rc;
 }
 
@@ -320,15 +320,15 @@ int place_from_scratch(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, in
     int rc = 0;
     if (src->matrix) d01 = src->matrix->d + (size_t)src->matrix->n;   // row 1, column 0
     else {
-        DIPB_CUDA(cudaMalloc(&row1, sizeof(double) * 8));
+        DIPB_CUDA(pool_alloc(c, (void**)&row1, sizeof(double) * 8));
         rc = src->msa ? msa_block(src->msa, src->dist_type, 1, 2, 1, row1, 8) : dipb_mash_dist_block(src->mash, 1, 2, 1, row1, 8);
-        if (rc) { cudaFree(row1); return rc; }
+        if (rc) { pool_free(c, row1); return rc; }
         d01 = row1;
     }
     place_first_two_kernel<<<1, PL_THREADS, 0, c->stream>>>(t->head, t->e, t->nxt, t->belong, t->len, t->cid, t->cdis, t->rev, d01, n_alloc, sc->ps, sc->q_node, sc->q_from, sc->q_dis);
     DIPB_KERNEL_CHECK(c);
     rc = place_run(c, src, n_alloc, 2, end, t, sc);
-    if (row1) cudaFree(row1);
+    if (row1) pool_free(c, row1);
     return rc;
 }
 
@@ -359,7 +359,7 @@ int dipb_place_kclosest(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tr
     PlaceScratch sc;
     rc = place_scratch_alloc(c, n, &sc);
     if (!rc) rc = place_from_scratch(c, src, n, n, t, &sc);
-    place_scratch_free(&sc);
+    place_scratch_free(c, &sc);
     if (rc) { dipb_tree_free(t); return rc; }
     rc = timer_end(c, DIPB_T_PLACE);
     if (rc) return rc;
@@ -394,7 +394,7 @@ int dipb_place_add(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone
     place_backbone_kernel<<<1, PL_THREADS, 0, c->stream>>>(t->head, t->e, t->nxt, t->belong, t->len, t->cid, t->cdis, t->rev, 4 * backbone - 4, backbone, sc.ps, sc.q_node, sc.q_from, sc.q_dis);
     DIPB_KERNEL_CHECK(c);
     rc = place_run(c, src, n, backbone, n, t, &sc);
-    place_scratch_free(&sc);
+    place_scratch_free(c, &sc);
     if (rc) { dipb_tree_free(t); return rc; }
     rc = timer_end(c, DIPB_T_PLACE);
     if (rc) return rc;

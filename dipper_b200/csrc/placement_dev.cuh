@@ -199,7 +199,7 @@ struct PlaceScratch {
 };
 int tree_alloc(dipb_ctx* c, int n, dipb_tree** out);
 int place_scratch_alloc(dipb_ctx* c, int n, PlaceScratch* s);
-void place_scratch_free(PlaceScratch* s);
+void place_scratch_free(dipb_ctx* c, PlaceScratch* s);
 // builds the 2-leaf tree from d(1,0) and places tips [2, end) (src/placement_close_k.cu:646-854)
 int place_from_scratch(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int end, dipb_tree* t, PlaceScratch* sc);
 int check_source(const dipb_dist_source* s, int n);
