@@ -217,6 +217,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     __shared__ double s_red[MAXW], s_blk[128 + 16];         // s_blk: one sum per 1024-row block (n <= 131 072)
     __shared__ double s_total, s_C;
     __shared__ unsigned int s_sel;          // selected-row counter (rank 0's copy is the live one)
+    __shared__ int s_list[TILE];            // first TILE selected rows, in rank 0's copy (the rest spill to sel_rows in global
+                                            // memory; a list that was just written by 16 SMs reads back slowly from L2)
     __shared__ int pool_i[CPOOL], pool_j[CPOOL];
     __shared__ double pool_d[CPOOL];        // d of a carried pair never changes while both ends survive
     __shared__ double pool_t[CPOOL];        // its value at the last re-evaluation: new candidates replace worse ones only
@@ -465,7 +467,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         if (lane == 0) base = atomicAdd(sel0, (unsigned int)__popc(bal));
                         base = __shfl_sync(0xffffffffu, base, 0);
                         if (take) {
-                            sel_rows[base + __popc(bal & ((1u << lane) - 1u))] = i;
+                            const unsigned int pos = base + __popc(bal & ((1u << lane) - 1u));
+                            if (pos < (unsigned int)TILE) st_peer_s32(&s_list[pos], 0, i); else sel_rows[pos] = i;
                         }
                     }
                 }
@@ -480,7 +483,10 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 unsigned int base = 0;
                 if (lane == 0) base = atomicAdd(sel0, (unsigned int)__popc(bal));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (take) sel_rows[base + __popc(bal & ((1u << lane) - 1u))] = i;
+                if (take) {
+                    const unsigned int pos = base + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < (unsigned int)TILE) st_peer_s32(&s_list[pos], 0, i); else sel_rows[pos] = i;
+                }
             }
         }
         CL_MARK(6);
@@ -512,7 +518,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 const int tn = nsel - t0 < TILE ? nsel - t0 : TILE;
                 // stage the tile: row index, u, v, f of the row (owner's shared memory), empty combined minimum
                 for (int k = tid; k < tn; k += CT) {
-                    const int r = __ldcg(&sel_rows[t0 + k]);
+                    const int r = t0 + k < TILE ? ld_peer_s32(&s_list[t0 + k], 0) : __ldcg(&sel_rows[t0 + k]);
                     const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
                     t_row[k] = r;
                     t_u[k] = ld_peer_f64(&u_s[rs], ro);
@@ -637,6 +643,15 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
 
         // ---------------------------------------------------------------- D: pick (identical in every CTA)
         {
+            if (HC > 0 && tid == 32 && iter > 0) {
+                // the next update reads whole rows: the helpers must have finished the columns of the previous merge
+                // (one thread of warp 1 polls while the other warps pick the pair; the __syncthreads below publish it)
+                const unsigned int want = (unsigned int)iter * (unsigned int)HC;
+                unsigned int dn;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(&ctl->done) : "memory");
+                } while ((int)(dn - want) < 0);
+            }
             // partner records of a selection that fitted one tile (larger selections did this per tile in phase C)
             if (s_nsel <= TILE) partner_records(s_nsel, !first, x, y, n);
             if (w == 0) {
@@ -675,14 +690,6 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     pool_d[slot] = md;
                     pool_t[slot] = mt;
                 }
-            }
-            if (HC > 0 && tid == 0 && iter > 0) {
-                // the next update reads whole rows: the helpers must have finished the columns of the previous merge
-                const unsigned int want = (unsigned int)iter * (unsigned int)HC;
-                unsigned int dn;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(&ctl->done) : "memory");
-                } while ((int)(dn - want) < 0);
             }
             __syncthreads();
             if (tid == 0) {
