@@ -86,6 +86,13 @@ SIGNATURES = {
     "dipb_nj_newick": (vp, [C.c_int, i32p, i32p, f64p, f64p, C.POINTER(C.c_char_p)]),
     "dipb_tree_newick": (vp, [C.c_int, C.c_int, i32p, i32p, i32p, f64p, C.POINTER(C.c_char_p)]),
     "dipb_free_str": (None, [vp]),
+    "dipb_fasta_open": (C.c_int, [C.c_char_p, C.c_int, C.c_int, vpp]),
+    "dipb_fasta_count": (C.c_size_t, [vp]),
+    "dipb_fasta_name": (C.c_char_p, [vp, C.c_size_t]),
+    "dipb_fasta_lengths": (C.POINTER(C.c_uint64), [vp]),
+    "dipb_fasta_word_offsets": (C.POINTER(C.c_uint64), [vp]),
+    "dipb_fasta_words": (C.POINTER(C.c_uint64), [vp]),
+    "dipb_fasta_close": (None, [vp]),
     "dipb_backbone_from_newick": (C.c_int, [C.c_char_p, C.c_int, i32p, i32p, i32p, i32p, f64p, vpp]),
 }
 

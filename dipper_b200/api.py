@@ -7,6 +7,7 @@ is a parameter (reference hard-codes device 1, src/tree_generation.cu:240), erro
 raise DipperError instead of exit(1), and device rows come back as numpy arrays.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -424,6 +425,25 @@ class KPlacementDeviceArrays:
         if self.h:
             lib().dipb_tree_free(self.h)
             self.h = None
+
+
+def read_fasta_packed(path, bits, threads=0):
+    """Parallel FASTA ingest + packing (dipb_fasta_open): returns (names, lengths[n], word_offsets[n+1], words).
+    bits = 4 for aligned input (-i m), 2 for unaligned (-i r).  Replaces readSequences + the packing loops
+    (src/tree_generation.cu:132-154, 350-362, 478-490)."""
+    h = C.c_void_p()
+    check(lib().dipb_fasta_open(os.fsencode(path), bits, threads, C.byref(h)))
+    try:
+        L = lib()
+        n = L.dipb_fasta_count(h)
+        names = [L.dipb_fasta_name(h, i).decode() for i in range(n)]
+        off = np.ctypeslib.as_array(L.dipb_fasta_word_offsets(h), shape=(n + 1,)).copy()
+        lens = np.ctypeslib.as_array(L.dipb_fasta_lengths(h), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        nw = int(off[-1])
+        words = np.ctypeslib.as_array(L.dipb_fasta_words(h), shape=(nw,)).copy() if nw else np.zeros(0, np.uint64)
+    finally:
+        lib().dipb_fasta_close(h)
+    return names, lens, off, words
 
 
 def pack4(seq):

@@ -226,9 +226,25 @@ int main(int argc, char** argv) {
     }
 
     // ------------------------------------------------------------------ FASTA inputs
+    // Plain FASTA goes through the parallel memory-mapped reader, which also packs (dipb_fasta_open); gzip input keeps the
+    // zlib line reader and is packed below.
+    const bool aligned = in == "m";
     std::vector<std::string> seqs, names_in;
-    if (!read_fasta(input, seqs, names_in)) { fprintf(stderr, "ERROR: cant open file: %s\n", input.c_str()); return 1; }
-    const size_t n = seqs.size();
+    dipb_fasta* fa = nullptr;
+    {
+        int frc = dipb_fasta_open(input.c_str(), aligned ? 4 : 2, 0, &fa);
+        if (frc == DIPB_E_UNSUPPORTED) {
+            fa = nullptr;
+            if (!read_fasta(input, seqs, names_in)) { fprintf(stderr, "ERROR: cant open file: %s\n", input.c_str()); return 1; }
+        } else if (frc != 0) {
+            fprintf(stderr, "ERROR: cant open file: %s\n", input.c_str());
+            return 1;
+        } else {
+            names_in.resize(dipb_fasta_count(fa));
+            for (size_t i = 0; i < names_in.size(); i++) names_in[i] = dipb_fasta_name(fa, i);
+        }
+    }
+    const size_t n = names_in.size();
     if (n < 2) { std::cerr << "ERROR: need at least two sequences\n"; return 1; }
     std::vector<std::string> names(n);
     std::vector<size_t> ids(n);          // ids[i] = row of input sequence i
@@ -266,19 +282,23 @@ int main(int argc, char** argv) {
             std::shuffle(ids.begin(), ids.end(), rnd);
         }
     }
-    std::vector<std::vector<uint64_t>> packed(n);
+    std::vector<std::vector<uint64_t>> packed(fa ? 0 : n);
     std::vector<uint64_t> lens(n);
-    const bool aligned = in == "m";
-    parallel_for(n, [&](size_t i) {
-        const std::string& s = seqs[i];
-        std::vector<uint64_t> w((s.size() + (aligned ? 15 : 31)) / (aligned ? 16 : 32));
-        if (aligned) dipb_pack4(s.data(), s.size(), w.data()); else dipb_pack2(s.data(), s.size(), w.data());
-        packed[ids[i]] = std::move(w);
-        lens[ids[i]] = s.size();
-        names[ids[i]] = names_in[i];
-    });
     std::vector<const uint64_t*> ptrs(n);
-    for (size_t i = 0; i < n; i++) ptrs[i] = packed[i].data();
+    if (fa) {
+        const uint64_t *fl = dipb_fasta_lengths(fa), *fo = dipb_fasta_word_offsets(fa), *fw = dipb_fasta_words(fa);
+        for (size_t i = 0; i < n; i++) { ptrs[ids[i]] = fw + fo[i]; lens[ids[i]] = fl[i]; names[ids[i]] = names_in[i]; }
+    } else {
+        parallel_for(n, [&](size_t i) {
+            const std::string& s = seqs[i];
+            std::vector<uint64_t> w((s.size() + (aligned ? 15 : 31)) / (aligned ? 16 : 32));
+            if (aligned) dipb_pack4(s.data(), s.size(), w.data()); else dipb_pack2(s.data(), s.size(), w.data());
+            packed[ids[i]] = std::move(w);
+            lens[ids[i]] = s.size();
+            names[ids[i]] = names_in[i];
+        });
+        for (size_t i = 0; i < n; i++) ptrs[i] = packed[i].data();
+    }
     std::cerr << "Input in: " << ms_since(t_input) << " ms\n";
 
     auto t_alloc = Clock::now();
@@ -335,6 +355,7 @@ int main(int argc, char** argv) {
     std::cerr << "Tree Created in: " << ms_since(t_tree) << " ms\n";
     if (msa) dipb_msa_free(msa);
     if (mash) dipb_mash_free(mash);
+    if (fa) dipb_fasta_close(fa);
     dipb_destroy(ctx);
     return 0;
 }

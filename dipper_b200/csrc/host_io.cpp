@@ -1,9 +1,18 @@
 // Host-side pieces of dipper_b200 (include/dipper_host.h): encoders, Newick writer /
 // backbone reader.  Plain C++17; no CUDA here.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cctype>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/dipper_b200.h"
 #include "../../include/dipper_host.h"
@@ -22,6 +31,14 @@ struct Code4 {
     }
 };
 const Code4 kCode4;
+struct Code2 {   // twoBitCompressor: anything but A C G T/U packs as 0
+    unsigned char t[256];
+    Code2() {
+        for (int i = 0; i < 256; i++) t[i] = 0;
+        t['C'] = 1; t['G'] = 2; t['T'] = 3; t['U'] = 3;
+    }
+};
+const Code2 kCode2;
 
 void append_g(std::string& s, double v) {
     char buf[64];
@@ -63,6 +80,177 @@ void dipb_pack2(const char* seq, size_t len, uint64_t* out) {
         out[w] = v;
     }
 }
+
+// ---- FASTA ingest (dipper_host.h) -----------------------------------------------------------------
+}  // extern "C"
+
+struct dipb_fasta {
+    std::vector<std::string> names;
+    std::vector<uint64_t> lens, word_off;
+    uint64_t* words = nullptr;      // malloc'd, not zero-filled: the packing threads write (and first-touch) every word
+    ~dipb_fasta() { free(words); }
+};
+
+namespace {
+// isgraph() in the C locale, branch-free so that the counting loop vectorises
+inline bool is_graphic(unsigned char c) { return (unsigned)(c - 33) < 94u; }
+inline uint64_t count_graphic(const unsigned char* p, const unsigned char* end) {
+    uint64_t n = 0;
+    while (end - p >= 32) {                     // byte lanes: vectorises (psubb / pcmpgtb / psadbw); FASTA lines are 60-100 bytes
+        unsigned char acc = 0;
+        for (int i = 0; i < 32; i++) acc += (unsigned char)((unsigned char)(p[i] - 33) < 94);
+        n += acc;
+        p += 32;
+    }
+    for (; p < end; p++) n += (unsigned)(*p - 33) < 94u;
+    return n;
+}
+template <class F>
+void run_threads(unsigned nt, size_t n, F fn) {   // contiguous blocks of [0, n)
+    if (nt <= 1 || n < 2) { fn((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; t++) {
+        const size_t a = std::min(n, t * per), b = std::min(n, a + per);
+        if (a < b) th.emplace_back([=]() { fn(a, b); });
+    }
+    for (auto& x : th) x.join();
+}
+}  // namespace
+
+extern "C" {
+
+int dipb_fasta_open(const char* path, int bits, int threads, dipb_fasta** out) {
+    if (!path || !out || (bits != 2 && bits != 4)) { dipb::set_error("dipb_fasta_open: bad argument"); return DIPB_E_ARG; }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { dipb::set_error("dipb_fasta_open: cannot open %s", path); return DIPB_E_ARG; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); dipb::set_error("dipb_fasta_open: cannot stat %s", path); return DIPB_E_ARG; }
+    const size_t size = (size_t)sb.st_size;
+    dipb_fasta* f = new dipb_fasta();
+    if (size == 0) { close(fd); f->word_off.push_back(0); *out = f; return 0; }
+    const unsigned char* d = (const unsigned char*)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (d == MAP_FAILED) { delete f; dipb::set_error("dipb_fasta_open: mmap of %s failed", path); return DIPB_E_NOMEM; }
+    if (size >= 2 && d[0] == 0x1f && d[1] == 0x8b) {
+        munmap((void*)d, size); delete f;
+        dipb::set_error("dipb_fasta_open: %s is gzip-compressed", path);
+        return DIPB_E_UNSUPPORTED;
+    }
+    madvise((void*)d, size, MADV_SEQUENTIAL);
+    const bool prof = getenv("DIPB_FASTA_PROFILE") != nullptr;
+    auto tp = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        auto now = std::chrono::steady_clock::now();
+        if (prof) fprintf(stderr, "[fasta] %s %.1f ms\n", what, std::chrono::duration<double, std::milli>(now - tp).count());
+        tp = now;
+    };
+    unsigned nt = threads > 0 ? (unsigned)threads : std::max(1u, std::thread::hardware_concurrency());
+    if (size < (1u << 20)) nt = 1;
+    // pass 0: record starts ('>' in column 0), found chunk by chunk
+    std::vector<std::vector<size_t>> part(nt);
+    {
+        std::vector<std::thread> th;
+        const size_t per = (size + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; t++)
+            th.emplace_back([&, t]() {
+                const size_t a = std::min(size, t * per), b = std::min(size, a + per);
+                const unsigned char* p = d + a;
+                while (p < d + b) {
+                    const unsigned char* q = (const unsigned char*)memchr(p, '>', (size_t)(d + b - p));
+                    if (!q) break;
+                    if (q == d || q[-1] == '\n') part[t].push_back((size_t)(q - d));
+                    p = q + 1;
+                }
+            });
+        for (auto& x : th) x.join();
+    }
+    lap("record search");
+    std::vector<size_t> start;
+    for (auto& v : part) start.insert(start.end(), v.begin(), v.end());
+    const size_t n = start.size();
+    start.push_back(size);
+    f->names.resize(n); f->lens.assign(n, 0); f->word_off.assign(n + 1, 0);
+    std::vector<size_t> body(n);
+    // pass 1: names and lengths
+    run_threads(nt, n, [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; i++) {
+            const unsigned char* h = d + start[i] + 1;
+            const unsigned char* end = d + start[i + 1];
+            const unsigned char* nl = (const unsigned char*)memchr(h, '\n', (size_t)(end - h));
+            const unsigned char* hend = nl ? nl : end;
+            const unsigned char* w = h;
+            while (w < hend && !isspace(*w)) w++;
+            f->names[i].assign((const char*)h, (size_t)(w - h));
+            const unsigned char* s0 = nl ? nl + 1 : end;
+            body[i] = (size_t)(s0 - d);
+            const uint64_t len = count_graphic(s0, end);
+            f->lens[i] = len;
+        }
+    });
+    lap("names + lengths");
+    const unsigned per_word = bits == 4 ? 16 : 32;
+    for (size_t i = 0; i < n; i++) f->word_off[i + 1] = f->word_off[i] + (f->lens[i] + per_word - 1) / per_word;
+    f->words = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(f->word_off[n] + 1));
+    if (!f->words) { munmap((void*)d, size); delete f; dipb::set_error("dipb_fasta_open: out of memory"); return DIPB_E_NOMEM; }
+    lap("output allocation");
+    // pass 2: pack (same code tables as dipb_pack4 / dipb_pack2)
+    run_threads(nt, n, [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; i++) {
+            uint64_t* o = f->words + f->word_off[i];
+            const unsigned char* end = d + start[i + 1];
+            uint64_t v = 0, k = 0;
+            // line by line: a line that is all graphic characters (the usual case) is packed without per-byte tests
+            const unsigned char* p = d + body[i];
+            while (p < end) {
+                const unsigned char* nl = (const unsigned char*)memchr(p, '\n', (size_t)(end - p));
+                const unsigned char* q = nl ? nl : end;
+                const bool clean = count_graphic(p, q) == (uint64_t)(q - p);
+                const unsigned char* r = p;
+                if (clean) {
+                    // whole words' worth of characters at a time: independent table look-ups, then one shift into place
+                    const unsigned sh = bits == 4 ? 4u : 2u;
+                    for (; r + per_word <= q; r += per_word) {
+                        uint64_t w = 0;
+                        if (bits == 4) {
+#pragma GCC unroll 16
+                            for (unsigned j = 0; j < 16; j++) w |= (uint64_t)kCode4.t[r[j]] << (4 * j);
+                        } else {
+#pragma GCC unroll 32
+                            for (unsigned j = 0; j < 32; j++) w |= (uint64_t)kCode2.t[r[j]] << (2 * j);
+                        }
+                        const unsigned ph = (unsigned)(k & (per_word - 1)) * sh;   // bit position inside the open word
+                        v |= w << ph;
+                        *o++ = v;
+                        v = ph ? w >> (64 - ph) : 0;
+                        k += per_word;
+                    }
+                }
+                for (; r < q; r++) {
+                    if (!clean && !is_graphic(*r)) continue;
+                    const uint64_t c = kCode4.t[*r];
+                    if (bits == 4) v |= c << (4 * (k & 15));
+                    else v |= (c & 3 & (uint64_t)-(int64_t)(c < 4)) << (2 * (k & 31));
+                    k++;
+                    if ((k & (per_word - 1)) == 0) { *o++ = v; v = 0; }
+                }
+                p = q + 1;
+            }
+            if (k & (per_word - 1)) *o = v;
+        }
+    });
+    lap("pack");
+    munmap((void*)d, size);
+    lap("munmap");
+    *out = f;
+    return 0;
+}
+size_t dipb_fasta_count(const dipb_fasta* f) { return f ? f->names.size() : 0; }
+const char* dipb_fasta_name(const dipb_fasta* f, size_t i) { return (f && i < f->names.size()) ? f->names[i].c_str() : ""; }
+const uint64_t* dipb_fasta_lengths(const dipb_fasta* f) { return f ? f->lens.data() : nullptr; }
+const uint64_t* dipb_fasta_word_offsets(const dipb_fasta* f) { return f ? f->word_off.data() : nullptr; }
+const uint64_t* dipb_fasta_words(const dipb_fasta* f) { return f ? f->words : nullptr; }
+void dipb_fasta_close(dipb_fasta* f) { delete f; }
 
 char* dipb_nj_newick(int n, const int32_t* c0, const int32_t* c1, const double* l0, const double* l1,
                      const char* const* names) {

@@ -19,6 +19,22 @@ void dipb_pack4(const char *seq, size_t len, uint64_t *out /* ceil(len/16) words
 /* twoBitCompressor(std::string, size_t, uint64_t*)   src/twoBitCompressor.cpp:5-41 */
 void dipb_pack2(const char *seq, size_t len, uint64_t *out /* ceil(len/32) words */);
 
+/* FASTA ingest: readSequences (src/tree_generation.cu:132-154, one kseq loop building std::string per record) and
+ * the packing loops (:350-362 four-bit, :478-490 two-bit) in one pass over a memory-mapped file with all host threads:
+ * record starts are found in parallel, every record is measured and then packed straight into one flat word array.
+ * kseq semantics: a record starts at '>' in column 0, its name is the header up to the first white space, its
+ * sequence is every graphic character up to the next record; text before the first '>' is ignored.
+ * bits = 4: fourBitCompressor codes, 16 per word; bits = 2: twoBitCompressor codes, 32 per word.
+ * Plain (uncompressed) files only: returns DIPB_E_UNSUPPORTED for gzip input (the CLI then uses its zlib reader). */
+typedef struct dipb_fasta dipb_fasta;
+int dipb_fasta_open(const char *path, int bits, int threads /* 0 = all hardware threads */, dipb_fasta **out);
+size_t dipb_fasta_count(const dipb_fasta *f);
+const char *dipb_fasta_name(const dipb_fasta *f, size_t i);
+const uint64_t *dipb_fasta_lengths(const dipb_fasta *f);      /* [count] characters per sequence */
+const uint64_t *dipb_fasta_word_offsets(const dipb_fasta *f); /* [count + 1] first word of each sequence */
+const uint64_t *dipb_fasta_words(const dipb_fasta *f);        /* packed sequences, back to back */
+void dipb_fasta_close(dipb_fasta *f);
+
 /* Newick of an NJ result (src/neighborJoining.cu:252-270: children in push order,
  * lengths as ostream<<double, trailing ";\n").  Returns a malloc'd string (dipb_free_str). */
 char *dipb_nj_newick(int n, const int32_t *child0, const int32_t *child1, const double *len0, const double *len1,
