@@ -5,8 +5,8 @@ Workload (config C3, BASELINE.json configs[2]): synthetic aligned MSA, 30 000 ti
 30 000 sites, JC distance matrix (-d 2) then conventional NJ (-m 2).  One "step" = one
 full pass: packed sequences -> fp64 distance matrix -> NJ tree.
 
-  value   whole-job pairs/s with the packed sequences already resident in HBM
-          (distance matrix + NJ, device-timed with CUDA events on the library stream)
+  value   whole-job pairs/s with the packed sequences already resident in HBM: K steps between two
+          barriers + synchronize, max over ranks ("phases" are CUDA-event times inside the library)
   e2e     same metric through the public C ABI from HOST buffers: H2D of the 4-bit
           sequences + repack + distances + NJ + D2H of the tree, wall-clocked
   roofline  the NJ kernel (dominant: ~93 % of the step) against the measured HBM copy
@@ -20,8 +20,8 @@ full pass: packed sequences -> fp64 distance matrix -> NJ tree.
 
 `--impl reference` runs the reference's own CUDA objects (oracle/_ref/dipper_ref; the
 reference has no CPU path) on a bounded sample of the same workload.
-Multi-GPU (torchrun): the distance matrix is row-block sharded over ranks and summed
-onto rank 0 (NCCL reduce), NJ runs on rank 0 (BASELINE.json configs[2]).
+Multi-GPU (torchrun): the distance matrix is row-block sharded over ranks and gathered
+onto rank 0 (NCCL send/recv of the row blocks + a mirror kernel), NJ runs on rank 0 (BASELINE.json configs[2]).
 """
 import argparse
 import json
@@ -250,6 +250,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    tip_names = ["T%d" % (i + 1) for i in range(n)]
+
     def one_step(msa, timed):
         """resident-input step: distances (sharded) -> reduce -> NJ on rank 0. Returns (dist_ms, comm_ms, nj_ms)."""
         r0, r1 = shard(rank)
@@ -260,20 +262,35 @@ def main():
         d_ms = ctx.elapsed_ms(api.T_MSA_DIST)
         c_ms = 0.0
         if world > 1:
-            from dipper_b200._lib import lib
+            # gather: every other rank sends its row block (rows r0..r1 are contiguous in the matrix) to rank 0 over
+            # NCCL point-to-point; rank 0 mirrors the received rows.  (A sum-reduce of the whole 7.2 GB matrix took
+            # 292 ms at 2 GPUs; the row blocks of the other ranks are 2 GB.)
+            from dipper_b200._lib import lib, check
             ptr = lib().dipb_matrix_device_ptr(M.h)
             t = torch.as_tensor(DevView(ptr, n * n), device="cuda")
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            dist.reduce(t, dst=0)
+            if rank == 0:
+                for src in range(1, world):
+                    s0, s1 = shard(src)
+                    if s1 > s0:
+                        dist.recv(t[s0 * n:s1 * n], src=src)
+            elif r1 > r0:
+                dist.send(t[r0 * n:r1 * n], dst=0)
             e1.record()
             torch.cuda.synchronize()
             c_ms = e0.elapsed_time(e1)
+            if rank == 0:
+                for src in range(1, world):
+                    s0, s1 = shard(src)
+                    check(lib().dipb_matrix_mirror_rows(M.h, s0, s1))
+                    ctx.sync()
+                    c_ms += ctx.elapsed_ms(api.T_MSA_DIST)
         nj_ms = 0.0
         if rank == 0:
             nj = api.NJDeviceArrays(ctx)
             nj.matrix, nj.d_numSequences = M, n
-            nj.findNeighbourJoiningTree(["T%d" % (i + 1) for i in range(n)], args.nj_algo)
+            nj.findNeighbourJoiningTree(tip_names, args.nj_algo)
             nj_ms = ctx.elapsed_ms(api.T_NJ)
             nj.deallocateDeviceArrays()
         else:
@@ -298,17 +315,24 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.kernel_launches() - launches0
     ph = np.array(phases)
-    # device time of a step = dist (max over ranks) + comm + nj; reduce the per-rank maxima
-    step_ms = ph.sum(axis=1).mean()
+    # A step = everything between the two barriers divided by K: device phases (CUDA events inside the library, reported
+    # under "phases") plus the host work between them (tree replay, Newick text).
+    step_ms = t_wall * 1e3 / args.steps
     if world > 1:
-        tt = torch.tensor([ph[:, 0].mean(), ph[:, 1].mean(), ph[:, 2].mean(), float(launches)], device="cuda", dtype=torch.float64)
+        # Ranks overlap: a rank without NJ work runs one step ahead and then waits in its send, so per-rank phase times
+        # do not add up.  The step time is the max over ranks; the phases are those of rank 0, which owns the
+        # critical path (its distances, the gather, NJ).
+        tt = torch.tensor([ph[:, 0].mean(), ph[:, 1].mean(), ph[:, 2].mean(), float(launches), t_wall * 1e3 / args.steps],
+                          device="cuda", dtype=torch.float64)
         mx = tt.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tt.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        d_ms, c_ms, nj_ms = float(mx[0]), float(mx[1]), float(mx[2])
+        r0v = tt.clone()
+        dist.broadcast(r0v, src=0)
+        d_ms, c_ms, nj_ms = float(mx[0]), float(r0v[1]), float(r0v[2])
         launches = int(sm[3])
-        step_ms = d_ms + c_ms + nj_ms
+        step_ms = float(mx[4])
     else:
         d_ms, c_ms, nj_ms = ph[:, 0].mean(), ph[:, 1].mean(), ph[:, 2].mean()
     nj_stats = ctx.nj_stats() if rank == 0 else {}

@@ -61,6 +61,7 @@ SIGNATURES = {
     "dipb_matrix_n": (C.c_int, [vp]),
     "dipb_matrix_to_host": (C.c_int, [vp, f64p]),
     "dipb_matrix_device_ptr": (vp, [vp]),
+    "dipb_matrix_mirror_rows": (C.c_int, [vp, C.c_int, C.c_int]),
     "dipb_matrix_free": (None, [vp]),
     "dipb_nj": (C.c_int, [vp, C.c_int, i32p, i32p, f64p, f64p]),
     "dipb_nj_stats": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -251,6 +251,36 @@ __global__ void symmetrize_kernel(double* __restrict__ D, int n) {
     D[(size_t)j * n + i] = D[(size_t)i * n + j];
 }
 
+// tiled transpose of rows [r0, r1) below the diagonal into the columns above it
+__global__ void mirror_rows_kernel(double* __restrict__ D, int n, int r0, int r1) {
+    __shared__ double tile[32][33];
+    const int i0 = r0 + blockIdx.y * 32, j0 = blockIdx.x * 32;
+    if (j0 > i0 + 31) return;                       // tile entirely above the diagonal
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int k = ty; k < 32; k += 8) {
+        const int i = i0 + k, j = j0 + tx;
+        tile[k][tx] = (i < r1 && j < i) ? D[(size_t)i * n + j] : 0.0;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int j = j0 + k, i = i0 + tx;          // write D[j][i], coalesced along i
+        if (i < r1 && j < i) D[(size_t)j * n + i] = tile[tx][k];
+    }
+}
+
+int dipb_matrix_mirror_rows(dipb_matrix* m, int r0, int r1) {
+    if (!m || r0 < 0 || r1 > m->n || r0 > r1) { set_error("dipb_matrix_mirror_rows: bad argument"); return DIPB_E_ARG; }
+    if (r0 == r1) return 0;
+    dipb_ctx* c = m->ctx;
+    DIPB_CUDA(cudaSetDevice(c->device));
+    int rc = timer_begin(c);
+    if (rc) return rc;
+    dim3 grid((r1 + 31) / 32, (r1 - r0 + 31) / 32), block(32, 8);
+    mirror_rows_kernel<<<grid, block, 0, c->stream>>>(m->d, m->n, r0, r1);
+    DIPB_KERNEL_CHECK(c);
+    return timer_end(c, DIPB_T_MSA_DIST);
+}
+
 int dipb_matrix_from_host(dipb_ctx* c, const double* h, int n, int full, dipb_matrix** out) {
     if (!c || !h || !out || n < 2) { set_error("dipb_matrix_from_host: bad argument"); return DIPB_E_ARG; }
     DIPB_CUDA(cudaSetDevice(c->device));

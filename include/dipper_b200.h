@@ -121,6 +121,9 @@ int dipb_matrix_from_host(dipb_ctx *ctx, const double *h, int n, int full, dipb_
 int dipb_matrix_n(const dipb_matrix *m);
 int dipb_matrix_to_host(dipb_matrix *m, double *h_out /* n*n */);
 double *dipb_matrix_device_ptr(dipb_matrix *m);
+/* multi-GPU gather of a row-sharded matrix: after the rows [r0, r1) of another rank's shard have been copied into this
+ * matrix (they are contiguous), fill the mirrored entries D[j][i] = D[i][j], j < i, r0 <= i < r1 (fillDismatrix :20-32) */
+int dipb_matrix_mirror_rows(dipb_matrix *m, int r0, int r1);
 void dipb_matrix_free(dipb_matrix *m);
 
 /* ---- neighbor joining ---------------------------------------------------- */

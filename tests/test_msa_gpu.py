@@ -175,3 +175,30 @@ def test_tensor_core_row_sharded_matrix(ctx, oracle, cut, pair, monkeypatch):
     b = msa.distMatrix(prm, cut, n).to_host()
     monkeypatch.delenv("DIPB_MSA_TC")
     assert np.array_equal(a + b, full)
+
+
+def test_row_block_gather_and_mirror_equals_full_matrix(ctx, oracle):
+    """The multi-GPU gather of bench.py on one device: copy the other shard's (contiguous) rows into rank 0's
+    matrix, mirror them (dipb_matrix_mirror_rows) and compare with the unsharded matrix."""
+    import torch
+    from dipper_b200._lib import check, lib
+
+    class DevView:
+        def __init__(self, ptr, count):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+    n, L = 700, 900
+    codes, P, _ = make_msa(n, L, seed=91)
+    msa = upload(ctx, P, L)
+    prm = api.Param(distanceType=2, in_="m")
+    full = msa.distMatrix(prm).to_host()
+    cut = 384
+    A = msa.distMatrix(prm, 0, cut)
+    B = msa.distMatrix(prm, cut, n)
+    tA = torch.as_tensor(DevView(lib().dipb_matrix_device_ptr(A.h), n * n), device="cuda")
+    tB = torch.as_tensor(DevView(lib().dipb_matrix_device_ptr(B.h), n * n), device="cuda")
+    tA[cut * n:].copy_(tB[cut * n:])
+    torch.cuda.synchronize()
+    check(lib().dipb_matrix_mirror_rows(A.h, cut, n))
+    ctx.sync()
+    assert np.array_equal(A.to_host(), full)
