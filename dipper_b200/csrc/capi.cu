@@ -137,6 +137,8 @@ void dipb_msa_free(dipb_msa* m) {
     cudaFree(m->nv);
     pool_free(m->ctx, m->tc_S);
     pool_free(m->ctx, m->tc_V);
+    pool_free(m->ctx, m->tc_Sx);
+    pool_free(m->ctx, m->tc_Vx);
     delete m;
 }
 

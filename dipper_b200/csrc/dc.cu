@@ -13,9 +13,11 @@
 //    DC/placement_close_k.cpp:752-760); everything stays device-resident, no per-cluster
 //    host gather + H2D.
 #include <algorithm>
+#include <chrono>
 #include <vector>
 #include "common.cuh"
 #include "mash.cuh"
+#include "msa.cuh"
 #include "msa_pair.cuh"
 #include "placement_dev.cuh"
 
@@ -279,6 +281,8 @@ int dipb_dc_begin(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone,
     DIPB_CUDA(cudaSetDevice(c->device));
     dipb_dc_state* st = new dipb_dc_state();
     st->ctx = c; st->src = *src; st->n = n; st->B = backbone;
+    // tensor-core operands: only the backbone rows stay expanded; query batches use a scratch pair (msa_tc.cu)
+    if (src->msa) msa_tc_reserve(src->msa, backbone);
     rc = tree_alloc(c, n, &st->tree);
     if (rc) { delete st; return rc; }
     PlaceScratch sc;
@@ -302,7 +306,9 @@ int dipb_dc_assign(dipb_dc_state* st, int q0, int q1, int32_t* h_cluster) {
     DIPB_CUDA(cudaSetDevice(c->device));
     int* d_cluster = nullptr;
     DIPB_CUDA(pool_alloc(c, (void**)&d_cluster, sizeof(int) * (q1 - q0)));
-    int qb = 1024;
+    // queries per distance block: as many as fit a 1 GB row buffer (each block costs a launch set-up, a sync and, on the
+    // tensor-core path, an operand expansion: 186 blocks of 1024 queries took 360 ms at 200 000 tips, B = 10 000)
+    int qb = 16384;
     const size_t ld = (size_t)((B + 127) / 128 * 128);
     while ((size_t)qb * ld * sizeof(double) > (1ull << 30) && qb > 128) qb /= 2;
     double* buf = nullptr;
@@ -543,17 +549,29 @@ int dipb_dc(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone, dipb_
     if (!c) { set_error("dipb_dc: bad argument"); return DIPB_E_ARG; }
     int rc = timer_begin(c);
     if (rc) return rc;
+    const bool prof = getenv("DIPB_PLACE_PROFILE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        auto now = std::chrono::steady_clock::now();
+        if (prof) fprintf(stderr, "[dc] %s %.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
+        t0 = now;
+    };
     dipb_dc_state* st = nullptr;
     rc = dipb_dc_begin(c, src, n, backbone, &st);
     if (rc) return rc;
+    lap("stage 1 (backbone placement)");
     std::vector<int32_t> cl(n, -1);
     rc = dipb_dc_assign(st, backbone, n, cl.data() + backbone);
+    lap("stage 2 (query x backbone distances + assignment)");
     int nc = 0;
     if (!rc) rc = dipb_dc_set_clusters(st, cl.data(), &nc);
+    lap("cluster lists");
     if (!rc) rc = dipb_dc_run_clusters(st, 0, nc);
+    lap("stage 3 (in-cluster placement)");
     if (rc) { dipb_dc_finish(st, nullptr); return rc; }
     rc = dipb_dc_finish(st, out);
     if (rc) return rc;
+    lap("finish");
     return timer_end(c, DIPB_T_PLACE);
 }
 

@@ -19,9 +19,15 @@ struct dipb_msa {
     uint32_t* planes = nullptr;  // [npad/128][nkc][3][16][128]
     int* nv = nullptr;           // valid sites per sequence [npad]
     // tensor-core operands (msa_tc.cu), built on first use: simplex int8 [tc_rows][tc_ks], validity int8 [tc_rows][tc_kv]
+    // Persistent buffers hold the expanded rows [0, tc_have) out of a capacity of tc_rows (tc_reserve rows are requested
+    // by the caller that knows how many it needs: all for a full matrix / placement, the backbone for D&C); row
+    // blocks beyond the capacity (D&C query batches) are expanded into the scratch pair just before they are used.
     int8_t* tc_S = nullptr;
     int8_t* tc_V = nullptr;
-    size_t tc_ks = 0, tc_kv = 0, tc_rows = 0;
+    size_t tc_ks = 0, tc_kv = 0, tc_rows = 0, tc_have = 0, tc_reserve = 0;
+    int8_t* tc_Sx = nullptr;
+    int8_t* tc_Vx = nullptr;
+    size_t tc_xrows = 0;
 };
 
 namespace dipb {
@@ -32,4 +38,5 @@ int msa_counts_dev(dipb_msa* m, int i0, int i1, int j1, int* d_match, int* d_bot
 bool msa_tc_supported(const dipb_msa* m, int type);
 int msa_tc_matrix(dipb_msa* m, int type, int row_begin, int row_end, double* d_out);
 int msa_tc_block(dipb_msa* m, int type, int r0, int r1, int ncols, double* d_out, size_t ld);
+void msa_tc_reserve(dipb_msa* m, int rows);   // how many leading rows the persistent operand buffers should hold
 }  // namespace dipb

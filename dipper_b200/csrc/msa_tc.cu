@@ -32,16 +32,18 @@ constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barr
 constexpr int TC_THREADS = 192;
 
 // ---- operand expansion: planes -> simplex int8 (S) and validity int8 (V), K-major rows ----------
-__global__ void msa_tc_expand_kernel(const uint32_t* __restrict__ planes, int n, int nkc, int w32, int8_t* __restrict__ S,
+// rows [row0, row0 + nrows) of the alignment into rows 0.. of S / V
+__global__ void msa_tc_expand_kernel(const uint32_t* __restrict__ planes, int row0, int nrows, int nkc, int w32, int8_t* __restrict__ S,
                                      size_t ks, int8_t* __restrict__ V, size_t kv) {
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)n * w32) return;
-    const int s = (int)(gid / w32), w = (int)(gid % w32);
+    if (gid >= (long long)nrows * w32) return;
+    const int sd = (int)(gid / w32), w = (int)(gid % w32);
+    const int s = row0 + sd;
     const int sb = s / MSA_TS, sl = s % MSA_TS, kc = w / MSA_KC, kk = w % MSA_KC;
     const size_t base = ((size_t)sb * nkc + kc) * MSA_SLAB_WORDS + (size_t)kk * MSA_TS + sl;
     const uint32_t b0 = planes[base], b1 = planes[base + MSA_KC * MSA_TS], v = planes[base + 2 * MSA_KC * MSA_TS];
-    int8_t* so = S + (size_t)s * ks + (size_t)w * 96;
-    int8_t* vo = V + (size_t)s * kv + (size_t)w * 32;
+    int8_t* so = S + (size_t)sd * ks + (size_t)w * 96;
+    int8_t* vo = V + (size_t)sd * kv + (size_t)w * 32;
 #pragma unroll 4
     for (int q = 0; q < 8; q++) {
         uint32_t e0 = 0, e1 = 0, e2 = 0, vv = 0;
@@ -131,6 +133,7 @@ struct TcParams {
     int dist_type;
     int rect;                   // 0: lower triangle + mirror into an n x n matrix; 1: rows [r0,r1) x cols [0,ncols)
     int r0, r1, ncols;
+    int a_row0;                 // the A operand buffers start at this alignment row (0: persistent buffers, else scratch)
 };
 
 // Epilogue of one 128 x 256 tile: thread (q, lane) owns row 32 q + lane of the tile; D1 in TMEM columns [0,256), D2 in
@@ -232,7 +235,7 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
             uint32_t stage = 0, phase = 0;
             for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
                 const int2 tl = p.tiles[t];
-                const int arow = (tl.x * CM + cr) * TC_M + cc * (TC_M / CN);   // my part of my tile row's A slab
+                const int arow = (tl.x * CM + cr) * TC_M + cc * (TC_M / CN) - p.a_row0;   // my part of my tile row's A slab
                 const int brow = (tl.y * CN + cc) * TC_N + cr * (TC_N / CM);   // my part of my tile column's B slab
                 for (int c = 0; c < nchunks; c++) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -355,7 +358,8 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {   // arrives on th
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-msa_tc2_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapV, TcParams p) {
+msa_tc2_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__ CUtensorMap mapSB,
+               const __grid_constant__ CUtensorMap mapVA, const __grid_constant__ CUtensorMap mapVB, TcParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE_BYTES);
@@ -393,7 +397,7 @@ msa_tc2_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__
             uint32_t stage = 0, phase = 0;
             for (int t = pair_id; t < p.num_tiles; t += num_pairs) {
                 const int2 tl = p.tiles[t];                                  // 256-row block, 256-column block
-                const int arow = tl.x * 256 + (int)crank * 128;              // my 128 A rows
+                const int arow = tl.x * 256 + (int)crank * 128 - p.a_row0;  // my 128 A rows
                 const int brow = tl.y * 256 + (int)crank * 128;              // my half of the B rows
                 for (int c = 0; c < nchunks; c++) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -402,8 +406,8 @@ msa_tc2_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__
                     mbar_arrive_expect_tx_cluster(lfull, T2_STAGE_BYTES);
                     const bool sv = c >= p.ns_chunks;
                     const int kc = (sv ? c - p.ns_chunks : c) * TC_KB;
-                    tma_load_2d_pair(a, sv ? &mapV : &mapS, kc, arow, lfull);
-                    tma_load_2d_pair(a + T2_HALF_BYTES, sv ? &mapV : &mapS, kc, brow, lfull);
+                    tma_load_2d_pair(a, sv ? &mapVA : &mapSA, kc, arow, lfull);
+                    tma_load_2d_pair(a + T2_HALF_BYTES, sv ? &mapVB : &mapSB, kc, brow, lfull);
                     if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -478,27 +482,92 @@ bool msa_tc_supported(const dipb_msa* m, int type) {
     return (type == DIPB_DIST_UNCORRECTED || type == DIPB_DIST_JC) && m->n >= 2;
 }
 
-int msa_tc_prepare(dipb_msa* m) {
-    if (m->tc_S) return 0;
+void msa_tc_reserve(dipb_msa* m, int rows) {
+    if (!m->tc_S && rows > 0) m->tc_reserve = (size_t)rows;
+}
+
+static int tc_expand(dipb_msa* m, size_t row0, size_t nrows, int8_t* S, int8_t* V) {
+    if (!nrows) return 0;
     dipb_ctx* c = m->ctx;
     const int w32 = (m->seq_len + 31) / 32;
-    m->tc_ks = ((size_t)w32 * 96 + TC_KB - 1) / TC_KB * TC_KB;
-    m->tc_kv = ((size_t)w32 * 32 + TC_KB - 1) / TC_KB * TC_KB;
-    m->tc_rows = ((size_t)m->n + TC_N - 1) / TC_N * TC_N;
-    DIPB_CUDA(pool_alloc(c, (void**)&m->tc_S, m->tc_rows * m->tc_ks));
-    DIPB_CUDA(pool_alloc(c, (void**)&m->tc_V, m->tc_rows * m->tc_kv));
-    DIPB_CUDA(cudaMemsetAsync(m->tc_S, 0, m->tc_rows * m->tc_ks, c->stream));
-    DIPB_CUDA(cudaMemsetAsync(m->tc_V, 0, m->tc_rows * m->tc_kv, c->stream));
-    long long total = (long long)m->n * w32;
-    msa_tc_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(m->planes, m->n, m->nkc, w32, m->tc_S, m->tc_ks, m->tc_V, m->tc_kv);
+    const long long total = (long long)nrows * w32;
+    msa_tc_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(m->planes, (int)row0, (int)nrows, m->nkc, w32, S, m->tc_ks, V, m->tc_kv);
     DIPB_KERNEL_CHECK(c);
+    return 0;
+}
+
+// persistent buffers hold at least the rows [0, rows)
+static int tc_ensure_prefix(dipb_msa* m, size_t rows) {
+    dipb_ctx* c = m->ctx;
+    if (rows > (size_t)m->n) rows = (size_t)m->n;
+    if (!m->tc_ks) {
+        const int w32 = (m->seq_len + 31) / 32;
+        m->tc_ks = ((size_t)w32 * 96 + TC_KB - 1) / TC_KB * TC_KB;
+        m->tc_kv = ((size_t)w32 * 32 + TC_KB - 1) / TC_KB * TC_KB;
+    }
+    const size_t full = ((size_t)m->n + 255) / 256 * 256;
+    if (rows > m->tc_rows) {
+        // (re)allocate: the reserved size when it is enough, else everything
+        size_t want = m->tc_reserve ? (m->tc_reserve + 255) / 256 * 256 : full;
+        if (want < rows || want > full) want = full;
+        int8_t *S = nullptr, *V = nullptr;
+        DIPB_CUDA(pool_alloc(c, (void**)&S, want * m->tc_ks));
+        DIPB_CUDA(pool_alloc(c, (void**)&V, want * m->tc_kv));
+        DIPB_CUDA(cudaMemsetAsync(S, 0, want * m->tc_ks, c->stream));   // K padding and rows never expanded read as 0
+        DIPB_CUDA(cudaMemsetAsync(V, 0, want * m->tc_kv, c->stream));
+        if (m->tc_have) {
+            DIPB_CUDA(cudaMemcpyAsync(S, m->tc_S, m->tc_have * m->tc_ks, cudaMemcpyDeviceToDevice, c->stream));
+            DIPB_CUDA(cudaMemcpyAsync(V, m->tc_V, m->tc_have * m->tc_kv, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        pool_free(c, m->tc_S); pool_free(c, m->tc_V);
+        m->tc_S = S; m->tc_V = V; m->tc_rows = want;
+    }
+    if (rows > m->tc_have) {
+        int rc = tc_expand(m, m->tc_have, rows - m->tc_have, m->tc_S + m->tc_have * m->tc_ks, m->tc_V + m->tc_have * m->tc_kv);
+        if (rc) return rc;
+        m->tc_have = rows;
+    }
+    return 0;
+}
+
+// operands of one launch: B rows (columns of the result) always from the persistent prefix; A rows from it too when
+// they fit its capacity, else from a scratch pair that holds just the 256-aligned row range of this call
+struct TcOperands {
+    int8_t *SA, *VA, *SB, *VB;
+    size_t rowsA, rowsB;
+    int a_row0;
+};
+static int tc_operands(dipb_msa* m, int r0, int r1, int ncols, TcOperands* o) {
+    dipb_ctx* c = m->ctx;
+    int rc = tc_ensure_prefix(m, (size_t)ncols);
+    if (rc) return rc;
+    const size_t cap_target = m->tc_reserve ? std::min<size_t>(((size_t)m->n + 255) / 256 * 256, (m->tc_reserve + 255) / 256 * 256) : ((size_t)m->n + 255) / 256 * 256;
+    if ((size_t)r1 <= m->tc_rows || (size_t)r1 <= cap_target) {
+        if ((rc = tc_ensure_prefix(m, (size_t)r1))) return rc;
+        o->SA = m->tc_S; o->VA = m->tc_V; o->rowsA = m->tc_rows; o->a_row0 = 0;
+    } else {
+        const size_t a0 = (size_t)r0 / 256 * 256, a1 = std::min<size_t>(((size_t)r1 + 255) / 256 * 256, (size_t)m->n);
+        const size_t need = ((size_t)r1 + 255) / 256 * 256 - a0;
+        if (need > m->tc_xrows) {
+            pool_free(c, m->tc_Sx); pool_free(c, m->tc_Vx);
+            m->tc_Sx = m->tc_Vx = nullptr;
+            DIPB_CUDA(pool_alloc(c, (void**)&m->tc_Sx, need * m->tc_ks));
+            DIPB_CUDA(pool_alloc(c, (void**)&m->tc_Vx, need * m->tc_kv));
+            DIPB_CUDA(cudaMemsetAsync(m->tc_Sx, 0, need * m->tc_ks, c->stream));
+            DIPB_CUDA(cudaMemsetAsync(m->tc_Vx, 0, need * m->tc_kv, c->stream));
+            m->tc_xrows = need;
+        }
+        if ((rc = tc_expand(m, a0, a1 - a0, m->tc_Sx, m->tc_Vx))) return rc;
+        o->SA = m->tc_Sx; o->VA = m->tc_Vx; o->rowsA = m->tc_xrows; o->a_row0 = (int)a0;
+    }
+    o->SB = m->tc_S; o->VB = m->tc_V; o->rowsB = m->tc_rows;
     return 0;
 }
 
 typedef std::vector<int2> (*TileListFn)(int tile_m, int tile_n, int sm_rows, int sm_cols, const void* arg);
 
 template <int CM, int CN>
-static int tc_launch_c(dipb_msa* m, TileListFn make_tiles, const void* arg, TcParams p, bool* launched) {
+static int tc_launch_c(dipb_msa* m, const TcOperands& op, TileListFn make_tiles, const void* arg, TcParams p, bool* launched) {
     dipb_ctx* c = m->ctx;
     *launched = false;
     static EncodeTiledFn encode = nullptr;
@@ -530,8 +599,8 @@ static int tc_launch_c(dipb_msa* m, TileListFn make_tiles, const void* arg, TcPa
     if (tiles.empty()) { *launched = true; return 0; }
     int rc;
     CUtensorMap mSA, mSB, mVA, mVB;
-    if ((rc = make_map(encode, &mSA, m->tc_S, m->tc_ks, m->tc_rows, TC_M / CN)) || (rc = make_map(encode, &mSB, m->tc_S, m->tc_ks, m->tc_rows, TC_N / CM)) ||
-        (rc = make_map(encode, &mVA, m->tc_V, m->tc_kv, m->tc_rows, TC_M / CN)) || (rc = make_map(encode, &mVB, m->tc_V, m->tc_kv, m->tc_rows, TC_N / CM)))
+    if ((rc = make_map(encode, &mSA, op.SA, m->tc_ks, op.rowsA, TC_M / CN)) || (rc = make_map(encode, &mSB, op.SB, m->tc_ks, op.rowsB, TC_N / CM)) ||
+        (rc = make_map(encode, &mVA, op.VA, m->tc_kv, op.rowsA, TC_M / CN)) || (rc = make_map(encode, &mVB, op.VB, m->tc_kv, op.rowsB, TC_N / CM)))
         return rc;
     int2* d_tiles = nullptr;
     DIPB_CUDA(pool_alloc(c, (void**)&d_tiles, sizeof(int2) * tiles.size()));
@@ -552,7 +621,7 @@ static int tc_launch_c(dipb_msa* m, TileListFn make_tiles, const void* arg, TcPa
 }
 
 // 2-CTA kernel: 256 x 256 tiles, one CTA pair (cluster of 2) each
-static int tc_launch_pair(dipb_msa* m, TileListFn make_tiles, const void* arg, TcParams p, bool force, bool* launched) {
+static int tc_launch_pair(dipb_msa* m, const TcOperands& op, TileListFn make_tiles, const void* arg, TcParams p, bool force, bool* launched) {
     dipb_ctx* c = m->ctx;
     *launched = false;
     static EncodeTiledFn encode = nullptr;
@@ -579,8 +648,10 @@ static int tc_launch_pair(dipb_msa* m, TileListFn make_tiles, const void* arg, T
     if (tiles.empty()) { *launched = true; return 0; }
     if (!force && (int)tiles.size() < 4 * npairs) return 0;      // too few 256 x 256 tiles to balance: 128 x 256 tiles of the 1-CTA kernel
     int rc;
-    CUtensorMap mS, mV;
-    if ((rc = make_map(encode, &mS, m->tc_S, m->tc_ks, m->tc_rows, 128)) || (rc = make_map(encode, &mV, m->tc_V, m->tc_kv, m->tc_rows, 128))) return rc;
+    CUtensorMap mSA, mSB, mVA, mVB;
+    if ((rc = make_map(encode, &mSA, op.SA, m->tc_ks, op.rowsA, 128)) || (rc = make_map(encode, &mSB, op.SB, m->tc_ks, op.rowsB, 128)) ||
+        (rc = make_map(encode, &mVA, op.VA, m->tc_kv, op.rowsA, 128)) || (rc = make_map(encode, &mVB, op.VB, m->tc_kv, op.rowsB, 128)))
+        return rc;
     int2* d_tiles = nullptr;
     DIPB_CUDA(pool_alloc(c, (void**)&d_tiles, sizeof(int2) * tiles.size()));
     DIPB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
@@ -589,7 +660,7 @@ static int tc_launch_pair(dipb_msa* m, TileListFn make_tiles, const void* arg, T
     p.nv = m->nv; p.n = m->n;
     const int use = p.num_tiles < npairs ? p.num_tiles : npairs;
     cfg.gridDim = dim3(use * 2);
-    void* args[] = {&mS, &mV, &p};
+    void* args[] = {&mSA, &mSB, &mVA, &mVB, &p};
     cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)msa_tc2_kernel, args);
     if (e != cudaSuccess) { pool_free(c, d_tiles); set_error("msa_tc2: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
     c->launches++;
@@ -599,15 +670,17 @@ static int tc_launch_pair(dipb_msa* m, TileListFn make_tiles, const void* arg, T
     return 0;
 }
 
-static int tc_launch(dipb_msa* m, TileListFn make_tiles, const void* arg, TcParams p) {
-    int rc = msa_tc_prepare(m);
+static int tc_launch(dipb_msa* m, int r0, int r1, int ncols, TileListFn make_tiles, const void* arg, TcParams p) {
+    TcOperands op;
+    int rc = tc_operands(m, r0, r1, ncols, &op);
     if (rc) return rc;
+    p.a_row0 = op.a_row0;
     {
         // 2-CTA kernel (39.9 ms vs 56.7 ms at C3) whenever there are enough 256 x 256 tiles; DIPB_MSA_TC2=0 never, =1 always
         const char* e2 = getenv("DIPB_MSA_TC2");
         if (!(e2 && e2[0] == '0')) {
             bool ok2 = false;
-            rc = tc_launch_pair(m, make_tiles, arg, p, e2 && e2[0] == '1', &ok2);
+            rc = tc_launch_pair(m, op, make_tiles, arg, p, e2 && e2[0] == '1', &ok2);
             if (rc || ok2) return rc;
         }
     }
@@ -618,12 +691,12 @@ static int tc_launch(dipb_msa* m, TileListFn make_tiles, const void* arg, TcPara
     int cm = 1, cn = 1;
     if (e && e[0] >= '1' && e[0] <= '4' && e[1] == 'x' && e[2] >= '1' && e[2] <= '4') { cm = e[0] - '0'; cn = e[2] - '0'; }
     bool ok = false;
-    if (cm == 4 && cn == 4) rc = tc_launch_c<4, 4>(m, make_tiles, arg, p, &ok);
-    else if (cm == 2 && cn == 4) rc = tc_launch_c<2, 4>(m, make_tiles, arg, p, &ok);
-    else if (cm == 4 && cn == 2) rc = tc_launch_c<4, 2>(m, make_tiles, arg, p, &ok);
-    else if (cm == 2 && cn == 2) rc = tc_launch_c<2, 2>(m, make_tiles, arg, p, &ok);
+    if (cm == 4 && cn == 4) rc = tc_launch_c<4, 4>(m, op, make_tiles, arg, p, &ok);
+    else if (cm == 2 && cn == 4) rc = tc_launch_c<2, 4>(m, op, make_tiles, arg, p, &ok);
+    else if (cm == 4 && cn == 2) rc = tc_launch_c<4, 2>(m, op, make_tiles, arg, p, &ok);
+    else if (cm == 2 && cn == 2) rc = tc_launch_c<2, 2>(m, op, make_tiles, arg, p, &ok);
     if (rc || ok) return rc;
-    return tc_launch_c<1, 1>(m, make_tiles, arg, p, &ok);
+    return tc_launch_c<1, 1>(m, op, make_tiles, arg, p, &ok);
 }
 
 struct TriArg { int row_begin, row_end; };
@@ -660,7 +733,7 @@ int msa_tc_matrix(dipb_msa* m, int type, int row_begin, int row_end, double* d_o
     TriArg a{row_begin, row_end};
     TcParams p{};
     p.out = d_out; p.ld = (size_t)m->n; p.dist_type = type; p.rect = 0; p.r0 = row_begin; p.r1 = row_end;
-    return tc_launch(m, tri_tiles, &a, p);
+    return tc_launch(m, row_begin, row_end, row_end, tri_tiles, &a, p);
 }
 
 // rows [r0, r1) x columns [0, ncols) into out[(i - r0) * ld + j]  (placement row blocks, D&C stage 2)
@@ -668,7 +741,7 @@ int msa_tc_block(dipb_msa* m, int type, int r0, int r1, int ncols, double* d_out
     RectArg a{r0, r1, ncols};
     TcParams p{};
     p.out = d_out; p.ld = ld; p.dist_type = type; p.rect = 1; p.r0 = r0; p.r1 = r1; p.ncols = ncols;
-    return tc_launch(m, rect_tiles, &a, p);
+    return tc_launch(m, r0, r1, ncols, rect_tiles, &a, p);
 }
 
 }  // namespace dipb
