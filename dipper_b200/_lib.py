@@ -66,6 +66,8 @@ SIGNATURES = {
     "dipb_nj": (C.c_int, [vp, C.c_int, i32p, i32p, f64p, f64p]),
     "dipb_nj_stats": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dipb_place_kclosest": (C.c_int, [vp, C.POINTER(DistSource), C.c_int, vpp]),
+    "dipb_place_exact": (C.c_int, [vp, C.POINTER(DistSource), C.c_int, vpp]),
+    "dipb_place_exact_max_tips": (C.c_int, []),
     "dipb_place_add": (C.c_int, [vp, C.POINTER(DistSource), C.c_int, C.c_int, i32p, i32p, i32p, i32p, f64p, vpp]),
     "dipb_dc": (C.c_int, [vp, C.POINTER(DistSource), C.c_int, C.c_int, vpp]),
     "dipb_dc_cluster_ids": (C.c_int, [vp, i32p, C.c_int]),

@@ -427,6 +427,21 @@ class KPlacementDeviceArrays:
             self.h = None
 
 
+class PlacementDeviceArrays(KPlacementDeviceArrays):
+    """MashPlacement::PlacementDeviceArrays, the exact placement mode (src/mash_placement.cuh:137-165,
+    src/placement.cu:505-789); printTree starts at node numSequences (src/placement.cu:500) like the k-closest one."""
+
+    def findPlacementTree(self, params, mashDeviceArrays=None, matrix=None, msaDeviceArrays=None):
+        s = self._source(params, mashDeviceArrays, matrix, msaDeviceArrays)
+        h = C.c_void_p()
+        check(lib().dipb_place_exact(self.ctx.h, C.byref(s), self.numSequences, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def maxTips():
+        return lib().dipb_place_exact_max_tips()
+
+
 def read_fasta_packed(path, bits, threads=0):
     """Parallel FASTA ingest + packing (dipb_fasta_open): returns (names, lengths[n], word_offsets[n+1], words).
     bits = 4 for aligned input (-i m), 2 for unaligned (-i r).  Replaces readSequences + the packing loops

@@ -206,11 +206,12 @@ int main(int argc, char** argv) {
         CHECK(dipb_matrix_from_host(ctx, tri.data(), n, 0, &M));
         bool place = algo == "1" || (algo == "0" && n >= placement_thr && n < dc_thr);
         if (place) {
-            std::cerr << "Using k-closest placement mode\n";
+            std::cerr << (placemode == "0" ? "Using exact placement mode\n" : "Using k-closest placement mode\n");
             dipb_dist_source src{};
             src.matrix = M;
             dipb_tree* T = nullptr;
-            CHECK(dipb_place_kclosest(ctx, &src, n, &T));
+            if (placemode == "0") CHECK(dipb_place_exact(ctx, &src, n, &T));
+            else CHECK(dipb_place_kclosest(ctx, &src, n, &T));
             if (write_tree(T, names, output_)) return 1;
             dipb_tree_free(T);
         } else if (algo == "3" || (algo == "0" && n >= dc_thr)) {
@@ -326,15 +327,10 @@ int main(int argc, char** argv) {
         if (write_tree(T, names, output_)) return 1;
         dipb_tree_free(T);
     } else if (algo == "1" || (algo == "0" && n >= (size_t)placement_thr && n < (size_t)dc_thr)) {
-        std::cerr << "Using ";
-        if (placemode == "0") {
-            std::cerr << " exact placement mode\n";
-            std::cerr << "dipper: exact placement (-p 0) is not built in this version; use -p 1\n";
-            return 1;
-        }
-        std::cerr << "k-closest placement mode\n";
+        std::cerr << "Using " << (placemode == "0" ? "exact placement mode\n" : "k-closest placement mode\n");
         dipb_tree* T = nullptr;
-        CHECK(dipb_place_kclosest(ctx, &src, (int)n, &T));
+        if (placemode == "0") CHECK(dipb_place_exact(ctx, &src, (int)n, &T));
+        else CHECK(dipb_place_kclosest(ctx, &src, (int)n, &T));
         if (write_tree(T, names, output_)) return 1;
         dipb_tree_free(T);
     } else if (algo == "3" || (algo == "0" && n >= (size_t)dc_thr)) {

@@ -254,8 +254,8 @@ void place_scratch_free(dipb_ctx* c, PlaceScratch* s) {
 }
 
 // rows [r0, r1) x cols [0, r1) of the selected provider into buf (or the matrix itself)
-static int fetch_rows(const dipb_dist_source* src, int r0, int r1, double* buf, size_t ld, const double** rows, int* row_base,
-                      size_t* ld_out) {
+int place_fetch_rows(const dipb_dist_source* src, int r0, int r1, double* buf, size_t ld, const double** rows, int* row_base,
+                     size_t* ld_out) {
     if (src->matrix) { *rows = src->matrix->d; *row_base = 0; *ld_out = (size_t)src->matrix->n; return 0; }
     *rows = buf; *row_base = r0; *ld_out = ld;
     if (src->msa) return msa_block(src->msa, src->dist_type, r0, r1, r1, buf, ld);
@@ -288,7 +288,7 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int 
     for (int i0 = first_tip; i0 < end && !rc; i0 += batch) {
         int i1 = i0 + batch < end ? i0 + batch : end;
         const double* rows; int row_base; size_t ldr;
-        rc = fetch_rows(src, i0, i1, buf, ld, &rows, &row_base, &ldr);
+        rc = place_fetch_rows(src, i0, i1, buf, ld, &rows, &row_base, &ldr);
         if (rc) break;
         int node_off = n_alloc;
         void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &t->cid, &t->cdis, &t->rev, &rows, &ldr, &row_base,

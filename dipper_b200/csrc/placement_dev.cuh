@@ -203,5 +203,8 @@ void place_scratch_free(dipb_ctx* c, PlaceScratch* s);
 // builds the 2-leaf tree from d(1,0) and places tips [2, end) (src/placement_close_k.cu:646-854)
 int place_from_scratch(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int end, dipb_tree* t, PlaceScratch* sc);
 int check_source(const dipb_dist_source* s, int n);
+// rows [r0, r1) x cols [0, r1) of the selected provider into buf (or the matrix itself)
+int place_fetch_rows(const dipb_dist_source* src, int r0, int r1, double* buf, size_t ld, const double** rows, int* row_base,
+                     size_t* ld_out);
 
 }  // namespace dipb

@@ -1,0 +1,470 @@
+// Exact placement mode (-p 0): replaces PlacementDeviceArrays::findPlacementTree, src/placement.cu:505-789, with its
+// kernels initialize / buildInitialTree / updateFromBottomToTop / updateFromTopToBottom / calculateBranchLength /
+// updateTreeStructure / updateDfsRk / findEndRk / updateDepth / updateLevelStEd (:118-436) and the thrust min_element,
+// reduce and stable_sort_by_key calls between them.
+//
+// The reference keeps the tree rooted at the first internal node and, for every tip, (1) sweeps the levels bottom-up
+// and top-down (2 x depth kernel launches) so that lim[slot] = max over ALL leaves behind the slot's source of
+// (distance - path), (2) scores every parent->child slot with those two limits, takes the first minimum of the pendant
+// length, splits that edge, and (3) renumbers preorder ranks, bumps the depth of the split child's subtree and re-sorts
+// the breadth-first order on the device -- about 2 x depth + 12 launches, 4 device->host copies and one sort per tip.
+//
+// Here ONE 16-CTA thread-block cluster runs the whole loop for a batch of tips with the tree in (distributed) shared
+// memory.  Every node belongs to one thread of one CTA (32-node chunks dealt round-robin over the CTAs) which keeps
+// its parent, edge length, depth, preorder rank and subtree size; a level step is "the owners of the nodes at this
+// depth compute and PUSH the value into the parent's / children's slot in the owner CTA's shared memory
+// (st.shared::cluster)" followed by one hardware cluster barrier, so a tip costs 2 x depth + 2 barriers of ~0.3 us and
+// no global-memory round trip.  Preorder ranks / subtree sizes make the rank shift, the ancestor size update and the
+// subtree depth bump three independent per-node tests (no sort, no reduction).  The reference slot arrays
+// (head / e / nxt / belong / len) are written with the slot numbers the reference would produce (they are arithmetic:
+// tip t appends slots 4t-4 .. 4t-1), so the exported tree prints the same Newick text.
+//
+// Arithmetic is the reference's, expression by expression: the per-edge `lim - len` subtractions happen in the same
+// order along every path and max() is exact, so limits, pendant lengths, the argmin (ties -> smallest slot) and all
+// branch lengths are bit-identical to the oracle restatement (oracle/dipper_oracle.c: orc_place_exact_all).
+// One deviation: when no candidate has a pendant length < 2 the reference "places" on slot 0 through its (0,0,2)
+// default tuple and corrupts its depth table (the no-op swap at :246-249); this kernel reports DIPB_E_UNSUPPORTED.
+#include <cooperative_groups.h>
+#include <cstdlib>
+#include "common.cuh"
+#include "placement_dev.cuh"
+
+namespace dipb {
+
+namespace {
+
+constexpr int EX_THREADS = 1024;
+constexpr int EX_KM = 3;               // owned nodes of each kind per thread at most (NL <= 3072)
+constexpr int EX_BYTES_PER_NODE = 90;  // per local index: leaf 31 B + internal 59 B of state
+
+struct ExCtl {
+    int maxdep;
+    int error;
+    unsigned long long levels;   // sum over tips of the tree depth (profile)
+    unsigned long long cycles;   // CTA 0, whole batch loop
+};
+
+struct ExState {   // views into this CTA's dynamic shared memory
+    double *l_dn, *l_plen, *i_dn, *i_in0, *i_in1, *i_plen;
+    int *l_par, *l_sdn, *l_rank, *i_par, *i_kid0, *i_kid1, *i_sdn, *i_rank, *i_sz;
+    unsigned short *l_dep, *i_dep;
+    unsigned char *l_cidx, *i_cidx;
+};
+
+__device__ __forceinline__ ExState ex_carve(unsigned char* base, int NL) {
+    ExState s;
+    double* d = reinterpret_cast<double*>(base);
+    s.l_dn = d; s.l_plen = d + NL; s.i_dn = d + 2 * NL; s.i_in0 = d + 3 * NL; s.i_in1 = d + 4 * NL; s.i_plen = d + 5 * NL;
+    int* q = reinterpret_cast<int*>(d + 6 * NL);
+    s.l_par = q; s.l_sdn = q + NL; s.l_rank = q + 2 * NL; s.i_par = q + 3 * NL; s.i_kid0 = q + 4 * NL; s.i_kid1 = q + 5 * NL;
+    s.i_sdn = q + 6 * NL; s.i_rank = q + 7 * NL; s.i_sz = q + 8 * NL;
+    unsigned short* h = reinterpret_cast<unsigned short*>(q + 9 * NL);
+    s.l_dep = h; s.i_dep = h + NL;
+    unsigned char* b = reinterpret_cast<unsigned char*>(h + 2 * NL);
+    s.l_cidx = b; s.i_cidx = b + NL;
+    return s;
+}
+
+__device__ __forceinline__ unsigned int ex_peer(const void* p, int rank) {
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(p);
+    unsigned int ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ void ex_push_f64(double* p, int rank, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ex_peer(p, rank)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void ex_push_s32(int* p, int rank, int v) {
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(ex_peer(p, rank)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void ex_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+struct ExBest {
+    double add, frac;
+    int slot, node;
+};
+__device__ __forceinline__ bool ex_before(double a_add, int a_slot, double b_add, int b_slot) {
+    return a_add < b_add || (a_add == b_add && a_slot < b_slot);   // min_element: first minimum in slot order
+}
+
+// calculateBranchLength :153-198 for the parent->child slot of one node (dis1 = limit on the parent side)
+__device__ __forceinline__ void ex_score(double dis1, double dis2, double L, int slot, int node, ExBest& b) {
+    double a = (dis1 + dis2 - L) / 2;
+    if (a < 0) a = 0;
+    dis1 -= a; dis2 -= a;
+    if (dis1 < 0) dis1 = 0;
+    if (dis2 < 0) dis2 = 0;
+    if (dis1 > L) { a += dis1 - L; dis1 = L; }
+    if (dis2 > L) { a += dis2 - L; dis2 = L; }
+    const double rest = L - dis1 - dis2;
+    dis1 += rest / 2;
+    if (ex_before(a, slot, b.add, b.slot)) { b.add = a; b.frac = dis1; b.slot = slot; b.node = node; }
+}
+
+template <int CS>
+__global__ void __launch_bounds__(EX_THREADS, 1)
+place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict__ nxt, int* __restrict__ belong,
+                   double* __restrict__ len, const double* __restrict__ rows, size_t ld, int row_base, int i0, int i1, int N,
+                   int NL, const double* __restrict__ d01, uint4* __restrict__ saved, ExCtl* __restrict__ ctl) {
+    extern __shared__ __align__(16) unsigned char ex_smem[];
+    __shared__ double rec_d[CS][3];     // every CTA's best candidate of this tip: add, frac, edge length
+    __shared__ int rec_i[CS][8];        // slot, node y, parent x, rank, subtree size, depth, child index of y
+    __shared__ int s_grow[2];
+    __shared__ ExBest s_warp[EX_THREADS / 32];
+    constexpr int LOGCS = CS == 16 ? 4 : (CS == 8 ? 3 : (CS == 4 ? 2 : (CS == 2 ? 1 : 0)));
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rank = (int)cooperative_groups::this_cluster().block_rank();
+    const ExState S = ex_carve(ex_smem, NL);
+    const size_t state_words = (size_t)NL * EX_BYTES_PER_NODE / 16;
+    uint4* sm4 = reinterpret_cast<uint4*>(ex_smem);
+    auto cta_of = [&](int id) { return (id >> 5) & (CS - 1); };
+    auto loc_of = [&](int id) { return ((id >> (5 + LOGCS)) << 5) | (id & 31); };
+    auto id_of = [&](int k) { return ((((k >> 5) << LOGCS) | rank) << 5) | (k & 31); };
+
+    // ---- state: fresh 2-leaf tree (buildInitialTree :253-295) or the previous batch's
+    if (i0 == 2) {
+        for (int k = tid; k < NL; k += EX_THREADS) {
+            S.l_dep[k] = 0xFFFF; S.i_dep[k] = 0xFFFF; S.l_rank[k] = -1; S.i_rank[k] = -1; S.i_sz[k] = 0;
+            S.l_par[k] = -1; S.i_par[k] = -1; S.i_kid0[k] = -1; S.i_kid1[k] = -1; S.l_sdn[k] = 0; S.i_sdn[k] = 0;
+            S.l_cidx[k] = 0; S.i_cidx[k] = 0;
+            S.l_dn[k] = 0; S.l_plen[k] = 0; S.i_dn[k] = 0; S.i_in0[k] = 0; S.i_in1[k] = 0; S.i_plen[k] = 0;
+        }
+        __syncthreads();
+        if (rank == 0 && tid == 0) {   // nodes 0, 1 (leaves) and N (internal index 0) all live in CTA 0, local 0 / 1 / 0
+            const double d = d01[0];
+            S.i_dep[0] = 0; S.i_rank[0] = 0; S.i_sz[0] = 3; S.i_kid0[0] = 0; S.i_kid1[0] = 1;
+            S.l_par[0] = N; S.l_cidx[0] = 0; S.l_plen[0] = d / 2; S.l_sdn[0] = 2; S.l_rank[0] = 1; S.l_dep[0] = 1;
+            S.l_par[1] = N; S.l_cidx[1] = 1; S.l_plen[1] = d / 2; S.l_sdn[1] = 3; S.l_rank[1] = 2; S.l_dep[1] = 1;
+            e[0] = N; len[0] = d / 2; nxt[0] = -1; belong[0] = 0; head[0] = 0;
+            e[1] = N; len[1] = d / 2; nxt[1] = -1; belong[1] = 1; head[1] = 1;
+            e[2] = 0; len[2] = d / 2; nxt[2] = -1; belong[2] = N;
+            e[3] = 1; len[3] = d / 2; nxt[3] = 2; belong[3] = N; head[N] = 3;
+        }
+    } else {
+        const uint4* src = saved + (size_t)rank * state_words;
+        for (size_t w = tid; w < state_words; w += EX_THREADS) sm4[w] = src[w];
+    }
+    if (tid < 2) s_grow[tid] = 0;
+    int maxdep = i0 == 2 ? 1 : ctl->maxdep;
+    bool failed = false;
+    unsigned long long levels = 0;
+    const long long t_begin = clock64();
+    __syncthreads();
+    ex_cluster_sync();
+
+    for (int i = i0; i < i1; i++) {
+        // distances of this tip to the leaves this thread owns
+        const double* row = rows + (size_t)(i - row_base) * ld;
+        double myd[EX_KM];
+#pragma unroll
+        for (int u = 0; u < EX_KM; u++) {
+            const int k = tid + u * EX_THREADS;
+            myd[u] = 0;
+            if (k < NL) { const int lid = id_of(k); if (lid < i) myd[u] = __ldg(&row[lid]); }
+        }
+        // ---- bottom-up (updateFromBottomToTop :298-332): a node's limit towards its parent, pushed to the parent
+        for (int lev = maxdep; lev >= 1; lev--) {
+#pragma unroll
+            for (int u = 0; u < EX_KM; u++) {
+                const int k = tid + u * EX_THREADS;
+                if (k < NL) {
+                    if (S.l_dep[k] == lev) {
+                        const double req = myd[u] - S.l_plen[k];
+                        const int j = S.l_par[k] - N;
+                        ex_push_f64((S.l_cidx[k] ? S.i_in1 : S.i_in0) + loc_of(j), cta_of(j), req);
+                    }
+                    if (S.i_dep[k] == lev) {
+                        double m = 0;
+                        const double a = S.i_in0[k], b = S.i_in1[k];
+                        if (a > m) m = a;
+                        if (b > m) m = b;
+                        const double req = m - S.i_plen[k];
+                        const int j = S.i_par[k] - N;
+                        ex_push_f64((S.i_cidx[k] ? S.i_in1 : S.i_in0) + loc_of(j), cta_of(j), req);
+                    }
+                }
+            }
+            ex_cluster_sync();
+        }
+        // ---- top-down (updateFromTopToBottom :334-366) fused with the scoring of the parent->child slots
+        ExBest best;
+        best.add = 2.0; best.frac = 0.0; best.slot = 0; best.node = -1;   // the (0,0,2) default tuple
+        for (int lev = 0; lev <= maxdep; lev++) {
+#pragma unroll
+            for (int u = 0; u < EX_KM; u++) {
+                const int k = tid + u * EX_THREADS;
+                if (k < NL) {
+                    if (S.l_dep[k] == lev) ex_score(S.l_dn[k], myd[u], S.l_plen[k], S.l_sdn[k], id_of(k), best);
+                    if (S.i_dep[k] == lev) {
+                        const double a = S.i_in0[k], b = S.i_in1[k];
+                        double basev = 0;
+                        if (lev > 0) {
+                            double up = 0;
+                            if (a > up) up = a;
+                            if (b > up) up = b;
+                            const double dn = S.i_dn[k];
+                            ex_score(dn, up, S.i_plen[k], S.i_sdn[k], N + id_of(k), best);
+                            basev = dn - S.i_plen[k];
+                        }
+                        double v0 = 0, v1 = 0;
+                        if (b > v0) v0 = b;
+                        if (a > v1) v1 = a;
+                        if (lev > 0) { if (basev > v0) v0 = basev; if (basev > v1) v1 = basev; }
+                        const int k0 = S.i_kid0[k], k1 = S.i_kid1[k];
+                        if (k0 < N) ex_push_f64(S.l_dn + loc_of(k0), cta_of(k0), v0);
+                        else ex_push_f64(S.i_dn + loc_of(k0 - N), cta_of(k0 - N), v0);
+                        if (k1 < N) ex_push_f64(S.l_dn + loc_of(k1), cta_of(k1), v1);
+                        else ex_push_f64(S.i_dn + loc_of(k1 - N), cta_of(k1 - N), v1);
+                    }
+                }
+            }
+            if (lev < maxdep) ex_cluster_sync();
+        }
+        levels += (unsigned long long)maxdep;
+        // ---- first minimum over the cluster (thrust::min_element :657)
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const double oa = __shfl_xor_sync(0xffffffffu, best.add, s), of = __shfl_xor_sync(0xffffffffu, best.frac, s);
+            const int os = __shfl_xor_sync(0xffffffffu, best.slot, s), on = __shfl_xor_sync(0xffffffffu, best.node, s);
+            if (ex_before(oa, os, best.add, best.slot)) { best.add = oa; best.frac = of; best.slot = os; best.node = on; }
+        }
+        if (lane == 0) s_warp[wid] = best;
+        __syncthreads();
+        if (wid == 0) {
+            best = s_warp[lane];
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const double oa = __shfl_xor_sync(0xffffffffu, best.add, s), of = __shfl_xor_sync(0xffffffffu, best.frac, s);
+                const int os = __shfl_xor_sync(0xffffffffu, best.slot, s), on = __shfl_xor_sync(0xffffffffu, best.node, s);
+                if (ex_before(oa, os, best.add, best.slot)) { best.add = oa; best.frac = of; best.slot = os; best.node = on; }
+            }
+            // the winner's owner is in this CTA: attach what the update needs
+            double pl = 0;
+            int px = -1, rk = -1, sz = 0, dp = 0, ci = 0;
+            const int y = best.node;
+            if (y >= 0) {
+                if (y < N) { const int k = loc_of(y); pl = S.l_plen[k]; px = S.l_par[k]; rk = S.l_rank[k]; sz = 1; dp = S.l_dep[k]; ci = S.l_cidx[k]; }
+                else { const int k = loc_of(y - N); pl = S.i_plen[k]; px = S.i_par[k]; rk = S.i_rank[k]; sz = S.i_sz[k]; dp = S.i_dep[k]; ci = S.i_cidx[k]; }
+            }
+            if (lane < CS) {
+                ex_push_f64(&rec_d[rank][0], lane, best.add); ex_push_f64(&rec_d[rank][1], lane, best.frac); ex_push_f64(&rec_d[rank][2], lane, pl);
+                ex_push_s32(&rec_i[rank][0], lane, best.slot); ex_push_s32(&rec_i[rank][1], lane, y); ex_push_s32(&rec_i[rank][2], lane, px);
+                ex_push_s32(&rec_i[rank][3], lane, rk); ex_push_s32(&rec_i[rank][4], lane, sz); ex_push_s32(&rec_i[rank][5], lane, dp);
+                ex_push_s32(&rec_i[rank][6], lane, ci);
+            }
+        }
+        ex_cluster_sync();
+        int w = 0;
+        {
+            double wa = rec_d[0][0];
+            int ws = rec_i[0][0];
+#pragma unroll
+            for (int c = 1; c < CS; c++) {
+                const double ca = rec_d[c][0];
+                const int cs = rec_i[c][0];
+                if (ex_before(ca, cs, wa, ws)) { wa = ca; ws = cs; w = c; }
+            }
+        }
+        const double addLen = rec_d[w][0], fracLen = rec_d[w][1], pleny = rec_d[w][2];
+        const int slot = rec_i[w][0], y = rec_i[w][1], x = rec_i[w][2], r = rec_i[w][3], szy = rec_i[w][4], depy = rec_i[w][5], cidxy = rec_i[w][6];
+        if (y < 0) { failed = true; break; }   // uniform over the cluster
+        // ---- update: ranks (updateDfsRk :368-381), ancestors' sizes, subtree depth (findEndRk / updateDepth :384-417)
+        bool grow = false;
+#pragma unroll
+        for (int u = 0; u < EX_KM; u++) {
+            const int k = tid + u * EX_THREADS;
+            if (k < NL) {
+                int rk = S.l_rank[k];
+                if (rk >= r) {
+                    if (rk < r + szy) { const int d = S.l_dep[k] + 1; S.l_dep[k] = (unsigned short)d; if (d > maxdep) grow = true; }
+                    S.l_rank[k] = rk + 2;
+                }
+                rk = S.i_rank[k];
+                if (rk >= r) {
+                    if (rk < r + szy) { const int d = S.i_dep[k] + 1; S.i_dep[k] = (unsigned short)d; if (d > maxdep) grow = true; }
+                    S.i_rank[k] = rk + 2;
+                } else if (rk >= 0 && r < rk + S.i_sz[k]) S.i_sz[k] += 2;
+            }
+        }
+        __syncthreads();
+        // ---- split (updateTreeStructure :200-251): middle m between x and y, new leaf i below m
+        const int m = i + N - 1, jm = i - 1, c0 = 4 * i - 4;
+        if (tid == 0 && cta_of(x - N) == rank) (cidxy ? S.i_kid1 : S.i_kid0)[loc_of(x - N)] = m;
+        if (tid == 32) {
+            if (y < N) { if (cta_of(y) == rank) { const int k = loc_of(y); S.l_par[k] = m; S.l_cidx[k] = 0; S.l_plen[k] = pleny - fracLen; S.l_sdn[k] = c0 + 1; } }
+            else if (cta_of(y - N) == rank) { const int k = loc_of(y - N); S.i_par[k] = m; S.i_cidx[k] = 0; S.i_plen[k] = pleny - fracLen; S.i_sdn[k] = c0 + 1; }
+        }
+        if (tid == 64 && cta_of(jm) == rank) {
+            const int k = loc_of(jm);
+            S.i_par[k] = x; S.i_cidx[k] = (unsigned char)cidxy; S.i_kid0[k] = y; S.i_kid1[k] = i; S.i_plen[k] = fracLen; S.i_sdn[k] = slot;
+            S.i_rank[k] = r; S.i_sz[k] = szy + 2; S.i_dep[k] = (unsigned short)depy;
+        }
+        if (tid == 96 && cta_of(i) == rank) {
+            const int k = loc_of(i);
+            S.l_par[k] = m; S.l_cidx[k] = 1; S.l_plen[k] = addLen; S.l_sdn[k] = c0 + 3; S.l_rank[k] = r + 1; S.l_dep[k] = (unsigned short)(depy + 1);
+        }
+        if (tid == 128 && rank == (i & (CS - 1))) {
+            // the reference's slot arrays; slot numbers are arithmetic: x->y is the winning slot, y->x was appended when y was
+            // created (leaf t: 4t-2, internal node of tip t: 4t-4, the first two leaves: 0 and 1)
+            const int xe = slot, ye = y < N ? (y < 2 ? y : 4 * y - 2) : 4 * (y - N);
+            const int c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3;
+            e[xe] = m; len[xe] = fracLen;
+            e[ye] = m; len[ye] = pleny - fracLen;
+            e[c0] = x; len[c0] = fracLen; nxt[c0] = -1; belong[c0] = m;
+            e[c1] = y; len[c1] = pleny - fracLen; nxt[c1] = c0; belong[c1] = m;
+            e[c2] = m; len[c2] = addLen; nxt[c2] = -1; belong[c2] = i; head[i] = c2;
+            e[c3] = i; len[c3] = addLen; nxt[c3] = c1; belong[c3] = m; head[m] = c3;
+        }
+        // ---- did the tree get deeper?
+        const int par = i & 1;
+        if (tid == 0) s_grow[par ^ 1] = 0;
+        const int g = __syncthreads_or(grow ? 1 : 0);
+        if (g && tid < CS) ex_push_s32(&s_grow[par], tid, 1);
+        ex_cluster_sync();
+        if (s_grow[par]) maxdep++;
+    }
+
+    // ---- keep the state for the next batch
+    __syncthreads();
+    ex_cluster_sync();   // no CTA may leave while peers can still push into its shared memory
+    {
+        uint4* dst = saved + (size_t)rank * state_words;
+        for (size_t w = tid; w < state_words; w += EX_THREADS) dst[w] = sm4[w];
+    }
+    if (rank == 0 && tid == 0) {
+        ctl->maxdep = maxdep;
+        if (failed) ctl->error = 1;
+        ctl->levels += levels;
+        ctl->cycles += (unsigned long long)(clock64() - t_begin);
+    }
+}
+
+template <int CS>
+int ex_launch(dipb_ctx* c, void** args, size_t smem, bool* ok) {
+    auto kern = place_exact_kernel<CS>;
+    *ok = false;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (CS > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS); cfg.blockDim = dim3(EX_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return 0; }
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
+    if (e != cudaSuccess) { set_error("exact placement: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
+    *ok = true;
+    return 0;
+}
+
+// local node capacity per CTA for n tips on CS CTAs, and the dynamic shared memory it needs
+inline int ex_local(int n, int CS) { const int chunks = (n + 31) / 32; return ((chunks + CS - 1) / CS) * 32; }
+inline size_t ex_smem_bytes(int NL) { return (size_t)NL * EX_BYTES_PER_NODE; }
+constexpr size_t EX_SMEM_MAX = 224u * 1024u;   // 227 KB minus the static records
+
+}  // namespace
+
+static int ex_max_tips() { return (int)(EX_SMEM_MAX / EX_BYTES_PER_NODE / 32) * 32 * 16; }
+
+int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* t) {
+    int CS = 16;
+    const char* force = getenv("DIPB_EXACT_CLUSTER");
+    if (force && atoi(force) == 8) CS = 8;
+    int NL = ex_local(n, CS);
+    if (ex_smem_bytes(NL) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS) {
+        set_error("exact placement: %d tips exceed the shared-memory tree of one %d-CTA cluster (at most %d tips); use -p 1 or -m 3", n, CS,
+                  ex_max_tips() / (16 / CS));
+        return DIPB_E_UNSUPPORTED;
+    }
+    // d(1,0) for the 2-leaf tree
+    const double* d01 = nullptr;
+    double* row1 = nullptr;
+    int rc = 0;
+    if (src->matrix) d01 = src->matrix->d + (size_t)src->matrix->n;
+    else {
+        DIPB_CUDA(pool_alloc(c, (void**)&row1, sizeof(double) * 8));
+        rc = src->msa ? msa_block(src->msa, src->dist_type, 1, 2, 1, row1, 8) : dipb_mash_dist_block(src->mash, 1, 2, 1, row1, 8);
+        if (rc) { pool_free(c, row1); return rc; }
+        d01 = row1;
+    }
+    int batch = 512;
+    double* buf = nullptr;
+    const size_t ld = (size_t)n;
+    if (!src->matrix) {
+        size_t want = (size_t)batch * ld * sizeof(double);
+        while (want > (1ull << 28) && batch > 128) { batch /= 2; want /= 2; }
+        DIPB_CUDA(pool_alloc(c, (void**)&buf, (size_t)batch * ld * sizeof(double)));
+    } else batch = n;   // all rows are there: one launch
+    uint4* saved = nullptr;
+    ExCtl* ctl = nullptr;
+    DIPB_CUDA(pool_alloc(c, (void**)&saved, ex_smem_bytes(NL) * 16));
+    DIPB_CUDA(pool_alloc(c, (void**)&ctl, sizeof(ExCtl)));
+    DIPB_CUDA(cudaMemsetAsync(ctl, 0, sizeof(ExCtl), c->stream));
+    for (int i0 = 2; (i0 < n || i0 == 2) && !rc; i0 += batch) {   // (n == 2: one launch that only builds the 2-leaf tree)
+        int i1 = i0 + batch < n ? i0 + batch : n;
+        const double* rows = nullptr; int row_base = 0; size_t ldr = ld;
+        if (i1 > i0) rc = place_fetch_rows(src, i0, i1, buf, ld, &rows, &row_base, &ldr);
+        if (rc) break;
+        int N = n;
+        int i0v = i0;
+        void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &rows, &ldr, &row_base, &i0v, &i1, &N, &NL, &d01, &saved, &ctl};
+        bool ok = false;
+        if (CS == 16) {
+            rc = ex_launch<16>(c, args, ex_smem_bytes(NL), &ok);
+            if (!rc && !ok && i0 == 2) {   // device cannot co-schedule 16 CTAs: portable cluster size, half the capacity
+                CS = 8; NL = ex_local(n, 8);
+                if (ex_smem_bytes(NL) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS) { set_error("exact placement: 16-CTA clusters unavailable and %d tips do not fit 8 CTAs", n); rc = DIPB_E_UNSUPPORTED; break; }
+                pool_free(c, saved);
+                DIPB_CUDA(pool_alloc(c, (void**)&saved, ex_smem_bytes(NL) * 8));
+            }
+        }
+        if (!rc && !ok && CS == 8) rc = ex_launch<8>(c, args, ex_smem_bytes(NL), &ok);
+        if (!rc && !ok) { set_error("exact placement: no cluster configuration fits this device"); rc = DIPB_E_UNSUPPORTED; }
+        if (!rc) c->launches++;
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (!rc && e != cudaSuccess) { set_error("exact placement: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; }
+    if (!rc) {
+        ExCtl h;
+        if (cudaMemcpy(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("exact placement: control block copy failed"); rc = DIPB_E_CUDA; }
+        else if (h.error) {
+            set_error("exact placement: a tip has no candidate edge with pendant length < 2 (the reference's (0,0,2) default tuple would win; src/placement.cu:166-170)");
+            rc = DIPB_E_UNSUPPORTED;
+        } else if (getenv("DIPB_PLACE_PROFILE"))
+            fprintf(stderr, "[exact placement] %d tips on a %d-CTA cluster: final depth %d, %.1f levels and %.0f cycles per tip\n", n, CS, h.maxdep,
+                    (double)h.levels / (n - 2), (double)h.cycles / (n - 2));
+    }
+    pool_free(c, saved); pool_free(c, ctl);
+    if (buf) pool_free(c, buf);
+    if (row1) pool_free(c, row1);
+    return rc;
+}
+
+}  // namespace dipb
+
+using namespace dipb;
+
+extern "C" int dipb_place_exact_max_tips(void) { return ex_max_tips(); }
+
+extern "C" int dipb_place_exact(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree** out) {
+    if (!c || !src || !out || n < 2) { set_error("dipb_place_exact: bad argument"); return DIPB_E_ARG; }
+    int rc = check_source(src, n);
+    if (rc) return rc;
+    DIPB_CUDA(cudaSetDevice(c->device));
+    rc = timer_begin(c);
+    if (rc) return rc;
+    dipb_tree* t = nullptr;
+    rc = tree_alloc(c, n, &t);
+    if (rc) return rc;
+    rc = place_exact_run(c, src, n, t);
+    if (rc) { dipb_tree_free(t); return rc; }
+    rc = timer_end(c, DIPB_T_PLACE);
+    if (rc) return rc;
+    *out = t;
+    return 0;
+}

@@ -148,6 +148,13 @@ typedef struct {
 /* KPlacementDeviceArrays::allocateDeviceArrays + findPlacementTree
  * src/mash_placement.cuh:180-188, src/placement_close_k.cu:15-68,646-854 */
 int dipb_place_kclosest(dipb_ctx *ctx, const dipb_dist_source *src, int n, dipb_tree **out);
+/* PlacementDeviceArrays::allocateDeviceArrays + findPlacementTree (exact placement mode, -p 0)
+ * src/mash_placement.cuh:137-165, src/placement.cu:28-116,505-789.  Same slot arrays as above
+ * (print from node n, src/placement.cu:500).  The tree lives in the shared memory of one
+ * thread-block cluster: at most dipb_place_exact_max_tips() tips, DIPB_E_UNSUPPORTED beyond,
+ * and when a tip has no candidate edge with pendant length < 2 (see placement_exact.cu). */
+int dipb_place_exact(dipb_ctx *ctx, const dipb_dist_source *src, int n, dipb_tree **out);
+int dipb_place_exact_max_tips(void);
 /* initializeDeviceArrays(Tree*) + addQuery, src/placement_close_k.cu:126-264,858-990.
  * The backbone is given as the adjacency arrays the reference builds from its Tree
  * (host pointers; see dipb_backbone_from_newick in dipper_host.h): 4B-4 slots. */

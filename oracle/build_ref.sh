@@ -11,7 +11,7 @@ if [ ! -d "$REF/src" ]; then echo "build_ref: $REF not present, skipping"; exit 
 mkdir -p "$OUT"
 NVCC=/usr/local/cuda/bin/nvcc
 FLAGS="-gencode arch=compute_100a,code=sm_100a -rdc=true --extended-lambda -std=c++17 -O3 -w -ccbin /usr/bin/g++ -I$HERE/stubs -I$REF/src"
-SRCS="src/MSA.cu src/mash.cu src/neighborJoining.cu src/placement_close_k.cu src/matrix_reader.cu src/tree.cpp"
+SRCS="src/MSA.cu src/mash.cu src/neighborJoining.cu src/placement_close_k.cu src/placement.cu src/matrix_reader.cu src/tree.cpp"
 pids=""
 for s in $SRCS; do
   o="$OUT/$(basename ${s%.*}).o"

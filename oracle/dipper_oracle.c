@@ -820,6 +820,151 @@ ORC_API int orc_num_threads(void) {
 }
 
 /* ------------------------------------------------------------------------- */
+/* A.6b exact placement mode (src/placement.cu)                              */
+/* ------------------------------------------------------------------------- */
+/* Same edge rule as k-closest, but the two side limits of an edge come from lim[slot] =
+ * max over ALL leaves behind the slot's source node of (distance - path), computed by a
+ * level-ordered pass up (updateFromBottomToTop :298-332) and down (updateFromTopToBottom
+ * :334-366) a tree rooted at the first internal node; candidates are the parent->child
+ * slots (calculateBranchLength :153-198: dep[belong] <= dep[e]).  The bookkeeping of
+ * preorder ranks, depths and the level table is restated step by step, including
+ * updateTreeStructure's no-op swap (:246-249), so that degenerate inputs behave as in the
+ * reference.  qsort on (key, position) stands in for thrust::stable_sort_by_key (:735). */
+typedef struct { int key, pos, val; } orc_kv;
+static int cmp_kv(const void *a, const void *b) {
+    const orc_kv *x = (const orc_kv *)a, *y = (const orc_kv *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->pos < y->pos ? -1 : (x->pos > y->pos);
+}
+
+ORC_API orc_ptree *orc_place_exact_all(int n, orc_row_fn rows, void *ctx) {
+    orc_ptree *t = orc_ptree_new(n);
+    const int N = n, nodes = 2 * N - 1;
+    int *rev = (int *)malloc(8 * (size_t)N * sizeof(int));
+    int *dep = (int *)malloc(2 * (size_t)N * sizeof(int)), *dfsrk = (int *)malloc(2 * (size_t)N * sizeof(int));
+    int *bfs = (int *)calloc(2 * (size_t)N, sizeof(int)), *tmp = (int *)malloc(2 * (size_t)N * sizeof(int));
+    int *levelst = (int *)malloc(2 * (size_t)N * sizeof(int)), *leveled = (int *)malloc(2 * (size_t)N * sizeof(int));
+    double *lim = (double *)calloc(8 * (size_t)N, sizeof(double));
+    double *dis = (double *)calloc((size_t)N, sizeof(double));
+    orc_kv *kv = (orc_kv *)malloc(2 * (size_t)N * sizeof(orc_kv));
+    /* initialize :118-137 */
+    for (int i = 0; i < nodes; i++) { dep[i] = nodes * 10; dfsrk[i] = levelst[i] = leveled[i] = -1; }
+    for (int i = 0; i < 8 * N; i++) rev[i] = -1;
+    /* buildInitialTree :253-295 */
+    rows(ctx, 1, dis);
+    {
+        const int nv = N; const double d = dis[0];
+        link_slot(t, 0, 0, nv, d / 2); link_slot(t, 1, 1, nv, d / 2);
+        link_slot(t, 2, nv, 0, d / 2); link_slot(t, 3, nv, 1, d / 2);
+        bfs[0] = nv; bfs[1] = 0; bfs[2] = 1;
+        dep[nv] = 0; dep[0] = dep[1] = 1;
+        dfsrk[nv] = 0; dfsrk[0] = 1; dfsrk[1] = 2;
+        levelst[0] = leveled[0] = 0; levelst[1] = 1; leveled[1] = 2;
+        rev[0] = 2; rev[2] = 0; rev[1] = 3; rev[3] = 1;
+    }
+    int idx = 4;
+    for (int i = 2; i < N; i++) {
+        rows(ctx, i, dis);
+        const int mx = dep[bfs[i * 2 - 2]];
+        for (int j = mx; j >= 0; j--)                       /* updateFromBottomToTop */
+            for (int k = levelst[j]; k <= leveled[j]; k++) {
+                const int v = bfs[k];
+                double m = 0;
+                if (v < N) m = dis[v];
+                for (int s = t->head[v]; s != -1; s = t->nxt[s])
+                    if (dep[t->e[s]] > dep[v]) { double req = lim[rev[s]] - t->len[s]; if (req > m) m = req; }
+                for (int s = t->head[v]; s != -1; s = t->nxt[s])
+                    if (dep[t->e[s]] < dep[v]) lim[s] = m;
+            }
+        for (int j = 0; j <= mx; j++)                       /* updateFromTopToBottom */
+            for (int k = levelst[j]; k <= leveled[j]; k++) {
+                const int v = bfs[k];
+                for (int s = t->head[v]; s != -1; s = t->nxt[s])
+                    if (dep[t->e[s]] > dep[v]) {
+                        double m = 0;
+                        for (int q = t->head[v]; q != -1; q = t->nxt[q])
+                            if (t->e[q] != t->e[s]) { double req = lim[rev[q]] - t->len[q]; if (req > m) m = req; }
+                        lim[s] = m;
+                    }
+            }
+        /* calculateBranchLength + min_element (first minimum of the third field) */
+        int best = 0; double bfrac = 0, badd = 2;
+        for (int q = 0; q < 4 * i - 4; q++) {
+            if (dep[t->belong[q]] > dep[t->e[q]]) continue;            /* emits (0,0,2) */
+            const int x = t->belong[q], oth = t->e[q];
+            double d1 = lim[q];
+            int r = t->head[oth];
+            while (t->e[r] != x) r = t->nxt[r];
+            double d2 = lim[r];
+            const double L = t->len[q];
+            double add = (d1 + d2 - L) / 2;
+            if (add < 0) add = 0;
+            d1 -= add; d2 -= add;
+            if (d1 < 0) d1 = 0;
+            if (d2 < 0) d2 = 0;
+            if (d1 > L) { add += d1 - L; d1 = L; }
+            if (d2 > L) { add += d2 - L; d2 = L; }
+            const double rest = L - d1 - d2;
+            d1 += rest / 2; d2 += rest / 2;
+            if (add < badd) { best = q; bfrac = d1; badd = add; }
+        }
+        /* updateTreeStructure :200-251 */
+        {
+            const int middle = i + N - 1, outside = i, eid = best;
+            int x = t->belong[eid], y = t->e[eid];
+            const double orig = t->len[eid];
+            int xe = -1, ye = -1;
+            for (int s = t->head[x]; s != -1; s = t->nxt[s])
+                if (t->e[s] == y) { t->e[s] = middle; t->len[s] = bfrac; xe = s; rev[xe] = idx; break; }
+            for (int s = t->head[y]; s != -1; s = t->nxt[s])
+                if (t->e[s] == x) { t->e[s] = middle; t->len[s] -= bfrac; ye = s; rev[ye] = idx + 1; break; }
+            link_slot(t, idx, middle, x, bfrac); rev[idx] = xe;
+            link_slot(t, idx + 1, middle, y, orig - bfrac); rev[idx + 1] = ye;
+            link_slot(t, idx + 2, outside, middle, badd); rev[idx + 2] = idx + 3;
+            link_slot(t, idx + 3, middle, outside, badd); rev[idx + 3] = idx + 2;
+            if (dfsrk[x] > dfsrk[y]) { int temp = x; y = x; x = temp; }   /* as written in the reference */
+            dfsrk[middle] = dfsrk[y];
+            dfsrk[outside] = dfsrk[middle] + 1;
+            dep[middle] = dep[x]; dep[outside] = dep[middle] + 1;
+            idx += 4;
+        }
+        const int tot = N + i, ref = N + i - 1;
+        for (int v = 0; v < tot; v++) {                      /* updateDfsRk :368-381 */
+            if (v > i && v < N) continue;
+            if (v == ref || v == i) continue;
+            if (dfsrk[v] >= dfsrk[ref]) dfsrk[v] += 2;
+        }
+        int small = N + i - 1;                               /* findEndRk :384-399 + reduce(min) */
+        for (int v = 0; v < tot; v++) {
+            int tv;
+            if (v > i && v < N) tv = 1000000000;
+            else if (dfsrk[v] <= dfsrk[ref] + 2 || dep[v] > dep[ref] + 1) tv = 1000000000;
+            else tv = dfsrk[v] - 1;
+            if (tv < small) small = tv;
+        }
+        for (int v = 0; v < tot; v++) {                      /* updateDepth :401-417 */
+            if (v > i && v < N) continue;
+            bfs[v] = v;
+            if (dfsrk[v] <= small && dfsrk[v] >= dfsrk[ref]) dep[v]++;
+        }
+        for (int v = 0; v < tot; v++) { kv[v].key = dep[v]; kv[v].pos = v; kv[v].val = bfs[v]; }
+        qsort(kv, (size_t)tot, sizeof(orc_kv), cmp_kv);
+        for (int v = 0; v < tot; v++) { bfs[v] = kv[v].val; tmp[v] = kv[v].key; }
+        for (int k = 0; k < 2 * i + 1; k++) {                /* updateLevelStEd :420-436 */
+            if (k == 0 || dep[bfs[k - 1]] != dep[bfs[k]]) levelst[dep[bfs[k]]] = k;
+            if (k + 1 == 2 * i + 1 || dep[bfs[k + 1]] != dep[bfs[k]]) leveled[dep[bfs[k]]] = k;
+        }
+    }
+    free(rev); free(dep); free(dfsrk); free(bfs); free(tmp); free(levelst); free(leveled); free(lim); free(dis); free(kv);
+    return t;
+}
+
+ORC_API orc_ptree *orc_place_exact_matrix(const double *D, int n) {
+    mat_ctx c = {D, n};
+    return orc_place_exact_all(n, mat_rows, &c);
+}
+
+/* ------------------------------------------------------------------------- */
 /* A.7 divide and conquer                                                    */
 /* ------------------------------------------------------------------------- */
 

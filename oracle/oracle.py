@@ -63,6 +63,8 @@ def lib():
         L.orc_ptree_free.argtypes = [C.c_void_p]
         L.orc_place_all_matrix.argtypes = [f64p, C.c_int]
         L.orc_place_all_matrix.restype = C.c_void_p
+        L.orc_place_exact_matrix.argtypes = [f64p, C.c_int]
+        L.orc_place_exact_matrix.restype = C.c_void_p
         L.orc_place_add_matrix.argtypes = [C.c_void_p, f64p, C.c_int, C.c_int]
         L.orc_ptree_load_backbone.argtypes = [C.c_void_p, C.c_int, i32p, i32p, i32p, f64p, C.c_int]
         L.orc_dc_matrix.argtypes = [f64p, C.c_int, C.c_int, i32p]
@@ -234,6 +236,12 @@ class PTree:
 def place_all(D):
     D = np.ascontiguousarray(D, np.float64)
     return PTree(lib().orc_place_all_matrix(D, D.shape[0]), D.shape[0])
+
+
+def place_exact(D):
+    """Exact placement mode (src/placement.cu:505-789) from a full distance matrix; print from node n."""
+    D = np.ascontiguousarray(D, np.float64)
+    return PTree(lib().orc_place_exact_matrix(D, D.shape[0]), D.shape[0])
 
 
 def place_add(D, B, root, child_off, child_idx, parent, bl):

@@ -16,6 +16,7 @@
 //   modes: msa_rows   -> <out>.rows   lower-triangle distances (row i: i doubles)
 //          msa_nj     -> <out>.nwk    conventional NJ tree from aligned input
 //          msa_place  -> <out>.nwk    k-closest placement tree from aligned input
+//          msa_place_exact / mash_place_exact -> <out>.nwk  exact placement mode (src/placement.cu)
 //          mash_sketch-> <out>.sk     uint64 [n][1000] sketches
 //          mash_rows  -> <out>.rows
 //          mash_nj    -> <out>.nwk
@@ -113,6 +114,14 @@ int main(int argc, char** argv) {
                                                                 MashPlacement::matrixReader, MashPlacement::msaDeviceArrays);
         t_tree = ms_since(t0);
         MashPlacement::kplacementDeviceArrays.printTree(names, os);
+    } else if (mode == "msa_place_exact" || mode == "mash_place_exact") {
+        std::ofstream os(out + ".nwk");
+        MashPlacement::placementDeviceArrays.allocateDeviceArrays(n);
+        t0 = Clock::now();
+        MashPlacement::placementDeviceArrays.findPlacementTree(params, MashPlacement::mashDeviceArrays,
+                                                               MashPlacement::matrixReader, MashPlacement::msaDeviceArrays);
+        t_tree = ms_since(t0);
+        MashPlacement::placementDeviceArrays.printTree(names, os);
     } else {
         fprintf(stderr, "unknown mode %s\n", mode.c_str());
         return 2;

@@ -225,3 +225,40 @@ def test_golden_fixtures(oracle):
             assert np.array_equal(sk, z["sketches"]), fn
             D = oracle.mash_dist_matrix(sk, int(z["k"]))
             assert np.allclose(D, z["dist"], rtol=1e-6, atol=0), fn
+
+
+def test_exact_placement_oracle_recovers_an_additive_tree(oracle):
+    """Exact placement mode (src/placement.cu) on the path metric of a random tree returns that tree."""
+    from dipper_b200 import newick as nw
+    n, rng = 120, np.random.default_rng(5)
+    adj = {0: {1: 0.05}, 1: {0: 0.05}}
+    nxt = n
+    for leaf in range(2, n):
+        a = int(rng.choice(list(adj.keys())))
+        b = int(rng.choice(list(adj[a].keys())))
+        L = adj[a][b]
+        f = rng.uniform(0.2, 0.8) * L
+        m, nxt = nxt, nxt + 1
+        del adj[a][b]; del adj[b][a]
+        pend = rng.uniform(0.01, 0.1)
+        adj[m] = {a: f, b: L - f, leaf: pend}
+        adj[a][m] = f; adj[b][m] = L - f; adj[leaf] = {m: pend}
+    D = np.zeros((n, n))
+    for s in range(n):
+        st = [(s, -1, 0.0)]
+        while st:
+            v, p, d = st.pop()
+            if v < n:
+                D[s, v] = d
+            st.extend((w, v, d + l) for w, l in adj[v].items() if w != p)
+    names = ["T%d" % (i + 1) for i in range(n)]
+
+    def nwk(v, p):
+        ch = [w for w in adj[v] if w != p]
+        return names[v] if not ch else "(" + ",".join(nwk(w, v) + ":%g" % adj[v][w] for w in ch) + ")"
+    truth = nwk(n, -1) + ";"
+    mine = oracle.place_exact(D).newick(names)
+    assert nw.rf_distance(mine, truth) == 0
+    assert nw.max_branch_diff(mine, truth) < 1e-6   # %g text: 6 significant digits
+    # the k-closest rule agrees on an additive metric
+    assert nw.rf_distance(oracle.place_all(D).newick(names), truth) == 0

@@ -106,3 +106,25 @@ def test_msa_placement_tree_vs_reference_cuda(ctx, oracle, tmp_path):
     assert newick.rf_distance(nwk, ref_nwk) == 0
     assert newick.max_branch_diff(nwk, ref_nwk) < 1e-5
     assert nwk == ref_nwk      # same slots, same adjacency order, same %g text
+
+
+def test_msa_exact_placement_tree_vs_reference_cuda(ctx, oracle, tmp_path):
+    """-p 0 exact placement (src/placement.cu): our tree and the oracle's vs the reference's own kernels."""
+    n, L = 500, 3000
+    codes, P, _ = make_msa(n, L, seed=47)
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "o")
+    write_bin(inp, P, [L] * n, 4)
+    run_ref("msa_place_exact", inp, out, 2)
+    ref_nwk = open(out + ".nwk").read()
+    prm = api.Param(distanceType=2, in_="m")
+    msa = api.MSADeviceArrays(ctx)
+    msa.allocateDeviceArrays(P, np.full(n, L, np.uint64), n, prm)
+    pl = api.PlacementDeviceArrays(ctx)
+    pl.allocateDeviceArrays(n)
+    pl.findPlacementTree(prm, msaDeviceArrays=msa)
+    nwk = pl.printTree(synth.names(n))
+    assert newick.rf_distance(nwk, ref_nwk) == 0
+    assert newick.max_branch_diff(nwk, ref_nwk) < 1e-5
+    assert nwk == ref_nwk      # same slots, same adjacency order, same %g text
+    D = msa.distMatrix(prm).to_host()
+    assert oracle.place_exact(D).newick(synth.names(n)) == ref_nwk   # pins the oracle restatement
