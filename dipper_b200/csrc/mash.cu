@@ -15,6 +15,7 @@
 #include "common.cuh"
 
 #include "mash.cuh"
+#include <cub/cub.cuh>
 
 namespace dipb {
 
@@ -229,6 +230,247 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mash_tile_kernel(MashTileParams
     }
 }
 
+// Warp-per-pair variant (default for sketch sizes up to 1024): the thread-per-pair merge above is a chain of up to 2s
+// dependent shared-memory loads with only 4 warps per SM (the tile fills shared memory).  Here the same 16 x 8 tile is
+// worked on by 16 warps and each pair's merge is cut into 32 diagonal chunks (merge path): lane l finds by binary search
+// the (a, b) at which the merged order -- B before A on ties, exactly the order of the reference's loop -- reaches
+// element l * CH, walks its CH <= 64 elements and records one bit per element (union event / intersection event).
+// The reference's stop rule "the union counter reaches s" becomes: find the s-th union bit in lane order and count the
+// intersection bits before it.  Same integers as src/mash.cu:437-454, so the distances are bit-identical.
+constexpr int MW_WARPS = 16;
+constexpr int MW_THREADS = MW_WARPS * 32;
+
+__global__ void __launch_bounds__(MW_THREADS, 1) mash_warp_kernel(MashTileParams p, long long num_tiles, int tiles_x) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* sA = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* sB = sA + (size_t)MD_TA * p.s;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sB + (size_t)MD_TB * p.s);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    uint32_t phase = 0;
+    const int s = p.s, total = 2 * s, CH = (total + 31) >> 5;
+    const uint32_t sk_bytes = (uint32_t)s * 8u;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tb = (int)(t / tiles_x), ta = (int)(t % tiles_x);
+        const int row0 = p.r0 + tb * MD_TB, col0 = ta * MD_TA;
+        const int row_max = min(row0 + MD_TB, p.r1) - 1;
+        if (p.tri && col0 > row_max) continue;   // strictly above the diagonal (uniform per CTA)
+        if (tid == 0) {
+            int na = min(MD_TA, p.n - col0), nb = min(MD_TB, p.r1 - row0);
+            mbar_arrive_expect_tx(bar, (uint32_t)(na + nb) * sk_bytes);
+            for (int q = 0; q < na; q++) tma_bulk_g2s(sA + (size_t)q * s, p.sk + (size_t)(col0 + q) * s, sk_bytes, bar);
+            for (int q = 0; q < nb; q++) tma_bulk_g2s(sB + (size_t)q * s, p.sk + (size_t)(row0 + q) * s, sk_bytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        for (int pp = wid; pp < MD_TA * MD_TB; pp += MW_WARPS) {
+            const int ia = pp % MD_TA, ib = pp / MD_TA;
+            const int i = row0 + ib, j = col0 + ia;
+            const int jlim = p.tri ? i : p.ncols;
+            if (!(i < p.r1 && j < jlim && j < p.n)) continue;   // warp-uniform
+            const uint64_t* A = sA + (size_t)ia * s;
+            const uint64_t* B = sB + (size_t)ib * s;
+            const int d0 = min(lane * CH, total), d1 = min(d0 + CH, total);
+            // merge-path split: a = how many A elements are among the first d0 merged ones
+            int lo = max(0, d0 - s), hi = min(d0, s);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (A[mid] < B[d0 - mid - 1]) lo = mid + 1; else hi = mid;
+            }
+            int a = lo, b = d0 - lo;
+            uint64_t av = A[min(a, s - 1)], bv = B[min(b, s - 1)];
+            uint32_t um[2] = {0u, 0u}, im[2] = {0u, 0u};
+            const int steps = d1 - d0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int cnt = min(32, steps - 32 * h);
+                uint32_t u = 0, m = 0;
+                for (int q = 0; q < cnt; q++) {
+                    const bool takeB = (b < s) && (a >= s || bv <= av);
+                    const bool eq = takeB && a < s && bv == av;
+                    const uint32_t bit = 1u << q;
+                    u |= eq ? 0u : bit;
+                    m |= eq ? bit : 0u;
+                    a += takeB ? 0 : 1;
+                    b += takeB ? 1 : 0;
+                    const uint64_t v = takeB ? B[min(b, s - 1)] : A[min(a, s - 1)];
+                    if (takeB) bv = v; else av = v;
+                }
+                um[h] = u; im[h] = m;
+            }
+            const int uc = __popc(um[0]) + __popc(um[1]);
+            int P = uc;
+#pragma unroll
+            for (int sh = 1; sh < 32; sh <<= 1) { const int o = __shfl_up_sync(0xffffffffu, P, sh); if (lane >= sh) P += o; }
+            const unsigned int reached = __ballot_sync(0xffffffffu, P >= s);   // never empty: the A list alone holds s union events
+            const int Ls = __ffs(reached) - 1;
+            int contrib = 0;
+            if (lane < Ls) contrib = __popc(im[0]) + __popc(im[1]);
+            else if (lane == Ls) {
+                const int tth = s - (P - uc);             // the s-th union event overall is this lane's tth (1-based)
+                const int c0 = __popc(um[0]);
+                const bool low = tth <= c0;
+                uint32_t m = low ? um[0] : um[1];
+                const int skip = (low ? tth : tth - c0) - 1;
+                for (int r = 0; r < skip; r++) m &= m - 1;
+                const int pos = __ffs(m) - 1;              // intersection events after it are never consumed by the reference loop
+                const uint32_t below = pos ? (0xffffffffu >> (32 - pos)) : 0u;
+                contrib = low ? __popc(im[0] & below) : __popc(im[0]) + __popc(im[1] & below);
+            }
+            const int inter = __reduce_add_sync(0xffffffffu, contrib);
+            if (lane == 0) {
+                // :453-454 (the union counter is exactly s on exit)
+                double jac = fmax(double(inter), 1.0) / s;
+                double d = fmin(1.0, fabs(log(2.0 * jac / (1.0 + jac)) / p.k));
+                if (p.tri) {
+                    p.out[(size_t)i * p.ld + j] = d;
+                    p.out[(size_t)j * p.ld + i] = d;
+                } else {
+                    p.out[(size_t)(i - p.row_off) * p.ld + j] = d;
+                }
+            }
+        }
+        __syncthreads();   // tile buffers are reused
+    }
+}
+
+// Rank-compressed variant (default while n * s < 2^32 - 1 and the tile fits shared memory).  The merge only asks "is
+// B[b] <= A[a]" and "is B[b] == A[a]", so every 64-bit hash can be replaced by its dense rank among ALL n * s hashes of the
+// data set (one radix sort + scan + scatter, mash_build_ranks): same order, same equalities, hence the same inter / union
+// integers -- but 4-byte keys.  That halves the shared-memory bytes per step, lets a tile hold 32 column sketches x 16
+// row sketches (512 pairs, 16 warps instead of 4) and, above all, allows a bank-conflict-free layout: the tile is stored
+// INTERLEAVED (element t of column sketch q at word t * 32 + q, of row sketch q at t * 16 + q) and lane l of warp r works
+// on the pair (column l, row (l + r) mod 16).  Every lane then reads its column list through its own bank whatever its
+// position, and at most two lanes meet on a row-list bank -- the thread-per-pair kernel above spends ~5.5 shared-memory
+// wavefronts per step on random 8-byte reads.  Two extra rows of 0xFFFFFFFF after each list replace the index clamps.
+constexpr int MR_TA = 32;   // column sketches ("A" lists) per tile = lanes
+constexpr int MR_TB = 16;   // row sketches ("B" lists) per tile = warps
+constexpr int MR_THREADS = MR_TB * 32;
+
+__global__ void __launch_bounds__(MR_THREADS, 1) mash_rank_kernel(MashTileParams p, const uint32_t* __restrict__ rk, long long num_tiles, int tiles_x) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int s = p.s;
+    uint32_t* sA = reinterpret_cast<uint32_t*>(smem_raw);          // [(s + 2)][32]
+    uint32_t* sB = sA + (size_t)(s + 2) * MR_TA;                   // [(s + 2)][16]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < 2 * MR_TA) sA[(size_t)s * MR_TA + tid] = 0xFFFFFFFFu;   // two rows past the end: the look-ahead reads them
+    if (tid < 2 * MR_TB) sB[(size_t)s * MR_TB + tid] = 0xFFFFFFFFu;
+    const int half = s >> 1;                                       // sketch sizes are even: 8-byte global loads
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tb = (int)(t / tiles_x), ta = (int)(t % tiles_x);
+        const int row0 = p.r0 + tb * MR_TB, col0 = ta * MR_TA;
+        const int row_max = min(row0 + MR_TB, p.r1) - 1;
+        if (p.tri && col0 > row_max) continue;   // strictly above the diagonal (uniform per CTA)
+        __syncthreads();                         // the previous tile is done with the buffers
+        {
+            // columns: lane = sketch, the 16 warps split the element pairs; stores hit bank = lane
+            const int q = col0 + lane;
+            if (q < p.n) {
+                const uint2* src = reinterpret_cast<const uint2*>(rk + (size_t)q * s);
+#pragma unroll 8
+                for (int h = wid; h < half; h += MR_TB) {
+                    const uint2 v = __ldg(src + h);
+                    sA[(size_t)(2 * h) * MR_TA + lane] = v.x;
+                    sA[(size_t)(2 * h + 1) * MR_TA + lane] = v.y;
+                }
+            }
+            // rows: lanes 0-15 / 16-31 = sketch, alternate element pairs
+            const int qb = lane & 15, r = row0 + qb;
+            if (r < p.r1) {
+                const uint2* src = reinterpret_cast<const uint2*>(rk + (size_t)r * s);
+#pragma unroll 8
+                for (int h = wid * 2 + (lane >> 4); h < half; h += 2 * MR_TB) {
+                    const uint2 v = __ldg(src + h);
+                    sB[(size_t)(2 * h) * MR_TB + qb] = v.x;
+                    sB[(size_t)(2 * h + 1) * MR_TB + qb] = v.y;
+                }
+            }
+        }
+        __syncthreads();
+        const int ib = (lane + wid) & (MR_TB - 1);
+        const int i = row0 + ib, j = col0 + lane;
+        const int jlim = p.tri ? i : p.ncols;
+        if (i < p.r1 && j < jlim && j < p.n) {
+            // src/mash.cu:439-450, one consumed element per step.  Current and next element of both lists live in registers, so
+            // the shared-memory load of a step (the element after next of the consumed list) is off the compare -> select
+            // critical path; an exhausted B list reads 0xFFFFFFFF (> every rank).  Every step consumes one element, so
+            // inter = steps - uni.
+            uint32_t pa = (uint32_t)__cvta_generic_to_shared(sA + lane), pb = (uint32_t)__cvta_generic_to_shared(sB + ib);
+            uint32_t av, an, bv, bn;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(av) : "r"(pa));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(an) : "r"(pa + MR_TA * 4));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bv) : "r"(pb));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bn) : "r"(pb + MR_TB * 4));
+            int uni = 0, steps = 0;
+            while (uni < s) {
+                const bool takeB = bv <= av;
+                uni += (bv == av) ? 0 : 1;
+                steps++;
+                const uint32_t addr = takeB ? pb + 2 * MR_TB * 4 : pa + 2 * MR_TA * 4;
+                uint32_t v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+                if (takeB) { bv = bn; bn = v; pb += MR_TB * 4; }
+                else { av = an; an = v; pa += MR_TA * 4; }
+            }
+            const int inter = steps - uni;
+            // :453-454
+            double jac = fmax(double(inter), 1.0) / uni;
+            double d = fmin(1.0, fabs(log(2.0 * jac / (1.0 + jac)) / p.k));
+            if (p.tri) {
+                p.out[(size_t)i * p.ld + j] = d;
+                p.out[(size_t)j * p.ld + i] = d;
+            } else {
+                p.out[(size_t)(i - p.row_off) * p.ld + j] = d;
+            }
+        }
+    }
+}
+
+__global__ void iota_u32_kernel(uint32_t* v, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] = (uint32_t)i;
+}
+__global__ void rank_flag_kernel(const uint64_t* __restrict__ sorted, uint32_t* __restrict__ flag, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        flag[i] = (i > 0 && sorted[i] != sorted[i - 1]) ? 1u : 0u;
+}
+__global__ void rank_scatter_kernel(const uint32_t* __restrict__ rank_sorted, const uint32_t* __restrict__ idx, uint32_t* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[idx[i]] = rank_sorted[i];
+}
+
+// dense ranks of all n * s hashes: radix sort (hash, position), mark value changes, prefix sum, scatter back
+static int mash_build_ranks(dipb_mash* m) {
+    dipb_ctx* c = m->ctx;
+    const size_t M = (size_t)m->n * m->s;
+    uint64_t* keys_out = nullptr;
+    uint32_t *idx = nullptr, *idx_out = nullptr, *flag = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_sort = 0, tmp_scan = 0;
+    DIPB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, M, 0, 64, c->stream));
+    DIPB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, (const uint32_t*)nullptr, (uint32_t*)nullptr, M, c->stream));
+    const size_t tmp_bytes = tmp_sort > tmp_scan ? tmp_sort : tmp_scan;
+    DIPB_CUDA(cudaMalloc(&m->ranks, M * sizeof(uint32_t)));   // (lives as long as the sketches)
+    DIPB_CUDA(pool_alloc(c, (void**)&keys_out, M * sizeof(uint64_t)));
+    DIPB_CUDA(pool_alloc(c, (void**)&idx, M * sizeof(uint32_t)));
+    DIPB_CUDA(pool_alloc(c, (void**)&idx_out, M * sizeof(uint32_t)));
+    DIPB_CUDA(pool_alloc(c, (void**)&flag, M * sizeof(uint32_t)));
+    DIPB_CUDA(pool_alloc(c, &tmp, tmp_bytes ? tmp_bytes : 16));
+    const int grid = c->num_sms * 8;
+    iota_u32_kernel<<<grid, 256, 0, c->stream>>>(idx, M);
+    DIPB_KERNEL_CHECK(c);
+    size_t tb = tmp_bytes;
+    DIPB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint64_t*)m->sketches, keys_out, (const uint32_t*)idx, idx_out, M, 0, 64, c->stream));
+    rank_flag_kernel<<<grid, 256, 0, c->stream>>>(keys_out, flag, M);
+    DIPB_KERNEL_CHECK(c);
+    tb = tmp_bytes;
+    DIPB_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, (const uint32_t*)flag, idx, M, c->stream));   // idx now holds the rank of sorted position i
+    rank_scatter_kernel<<<grid, 256, 0, c->stream>>>(idx, idx_out, m->ranks, M);
+    DIPB_KERNEL_CHECK(c);
+    c->launches += 4;   // the library's sort and scan passes (approximate; not hand-written kernels)
+    pool_free(c, keys_out); pool_free(c, idx); pool_free(c, idx_out); pool_free(c, flag); pool_free(c, tmp);
+    return 0;
+}
+
 __global__ void zero_diag_kernel(double* D, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) D[(size_t)i * n + i] = 0.0;
@@ -236,20 +478,42 @@ __global__ void zero_diag_kernel(double* D, int n) {
 
 static int mash_launch(dipb_mash* m, MashTileParams p) {
     dipb_ctx* c = m->ctx;
+    const int rows = p.r1 - p.r0;
+    const int ncols = p.tri ? p.r1 : p.ncols;
+    if (rows <= 0 || ncols <= 0) return 0;
+    // ---- rank-compressed, interleaved tiles (default)
+    const char* er = getenv("DIPB_MASH_RANKS");   // 0: keep the 64-bit hashes (first versions, kept for comparison)
+    const size_t rk_smem = (size_t)(m->s + 2) * (MR_TA + MR_TB) * sizeof(uint32_t);
+    if (!(er && atoi(er) == 0) && (size_t)m->n * m->s < 0xFFFFFFFFull && rk_smem <= 227 * 1024) {
+        if (!m->ranks) { int rc = mash_build_ranks(m); if (rc) return rc; }
+        static size_t attr_rk = 0;
+        if (rk_smem > attr_rk) {
+            DIPB_CUDA(cudaFuncSetAttribute(mash_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rk_smem));
+            attr_rk = rk_smem;
+        }
+        const int tiles_y = (rows + MR_TB - 1) / MR_TB, tiles_x = (ncols + MR_TA - 1) / MR_TA;
+        const long long tiles = (long long)tiles_y * tiles_x;
+        const int grid = (int)(tiles < (long long)c->num_sms * 4 ? tiles : (long long)c->num_sms * 4);
+        mash_rank_kernel<<<grid, MR_THREADS, rk_smem, c->stream>>>(p, m->ranks, tiles, tiles_x);
+        DIPB_KERNEL_CHECK(c);
+        return 0;
+    }
+    // ---- 64-bit hashes
     size_t smem = (size_t)(MD_TA + MD_TB) * m->s * 8 + 64;
     if (smem > 227 * 1024) { set_error("mash distance: sketch size %d does not fit shared memory tiles", m->s); return DIPB_E_ARG; }
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         DIPB_CUDA(cudaFuncSetAttribute(mash_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DIPB_CUDA(cudaFuncSetAttribute(mash_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
-    int rows = p.r1 - p.r0;
-    int ncols = p.tri ? p.r1 : p.ncols;
+    const char* ew = getenv("DIPB_MASH_WARP");   // 1: merge-path warp-per-pair kernel (measured equal to the thread-per-pair one: both sit on
+    const bool warp_merge = m->s <= 1024 && ew && atoi(ew) == 1;   // the shared-memory wavefronts of random 8-byte reads)
     int tiles_y = (rows + MD_TB - 1) / MD_TB, tiles_x = (ncols + MD_TA - 1) / MD_TA;
     long long tiles = (long long)tiles_y * tiles_x;
-    if (tiles <= 0) return 0;
     int grid = (int)(tiles < (long long)c->num_sms * 8 ? tiles : (long long)c->num_sms * 8);
-    mash_tile_kernel<<<grid, MD_THREADS, smem, c->stream>>>(p, tiles, tiles_x);
+    if (warp_merge) mash_warp_kernel<<<grid, MW_THREADS, smem, c->stream>>>(p, tiles, tiles_x);
+    else mash_tile_kernel<<<grid, MD_THREADS, smem, c->stream>>>(p, tiles, tiles_x);
     DIPB_KERNEL_CHECK(c);
     return 0;
 }
@@ -307,7 +571,7 @@ int dipb_mash_set_sketches(dipb_ctx* c, const uint64_t* h_sk, size_t n, int k, i
 void dipb_mash_free(dipb_mash* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
-    cudaFree(m->seqs); cudaFree(m->word_off); cudaFree(m->lens); cudaFree(m->sketches);
+    cudaFree(m->seqs); cudaFree(m->word_off); cudaFree(m->lens); cudaFree(m->sketches); cudaFree(m->ranks);
     delete m;
 }
 
@@ -322,6 +586,7 @@ int dipb_mash_sketch(dipb_mash* m) {
     DIPB_KERNEL_CHECK(c);
     rc = timer_end(c, DIPB_T_SKETCH);
     if (rc) return rc;
+    if (m->ranks) { cudaFree(m->ranks); m->ranks = nullptr; }   // ranks belong to the previous sketches
     m->sketched = true;
     return 0;
 }

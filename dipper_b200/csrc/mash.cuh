@@ -9,6 +9,7 @@ struct dipb_mash {
     uint64_t* word_off = nullptr;  // [n]
     uint64_t* lens = nullptr;      // [n] bases
     uint64_t* sketches = nullptr;  // [n][s]
+    uint32_t* ranks = nullptr;     // [n][s]: dense rank of every hash among all n*s hashes (same order, same equalities), built lazily
     bool sketched = false;
 };
 

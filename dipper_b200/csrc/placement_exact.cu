@@ -35,7 +35,8 @@ namespace {
 
 constexpr int EX_THREADS = 1024;
 constexpr int EX_KM = 3;               // owned nodes of each kind per thread at most (NL <= 3072)
-constexpr int EX_BYTES_PER_NODE = 90;  // per local index: leaf 31 B + internal 59 B of state
+constexpr int EX_BYTES_PER_NODE = 90;
+constexpr unsigned long long EX_EMPTY = 0xFFF8DEADBEEF0001ull;   // "no value yet": a NaN payload no arithmetic produces  // per local index: leaf 31 B + internal 59 B of state
 
 struct ExCtl {
     int maxdep;
@@ -104,14 +105,15 @@ __device__ __forceinline__ void ex_score(double dis1, double dis2, double L, int
     if (ex_before(a, slot, b.add, b.slot)) { b.add = a; b.frac = dis1; b.slot = slot; b.node = node; }
 }
 
-template <int CS>
+template <int CS, bool FLOW>
 __global__ void __launch_bounds__(EX_THREADS, 1)
 place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict__ nxt, int* __restrict__ belong,
                    double* __restrict__ len, const double* __restrict__ rows, size_t ld, int row_base, int i0, int i1, int N,
                    int NL, const double* __restrict__ d01, uint4* __restrict__ saved, ExCtl* __restrict__ ctl) {
     extern __shared__ __align__(16) unsigned char ex_smem[];
-    __shared__ double rec_d[CS][3];     // every CTA's best candidate of this tip: add, frac, edge length
-    __shared__ int rec_i[CS][8];        // slot, node y, parent x, rank, subtree size, depth, child index of y
+    __shared__ double rec_d[2][CS][3];  // every CTA's best candidate of this tip: add, frac, edge length (double-buffered by tip parity:
+    __shared__ int rec_i[2][CS][8];     // slot, node y, parent x, rank, subtree size, depth, child index of y   in FLOW mode a CTA that owns
+                                        // no nodes yet can be a whole tip behind its peers)
     __shared__ int s_grow[2];
     __shared__ ExBest s_warp[EX_THREADS / 32];
     constexpr int LOGCS = CS == 16 ? 4 : (CS == 8 ? 3 : (CS == 4 ? 2 : (CS == 2 ? 1 : 0)));
@@ -130,7 +132,8 @@ place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict_
             S.l_dep[k] = 0xFFFF; S.i_dep[k] = 0xFFFF; S.l_rank[k] = -1; S.i_rank[k] = -1; S.i_sz[k] = 0;
             S.l_par[k] = -1; S.i_par[k] = -1; S.i_kid0[k] = -1; S.i_kid1[k] = -1; S.l_sdn[k] = 0; S.i_sdn[k] = 0;
             S.l_cidx[k] = 0; S.i_cidx[k] = 0;
-            S.l_dn[k] = 0; S.l_plen[k] = 0; S.i_dn[k] = 0; S.i_in0[k] = 0; S.i_in1[k] = 0; S.i_plen[k] = 0;
+            const double empty = FLOW ? __longlong_as_double((long long)EX_EMPTY) : 0.0;
+            S.l_dn[k] = empty; S.i_dn[k] = empty; S.i_in0[k] = empty; S.i_in1[k] = empty; S.l_plen[k] = 0; S.i_plen[k] = 0;
         }
         __syncthreads();
         if (rank == 0 && tid == 0) {   // nodes 0, 1 (leaves) and N (internal index 0) all live in CTA 0, local 0 / 1 / 0
@@ -165,6 +168,95 @@ place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict_
             myd[u] = 0;
             if (k < NL) { const int lid = id_of(k); if (lid < i) myd[u] = __ldg(&row[lid]); }
         }
+        ExBest best;
+        best.add = 2.0; best.frac = 0.0; best.slot = 0; best.node = -1;   // the (0,0,2) default tuple
+        if constexpr (FLOW) {
+            // ---- data flow instead of level steps: a value IS its own arrival flag (slots hold EX_EMPTY, a NaN no arithmetic
+            // produces, until the producer's st.shared::cluster lands).  Leaves push their limit at once; an internal node
+            // waits for both children (updateFromBottomToTop), pushes upwards, then waits for its parent's value
+            // (updateFromTopToBottom), scores its parent->child slot and feeds its children.  No barrier, no fence: the
+            // bottom-up / top-down sweeps cost one shared-memory store latency per tree level.
+            int st_l[EX_KM], st_i[EX_KM], pending = 0;
+            double ra[EX_KM], rb[EX_KM];
+#pragma unroll
+            for (int u = 0; u < EX_KM; u++) {
+                const int k = tid + u * EX_THREADS;
+                st_l[u] = 0; st_i[u] = 0; ra[u] = 0; rb[u] = 0;
+                if (k < NL) {
+                    if (S.l_dep[k] != 0xFFFF) {
+                        const int j = S.l_par[k] - N;
+                        ex_push_f64((S.l_cidx[k] ? S.i_in1 : S.i_in0) + loc_of(j), cta_of(j), myd[u] - S.l_plen[k]);
+                        st_l[u] = 2; pending++;
+                    }
+                    if (S.i_dep[k] != 0xFFFF) { st_i[u] = 1; pending++; }
+                }
+            }
+            while (pending) {
+#pragma unroll
+                for (int u = 0; u < EX_KM; u++) {
+                    const int k = tid + u * EX_THREADS;
+                    if (st_i[u] == 1) {
+                        const unsigned long long ua = *reinterpret_cast<volatile unsigned long long*>(S.i_in0 + k);
+                        const unsigned long long ub = *reinterpret_cast<volatile unsigned long long*>(S.i_in1 + k);
+                        if (ua != EX_EMPTY && ub != EX_EMPTY) {
+                            const double a = __longlong_as_double((long long)ua), b = __longlong_as_double((long long)ub);
+                            *reinterpret_cast<volatile unsigned long long*>(S.i_in0 + k) = EX_EMPTY;
+                            *reinterpret_cast<volatile unsigned long long*>(S.i_in1 + k) = EX_EMPTY;
+                            ra[u] = a; rb[u] = b;
+                            if (S.i_dep[k] == 0) {   // the root: nothing above it
+                                double v0 = 0, v1 = 0;
+                                if (b > v0) v0 = b;
+                                if (a > v1) v1 = a;
+                                const int k0 = S.i_kid0[k], k1 = S.i_kid1[k];
+                                if (k0 < N) ex_push_f64(S.l_dn + loc_of(k0), cta_of(k0), v0);
+                                else ex_push_f64(S.i_dn + loc_of(k0 - N), cta_of(k0 - N), v0);
+                                if (k1 < N) ex_push_f64(S.l_dn + loc_of(k1), cta_of(k1), v1);
+                                else ex_push_f64(S.i_dn + loc_of(k1 - N), cta_of(k1 - N), v1);
+                                st_i[u] = 0; pending--;
+                            } else {
+                                double m = 0;
+                                if (a > m) m = a;
+                                if (b > m) m = b;
+                                const int j = S.i_par[k] - N;
+                                ex_push_f64((S.i_cidx[k] ? S.i_in1 : S.i_in0) + loc_of(j), cta_of(j), m - S.i_plen[k]);
+                                st_i[u] = 2;
+                            }
+                        }
+                    } else if (st_i[u] == 2) {
+                        const unsigned long long ud = *reinterpret_cast<volatile unsigned long long*>(S.i_dn + k);
+                        if (ud != EX_EMPTY) {
+                            *reinterpret_cast<volatile unsigned long long*>(S.i_dn + k) = EX_EMPTY;
+                            const double dn = __longlong_as_double((long long)ud), a = ra[u], b = rb[u];
+                            double up = 0;
+                            if (a > up) up = a;
+                            if (b > up) up = b;
+                            const double pl = S.i_plen[k];
+                            ex_score(dn, up, pl, S.i_sdn[k], N + id_of(k), best);
+                            const double basev = dn - pl;
+                            double v0 = 0, v1 = 0;
+                            if (b > v0) v0 = b;
+                            if (a > v1) v1 = a;
+                            if (basev > v0) v0 = basev;
+                            if (basev > v1) v1 = basev;
+                            const int k0 = S.i_kid0[k], k1 = S.i_kid1[k];
+                            if (k0 < N) ex_push_f64(S.l_dn + loc_of(k0), cta_of(k0), v0);
+                            else ex_push_f64(S.i_dn + loc_of(k0 - N), cta_of(k0 - N), v0);
+                            if (k1 < N) ex_push_f64(S.l_dn + loc_of(k1), cta_of(k1), v1);
+                            else ex_push_f64(S.i_dn + loc_of(k1 - N), cta_of(k1 - N), v1);
+                            st_i[u] = 0; pending--;
+                        }
+                    }
+                    if (st_l[u] == 2) {
+                        const unsigned long long ud = *reinterpret_cast<volatile unsigned long long*>(S.l_dn + k);
+                        if (ud != EX_EMPTY) {
+                            *reinterpret_cast<volatile unsigned long long*>(S.l_dn + k) = EX_EMPTY;
+                            ex_score(__longlong_as_double((long long)ud), myd[u], S.l_plen[k], S.l_sdn[k], id_of(k), best);
+                            st_l[u] = 0; pending--;
+                        }
+                    }
+                }
+            }
+        } else {
         // ---- bottom-up (updateFromBottomToTop :298-332): a node's limit towards its parent, pushed to the parent
         for (int lev = maxdep; lev >= 1; lev--) {
 #pragma unroll
@@ -190,8 +282,6 @@ place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict_
             ex_cluster_sync();
         }
         // ---- top-down (updateFromTopToBottom :334-366) fused with the scoring of the parent->child slots
-        ExBest best;
-        best.add = 2.0; best.frac = 0.0; best.slot = 0; best.node = -1;   // the (0,0,2) default tuple
         for (int lev = 0; lev <= maxdep; lev++) {
 #pragma unroll
             for (int u = 0; u < EX_KM; u++) {
@@ -223,6 +313,7 @@ place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict_
             }
             if (lev < maxdep) ex_cluster_sync();
         }
+        }
         levels += (unsigned long long)maxdep;
         // ---- first minimum over the cluster (thrust::min_element :657)
 #pragma unroll
@@ -250,29 +341,31 @@ place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict_
                 else { const int k = loc_of(y - N); pl = S.i_plen[k]; px = S.i_par[k]; rk = S.i_rank[k]; sz = S.i_sz[k]; dp = S.i_dep[k]; ci = S.i_cidx[k]; }
             }
             if (lane < CS) {
-                ex_push_f64(&rec_d[rank][0], lane, best.add); ex_push_f64(&rec_d[rank][1], lane, best.frac); ex_push_f64(&rec_d[rank][2], lane, pl);
-                ex_push_s32(&rec_i[rank][0], lane, best.slot); ex_push_s32(&rec_i[rank][1], lane, y); ex_push_s32(&rec_i[rank][2], lane, px);
-                ex_push_s32(&rec_i[rank][3], lane, rk); ex_push_s32(&rec_i[rank][4], lane, sz); ex_push_s32(&rec_i[rank][5], lane, dp);
-                ex_push_s32(&rec_i[rank][6], lane, ci);
+                ex_push_f64(&rec_d[i & 1][rank][0], lane, best.add); ex_push_f64(&rec_d[i & 1][rank][1], lane, best.frac); ex_push_f64(&rec_d[i & 1][rank][2], lane, pl);
+                ex_push_s32(&rec_i[i & 1][rank][0], lane, best.slot); ex_push_s32(&rec_i[i & 1][rank][1], lane, y); ex_push_s32(&rec_i[i & 1][rank][2], lane, px);
+                ex_push_s32(&rec_i[i & 1][rank][3], lane, rk); ex_push_s32(&rec_i[i & 1][rank][4], lane, sz); ex_push_s32(&rec_i[i & 1][rank][5], lane, dp);
+                ex_push_s32(&rec_i[i & 1][rank][6], lane, ci);
             }
         }
         ex_cluster_sync();
         int w = 0;
         {
-            double wa = rec_d[0][0];
-            int ws = rec_i[0][0];
+            double wa = rec_d[i & 1][0][0];
+            int ws = rec_i[i & 1][0][0];
 #pragma unroll
             for (int c = 1; c < CS; c++) {
-                const double ca = rec_d[c][0];
-                const int cs = rec_i[c][0];
+                const double ca = rec_d[i & 1][c][0];
+                const int cs = rec_i[i & 1][c][0];
                 if (ex_before(ca, cs, wa, ws)) { wa = ca; ws = cs; w = c; }
             }
         }
-        const double addLen = rec_d[w][0], fracLen = rec_d[w][1], pleny = rec_d[w][2];
-        const int slot = rec_i[w][0], y = rec_i[w][1], x = rec_i[w][2], r = rec_i[w][3], szy = rec_i[w][4], depy = rec_i[w][5], cidxy = rec_i[w][6];
+        const double addLen = rec_d[i & 1][w][0], fracLen = rec_d[i & 1][w][1], pleny = rec_d[i & 1][w][2];
+        const int slot = rec_i[i & 1][w][0], y = rec_i[i & 1][w][1], x = rec_i[i & 1][w][2], r = rec_i[i & 1][w][3], szy = rec_i[i & 1][w][4],
+                  depy = rec_i[i & 1][w][5], cidxy = rec_i[i & 1][w][6];
         if (y < 0) { failed = true; break; }   // uniform over the cluster
         // ---- update: ranks (updateDfsRk :368-381), ancestors' sizes, subtree depth (findEndRk / updateDepth :384-417)
         bool grow = false;
+        if constexpr (!FLOW) {
 #pragma unroll
         for (int u = 0; u < EX_KM; u++) {
             const int k = tid + u * EX_THREADS;
@@ -289,6 +382,7 @@ place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict_
                 } else if (rk >= 0 && r < rk + S.i_sz[k]) S.i_sz[k] += 2;
             }
         }
+        }
         __syncthreads();
         // ---- split (updateTreeStructure :200-251): middle m between x and y, new leaf i below m
         const int m = i + N - 1, jm = i - 1, c0 = 4 * i - 4;
@@ -300,7 +394,7 @@ place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict_
         if (tid == 64 && cta_of(jm) == rank) {
             const int k = loc_of(jm);
             S.i_par[k] = x; S.i_cidx[k] = (unsigned char)cidxy; S.i_kid0[k] = y; S.i_kid1[k] = i; S.i_plen[k] = fracLen; S.i_sdn[k] = slot;
-            S.i_rank[k] = r; S.i_sz[k] = szy + 2; S.i_dep[k] = (unsigned short)depy;
+            S.i_rank[k] = r; S.i_sz[k] = szy + 2; S.i_dep[k] = (unsigned short)(FLOW ? 1 : depy);   // FLOW: depth is only a placed / root marker
         }
         if (tid == 96 && cta_of(i) == rank) {
             const int k = loc_of(i);
@@ -318,13 +412,18 @@ place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict_
             e[c2] = m; len[c2] = addLen; nxt[c2] = -1; belong[c2] = i; head[i] = c2;
             e[c3] = i; len[c3] = addLen; nxt[c3] = c1; belong[c3] = m; head[m] = c3;
         }
-        // ---- did the tree get deeper?
-        const int par = i & 1;
-        if (tid == 0) s_grow[par ^ 1] = 0;
-        const int g = __syncthreads_or(grow ? 1 : 0);
-        if (g && tid < CS) ex_push_s32(&s_grow[par], tid, 1);
-        ex_cluster_sync();
-        if (s_grow[par]) maxdep++;
+        // ---- did the tree get deeper?  (level mode only; in FLOW mode the local __syncthreads is all the next tip needs:
+        // peers' early pushes land in slots that are EX_EMPTY again, and nothing else of a peer is read)
+        if constexpr (FLOW) {
+            __syncthreads();
+        } else {
+            const int par = i & 1;
+            if (tid == 0) s_grow[par ^ 1] = 0;
+            const int g = __syncthreads_or(grow ? 1 : 0);
+            if (g && tid < CS) ex_push_s32(&s_grow[par], tid, 1);
+            ex_cluster_sync();
+            if (s_grow[par]) maxdep++;
+        }
     }
 
     // ---- keep the state for the next batch
@@ -342,9 +441,9 @@ place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict_
     }
 }
 
-template <int CS>
+template <int CS, bool FLOW>
 int ex_launch(dipb_ctx* c, void** args, size_t smem, bool* ok) {
-    auto kern = place_exact_kernel<CS>;
+    auto kern = place_exact_kernel<CS, FLOW>;
     *ok = false;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     if (CS > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -375,6 +474,8 @@ int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* 
     int CS = 16;
     const char* force = getenv("DIPB_EXACT_CLUSTER");
     if (force && atoi(force) == 8) CS = 8;
+    const char* fl = getenv("DIPB_EXACT_FLOW");   // 0: level steps with cluster barriers (first version, kept for comparison)
+    const bool flow = !(fl && atoi(fl) == 0);
     int NL = ex_local(n, CS);
     if (ex_smem_bytes(NL) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS) {
         set_error("exact placement: %d tips exceed the shared-memory tree of one %d-CTA cluster (at most %d tips); use -p 1 or -m 3", n, CS,
@@ -415,7 +516,7 @@ int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* 
         void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &rows, &ldr, &row_base, &i0v, &i1, &N, &NL, &d01, &saved, &ctl};
         bool ok = false;
         if (CS == 16) {
-            rc = ex_launch<16>(c, args, ex_smem_bytes(NL), &ok);
+            rc = flow ? ex_launch<16, true>(c, args, ex_smem_bytes(NL), &ok) : ex_launch<16, false>(c, args, ex_smem_bytes(NL), &ok);
             if (!rc && !ok && i0 == 2) {   // device cannot co-schedule 16 CTAs: portable cluster size, half the capacity
                 CS = 8; NL = ex_local(n, 8);
                 if (ex_smem_bytes(NL) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS) { set_error("exact placement: 16-CTA clusters unavailable and %d tips do not fit 8 CTAs", n); rc = DIPB_E_UNSUPPORTED; break; }
@@ -423,7 +524,7 @@ int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* 
                 DIPB_CUDA(pool_alloc(c, (void**)&saved, ex_smem_bytes(NL) * 8));
             }
         }
-        if (!rc && !ok && CS == 8) rc = ex_launch<8>(c, args, ex_smem_bytes(NL), &ok);
+        if (!rc && !ok && CS == 8) rc = flow ? ex_launch<8, true>(c, args, ex_smem_bytes(NL), &ok) : ex_launch<8, false>(c, args, ex_smem_bytes(NL), &ok);
         if (!rc && !ok) { set_error("exact placement: no cluster configuration fits this device"); rc = DIPB_E_UNSUPPORTED; }
         if (!rc) c->launches++;
     }

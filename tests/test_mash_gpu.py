@@ -93,6 +93,45 @@ def test_mash_merge_rule_on_crafted_sketches(ctx, oracle):
     assert D[1, 0] == min(1.0, abs(np.log(2 * (1 / 1000) / (1 + 1 / 1000)) / 15))
 
 
+@pytest.mark.parametrize("s", [2, 10, 64, 500, 1000, 1024, 1100])
+def test_warp_merge_equals_thread_merge_and_oracle(ctx, oracle, monkeypatch, s):
+    """mash_rank_kernel (default: rank-compressed keys, interleaved conflict-free tiles) vs mash_tile_kernel (the reference's
+    sequential loop per thread on the 64-bit hashes) vs mash_warp_kernel (merge path, 32 lanes per pair) and the oracle:
+    overlapping, duplicated and padded sketches of every density."""
+    rng = np.random.default_rng(100 + s)
+    pool = np.sort(rng.integers(0, 2**63, 3 * s, dtype=np.uint64))
+    rows = []
+    for r in range(37):
+        kind = r % 6
+        if kind == 0:
+            v = rng.choice(pool, s, replace=False)
+        elif kind == 1:
+            v = rng.choice(pool[: s + s // 2], s, replace=False)           # heavy overlap
+        elif kind == 2:
+            v = rng.choice(pool[: max(2, s // 3)], s, replace=True)        # many duplicates
+        elif kind == 3:
+            v = rng.choice(pool, s, replace=False); v[rng.integers(1, s):] = np.uint64(0xFFFFFFFFFFFFFFFF)   # padded
+        elif kind == 4:
+            v = pool[:s].copy()                                            # identical lists
+        else:
+            v = rng.integers(0, 2**63, s, dtype=np.uint64)                 # disjoint
+        rows.append(np.sort(v.astype(np.uint64)))
+    sk = np.stack(rows)
+    prm = api.Param(kmerSize=15, sketchSize=s, in_="r")
+    m = api.MashDeviceArrays(ctx)
+    m.setSketches(sk, prm)
+    D = m.distMatrix().to_host()
+    R = m.distConstructionOnGpu(prm, 29)
+    monkeypatch.setenv("DIPB_MASH_RANKS", "0")     # 64-bit hashes, thread-per-pair (the reference's loop verbatim)
+    D0 = m.distMatrix().to_host()
+    monkeypatch.setenv("DIPB_MASH_WARP", "1")      # 64-bit hashes, merge-path warp-per-pair
+    D1 = m.distMatrix().to_host()
+    assert np.array_equal(D, D0) and np.array_equal(D1, D0)
+    assert np.array_equal(R, D0[29, :29])
+    O = oracle.mash_dist_matrix(sk, 15)
+    assert np.allclose(D, O, rtol=1e-12, atol=0)
+
+
 def test_mash_golden_fixture(ctx):
     for fn in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*mash*.npz"))):
         z = np.load(fn)
