@@ -441,9 +441,259 @@ place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict_
     }
 }
 
-template <int CS, bool FLOW>
+// ---- data flow, second version (default): leaves are not nodes of the flow at all.  A leaf's limit towards its parent is
+// dist - len, and its own score needs only the parent's values, so the PARENT's owner keeps the edge length and slot of
+// its leaf children, prefetches their distances at the start of the tip and scores them when its own value from above
+// arrives.  Half the nodes, half the pushes and half the polled slots disappear; cherries fire immediately.
+// State per internal node: 74 B (3 value slots, own edge length, 2 leaf-child edge lengths, parent, 2 children, own slot,
+// 2 leaf-child slots, child index, placed / root flag) -> 49 152 tips in one 16-CTA cluster.
+constexpr int F2_BYTES_PER_NODE = 74;
+
+struct F2State {
+    double *dn, *in0, *in1, *plen, *klen0, *klen1;
+    int *par, *kid0, *kid1, *sdn, *ksdn0, *ksdn1;
+    unsigned char *cidx, *flag;   // flag: 0 not placed, 1 placed, 2 root
+};
+__device__ __forceinline__ F2State f2_carve(unsigned char* base, int NL) {
+    F2State s;
+    double* d = reinterpret_cast<double*>(base);
+    s.dn = d; s.in0 = d + NL; s.in1 = d + 2 * NL; s.plen = d + 3 * NL; s.klen0 = d + 4 * NL; s.klen1 = d + 5 * NL;
+    int* q = reinterpret_cast<int*>(d + 6 * NL);
+    s.par = q; s.kid0 = q + NL; s.kid1 = q + 2 * NL; s.sdn = q + 3 * NL; s.ksdn0 = q + 4 * NL; s.ksdn1 = q + 5 * NL;
+    unsigned char* b = reinterpret_cast<unsigned char*>(q + 6 * NL);
+    s.cidx = b; s.flag = b + NL;
+    return s;
+}
+
+template <int CS>
+__global__ void __launch_bounds__(EX_THREADS, 1)
+place_exact_flow2_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict__ nxt, int* __restrict__ belong,
+                         double* __restrict__ len, const double* __restrict__ rows, size_t ld, int row_base, int i0, int i1, int N,
+                         int NL, const double* __restrict__ d01, uint4* __restrict__ saved, ExCtl* __restrict__ ctl) {
+    extern __shared__ __align__(16) unsigned char ex_smem[];
+    __shared__ double rec_d[2][CS][3];  // add, frac, edge length of the winner's edge (double-buffered by tip parity)
+    __shared__ int rec_i[2][CS][4];     // slot, node y, parent x, child index of y
+    __shared__ ExBest s_warp[EX_THREADS / 32];
+    __shared__ double s_wpl[EX_THREADS / 32];
+    __shared__ int s_wx[EX_THREADS / 32], s_wc[EX_THREADS / 32];
+    constexpr int LOGCS = CS == 16 ? 4 : (CS == 8 ? 3 : (CS == 4 ? 2 : (CS == 2 ? 1 : 0)));
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rank = (int)cooperative_groups::this_cluster().block_rank();
+    const F2State S = f2_carve(ex_smem, NL);
+    const size_t state_words = (size_t)NL * F2_BYTES_PER_NODE / 16;
+    uint4* sm4 = reinterpret_cast<uint4*>(ex_smem);
+    auto cta_of = [&](int id) { return (id >> 5) & (CS - 1); };
+    auto loc_of = [&](int id) { return ((id >> (5 + LOGCS)) << 5) | (id & 31); };
+    auto id_of = [&](int k) { return ((((k >> 5) << LOGCS) | rank) << 5) | (k & 31); };
+    const double empty = __longlong_as_double((long long)EX_EMPTY);
+
+    if (i0 == 2) {
+        for (int k = tid; k < NL; k += EX_THREADS) {
+            S.dn[k] = empty; S.in0[k] = empty; S.in1[k] = empty; S.plen[k] = 0; S.klen0[k] = 0; S.klen1[k] = 0;
+            S.par[k] = -1; S.kid0[k] = -1; S.kid1[k] = -1; S.sdn[k] = 0; S.ksdn0[k] = 0; S.ksdn1[k] = 0; S.cidx[k] = 0; S.flag[k] = 0;
+        }
+        __syncthreads();
+        if (rank == 0 && tid == 0) {   // buildInitialTree :253-295: root N (internal index 0) with the leaves 0 and 1
+            const double d = d01[0];
+            S.flag[0] = 2; S.kid0[0] = 0; S.kid1[0] = 1; S.klen0[0] = d / 2; S.klen1[0] = d / 2; S.ksdn0[0] = 2; S.ksdn1[0] = 3;
+            e[0] = N; len[0] = d / 2; nxt[0] = -1; belong[0] = 0; head[0] = 0;
+            e[1] = N; len[1] = d / 2; nxt[1] = -1; belong[1] = 1; head[1] = 1;
+            e[2] = 0; len[2] = d / 2; nxt[2] = -1; belong[2] = N;
+            e[3] = 1; len[3] = d / 2; nxt[3] = 2; belong[3] = N; head[N] = 3;
+        }
+    } else {
+        const uint4* src = saved + (size_t)rank * state_words;
+        for (size_t w = tid; w < state_words; w += EX_THREADS) sm4[w] = src[w];
+    }
+    bool failed = false;
+    const long long t_begin = clock64();
+    __syncthreads();
+    ex_cluster_sync();
+
+    for (int i = i0; i < i1; i++) {
+        const double* row = rows + (size_t)(i - row_base) * ld;
+        ExBest best;
+        best.add = 2.0; best.frac = 0.0; best.slot = 0; best.node = -1;   // the (0,0,2) default tuple
+        double bpl = 0;          // edge length, parent and child index of this thread's best candidate
+        int bx = -1, bc = 0;
+        int st[EX_KM], pending = 0;
+        double ra[EX_KM], rb[EX_KM], r0[EX_KM], r1[EX_KM];
+        bool l0[EX_KM], l1[EX_KM];
+#pragma unroll
+        for (int u = 0; u < EX_KM; u++) {
+            const int k = tid + u * EX_THREADS;
+            st[u] = 0; ra[u] = empty; rb[u] = empty; r0[u] = 0; r1[u] = 0; l0[u] = false; l1[u] = false;
+            if (k < NL && S.flag[k]) {
+                const int k0 = S.kid0[k], k1 = S.kid1[k];
+                l0[u] = k0 < N; l1[u] = k1 < N;
+                if (l0[u]) { r0[u] = __ldg(&row[k0]); ra[u] = r0[u] - S.klen0[k]; }   // the leaf's limit towards this node (:298-332)
+                if (l1[u]) { r1[u] = __ldg(&row[k1]); rb[u] = r1[u] - S.klen1[k]; }
+                st[u] = 1; pending++;
+            }
+        }
+        while (pending) {
+#pragma unroll
+            for (int u = 0; u < EX_KM; u++) {
+                const int k = tid + u * EX_THREADS;
+                if (st[u] == 1) {
+                    if (!l0[u] && __double_as_longlong(ra[u]) == (long long)EX_EMPTY) {
+                        const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(S.in0 + k);
+                        if (v != EX_EMPTY) { ra[u] = __longlong_as_double((long long)v); *reinterpret_cast<volatile unsigned long long*>(S.in0 + k) = EX_EMPTY; }
+                    }
+                    if (!l1[u] && __double_as_longlong(rb[u]) == (long long)EX_EMPTY) {
+                        const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(S.in1 + k);
+                        if (v != EX_EMPTY) { rb[u] = __longlong_as_double((long long)v); *reinterpret_cast<volatile unsigned long long*>(S.in1 + k) = EX_EMPTY; }
+                    }
+                    if (__double_as_longlong(ra[u]) != (long long)EX_EMPTY && __double_as_longlong(rb[u]) != (long long)EX_EMPTY) {
+                        if (S.flag[k] == 2) st[u] = 3;   // the root has nothing above it: feed the children now (below)
+                        else {
+                            double m = 0;
+                            if (ra[u] > m) m = ra[u];
+                            if (rb[u] > m) m = rb[u];
+                            const int j = S.par[k] - N;
+                            ex_push_f64((S.cidx[k] ? S.in1 : S.in0) + loc_of(j), cta_of(j), m - S.plen[k]);
+                            st[u] = 2;
+                        }
+                    }
+                }
+                if (st[u] == 2 || st[u] == 3) {
+                    // top-down step (:334-366), kept short: every firing is executed by a whole warp for the one or two lanes
+                    // that are ready, so the scoring is left to the dense pass below
+                    unsigned long long ud = 0;
+                    if (st[u] == 2) ud = *reinterpret_cast<volatile unsigned long long*>(S.dn + k);
+                    if (st[u] == 3 || ud != EX_EMPTY) {
+                        const double a = ra[u], b = rb[u];
+                        double v0 = 0, v1 = 0;
+                        if (b > v0) v0 = b;
+                        if (a > v1) v1 = a;
+                        if (st[u] == 2) {
+                            const double basev = __longlong_as_double((long long)ud) - S.plen[k];
+                            if (basev > v0) v0 = basev;
+                            if (basev > v1) v1 = basev;
+                        }
+                        if (!l0[u]) { const int j = S.kid0[k] - N; ex_push_f64(S.dn + loc_of(j), cta_of(j), v0); }
+                        if (!l1[u]) { const int j = S.kid1[k] - N; ex_push_f64(S.dn + loc_of(j), cta_of(j), v1); }
+                        st[u] = st[u] == 3 ? 5 : 4;   // done; 4: the value from above is still in the slot
+                        pending--;
+                    }
+                }
+            }
+        }
+        // ---- scoring (calculateBranchLength :153-198), all lanes at once: own parent->node slot and the leaf children's slots
+#pragma unroll
+        for (int u = 0; u < EX_KM; u++) {
+            const int k = tid + u * EX_THREADS;
+            if (st[u] >= 4) {
+                const double a = ra[u], b = rb[u];
+                double v0 = 0, v1 = 0;
+                if (b > v0) v0 = b;
+                if (a > v1) v1 = a;
+                const int me = N + id_of(k);
+                if (st[u] == 4) {
+                    const double dn = S.dn[k], pl = S.plen[k];
+                    S.dn[k] = empty;
+                    double up = 0;
+                    if (a > up) up = a;
+                    if (b > up) up = b;
+                    const int before = best.node;
+                    ex_score(dn, up, pl, S.sdn[k], me, best);
+                    if (best.node != before) { bpl = pl; bx = S.par[k]; bc = S.cidx[k]; }
+                    const double basev = dn - pl;
+                    if (basev > v0) v0 = basev;
+                    if (basev > v1) v1 = basev;
+                }
+                if (l0[u]) {
+                    const int before = best.node;
+                    ex_score(v0, r0[u], S.klen0[k], S.ksdn0[k], S.kid0[k], best);
+                    if (best.node != before) { bpl = S.klen0[k]; bx = me; bc = 0; }
+                }
+                if (l1[u]) {
+                    const int before = best.node;
+                    ex_score(v1, r1[u], S.klen1[k], S.ksdn1[k], S.kid1[k], best);
+                    if (best.node != before) { bpl = S.klen1[k]; bx = me; bc = 1; }
+                }
+            }
+        }
+        // ---- first minimum over the cluster (thrust::min_element :657)
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const double oa = __shfl_xor_sync(0xffffffffu, best.add, s), of = __shfl_xor_sync(0xffffffffu, best.frac, s), op = __shfl_xor_sync(0xffffffffu, bpl, s);
+            const int os = __shfl_xor_sync(0xffffffffu, best.slot, s), on = __shfl_xor_sync(0xffffffffu, best.node, s);
+            const int ox = __shfl_xor_sync(0xffffffffu, bx, s), oc = __shfl_xor_sync(0xffffffffu, bc, s);
+            if (ex_before(oa, os, best.add, best.slot)) { best.add = oa; best.frac = of; best.slot = os; best.node = on; bpl = op; bx = ox; bc = oc; }
+        }
+        if (lane == 0) { s_warp[wid] = best; s_wpl[wid] = bpl; s_wx[wid] = bx; s_wc[wid] = bc; }
+        __syncthreads();
+        if (wid == 0) {
+            best = s_warp[lane]; bpl = s_wpl[lane]; bx = s_wx[lane]; bc = s_wc[lane];
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const double oa = __shfl_xor_sync(0xffffffffu, best.add, s), of = __shfl_xor_sync(0xffffffffu, best.frac, s), op = __shfl_xor_sync(0xffffffffu, bpl, s);
+                const int os = __shfl_xor_sync(0xffffffffu, best.slot, s), on = __shfl_xor_sync(0xffffffffu, best.node, s);
+                const int ox = __shfl_xor_sync(0xffffffffu, bx, s), oc = __shfl_xor_sync(0xffffffffu, bc, s);
+                if (ex_before(oa, os, best.add, best.slot)) { best.add = oa; best.frac = of; best.slot = os; best.node = on; bpl = op; bx = ox; bc = oc; }
+            }
+            if (lane < CS) {
+                ex_push_f64(&rec_d[i & 1][rank][0], lane, best.add); ex_push_f64(&rec_d[i & 1][rank][1], lane, best.frac); ex_push_f64(&rec_d[i & 1][rank][2], lane, bpl);
+                ex_push_s32(&rec_i[i & 1][rank][0], lane, best.slot); ex_push_s32(&rec_i[i & 1][rank][1], lane, best.node);
+                ex_push_s32(&rec_i[i & 1][rank][2], lane, bx); ex_push_s32(&rec_i[i & 1][rank][3], lane, bc);
+            }
+        }
+        ex_cluster_sync();
+        int w = 0;
+        {
+            double wa = rec_d[i & 1][0][0];
+            int ws = rec_i[i & 1][0][0];
+#pragma unroll
+            for (int c = 1; c < CS; c++) {
+                const double ca = rec_d[i & 1][c][0];
+                const int cs = rec_i[i & 1][c][0];
+                if (ex_before(ca, cs, wa, ws)) { wa = ca; ws = cs; w = c; }
+            }
+        }
+        const double addLen = rec_d[i & 1][w][0], fracLen = rec_d[i & 1][w][1], pleny = rec_d[i & 1][w][2];
+        const int slot = rec_i[i & 1][w][0], y = rec_i[i & 1][w][1], x = rec_i[i & 1][w][2], cidxy = rec_i[i & 1][w][3];
+        if (y < 0) { failed = true; break; }   // uniform over the cluster
+        // ---- split (updateTreeStructure :200-251): middle m between x and y, new leaf i below m
+        const int m = i + N - 1, jm = i - 1, c0 = 4 * i - 4;
+        if (tid == 0 && cta_of(x - N) == rank) (cidxy ? S.kid1 : S.kid0)[loc_of(x - N)] = m;
+        if (tid == 32 && y >= N && cta_of(y - N) == rank) {
+            const int k = loc_of(y - N);
+            S.par[k] = m; S.cidx[k] = 0; S.plen[k] = pleny - fracLen; S.sdn[k] = c0 + 1;
+        }
+        if (tid == 64 && cta_of(jm) == rank) {
+            const int k = loc_of(jm);
+            S.par[k] = x; S.cidx[k] = (unsigned char)cidxy; S.kid0[k] = y; S.kid1[k] = i; S.plen[k] = fracLen; S.sdn[k] = slot;
+            S.klen0[k] = pleny - fracLen; S.ksdn0[k] = c0 + 1; S.klen1[k] = addLen; S.ksdn1[k] = c0 + 3; S.flag[k] = 1;
+        }
+        if (tid == 128 && rank == (i & (CS - 1))) {
+            const int xe = slot, ye = y < N ? (y < 2 ? y : 4 * y - 2) : 4 * (y - N);
+            const int c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3;
+            e[xe] = m; len[xe] = fracLen;
+            e[ye] = m; len[ye] = pleny - fracLen;
+            e[c0] = x; len[c0] = fracLen; nxt[c0] = -1; belong[c0] = m;
+            e[c1] = y; len[c1] = pleny - fracLen; nxt[c1] = c0; belong[c1] = m;
+            e[c2] = m; len[c2] = addLen; nxt[c2] = -1; belong[c2] = i; head[i] = c2;
+            e[c3] = i; len[c3] = addLen; nxt[c3] = c1; belong[c3] = m; head[m] = c3;
+        }
+        __syncthreads();
+    }
+
+    __syncthreads();
+    ex_cluster_sync();   // no CTA may leave while peers can still push into its shared memory
+    {
+        uint4* dst = saved + (size_t)rank * state_words;
+        for (size_t w = tid; w < state_words; w += EX_THREADS) dst[w] = sm4[w];
+    }
+    if (rank == 0 && tid == 0) {
+        if (failed) ctl->error = 1;
+        ctl->cycles += (unsigned long long)(clock64() - t_begin);
+    }
+}
+
+template <int CS, int MODE>   // MODE 0: level steps, 1: data flow over all nodes, 2: data flow over internal nodes (default)
 int ex_launch(dipb_ctx* c, void** args, size_t smem, bool* ok) {
-    auto kern = place_exact_kernel<CS, FLOW>;
+    auto kern = MODE == 2 ? place_exact_flow2_kernel<CS> : (MODE == 1 ? place_exact_kernel<CS, true> : place_exact_kernel<CS, false>);
     *ok = false;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     if (CS > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -463,23 +713,27 @@ int ex_launch(dipb_ctx* c, void** args, size_t smem, bool* ok) {
 
 // local node capacity per CTA for n tips on CS CTAs, and the dynamic shared memory it needs
 inline int ex_local(int n, int CS) { const int chunks = (n + 31) / 32; return ((chunks + CS - 1) / CS) * 32; }
-inline size_t ex_smem_bytes(int NL) { return (size_t)NL * EX_BYTES_PER_NODE; }
+inline size_t ex_smem_bytes(int NL, int mode) { return (size_t)NL * (mode == 2 ? F2_BYTES_PER_NODE : EX_BYTES_PER_NODE); }
 constexpr size_t EX_SMEM_MAX = 224u * 1024u;   // 227 KB minus the static records
 
 }  // namespace
 
-static int ex_max_tips() { return (int)(EX_SMEM_MAX / EX_BYTES_PER_NODE / 32) * 32 * 16; }
+static int ex_max_tips(int mode) {
+    int nl = (int)(EX_SMEM_MAX / (mode == 2 ? F2_BYTES_PER_NODE : EX_BYTES_PER_NODE) / 32) * 32;
+    if (nl > EX_KM * EX_THREADS) nl = EX_KM * EX_THREADS;
+    return nl * 16;
+}
 
 int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* t) {
     int CS = 16;
     const char* force = getenv("DIPB_EXACT_CLUSTER");
     if (force && atoi(force) == 8) CS = 8;
-    const char* fl = getenv("DIPB_EXACT_FLOW");   // 0: level steps with cluster barriers (first version, kept for comparison)
-    const bool flow = !(fl && atoi(fl) == 0);
+    const char* fl = getenv("DIPB_EXACT_FLOW");   // 0: level steps with cluster barriers, 1: data flow over all nodes (kept for comparison)
+    const int mode = fl ? (atoi(fl) == 0 ? 0 : (atoi(fl) == 1 ? 1 : 2)) : 2;
     int NL = ex_local(n, CS);
-    if (ex_smem_bytes(NL) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS) {
+    if (ex_smem_bytes(NL, mode) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS) {
         set_error("exact placement: %d tips exceed the shared-memory tree of one %d-CTA cluster (at most %d tips); use -p 1 or -m 3", n, CS,
-                  ex_max_tips() / (16 / CS));
+                  ex_max_tips(mode) / (16 / CS));
         return DIPB_E_UNSUPPORTED;
     }
     // d(1,0) for the 2-leaf tree
@@ -503,7 +757,7 @@ int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* 
     } else batch = n;   // all rows are there: one launch
     uint4* saved = nullptr;
     ExCtl* ctl = nullptr;
-    DIPB_CUDA(pool_alloc(c, (void**)&saved, ex_smem_bytes(NL) * 16));
+    DIPB_CUDA(pool_alloc(c, (void**)&saved, ex_smem_bytes(NL, mode) * 16));
     DIPB_CUDA(pool_alloc(c, (void**)&ctl, sizeof(ExCtl)));
     DIPB_CUDA(cudaMemsetAsync(ctl, 0, sizeof(ExCtl), c->stream));
     for (int i0 = 2; (i0 < n || i0 == 2) && !rc; i0 += batch) {   // (n == 2: one launch that only builds the 2-leaf tree)
@@ -516,15 +770,15 @@ int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* 
         void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &rows, &ldr, &row_base, &i0v, &i1, &N, &NL, &d01, &saved, &ctl};
         bool ok = false;
         if (CS == 16) {
-            rc = flow ? ex_launch<16, true>(c, args, ex_smem_bytes(NL), &ok) : ex_launch<16, false>(c, args, ex_smem_bytes(NL), &ok);
+            rc = mode == 2 ? ex_launch<16, 2>(c, args, ex_smem_bytes(NL, mode), &ok) : (mode == 1 ? ex_launch<16, 1>(c, args, ex_smem_bytes(NL, mode), &ok) : ex_launch<16, 0>(c, args, ex_smem_bytes(NL, mode), &ok));
             if (!rc && !ok && i0 == 2) {   // device cannot co-schedule 16 CTAs: portable cluster size, half the capacity
                 CS = 8; NL = ex_local(n, 8);
-                if (ex_smem_bytes(NL) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS) { set_error("exact placement: 16-CTA clusters unavailable and %d tips do not fit 8 CTAs", n); rc = DIPB_E_UNSUPPORTED; break; }
+                if (ex_smem_bytes(NL, mode) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS) { set_error("exact placement: 16-CTA clusters unavailable and %d tips do not fit 8 CTAs", n); rc = DIPB_E_UNSUPPORTED; break; }
                 pool_free(c, saved);
-                DIPB_CUDA(pool_alloc(c, (void**)&saved, ex_smem_bytes(NL) * 8));
+                DIPB_CUDA(pool_alloc(c, (void**)&saved, ex_smem_bytes(NL, mode) * 8));
             }
         }
-        if (!rc && !ok && CS == 8) rc = flow ? ex_launch<8, true>(c, args, ex_smem_bytes(NL), &ok) : ex_launch<8, false>(c, args, ex_smem_bytes(NL), &ok);
+        if (!rc && !ok && CS == 8) rc = mode == 2 ? ex_launch<8, 2>(c, args, ex_smem_bytes(NL, mode), &ok) : (mode == 1 ? ex_launch<8, 1>(c, args, ex_smem_bytes(NL, mode), &ok) : ex_launch<8, false>(c, args, ex_smem_bytes(NL, mode), &ok));
         if (!rc && !ok) { set_error("exact placement: no cluster configuration fits this device"); rc = DIPB_E_UNSUPPORTED; }
         if (!rc) c->launches++;
     }
@@ -550,7 +804,7 @@ int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* 
 
 using namespace dipb;
 
-extern "C" int dipb_place_exact_max_tips(void) { return ex_max_tips(); }
+extern "C" int dipb_place_exact_max_tips(void) { return ex_max_tips(2); }
 
 extern "C" int dipb_place_exact(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree** out) {
     if (!c || !src || !out || n < 2) { set_error("dipb_place_exact: bad argument"); return DIPB_E_ARG; }

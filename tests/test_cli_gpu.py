@@ -55,6 +55,9 @@ def test_unaligned_fasta_placement_and_dc(ctx, oracle, tmp_path):
     err = run("-i", "r", "-I", fa, "-O", out, "-m", 1, "--no-shuffle")
     assert "k-closest placement mode" in err
     assert open(out).read() == oracle.place_all(D).newick(names)
+    err = run("-i", "r", "-I", fa, "-O", out, "-m", 1, "-p", 0, "--no-shuffle")
+    assert "exact placement mode" in err
+    assert open(out).read() == oracle.place_exact(D).newick(names)
     err = run("-i", "r", "-I", fa, "-O", out, "-m", 3, "--no-shuffle")
     assert "divide-and-conquer" in err
     assert open(out).read() == oracle.dc(D, n // 20)[0].newick(names)

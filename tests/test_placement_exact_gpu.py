@@ -118,6 +118,22 @@ def test_exact_placement_from_mash(ctx, oracle):
     compare_trees(pl, oracle.place_exact(Dl + Dl.T), n)
 
 
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_exact_placement_earlier_kernel_variants(ctx, oracle, monkeypatch, mode):
+    """DIPB_EXACT_FLOW=0: level steps with cluster barriers; 1: data flow over all nodes (the default flows over
+    internal nodes only).  Same arrays."""
+    monkeypatch.setenv("DIPB_EXACT_FLOW", mode)
+    n, L = 900, 900
+    codes, P, _ = make_msa(n, L, seed=78)
+    prm = api.Param(distanceType=2, in_="m")
+    msa = api.MSADeviceArrays(ctx)
+    msa.allocateDeviceArrays(P, np.full(n, L, np.uint64), n, prm)
+    pl = api.PlacementDeviceArrays(ctx)
+    pl.allocateDeviceArrays(n)
+    pl.findPlacementTree(prm, msaDeviceArrays=msa)
+    compare_trees(pl, oracle.place_exact(msa.distMatrix(prm).to_host()), n)
+
+
 def test_exact_placement_8_cta_cluster(ctx, oracle, monkeypatch):
     monkeypatch.setenv("DIPB_EXACT_CLUSTER", "8")
     n = 500
