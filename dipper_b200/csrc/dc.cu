@@ -127,6 +127,126 @@ dc_assign_batched_kernel(const int* __restrict__ e, const int* __restrict__ belo
     }
 }
 
+// Transposed variant (default): at 2 000 000 tips with a 100 000-tip backbone the assignment is 3.8 * 10^11 (query, slot)
+// scores with 10 gathers each -- 93 % of the whole divide-and-conquer run with the kernel above, which fetches one 32-byte
+// sector per 8-byte gather and offers only (queries per block) / DCQ CTAs.  Here the block of distances is transposed to
+// T[leaf][query], so one gather of 64 contiguous bytes (2 sectors) serves 8 queries (4x fewer sectors per score), and
+// the grid is two-dimensional, (slot range) x (group of 8 queries), with the slot range fastest: CTAs that run together
+// share one 6.4 MB column strip of T in L2.  Per-range minima go to `part` and are folded in slot order, so the first
+// minimum of the reference's min_element is kept.  Arithmetic per score is unchanged.
+constexpr int DQ = 8;       // queries per CTA
+constexpr int DSR = 2048;   // slots per CTA
+struct DcPart { double add; int slot; int pad; };
+
+__global__ void __launch_bounds__(256) dc_transpose_kernel(const double* __restrict__ in, size_t ld, int nq, int ncols, double* __restrict__ out, size_t ldq) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, q0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int q = q0 + r, c = c0 + tx;
+        tile[r][tx] = (q < nq && c < ncols) ? in[(size_t)q * ld + c] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, q = q0 + tx;
+        if (c < ncols && (size_t)q < ldq) out[(size_t)c * ldq + q] = tile[tx][r];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dc_assign_t_kernel(const int* __restrict__ e, const int* __restrict__ belong, const double* __restrict__ len, const int* __restrict__ cid,
+                   const double* __restrict__ cdis, const int* __restrict__ rev, int nslots, const double* __restrict__ T, size_t ldq,
+                   DcPart* __restrict__ part, int nranges) {
+    __shared__ PlCand sb[DQ][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int range = blockIdx.x, qbase = blockIdx.y * DQ;
+    const int s0 = range * DSR, s1 = min(s0 + DSR, nslots);
+    double badd[DQ];
+    int bslot[DQ];
+#pragma unroll
+    for (int j = 0; j < DQ; j++) { badd[j] = 2.0; bslot[j] = 0; }
+    for (int q = s0 + threadIdx.x; q < s1; q += 256) {
+        if (!(belong[q] > e[q])) continue;
+        const int r = rev[q];
+        const double L = len[q];
+        double d1[DQ], d2[DQ];
+#pragma unroll
+        for (int j = 0; j < DQ; j++) { d1[j] = 0; d2[j] = 0; }
+#pragma unroll
+        for (int k = 0; k < KC5; k++) {
+            const int id = cid[q * KC5 + k];
+            if (id != -1) {
+                const double c = cdis[q * KC5 + k];
+                const double2* t = reinterpret_cast<const double2*>(T + (size_t)id * ldq + qbase);
+#pragma unroll
+                for (int h = 0; h < DQ / 2; h++) {
+                    const double2 v = __ldg(t + h);
+                    const double v0 = v.x - c, v1 = v.y - c;
+                    if (v0 > d1[2 * h]) d1[2 * h] = v0;
+                    if (v1 > d1[2 * h + 1]) d1[2 * h + 1] = v1;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KC5; k++) {
+            const int id = cid[r * KC5 + k];
+            if (id != -1) {
+                const double c = cdis[r * KC5 + k];
+                const double2* t = reinterpret_cast<const double2*>(T + (size_t)id * ldq + qbase);
+#pragma unroll
+                for (int h = 0; h < DQ / 2; h++) {
+                    const double2 v = __ldg(t + h);
+                    const double v0 = v.x - c, v1 = v.y - c;
+                    if (v0 > d2[2 * h]) d2[2 * h] = v0;
+                    if (v1 > d2[2 * h + 1]) d2[2 * h + 1] = v1;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DQ; j++) {
+            double x1 = d1[j], x2 = d2[j];
+            double a = (x1 + x2 - L) / 2;
+            if (a < 0) a = 0;
+            x1 -= a; x2 -= a;
+            if (x1 < 0) x1 = 0;
+            if (x2 < 0) x2 = 0;
+            if (x1 > L) { a += x1 - L; x1 = L; }
+            if (x2 > L) { a += x2 - L; x2 = L; }
+            if (a < badd[j] || (a == badd[j] && q < bslot[j])) { badd[j] = a; bslot[j] = q; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < DQ; j++) {
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const double oa = __shfl_xor_sync(0xffffffffu, badd[j], s);
+            const int os = __shfl_xor_sync(0xffffffffu, bslot[j], s);
+            if (oa < badd[j] || (oa == badd[j] && os < bslot[j])) { badd[j] = oa; bslot[j] = os; }
+        }
+        if (lane == 0) { sb[j][w].add = badd[j]; sb[j][w].slot = bslot[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < DQ) {
+        const int j = threadIdx.x;
+        PlCand b = sb[j][0];
+        for (int k = 1; k < 8; k++)
+            if (sb[j][k].add < b.add || (sb[j][k].add == b.add && sb[j][k].slot < b.slot)) b = sb[j][k];
+        DcPart o; o.add = b.add; o.slot = b.slot; o.pad = 0;
+        part[(size_t)(qbase + j) * nranges + range] = o;
+    }
+}
+
+__global__ void dc_assign_fold_kernel(const DcPart* __restrict__ part, int nranges, int q0, int nq, int* __restrict__ cluster) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    DcPart b = part[(size_t)q * nranges];
+    for (int r = 1; r < nranges; r++) {
+        const DcPart o = part[(size_t)q * nranges + r];
+        if (o.add < b.add || (o.add == b.add && o.slot < b.slot)) b = o;
+    }
+    cluster[q0 + q] = (b.add < 2.0) ? b.slot : 0;   // the (0,0,2) tuple at position 0 wins otherwise
+}
+
 // ---- stage 3: one cluster per CTA -------------------------------------------------------
 struct DcSource {
     // exactly one of the three
@@ -378,7 +498,22 @@ int dipb_dc_assign(dipb_dc_state* st, int q0, int q1, int32_t* h_cluster) {
     while ((size_t)qb * ld * sizeof(double) > (1ull << 30) && qb > 128) qb /= 2;
     double* buf = nullptr;
     if (!src->matrix) DIPB_CUDA(pool_alloc(c, (void**)&buf, (size_t)qb * ld * sizeof(double)));
+    // transposed block T[leaf][query] + per-(query, slot range) minima (DIPB_DC_ASSIGN_T=0: the row-major kernel)
+    const char* et = getenv("DIPB_DC_ASSIGN_T");
+    const bool transposed = !(et && atoi(et) == 0);
+    const int qcap = (q1 - q0) < qb ? (q1 - q0) : qb;
+    const size_t ldq = (size_t)((qcap + 31) / 32 * 32);
+    const int nranges = (nslots + DSR - 1) / DSR;
+    double* bufT = nullptr;
+    DcPart* part = nullptr;
+    if (transposed) {
+        DIPB_CUDA(pool_alloc(c, (void**)&bufT, (size_t)B * ldq * sizeof(double)));
+        DIPB_CUDA(pool_alloc(c, (void**)&part, ldq * (size_t)nranges * sizeof(DcPart)));
+    }
     int rc = 0;
+    const bool prof = getenv("DIPB_PLACE_PROFILE") != nullptr;
+    double t_dist = 0, t_assign = 0;
+    auto t_mark = std::chrono::steady_clock::now();
     for (int a0 = q0; a0 < q1 && !rc; a0 += qb) {
         int a1 = a0 + qb < q1 ? a0 + qb : q1;
         const double* rows; size_t ldr;
@@ -388,15 +523,28 @@ int dipb_dc_assign(dipb_dc_state* st, int q0, int q1, int32_t* h_cluster) {
             rc = src->msa ? msa_block(src->msa, src->dist_type, a0, a1, B, buf, ld) : dipb_mash_dist_block(src->mash, a0, a1, B, buf, ld);
             if (rc) break;
         }
-        // (a variant that first copies the queries' distance rows into shared memory and gathers there was measured
-        // slower, 315 ms vs 268 ms: the kernel sits on the L2 sector rate of the 10 random 8-byte gathers per slot and query)
-        const int groups = (a1 - a0 + DCQ - 1) / DCQ;
-        const int grid = groups < c->num_sms * 8 ? groups : c->num_sms * 8;
-        dc_assign_batched_kernel<<<grid, 256, 0, c->stream>>>(t->e, t->belong, t->len, t->cid, t->cdis, t->rev, nslots, rows, ldr, a0 - q0, a1 - a0, d_cluster);
-        c->launches++;
+        if (prof) { cudaStreamSynchronize(c->stream); const auto now = std::chrono::steady_clock::now(); t_dist += std::chrono::duration<double, std::milli>(now - t_mark).count(); t_mark = now; }
+        if (transposed) {
+            const int nq = a1 - a0;
+            dc_transpose_kernel<<<dim3((B + 31) / 32, (unsigned)((ldq + 31) / 32)), 256, 0, c->stream>>>(rows, ldr, nq, B, bufT, ldq);
+            dc_assign_t_kernel<<<dim3(nranges, (nq + DQ - 1) / DQ), 256, 0, c->stream>>>(t->e, t->belong, t->len, t->cid, t->cdis, t->rev, nslots, bufT, ldq, part, nranges);
+            dc_assign_fold_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(part, nranges, a0 - q0, nq, d_cluster);
+            c->launches += 3;
+        } else {
+            // (a variant that first copies the queries' distance rows into shared memory and gathers there was measured
+            // slower, 315 ms vs 268 ms: the kernel sits on the L2 sector rate of the 10 random 8-byte gathers per slot and query)
+            const int groups = (a1 - a0 + DCQ - 1) / DCQ;
+            const int grid = groups < c->num_sms * 8 ? groups : c->num_sms * 8;
+            dc_assign_batched_kernel<<<grid, 256, 0, c->stream>>>(t->e, t->belong, t->len, t->cid, t->cdis, t->rev, nslots, rows, ldr, a0 - q0, a1 - a0, d_cluster);
+            c->launches++;
+        }
+        if (prof) { cudaStreamSynchronize(c->stream); const auto now = std::chrono::steady_clock::now(); t_assign += std::chrono::duration<double, std::milli>(now - t_mark).count(); t_mark = now; }
     }
     cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (prof) fprintf(stderr, "[dc] stage 2 split: distances %.1f ms, assignment %.1f ms (%s)\n", t_dist, t_assign, transposed ? "transposed blocks" : "row-major blocks");
     if (buf) pool_free(c, buf);
+    if (bufT) pool_free(c, bufT);
+    if (part) pool_free(c, part);
     if (!rc && e != cudaSuccess) { set_error("dipb_dc_assign: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; }
     if (!rc && cudaMemcpy(h_cluster, d_cluster, sizeof(int) * (q1 - q0), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("dipb_dc_assign: D2H failed"); rc = DIPB_E_CUDA; }
     pool_free(c, d_cluster);
