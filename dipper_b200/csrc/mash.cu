@@ -403,15 +403,21 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mash_rank_kernel(MashTileParams
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bv) : "r"(pb));
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bn) : "r"(pb + MR_TB * 4));
             int uni = 0, steps = 0;
+            // The element loaded in a step is committed at the top of the NEXT step (warps issue in order: consuming it in
+            // the same step would park the warp on the load).  It becomes "next" then and "current" one step later at the
+            // earliest, so nothing is compared before it has arrived.
+            uint32_t v = bn;
+            bool pt = true;
             while (uni < s) {
+                if (pt) bn = v; else an = v;
                 const bool takeB = bv <= av;
                 uni += (bv == av) ? 0 : 1;
                 steps++;
                 const uint32_t addr = takeB ? pb + 2 * MR_TB * 4 : pa + 2 * MR_TA * 4;
-                uint32_t v;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-                if (takeB) { bv = bn; bn = v; pb += MR_TB * 4; }
-                else { av = an; an = v; pa += MR_TA * 4; }
+                if (takeB) { bv = bn; pb += MR_TB * 4; }
+                else { av = an; pa += MR_TA * 4; }
+                pt = takeB;
             }
             const int inter = steps - uni;
             // :453-454

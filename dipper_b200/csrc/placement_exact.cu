@@ -109,7 +109,7 @@ template <int CS, bool FLOW>
 __global__ void __launch_bounds__(EX_THREADS, 1)
 place_exact_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict__ nxt, int* __restrict__ belong,
                    double* __restrict__ len, const double* __restrict__ rows, size_t ld, int row_base, int i0, int i1, int N,
-                   int NL, const double* __restrict__ d01, uint4* __restrict__ saved, ExCtl* __restrict__ ctl) {
+                   int NL, const double* __restrict__ d01, uint4* __restrict__ saved, ExCtl* __restrict__ ctl, int /*backoff_ns*/) {
     extern __shared__ __align__(16) unsigned char ex_smem[];
     __shared__ double rec_d[2][CS][3];  // every CTA's best candidate of this tip: add, frac, edge length (double-buffered by tip parity:
     __shared__ int rec_i[2][CS][8];     // slot, node y, parent x, rank, subtree size, depth, child index of y   in FLOW mode a CTA that owns
@@ -469,7 +469,7 @@ template <int CS>
 __global__ void __launch_bounds__(EX_THREADS, 1)
 place_exact_flow2_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict__ nxt, int* __restrict__ belong,
                          double* __restrict__ len, const double* __restrict__ rows, size_t ld, int row_base, int i0, int i1, int N,
-                         int NL, const double* __restrict__ d01, uint4* __restrict__ saved, ExCtl* __restrict__ ctl) {
+                         int NL, const double* __restrict__ d01, uint4* __restrict__ saved, ExCtl* __restrict__ ctl, int backoff_ns) {
     extern __shared__ __align__(16) unsigned char ex_smem[];
     __shared__ double rec_d[2][CS][3];  // add, frac, edge length of the winner's edge (double-buffered by tip parity)
     __shared__ int rec_i[2][CS][4];     // slot, node y, parent x, child index of y
@@ -578,6 +578,7 @@ place_exact_flow2_kernel(int* __restrict__ head, int* __restrict__ e, int* __res
                     }
                 }
             }
+            if (backoff_ns && pending) __nanosleep(backoff_ns);   // polling competes with the peers' incoming stores for this SM's shared memory
         }
         // ---- scoring (calculateBranchLength :153-198), all lanes at once: own parent->node slot and the leaf children's slots
 #pragma unroll
@@ -730,6 +731,8 @@ int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* 
     if (force && atoi(force) == 8) CS = 8;
     const char* fl = getenv("DIPB_EXACT_FLOW");   // 0: level steps with cluster barriers, 1: data flow over all nodes (kept for comparison)
     const int mode = fl ? (atoi(fl) == 0 ? 0 : (atoi(fl) == 1 ? 1 : 2)) : 2;
+    const char* eb = getenv("DIPB_EXACT_BACKOFF");   // ns of __nanosleep between polling passes (default mode only)
+    int backoff = eb ? atoi(eb) : 0;
     int NL = ex_local(n, CS);
     if (ex_smem_bytes(NL, mode) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS) {
         set_error("exact placement: %d tips exceed the shared-memory tree of one %d-CTA cluster (at most %d tips); use -p 1 or -m 3", n, CS,
@@ -767,7 +770,7 @@ int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* 
         if (rc) break;
         int N = n;
         int i0v = i0;
-        void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &rows, &ldr, &row_base, &i0v, &i1, &N, &NL, &d01, &saved, &ctl};
+        void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &rows, &ldr, &row_base, &i0v, &i1, &N, &NL, &d01, &saved, &ctl, &backoff};
         bool ok = false;
         if (CS == 16) {
             rc = mode == 2 ? ex_launch<16, 2>(c, args, ex_smem_bytes(NL, mode), &ok) : (mode == 1 ? ex_launch<16, 1>(c, args, ex_smem_bytes(NL, mode), &ok) : ex_launch<16, 0>(c, args, ex_smem_bytes(NL, mode), &ok));
