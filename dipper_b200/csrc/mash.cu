@@ -343,19 +343,20 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mash_warp_kernel(MashTileParams
 // INTERLEAVED (element t of column sketch q at word t * 32 + q, of row sketch q at t * 16 + q) and lane l of warp r works
 // on the pair (column l, row (l + r) mod 16).  Every lane then reads its column list through its own bank whatever its
 // position, and at most two lanes meet on a row-list bank -- the thread-per-pair kernel above spends ~5.5 shared-memory
-// wavefronts per step on random 8-byte reads.  Two extra rows of 0xFFFFFFFF after each list replace the index clamps.
+// wavefronts per step on random 8-byte reads.  A few extra rows of 0xFFFFFFFF after each list replace the index clamps.
 constexpr int MR_TA = 32;   // column sketches ("A" lists) per tile = lanes
 constexpr int MR_TB = 16;   // row sketches ("B" lists) per tile = warps
 constexpr int MR_THREADS = MR_TB * 32;
+constexpr int MR_PAD = 6;   // 0xFFFFFFFF rows after each list
 
 __global__ void __launch_bounds__(MR_THREADS, 1) mash_rank_kernel(MashTileParams p, const uint32_t* __restrict__ rk, long long num_tiles, int tiles_x) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int s = p.s;
-    uint32_t* sA = reinterpret_cast<uint32_t*>(smem_raw);          // [(s + 2)][32]
-    uint32_t* sB = sA + (size_t)(s + 2) * MR_TA;                   // [(s + 2)][16]
+    uint32_t* sA = reinterpret_cast<uint32_t*>(smem_raw);          // [(s + MR_PAD)][32]
+    uint32_t* sB = sA + (size_t)(s + MR_PAD) * MR_TA;              // [(s + MR_PAD)][16]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid < 2 * MR_TA) sA[(size_t)s * MR_TA + tid] = 0xFFFFFFFFu;   // two rows past the end: the look-ahead reads them
-    if (tid < 2 * MR_TB) sB[(size_t)s * MR_TB + tid] = 0xFFFFFFFFu;
+    if (tid < MR_PAD * MR_TA) sA[(size_t)s * MR_TA + tid] = 0xFFFFFFFFu;   // rows past the end: the look-ahead and the up to 3 discarded steps read them
+    if (tid < MR_PAD * MR_TB) sB[(size_t)s * MR_TB + tid] = 0xFFFFFFFFu;
     const int half = s >> 1;                                       // sketch sizes are even: 8-byte global loads
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int tb = (int)(t / tiles_x), ta = (int)(t % tiles_x);
@@ -405,19 +406,25 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mash_rank_kernel(MashTileParams
             int uni = 0, steps = 0;
             // The element loaded in a step is committed at the top of the NEXT step (warps issue in order: consuming it in
             // the same step would park the warp on the load).  It becomes "next" then and "current" one step later at the
-            // earliest, so nothing is compared before it has arrived.
+            // earliest, so nothing is compared before it has arrived.  Four steps per loop trip: the steps past the one
+            // that brings the union counter to s only read the 0xFFFFFFFF rows and are discarded.
             uint32_t v = bn;
             bool pt = true;
-            while (uni < s) {
+            auto step = [&](int u) -> int {
                 if (pt) bn = v; else an = v;
                 const bool takeB = bv <= av;
-                uni += (bv == av) ? 0 : 1;
-                steps++;
+                u += (bv == av) ? 0 : 1;
                 const uint32_t addr = takeB ? pb + 2 * MR_TB * 4 : pa + 2 * MR_TA * 4;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
                 if (takeB) { bv = bn; pb += MR_TB * 4; }
                 else { av = an; pa += MR_TA * 4; }
                 pt = takeB;
+                return u;
+            };
+            for (;;) {
+                const int u1 = step(uni), u2 = step(u1), u3 = step(u2), u4 = step(u3);
+                if (u4 >= s) { steps += u1 >= s ? 1 : (u2 >= s ? 2 : (u3 >= s ? 3 : 4)); uni = s; break; }
+                uni = u4; steps += 4;
             }
             const int inter = steps - uni;
             // :453-454
@@ -489,7 +496,7 @@ static int mash_launch(dipb_mash* m, MashTileParams p) {
     if (rows <= 0 || ncols <= 0) return 0;
     // ---- rank-compressed, interleaved tiles (default)
     const char* er = getenv("DIPB_MASH_RANKS");   // 0: keep the 64-bit hashes (first versions, kept for comparison)
-    const size_t rk_smem = (size_t)(m->s + 2) * (MR_TA + MR_TB) * sizeof(uint32_t);
+    const size_t rk_smem = (size_t)(m->s + MR_PAD) * (MR_TA + MR_TB) * sizeof(uint32_t);
     if (!(er && atoi(er) == 0) && (size_t)m->n * m->s < 0xFFFFFFFFull && rk_smem <= 227 * 1024) {
         if (!m->ranks) { int rc = mash_build_ranks(m); if (rc) return rc; }
         static size_t attr_rk = 0;
