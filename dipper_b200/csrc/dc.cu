@@ -495,7 +495,15 @@ int dipb_dc_assign(dipb_dc_state* st, int q0, int q1, int32_t* h_cluster) {
     // tensor-core path, an operand expansion: 186 blocks of 1024 queries took 360 ms at 200 000 tips, B = 10 000)
     int qb = 16384;
     const size_t ld = (size_t)((B + 127) / 128 * 128);
-    while ((size_t)qb * ld * sizeof(double) > (1ull << 30) && qb > 128) qb /= 2;
+    // row buffer (and its transposed twin): up to 4 GB each when the device has room (a 180 GB B200 does), else 1 GB
+    size_t cap = 1ull << 30;
+    {
+        size_t free_b = 0, total_b = 0;
+        const char* eb = getenv("DIPB_DC_BLOCK_MB");
+        if (eb && atoi(eb) > 0) cap = (size_t)atoi(eb) << 20;
+        else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > (48ull << 30)) cap = 4ull << 30;
+    }
+    while ((size_t)qb * ld * sizeof(double) > cap && qb > 128) qb /= 2;
     double* buf = nullptr;
     if (!src->matrix) DIPB_CUDA(pool_alloc(c, (void**)&buf, (size_t)qb * ld * sizeof(double)));
     // transposed block T[leaf][query] + per-(query, slot range) minima (DIPB_DC_ASSIGN_T=0: the row-major kernel)

@@ -2,7 +2,7 @@
 
 The reference is CUDA-only and this container has no GPU, so fixtures come from two
 sources: (a) this script, which records the CPU oracle's outputs on seeded inputs
-(regression pins: files gold_*.npz), and (b) tools/make_ref_golden.sh, which runs the
+(regression pins: files gold_*.npz), and (b) tools/make_ref_golden.py, which runs the
 reference's own CUDA objects (oracle/_ref/dipper_ref) on the GPU box and stores their
 outputs (files ref_*.npz).  The oracle is checked against both in tests/test_oracle.py.
 Run from the repo root: python tests/golden/make_golden.py

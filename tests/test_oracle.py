@@ -225,6 +225,30 @@ def test_golden_fixtures(oracle):
             assert np.array_equal(sk, z["sketches"]), fn
             D = oracle.mash_dist_matrix(sk, int(z["k"]))
             assert np.allclose(D, z["dist"], rtol=1e-6, atol=0), fn
+        elif kind == "ref_msa":
+            # outputs of the reference's own CUDA kernels (tools/make_ref_golden.py on a B200)
+            P, L = z["packed"], int(z["seq_len"])
+            n = P.shape[0]
+            names = synth.names(n)
+            low = np.tril_indices(n, -1)
+            for t in (1, 2):
+                D = oracle.msa_dist_matrix(P, L, t)
+                assert np.allclose(D[low], z["rows_%d" % t][low], rtol=1e-6, atol=0), fn
+            D = oracle.msa_dist_matrix(P, L, 2)
+            nj = oracle.nj_newick(*oracle.nj(D), names)
+            assert newick.rf_distance(nj, str(z["nj_newick"])) == 0 and newick.max_branch_diff(nj, str(z["nj_newick"])) < 1e-5, fn
+            assert oracle.place_all(D).newick(names) == str(z["place_newick"]), fn
+            assert oracle.place_exact(D).newick(names) == str(z["place_exact_newick"]), fn
+        elif kind == "ref_mash":
+            sk = oracle.sketch_all(z["flat"], z["offsets"], z["lens"], int(z["k"]), int(z["s"]))
+            assert np.array_equal(sk, z["sketches"]), fn
+            n = sk.shape[0]
+            names = synth.names(n)
+            low = np.tril_indices(n, -1)
+            D = oracle.mash_dist_matrix(sk, int(z["k"]))
+            assert np.allclose(D[low], z["rows"][low], rtol=1e-6, atol=0), fn
+            assert oracle.place_all(D).newick(names) == str(z["place_newick"]), fn
+            assert oracle.place_exact(D).newick(names) == str(z["place_exact_newick"]), fn
 
 
 def test_exact_placement_oracle_recovers_an_additive_tree(oracle):
