@@ -22,7 +22,8 @@
 // Arithmetic is the reference's, expression by expression: the per-edge `lim - len` subtractions happen in the same
 // order along every path and max() is exact, so limits, pendant lengths, the argmin (ties -> smallest slot) and all
 // branch lengths are bit-identical to the oracle restatement (oracle/dipper_oracle.c: orc_place_exact_all).
-// One deviation: when no candidate has a pendant length < 2 the reference "places" on slot 0 through its (0,0,2)
+// Inputs beyond the cluster's shared memory (49 152 tips) run the same data flow through global memory on the whole grid
+// (place_exact_global_kernel).  One deviation: when no candidate has a pendant length < 2 the reference "places" on slot 0 through its (0,0,2)
 // default tuple and corrupts its depth table (the no-op swap at :246-249); this kernel reports DIPB_E_UNSUPPORTED.
 #include <cooperative_groups.h>
 #include <cstdlib>
@@ -692,6 +693,218 @@ place_exact_flow2_kernel(int* __restrict__ head, int* __restrict__ e, int* __res
     }
 }
 
+// ---- beyond one cluster's shared memory (more than 49 152 tips; DIPB_EXACT_GLOBAL=1 forces it): the same data flow over
+// internal nodes with the state in global memory and the whole grid (cooperative launch, one 1024-thread CTA per SM).
+// A value is still its own arrival flag -- volatile 8-byte stores / loads meet in L2, no fence -- node j belongs to
+// thread j mod T, the per-tip scratch of a node (state, the two limits from below) lives in global memory next to it,
+// and the one synchronisation per tip is a grid barrier around the argmin exchange.  A hop costs an L2 round trip
+// (~2 us) instead of a shared-memory one, so this path is for sizes the cluster cannot hold, not a replacement.
+struct G2State {
+    double *dn, *in0, *in1, *plen, *klen0, *klen1, *ra, *rb;
+    int *par, *kid0, *kid1, *sdn, *ksdn0, *ksdn1;
+    unsigned char *cidx, *flag, *st;
+};
+struct G2Rec { double add, frac, pl; int slot, node, x, c; };
+
+__device__ __forceinline__ unsigned long long g2_poll(const double* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ void g2_put(double* p, unsigned long long bits) { *reinterpret_cast<volatile unsigned long long*>(p) = bits; }
+__device__ __forceinline__ void g2_push(double* p, double v) { g2_put(p, (unsigned long long)__double_as_longlong(v)); }
+
+__global__ void __launch_bounds__(EX_THREADS, 1)
+place_exact_global_kernel(int* __restrict__ head, int* __restrict__ e, int* __restrict__ nxt, int* __restrict__ belong,
+                          double* __restrict__ len, const double* __restrict__ rows, size_t ld, int row_base, int i0, int i1, int N,
+                          const double* __restrict__ d01, G2State S, G2Rec* __restrict__ part, unsigned int* __restrict__ bar,
+                          ExCtl* __restrict__ ctl) {
+    __shared__ ExBest s_warp[EX_THREADS / 32];
+    __shared__ double s_wpl[EX_THREADS / 32];
+    __shared__ int s_wx[EX_THREADS / 32], s_wc[EX_THREADS / 32];
+    __shared__ G2Rec s_win;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = (int)gridDim.x, T = G * EX_THREADS, gtid = (int)blockIdx.x * EX_THREADS + tid;
+    unsigned int gen = 0;
+    if (i0 == 2) {
+        for (int j = gtid; j < N; j += T) {
+            g2_put(S.dn + j, EX_EMPTY); g2_put(S.in0 + j, EX_EMPTY); g2_put(S.in1 + j, EX_EMPTY);
+            S.plen[j] = 0; S.klen0[j] = 0; S.klen1[j] = 0; S.par[j] = -1; S.kid0[j] = -1; S.kid1[j] = -1;
+            S.sdn[j] = 0; S.ksdn0[j] = 0; S.ksdn1[j] = 0; S.cidx[j] = 0; S.flag[j] = 0; S.st[j] = 0;
+        }
+        if (gtid == 0) {   // buildInitialTree :253-295 (node 0 of the internal nodes is written by its owner, thread 0)
+            const double d = d01[0];
+            S.flag[0] = 2; S.kid0[0] = 0; S.kid1[0] = 1; S.klen0[0] = d / 2; S.klen1[0] = d / 2; S.ksdn0[0] = 2; S.ksdn1[0] = 3;
+            e[0] = N; len[0] = d / 2; nxt[0] = -1; belong[0] = 0; head[0] = 0;
+            e[1] = N; len[1] = d / 2; nxt[1] = -1; belong[1] = 1; head[1] = 1;
+            e[2] = 0; len[2] = d / 2; nxt[2] = -1; belong[2] = N;
+            e[3] = 1; len[3] = d / 2; nxt[3] = 2; belong[3] = N; head[N] = 3;
+        }
+    }
+    pl_grid_barrier(bar, (unsigned int)G, gen);
+    bool failed = false;
+    const long long t_begin = clock64();
+    for (int i = i0; i < i1; i++) {
+        const double* row = rows + (size_t)(i - row_base) * ld;
+        const int placed = i - 1;   // internal nodes 0 .. i-2
+        int pending = 0;
+        for (int j = gtid; j < placed; j += T) {
+            const int k0 = S.kid0[j], k1 = S.kid1[j];
+            S.ra[j] = k0 < N ? __ldg(&row[k0]) - S.klen0[j] : __longlong_as_double((long long)EX_EMPTY);
+            S.rb[j] = k1 < N ? __ldg(&row[k1]) - S.klen1[j] : __longlong_as_double((long long)EX_EMPTY);
+            S.st[j] = 1;
+            pending++;
+        }
+        while (pending) {
+            for (int j = gtid; j < placed; j += T) {
+                int st = S.st[j];
+                if (st == 0 || st >= 4) continue;
+                double a = S.ra[j], b = S.rb[j];
+                if (st == 1) {
+                    if (__double_as_longlong(a) == (long long)EX_EMPTY) {
+                        const unsigned long long v = g2_poll(S.in0 + j);
+                        if (v != EX_EMPTY) { a = __longlong_as_double((long long)v); S.ra[j] = a; g2_put(S.in0 + j, EX_EMPTY); }
+                    }
+                    if (__double_as_longlong(b) == (long long)EX_EMPTY) {
+                        const unsigned long long v = g2_poll(S.in1 + j);
+                        if (v != EX_EMPTY) { b = __longlong_as_double((long long)v); S.rb[j] = b; g2_put(S.in1 + j, EX_EMPTY); }
+                    }
+                    if (__double_as_longlong(a) != (long long)EX_EMPTY && __double_as_longlong(b) != (long long)EX_EMPTY) {
+                        if (S.flag[j] == 2) st = 3;
+                        else {
+                            double m = 0;
+                            if (a > m) m = a;
+                            if (b > m) m = b;
+                            const int pj = S.par[j] - N;
+                            g2_push((S.cidx[j] ? S.in1 : S.in0) + pj, m - S.plen[j]);
+                            st = 2;
+                        }
+                        S.st[j] = (unsigned char)st;
+                    }
+                }
+                if (st == 2 || st == 3) {
+                    unsigned long long ud = 0;
+                    if (st == 2) ud = g2_poll(S.dn + j);
+                    if (st == 3 || ud != EX_EMPTY) {
+                        double v0 = 0, v1 = 0;
+                        if (b > v0) v0 = b;
+                        if (a > v1) v1 = a;
+                        if (st == 2) {
+                            const double basev = __longlong_as_double((long long)ud) - S.plen[j];
+                            if (basev > v0) v0 = basev;
+                            if (basev > v1) v1 = basev;
+                        }
+                        const int k0 = S.kid0[j], k1 = S.kid1[j];
+                        if (k0 >= N) g2_push(S.dn + (k0 - N), v0);
+                        if (k1 >= N) g2_push(S.dn + (k1 - N), v1);
+                        S.st[j] = (unsigned char)(st == 3 ? 5 : 4);
+                        pending--;
+                    }
+                }
+            }
+        }
+        // ---- scoring (calculateBranchLength :153-198): own parent->node slot and the leaf children's slots
+        ExBest best;
+        best.add = 2.0; best.frac = 0.0; best.slot = 0; best.node = -1;
+        double bpl = 0;
+        int bx = -1, bc = 0;
+        for (int j = gtid; j < placed; j += T) {
+            const int st = S.st[j];
+            const double a = S.ra[j], b = S.rb[j];
+            double v0 = 0, v1 = 0;
+            if (b > v0) v0 = b;
+            if (a > v1) v1 = a;
+            const int me = N + j;
+            if (st == 4) {
+                const double dn = __longlong_as_double((long long)g2_poll(S.dn + j)), pl = S.plen[j];
+                g2_put(S.dn + j, EX_EMPTY);
+                double up = 0;
+                if (a > up) up = a;
+                if (b > up) up = b;
+                const int before = best.node;
+                ex_score(dn, up, pl, S.sdn[j], me, best);
+                if (best.node != before) { bpl = pl; bx = S.par[j]; bc = S.cidx[j]; }
+                const double basev = dn - pl;
+                if (basev > v0) v0 = basev;
+                if (basev > v1) v1 = basev;
+            }
+            const int k0 = S.kid0[j], k1 = S.kid1[j];
+            if (k0 < N) {
+                const int before = best.node;
+                ex_score(v0, __ldg(&row[k0]), S.klen0[j], S.ksdn0[j], k0, best);
+                if (best.node != before) { bpl = S.klen0[j]; bx = me; bc = 0; }
+            }
+            if (k1 < N) {
+                const int before = best.node;
+                ex_score(v1, __ldg(&row[k1]), S.klen1[j], S.ksdn1[j], k1, best);
+                if (best.node != before) { bpl = S.klen1[j]; bx = me; bc = 1; }
+            }
+        }
+        // ---- first minimum over the grid (thrust::min_element :657)
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const double oa = __shfl_xor_sync(0xffffffffu, best.add, s), of = __shfl_xor_sync(0xffffffffu, best.frac, s), op = __shfl_xor_sync(0xffffffffu, bpl, s);
+            const int os = __shfl_xor_sync(0xffffffffu, best.slot, s), on = __shfl_xor_sync(0xffffffffu, best.node, s);
+            const int ox = __shfl_xor_sync(0xffffffffu, bx, s), oc = __shfl_xor_sync(0xffffffffu, bc, s);
+            if (ex_before(oa, os, best.add, best.slot)) { best.add = oa; best.frac = of; best.slot = os; best.node = on; bpl = op; bx = ox; bc = oc; }
+        }
+        if (lane == 0) { s_warp[wid] = best; s_wpl[wid] = bpl; s_wx[wid] = bx; s_wc[wid] = bc; }
+        __syncthreads();
+        if (wid == 0) {
+            best = s_warp[lane]; bpl = s_wpl[lane]; bx = s_wx[lane]; bc = s_wc[lane];
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const double oa = __shfl_xor_sync(0xffffffffu, best.add, s), of = __shfl_xor_sync(0xffffffffu, best.frac, s), op = __shfl_xor_sync(0xffffffffu, bpl, s);
+                const int os = __shfl_xor_sync(0xffffffffu, best.slot, s), on = __shfl_xor_sync(0xffffffffu, best.node, s);
+                const int ox = __shfl_xor_sync(0xffffffffu, bx, s), oc = __shfl_xor_sync(0xffffffffu, bc, s);
+                if (ex_before(oa, os, best.add, best.slot)) { best.add = oa; best.frac = of; best.slot = os; best.node = on; bpl = op; bx = ox; bc = oc; }
+            }
+            if (lane == 0) {
+                G2Rec r; r.add = best.add; r.frac = best.frac; r.pl = bpl; r.slot = best.slot; r.node = best.node; r.x = bx; r.c = bc;
+                part[(size_t)(i & 1) * G + blockIdx.x] = r;
+            }
+        }
+        pl_grid_barrier(bar, (unsigned int)G, gen);
+        if (wid == 0) {
+            G2Rec w; w.add = 2.0; w.frac = 0; w.pl = 0; w.slot = 0; w.node = -1; w.x = -1; w.c = 0;
+            for (int c = lane; c < G; c += 32) {
+                const G2Rec o = part[(size_t)(i & 1) * G + c];
+                if (ex_before(o.add, o.slot, w.add, w.slot)) w = o;
+            }
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                G2Rec o;
+                o.add = __shfl_xor_sync(0xffffffffu, w.add, s); o.frac = __shfl_xor_sync(0xffffffffu, w.frac, s); o.pl = __shfl_xor_sync(0xffffffffu, w.pl, s);
+                o.slot = __shfl_xor_sync(0xffffffffu, w.slot, s); o.node = __shfl_xor_sync(0xffffffffu, w.node, s);
+                o.x = __shfl_xor_sync(0xffffffffu, w.x, s); o.c = __shfl_xor_sync(0xffffffffu, w.c, s);
+                if (ex_before(o.add, o.slot, w.add, w.slot)) w = o;
+            }
+            if (lane == 0) s_win = w;
+        }
+        __syncthreads();
+        const double addLen = s_win.add, fracLen = s_win.frac, pleny = s_win.pl;
+        const int slot = s_win.slot, y = s_win.node, x = s_win.x, cidxy = s_win.c;
+        __syncthreads();   // s_win is rewritten in the next tip
+        if (y < 0) { failed = true; break; }
+        // ---- split (updateTreeStructure :200-251), every node by its owner thread
+        const int m = i + N - 1, jm = i - 1, c0 = 4 * i - 4;
+        if ((x - N) % T == gtid) (cidxy ? S.kid1 : S.kid0)[x - N] = m;
+        if (y >= N && (y - N) % T == gtid) { const int k = y - N; S.par[k] = m; S.cidx[k] = 0; S.plen[k] = pleny - fracLen; S.sdn[k] = c0 + 1; }
+        if (jm % T == gtid) {
+            S.par[jm] = x; S.cidx[jm] = (unsigned char)cidxy; S.kid0[jm] = y; S.kid1[jm] = i; S.plen[jm] = fracLen; S.sdn[jm] = slot;
+            S.klen0[jm] = pleny - fracLen; S.ksdn0[jm] = c0 + 1; S.klen1[jm] = addLen; S.ksdn1[jm] = c0 + 3; S.flag[jm] = 1;
+            const int xe = slot, ye = y < N ? (y < 2 ? y : 4 * y - 2) : 4 * (y - N);
+            const int c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3;
+            e[xe] = m; len[xe] = fracLen;
+            e[ye] = m; len[ye] = pleny - fracLen;
+            e[c0] = x; len[c0] = fracLen; nxt[c0] = -1; belong[c0] = m;
+            e[c1] = y; len[c1] = pleny - fracLen; nxt[c1] = c0; belong[c1] = m;
+            e[c2] = m; len[c2] = addLen; nxt[c2] = -1; belong[c2] = i; head[i] = c2;
+            e[c3] = i; len[c3] = addLen; nxt[c3] = c1; belong[c3] = m; head[m] = c3;
+        }
+    }
+    if (gtid == 0) {
+        if (failed) ctl->error = 1;
+        ctl->cycles += (unsigned long long)(clock64() - t_begin);
+    }
+}
+
 template <int CS, int MODE>   // MODE 0: level steps, 1: data flow over all nodes, 2: data flow over internal nodes (default)
 int ex_launch(dipb_ctx* c, void** args, size_t smem, bool* ok) {
     auto kern = MODE == 2 ? place_exact_flow2_kernel<CS> : (MODE == 1 ? place_exact_kernel<CS, true> : place_exact_kernel<CS, false>);
@@ -725,6 +938,76 @@ static int ex_max_tips(int mode) {
     return nl * 16;
 }
 
+// tips beyond the cluster's shared memory: state in global memory, whole grid (see place_exact_global_kernel)
+static int place_exact_run_global(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* t) {
+    const double* d01 = nullptr;
+    double* row1 = nullptr;
+    int rc = 0;
+    if (src->matrix) d01 = src->matrix->d + (size_t)src->matrix->n;
+    else {
+        DIPB_CUDA(pool_alloc(c, (void**)&row1, sizeof(double) * 8));
+        rc = src->msa ? msa_block(src->msa, src->dist_type, 1, 2, 1, row1, 8) : dipb_mash_dist_block(src->mash, 1, 2, 1, row1, 8);
+        if (rc) { pool_free(c, row1); return rc; }
+        d01 = row1;
+    }
+    int batch = 512;
+    double* buf = nullptr;
+    const size_t ld = (size_t)n, N = (size_t)n;
+    if (!src->matrix) {
+        size_t want = (size_t)batch * ld * sizeof(double);
+        while (want > (1ull << 28) && batch > 128) { batch /= 2; want /= 2; }
+        DIPB_CUDA(pool_alloc(c, (void**)&buf, (size_t)batch * ld * sizeof(double)));
+    } else batch = n;
+    G2State S{};
+    double* dblk = nullptr;
+    int* iblk = nullptr;
+    unsigned char* bblk = nullptr;
+    DIPB_CUDA(pool_alloc(c, (void**)&dblk, 8 * N * sizeof(double)));
+    DIPB_CUDA(pool_alloc(c, (void**)&iblk, 6 * N * sizeof(int)));
+    DIPB_CUDA(pool_alloc(c, (void**)&bblk, 3 * N));
+    S.dn = dblk; S.in0 = dblk + N; S.in1 = dblk + 2 * N; S.plen = dblk + 3 * N; S.klen0 = dblk + 4 * N; S.klen1 = dblk + 5 * N; S.ra = dblk + 6 * N; S.rb = dblk + 7 * N;
+    S.par = iblk; S.kid0 = iblk + N; S.kid1 = iblk + 2 * N; S.sdn = iblk + 3 * N; S.ksdn0 = iblk + 4 * N; S.ksdn1 = iblk + 5 * N;
+    S.cidx = bblk; S.flag = bblk + N; S.st = bblk + 2 * N;
+    int per_sm = 0;
+    DIPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_exact_global_kernel, EX_THREADS, 0));
+    if (per_sm < 1) { set_error("exact placement (global): kernel does not fit"); return DIPB_E_CUDA; }
+    int G = c->num_sms;
+    G2Rec* part = nullptr;
+    unsigned int* bar = nullptr;
+    ExCtl* ctl = nullptr;
+    DIPB_CUDA(pool_alloc(c, (void**)&part, 2 * (size_t)G * sizeof(G2Rec)));
+    DIPB_CUDA(pool_alloc(c, (void**)&bar, sizeof(unsigned int)));
+    DIPB_CUDA(pool_alloc(c, (void**)&ctl, sizeof(ExCtl)));
+    DIPB_CUDA(cudaMemsetAsync(ctl, 0, sizeof(ExCtl), c->stream));
+    for (int i0 = 2; (i0 < n || i0 == 2) && !rc; i0 += batch) {
+        int i1 = i0 + batch < n ? i0 + batch : n;
+        const double* rows = nullptr; int row_base = 0; size_t ldr = ld;
+        if (i1 > i0) rc = place_fetch_rows(src, i0, i1, buf, ld, &rows, &row_base, &ldr);
+        if (rc) break;
+        DIPB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned int), c->stream));
+        int Nn = n, i0v = i0;
+        void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &rows, &ldr, &row_base, &i0v, &i1, &Nn, &d01, &S, &part, &bar, &ctl};
+        cudaError_t e = cudaLaunchCooperativeKernel((void*)place_exact_global_kernel, dim3(G), dim3(EX_THREADS), args, 0, c->stream);
+        if (e != cudaSuccess) { set_error("exact placement (global): cooperative launch failed: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; break; }
+        c->launches++;
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (!rc && e != cudaSuccess) { set_error("exact placement (global): %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; }
+    if (!rc) {
+        ExCtl h;
+        if (cudaMemcpy(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("exact placement: control block copy failed"); rc = DIPB_E_CUDA; }
+        else if (h.error) {
+            set_error("exact placement: a tip has no candidate edge with pendant length < 2 (the reference's (0,0,2) default tuple would win; src/placement.cu:166-170)");
+            rc = DIPB_E_UNSUPPORTED;
+        } else if (getenv("DIPB_PLACE_PROFILE"))
+            fprintf(stderr, "[exact placement] %d tips, global-memory data flow on %d CTAs: %.0f cycles per tip\n", n, G, (double)h.cycles / (n - 2));
+    }
+    pool_free(c, dblk); pool_free(c, iblk); pool_free(c, bblk); pool_free(c, part); pool_free(c, bar); pool_free(c, ctl);
+    if (buf) pool_free(c, buf);
+    if (row1) pool_free(c, row1);
+    return rc;
+}
+
 int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* t) {
     int CS = 16;
     const char* force = getenv("DIPB_EXACT_CLUSTER");
@@ -734,7 +1017,10 @@ int place_exact_run(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tree* 
     const char* eb = getenv("DIPB_EXACT_BACKOFF");   // ns of __nanosleep between polling passes (default mode only)
     int backoff = eb ? atoi(eb) : 0;
     int NL = ex_local(n, CS);
-    if (ex_smem_bytes(NL, mode) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS) {
+    const char* eg = getenv("DIPB_EXACT_GLOBAL");   // 1: always the global-memory kernel; 0: never (report the size limit instead)
+    const bool too_big = ex_smem_bytes(NL, mode) > EX_SMEM_MAX || NL > EX_KM * EX_THREADS;
+    if ((eg && atoi(eg) == 1) || (too_big && !(eg && atoi(eg) == 0))) return place_exact_run_global(c, src, n, t);
+    if (too_big) {
         set_error("exact placement: %d tips exceed the shared-memory tree of one %d-CTA cluster (at most %d tips); use -p 1 or -m 3", n, CS,
                   ex_max_tips(mode) / (16 / CS));
         return DIPB_E_UNSUPPORTED;

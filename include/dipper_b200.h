@@ -150,9 +150,10 @@ typedef struct {
 int dipb_place_kclosest(dipb_ctx *ctx, const dipb_dist_source *src, int n, dipb_tree **out);
 /* PlacementDeviceArrays::allocateDeviceArrays + findPlacementTree (exact placement mode, -p 0)
  * src/mash_placement.cuh:137-165, src/placement.cu:28-116,505-789.  Same slot arrays as above
- * (print from node n, src/placement.cu:500).  The tree lives in the shared memory of one
- * thread-block cluster: at most dipb_place_exact_max_tips() tips, DIPB_E_UNSUPPORTED beyond,
- * and when a tip has no candidate edge with pendant length < 2 (see placement_exact.cu). */
+ * (print from node n, src/placement.cu:500).  Up to dipb_place_exact_max_tips() tips the tree
+ * lives in the shared memory of one thread-block cluster; larger inputs run the same data flow
+ * through global memory on the whole grid.  DIPB_E_UNSUPPORTED when a tip has no candidate edge
+ * with pendant length < 2 (see placement_exact.cu). */
 int dipb_place_exact(dipb_ctx *ctx, const dipb_dist_source *src, int n, dipb_tree **out);
 int dipb_place_exact_max_tips(void);
 /* initializeDeviceArrays(Tree*) + addQuery, src/placement_close_k.cu:126-264,858-990.

@@ -134,6 +134,24 @@ def test_exact_placement_earlier_kernel_variants(ctx, oracle, monkeypatch, mode)
     compare_trees(pl, oracle.place_exact(msa.distMatrix(prm).to_host()), n)
 
 
+@pytest.mark.parametrize("n", [2, 3, 50, 1300])
+def test_exact_placement_global_memory_kernel(ctx, oracle, monkeypatch, n):
+    """The kernel used beyond one cluster's shared memory (> 49 152 tips), forced here on small inputs: whole grid,
+    state in global memory, values travel through L2.  Same arrays; 1300 tips cross the 512-tip launch boundary."""
+    monkeypatch.setenv("DIPB_EXACT_GLOBAL", "1")
+    L = 900
+    codes, P, _ = make_msa(n, L, seed=400 + n)
+    prm = api.Param(distanceType=2, in_="m")
+    msa = api.MSADeviceArrays(ctx)
+    msa.allocateDeviceArrays(P, np.full(n, L, np.uint64), n, prm)
+    pl = api.PlacementDeviceArrays(ctx)
+    pl.allocateDeviceArrays(n)
+    pl.findPlacementTree(prm, msaDeviceArrays=msa)
+    ot = oracle.place_exact(msa.distMatrix(prm).to_host())
+    compare_trees(pl, ot, n)
+    assert pl.printTree(synth.names(n)) == ot.newick(synth.names(n))
+
+
 def test_exact_placement_8_cta_cluster(ctx, oracle, monkeypatch):
     monkeypatch.setenv("DIPB_EXACT_CLUSTER", "8")
     n = 500
@@ -158,7 +176,8 @@ def test_exact_placement_reports_the_default_tuple_case(ctx):
         pl.findPlacementTree(api.Param(in_="d"), matrix=M)
 
 
-def test_exact_placement_rejects_too_many_tips(ctx):
+def test_exact_placement_size_limit_of_the_cluster_kernel(ctx, monkeypatch):
+    monkeypatch.setenv("DIPB_EXACT_GLOBAL", "0")     # without the global-memory kernel the cluster's capacity is reported
     n, L = api.PlacementDeviceArrays.maxTips() + 64, 64
     P = np.zeros((n, L // 16), np.uint64)
     prm = api.Param(distanceType=1, in_="m")
