@@ -94,6 +94,26 @@ def test_golden_fixtures_through_cuda(ctx):
         z = np.load(fn)
         P, L = z["packed"], int(z["seq_len"])
         msa = upload(ctx, P, L)
+        if str(z["kind"]) == "ref_msa":
+            # produced by the reference's own CUDA objects (tools/make_ref_golden.py): rows, NJ, k-closest and exact-mode trees
+            from dipper_b200 import newick
+            n = P.shape[0]
+            low = np.tril_indices(n, -1)
+            for t in (1, 2):
+                D = msa.distMatrix(api.Param(distanceType=t, in_="m")).to_host()
+                assert np.allclose(D[low], z["rows_%d" % t][low], rtol=1e-6, atol=0), (fn, t)
+            prm = api.Param(distanceType=2, in_="m")
+            nj = api.NJDeviceArrays(ctx)
+            nj.getDismatrix(n, prm, msaDeviceArrays=msa)
+            nwk = nj.findNeighbourJoiningTree(synth.names(n))
+            assert newick.rf_distance(nwk, str(z["nj_newick"])) == 0 and newick.max_branch_diff(nwk, str(z["nj_newick"])) < 1e-5, fn
+            kp = api.KPlacementDeviceArrays(ctx); kp.allocateDeviceArrays(n)
+            kp.findPlacementTree(prm, msaDeviceArrays=msa)
+            assert kp.printTree(synth.names(n)) == str(z["place_newick"]), fn
+            pl = api.PlacementDeviceArrays(ctx); pl.allocateDeviceArrays(n)
+            pl.findPlacementTree(prm, msaDeviceArrays=msa)
+            assert pl.printTree(synth.names(n)) == str(z["place_exact_newick"]), fn
+            continue
         m, u = msa.counts(0, P.shape[0], 0, P.shape[0])
         assert np.array_equal(m, z["match"]) and np.array_equal(u, z["useful"]), fn
         for t in z["dist_types"]:
