@@ -3,7 +3,9 @@
 // Host C++ only; the GPU is reached through the C ABI of libdipper_b200.so.
 // Deliberate differences: --device (reference hard-codes device 1),
 // --seed / --no-shuffle pin the input permutation (reference seeds with time(NULL)),
-// -p is honoured, Mash + NJ sketches first (reference bug B3), Boost/TBB are not needed.
+// -p is honoured (the reference fills its placement mode from -m, src/tree_generation.cu:222-223, so there an explicit
+// -m 0 on 30 000 .. 1 000 000 sequences runs the exact mode and -p is ignored; here -p 0 selects it, as documented),
+// Mash + NJ sketches first (reference bug B3), Boost/TBB are not needed.
 #include <getopt.h>
 #include <zlib.h>
 
