@@ -11,7 +11,11 @@
  *       (tests/test_oracle.py) and
  *   (2) against outputs of the reference's own CUDA objects built by
  *       oracle/build_ref.sh into oracle/_ref/ and run on the GPU box
- *       (tests/test_ref_parity.py, -m gpu).
+ *       (tests/test_ref_parity.py, -m gpu), and against the same kind of outputs
+ *       committed as fixtures (tests/golden/ref_*.npz, written on a B200 by
+ *       tools/make_ref_golden.py: distance rows, sketches, NJ / k-closest /
+ *       exact-mode placement trees), which the CPU-only suite checks
+ *       (tests/test_oracle.py::test_golden_fixtures).
  *
  * Every function cites the reference file:line (paths relative to /root/reference)
  * whose behaviour it restates.  Nothing here is copied from the reference; loops
