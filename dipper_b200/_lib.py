@@ -33,6 +33,7 @@ _lib = None
 SIGNATURES = {
     "dipb_init": (C.c_int, [C.c_int, vpp]),
     "dipb_destroy": (None, [vp]),
+    "dipb_ctx_refs": (C.c_int, [vp]),
     "dipb_last_error": (C.c_char_p, []),
     "dipb_version": (C.c_char_p, []),
     "dipb_elapsed_ms": (C.c_double, [vp, C.c_int]),

@@ -439,6 +439,12 @@ class KPlacementDeviceArrays:
             lib().dipb_tree_free(self.h)
             self.h = None
 
+    def __del__(self):
+        try:
+            self.deallocateDeviceArrays()
+        except Exception:
+            pass
+
 
 class PlacementDeviceArrays(KPlacementDeviceArrays):
     """MashPlacement::PlacementDeviceArrays, the exact placement mode (src/mash_placement.cuh:137-165,

@@ -12,6 +12,15 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
 }
+void ctx_release(dipb_ctx* c) {
+    if (!c || c->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);   // frees queued by the children are stream ordered
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
 }  // namespace dipb
 
 using namespace dipb;
@@ -35,14 +44,19 @@ int dipb_init(int device, dipb_ctx** out) {
     dipb_ctx* c = new dipb_ctx();
     c->device = device;
     cudaDeviceProp prop;
-    DIPB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("dipb_init: cudaGetDeviceProperties failed"); delete c; return DIPB_E_CUDA; }
     c->num_sms = prop.multiProcessorCount;
     if (prop.major < 10) {
         set_error("dipb_init: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         delete c;
         return DIPB_E_CUDA;
     }
-    DIPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+        cudaEventCreate(&c->ev1) != cudaSuccess) {
+        set_error("dipb_init: stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx_release(c);
+        return DIPB_E_CUDA;
+    }
     {
         // keep freed pool pages for re-use (see pool_alloc in common.cuh)
         cudaMemPool_t pool;
@@ -52,21 +66,17 @@ int dipb_init(int device, dipb_ctx** out) {
         }
         cudaGetLastError();
     }
-    DIPB_CUDA(cudaEventCreate(&c->ev0));
-    DIPB_CUDA(cudaEventCreate(&c->ev1));
     for (int i = 0; i < DIPB_T_COUNT; i++) c->elapsed[i] = -1.0;
     *out = c;
     return DIPB_OK;
 }
 
 void dipb_destroy(dipb_ctx* c) {
-    if (!c) return;
-    cudaSetDevice(c->device);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->stream) cudaStreamDestroy(c->stream);
-    delete c;
+    if (!c || c->destroyed) return;
+    c->destroyed = true;
+    ctx_release(c);
 }
+int dipb_ctx_refs(const dipb_ctx* c) { return c ? c->refs.load() : 0; }
 
 double dipb_elapsed_ms(dipb_ctx* c, int what) {
     if (!c || what < 0 || what >= DIPB_T_COUNT) return -1.0;
@@ -80,9 +90,8 @@ int dipb_sync(dipb_ctx* c) {
 }
 
 // ---- aligned MSA -------------------------------------------------------------
-static int msa_create(dipb_ctx* c, const uint64_t* d_in, size_t n, uint64_t seq_len, dipb_msa** out) {
-    dipb_msa* m = new dipb_msa();
-    m->ctx = c;
+static int msa_create_impl(dipb_msa* m, const uint64_t* d_in, size_t n, uint64_t seq_len) {
+    dipb_ctx* c = m->ctx;
     m->n = (int)n;
     m->seq_len = (int)seq_len;
     m->npad = (int)((n + MSA_TS - 1) / MSA_TS * MSA_TS);
@@ -93,8 +102,14 @@ static int msa_create(dipb_ctx* c, const uint64_t* d_in, size_t n, uint64_t seq_
     DIPB_CUDA(pool_alloc(c, (void**)&m->planes, words * sizeof(uint32_t)));
     DIPB_CUDA(cudaMalloc(&m->nv, sizeof(int) * m->npad));
     DIPB_CUDA(cudaMemsetAsync(m->nv, 0, sizeof(int) * m->npad, c->stream));
-    int rc = msa_repack(m, d_in, (int)((seq_len + 15) / 16));
-    if (rc) return rc;
+    return msa_repack(m, d_in, (int)((seq_len + 15) / 16));
+}
+static int msa_create(dipb_ctx* c, const uint64_t* d_in, size_t n, uint64_t seq_len, dipb_msa** out) {
+    dipb_msa* m = new dipb_msa();
+    m->ctx = c;
+    ctx_retain(c);
+    const int rc = msa_create_impl(m, d_in, n, seq_len);
+    if (rc) { dipb_msa_free(m); return rc; }   // nothing leaks on a failed upload
     *out = m;
     return 0;
 }
@@ -107,13 +122,18 @@ int dipb_msa_upload_flat(dipb_ctx* c, const uint64_t* flat, size_t n, uint64_t s
     uint64_t* d_in = nullptr;
     DIPB_CUDA(cudaMalloc(&d_in, n * comp * sizeof(uint64_t)));
     int rc = timer_begin(c);
-    if (rc) return rc;
-    DIPB_CUDA(cudaMemcpyAsync(d_in, flat, n * comp * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-    rc = msa_create(c, d_in, n, seq_len, out);
-    if (rc) { cudaFree(d_in); return rc; }
-    rc = timer_end(c, DIPB_T_MSA_UPLOAD);
+    if (!rc && cudaMemcpyAsync(d_in, flat, n * comp * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+        set_error("dipb_msa_upload_flat: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = DIPB_E_CUDA;
+    }
+    dipb_msa* m = nullptr;
+    if (!rc) rc = msa_create(c, d_in, n, seq_len, &m);
+    if (!rc) rc = timer_end(c, DIPB_T_MSA_UPLOAD);
+    cudaStreamSynchronize(c->stream);
     cudaFree(d_in);
-    return rc;
+    if (rc) { dipb_msa_free(m); return rc; }
+    *out = m;
+    return 0;
 }
 
 int dipb_msa_upload(dipb_ctx* c, const uint64_t* const* seq4, const uint64_t* len, size_t n, dipb_msa** out) {
@@ -139,6 +159,7 @@ void dipb_msa_free(dipb_msa* m) {
     pool_free(m->ctx, m->tc_V);
     pool_free(m->ctx, m->tc_Sx);
     pool_free(m->ctx, m->tc_Vx);
+    ctx_release(m->ctx);
     delete m;
 }
 
@@ -217,15 +238,17 @@ int dipb_msa_dist_matrix_rows(dipb_msa* m, int dist_type, int row_begin, int row
     DIPB_CUDA(cudaSetDevice(m->ctx->device));
     dipb_matrix* M = new dipb_matrix();
     M->ctx = m->ctx;
+    ctx_retain(M->ctx);
     M->n = m->n;
     size_t bytes = (size_t)m->n * m->n * sizeof(double);
     cudaError_t e = pool_alloc(m->ctx, (void**)&M->d, bytes);
-    if (e != cudaSuccess) { set_error("dipb_msa_dist_matrix: allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); delete M; return DIPB_E_NOMEM; }
-    if (row_begin != 0 || row_end != m->n) DIPB_CUDA(cudaMemsetAsync(M->d, 0, bytes, m->ctx->stream));
-    int rc = timer_begin(m->ctx);
+    if (e != cudaSuccess) { set_error("dipb_msa_dist_matrix: allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); M->d = nullptr; dipb_matrix_free(M); return DIPB_E_NOMEM; }
+    int rc = 0;
+    if ((row_begin != 0 || row_end != m->n) && cudaMemsetAsync(M->d, 0, bytes, m->ctx->stream) != cudaSuccess) { set_error("dipb_msa_dist_matrix: memset failed"); rc = DIPB_E_CUDA; }
+    if (!rc) rc = timer_begin(m->ctx);
     if (!rc) rc = msa_matrix(m, dist_type, row_begin, row_end, M->d);
     if (!rc) rc = timer_end(m->ctx, DIPB_T_MSA_DIST);
-    if (rc) { pool_free(M->ctx, M->d); delete M; return rc; }
+    if (rc) { dipb_matrix_free(M); return rc; }
     *out = M;
     return 0;
 }
@@ -288,26 +311,31 @@ int dipb_matrix_from_host(dipb_ctx* c, const double* h, int n, int full, dipb_ma
     DIPB_CUDA(cudaSetDevice(c->device));
     dipb_matrix* M = new dipb_matrix();
     M->ctx = c;
+    ctx_retain(c);
     M->n = n;
     size_t bytes = (size_t)n * n * sizeof(double);
     cudaError_t e = pool_alloc(c, (void**)&M->d, bytes);
-    if (e != cudaSuccess) { set_error("dipb_matrix_from_host: allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); delete M; return DIPB_E_NOMEM; }
+    if (e != cudaSuccess) { set_error("dipb_matrix_from_host: allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); M->d = nullptr; dipb_matrix_free(M); return DIPB_E_NOMEM; }
     dim3 grid((n + 255) / 256, n);
-    if (full) {
-        DIPB_CUDA(cudaMemcpyAsync(M->d, h, bytes, cudaMemcpyHostToDevice, c->stream));
-        symmetrize_kernel<<<grid, 256, 0, c->stream>>>(M->d, n);
-        DIPB_KERNEL_CHECK(c);
-    } else {
-        double* tri = nullptr;
-        size_t tb = (size_t)n * (n - 1) / 2 * sizeof(double);
-        DIPB_CUDA(cudaMalloc(&tri, tb));
-        DIPB_CUDA(cudaMemcpyAsync(tri, h, tb, cudaMemcpyHostToDevice, c->stream));
-        expand_lower_kernel<<<grid, 256, 0, c->stream>>>(tri, M->d, n);
-        DIPB_KERNEL_CHECK(c);
+    double* tri = nullptr;
+    auto body = [&]() -> int {
+        if (full) {
+            DIPB_CUDA(cudaMemcpyAsync(M->d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+            symmetrize_kernel<<<grid, 256, 0, c->stream>>>(M->d, n);
+            DIPB_KERNEL_CHECK(c);
+        } else {
+            size_t tb = (size_t)n * (n - 1) / 2 * sizeof(double);
+            DIPB_CUDA(cudaMalloc(&tri, tb));
+            DIPB_CUDA(cudaMemcpyAsync(tri, h, tb, cudaMemcpyHostToDevice, c->stream));
+            expand_lower_kernel<<<grid, 256, 0, c->stream>>>(tri, M->d, n);
+            DIPB_KERNEL_CHECK(c);
+        }
         DIPB_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(tri);
-    }
-    DIPB_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    const int rc = body();
+    if (tri) { cudaStreamSynchronize(c->stream); cudaFree(tri); }
+    if (rc) { dipb_matrix_free(M); return rc; }
     *out = M;
     return 0;
 }
@@ -325,6 +353,7 @@ void dipb_matrix_free(dipb_matrix* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     pool_free(m->ctx, m->d);
+    ctx_release(m->ctx);
     delete m;
 }
 

@@ -6,6 +6,8 @@
 #include <cstdarg>
 #include <cstring>
 #include <string>
+#include <atomic>
+#include <vector>
 #include "../../include/dipper_b200.h"
 
 namespace dipb {
@@ -43,9 +45,18 @@ struct dipb_ctx {
     double elapsed[DIPB_T_COUNT];
     uint64_t launches = 0;
     uint64_t nj_rows_scanned = 0, nj_bytes_scanned = 0, nj_iterations = 0;
+    // Life time: dipb_init holds one reference, every child handle (msa, mash, matrix, tree, D&C state) one more.
+    // dipb_destroy drops the creator's reference; the stream, the events and the struct go away with the LAST
+    // reference, so children may be freed after dipb_destroy (in any order) without touching freed memory.
+    std::atomic<int> refs{1};
+    bool destroyed = false;               // dipb_destroy was called
+    std::vector<int32_t> last_clusters;   // test hook storage of dipb_dc_cluster_ids (per context)
 };
 
 namespace dipb {
+
+inline void ctx_retain(dipb_ctx* c) { c->refs.fetch_add(1, std::memory_order_relaxed); }
+void ctx_release(dipb_ctx* c);   // capi.cu: tears the context down when the last reference goes
 
 // RAII-free helpers: time a region on the context's stream with CUDA events.
 inline int timer_begin(dipb_ctx* c) {

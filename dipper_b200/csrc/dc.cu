@@ -429,7 +429,6 @@ __global__ void fill_int_kernel(int* p, long long n, int v) {
 
 using namespace dipb;
 
-static std::vector<int32_t> g_last_clusters;   // test hook storage (dipb_dc_cluster_ids)
 
 // Staged divide-and-conquer state: lets one process per GPU shard stage 2 (queries) and
 // stage 3 (clusters) and merge the per-rank tree slices on rank 0.
@@ -469,15 +468,16 @@ int dipb_dc_begin(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone,
     DIPB_CUDA(cudaSetDevice(c->device));
     dipb_dc_state* st = new dipb_dc_state();
     st->ctx = c; st->src = *src; st->n = n; st->B = backbone;
+    ctx_retain(c);
     // tensor-core operands: only the backbone rows stay expanded; query batches use a scratch pair (msa_tc.cu)
     if (src->msa) msa_tc_reserve(src->msa, backbone);
     rc = tree_alloc(c, n, &st->tree);
-    if (rc) { delete st; return rc; }
+    if (rc) { ctx_release(c); delete st; return rc; }
     PlaceScratch sc;
     rc = place_scratch_alloc(c, n, &sc);
     if (!rc) rc = place_from_scratch(c, src, n, backbone, st->tree, &sc);
     place_scratch_free(c, &sc);
-    if (rc) { dipb_tree_free(st->tree); delete st; return rc; }
+    if (rc) { dipb_tree_free(st->tree); ctx_release(c); delete st; return rc; }
     st->cl.assign(n, -1);
     *out = st;
     return 0;
@@ -605,7 +605,7 @@ int dipb_dc_set_clusters(dipb_dc_state* st, const int32_t* h_cluster_all, int* n
     for (int i = 0; i < B; i++) st->cl[i] = -1;
     for (int i = B; i < n; i++)
         if (st->cl[i] < 0 || st->cl[i] >= 4 * B - 4) { set_error("dipb_dc_set_clusters: tip %d has cluster %d", i, st->cl[i]); return DIPB_E_ARG; }
-    g_last_clusters = st->cl;
+    c->last_clusters = st->cl;   // test hook (dipb_dc_cluster_ids), per context
     st->order.resize(ntips);
     for (int i = 0; i < ntips; i++) st->order[i] = B + i;
     std::stable_sort(st->order.begin(), st->order.end(), [&](int x, int y) { return st->cl[x] < st->cl[y]; });
@@ -752,6 +752,12 @@ int dipb_dc_import_slice(dipb_dc_state* st, const void* h_buf, size_t bytes) {
     DIPB_CUDA(cudaSetDevice(st->ctx->device));
     const size_t ns = (size_t)4 * nt, s0 = (size_t)4 * B - 4 + 4 * (size_t)T0;
     const size_t per_bb = 2 * sizeof(int32_t) + sizeof(double) + 5 * sizeof(int32_t) + 5 * sizeof(double);
+    {
+        // the header fixes the blob's length (same formula as dipb_dc_export_slice): check it before reading anything
+        const size_t need = 4 * sizeof(int32_t) + ns * (4 * sizeof(int32_t) + sizeof(double) + 5 * sizeof(int32_t) + 5 * sizeof(double)) +
+                            (size_t)nt * 2 * sizeof(int32_t) + (size_t)ncl * 2 * per_bb;
+        if (bytes != need) { set_error("dipb_dc_import_slice: blob is %zu bytes, its header implies %zu", bytes, need); return DIPB_E_ARG; }
+    }
     auto push = [&](void* dptr, size_t elem, size_t off, size_t cnt) -> int {
         if (cnt && cudaMemcpy((char*)dptr + off * elem, p, cnt * elem, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("dipb_dc_import_slice: H2D failed"); return DIPB_E_CUDA; }
         p += cnt * elem;
@@ -799,6 +805,7 @@ int dipb_dc_finish(dipb_dc_state* st, dipb_tree** out) {
     if (st->d_sorder) { cudaFree(st->d_sorder); st->d_sorder = nullptr; }
     if (out) { *out = st->tree; st->tree = nullptr; }
     if (st->tree) dipb_tree_free(st->tree);
+    ctx_release(st->ctx);
     delete st;
     return 0;
 }
@@ -835,8 +842,8 @@ int dipb_dc(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone, dipb_
 }
 
 int dipb_dc_cluster_ids(dipb_ctx* c, int32_t* h_out, int n) {
-    if (!c || !h_out || (int)g_last_clusters.size() != n) { set_error("dipb_dc_cluster_ids: no matching dipb_dc run"); return DIPB_E_STATE; }
-    memcpy(h_out, g_last_clusters.data(), sizeof(int32_t) * n);
+    if (!c || !h_out || (int)c->last_clusters.size() != n) { set_error("dipb_dc_cluster_ids: no matching dipb_dc run on this context"); return DIPB_E_STATE; }
+    memcpy(h_out, c->last_clusters.data(), sizeof(int32_t) * n);
     return 0;
 }
 

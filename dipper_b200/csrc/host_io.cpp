@@ -368,6 +368,13 @@ int dipb_backbone_from_newick(const char* newick, int total_leaves, int32_t* hea
         e[edge] = y; len[edge] = nodes[v].bl; belong[edge] = x; nxt[edge] = head[x]; head[x] = edge; edge++;
         e[edge] = x; len[edge] = nodes[v].bl; belong[edge] = y; nxt[edge] = head[y]; head[y] = edge; edge++;
     }
+    // The placement kernels take the backbone as a rooted binary tree: 2B-2 edges = 4B-4 directed slots
+    // (src/placement_close_k.cu:887 assumes it silently; a trifurcating root or unary nodes would leave unused
+    // slots that the device code walks).
+    if (edge != 4 * B - 4) {
+        dipb::set_error("newick: backbone with %d leaves has %d edges; a rooted binary tree (%d edges) is required", B, edge / 2, 2 * B - 2);
+        return DIPB_E_ARG;
+    }
     if (leaf_names_out) {
         std::vector<std::string> nm(B);
         for (auto& nd : nodes) if (nd.ch.empty() && nd.idx < B) nm[nd.idx] = nd.name;

@@ -545,16 +545,22 @@ int dipb_mash_upload_flat(dipb_ctx* c, const uint64_t* flat, const uint64_t* wor
     DIPB_CUDA(cudaSetDevice(c->device));
     dipb_mash* m = new dipb_mash();
     m->ctx = c; m->n = (int)n; m->k = k; m->s = s;
+    ctx_retain(c);
     size_t words = word_off[n - 1] + (len[n - 1] + 31) / 32;
-    DIPB_CUDA(cudaMalloc(&m->seqs, (words + 1) * 8));
-    DIPB_CUDA(cudaMalloc(&m->word_off, n * 8));
-    DIPB_CUDA(cudaMalloc(&m->lens, n * 8));
-    DIPB_CUDA(cudaMalloc(&m->sketches, n * (size_t)s * 8));
-    DIPB_CUDA(cudaMemsetAsync(m->seqs + words, 0, 8, c->stream));
-    DIPB_CUDA(cudaMemcpyAsync(m->seqs, flat, words * 8, cudaMemcpyHostToDevice, c->stream));
-    DIPB_CUDA(cudaMemcpyAsync(m->word_off, word_off, n * 8, cudaMemcpyHostToDevice, c->stream));
-    DIPB_CUDA(cudaMemcpyAsync(m->lens, len, n * 8, cudaMemcpyHostToDevice, c->stream));
-    DIPB_CUDA(cudaStreamSynchronize(c->stream));
+    auto body = [&]() -> int {
+        DIPB_CUDA(cudaMalloc(&m->seqs, (words + 1) * 8));
+        DIPB_CUDA(cudaMalloc(&m->word_off, n * 8));
+        DIPB_CUDA(cudaMalloc(&m->lens, n * 8));
+        DIPB_CUDA(cudaMalloc(&m->sketches, n * (size_t)s * 8));
+        DIPB_CUDA(cudaMemsetAsync(m->seqs + words, 0, 8, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(m->seqs, flat, words * 8, cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(m->word_off, word_off, n * 8, cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(m->lens, len, n * 8, cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    const int rc = body();
+    if (rc) { dipb_mash_free(m); return rc; }
     *out = m;
     return 0;
 }
@@ -574,8 +580,13 @@ int dipb_mash_set_sketches(dipb_ctx* c, const uint64_t* h_sk, size_t n, int k, i
     DIPB_CUDA(cudaSetDevice(c->device));
     dipb_mash* m = new dipb_mash();
     m->ctx = c; m->n = (int)n; m->k = k; m->s = s;
-    DIPB_CUDA(cudaMalloc(&m->sketches, n * (size_t)s * 8));
-    DIPB_CUDA(cudaMemcpy(m->sketches, h_sk, n * (size_t)s * 8, cudaMemcpyHostToDevice));
+    ctx_retain(c);
+    if (cudaMalloc(&m->sketches, n * (size_t)s * 8) != cudaSuccess ||
+        cudaMemcpy(m->sketches, h_sk, n * (size_t)s * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("dipb_mash_set_sketches: device allocation / copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        dipb_mash_free(m);
+        return DIPB_E_CUDA;
+    }
     m->sketched = true;
     *out = m;
     return 0;
@@ -585,6 +596,7 @@ void dipb_mash_free(dipb_mash* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     cudaFree(m->seqs); cudaFree(m->word_off); cudaFree(m->lens); cudaFree(m->sketches); cudaFree(m->ranks);
+    ctx_release(m->ctx);
     delete m;
 }
 
@@ -652,8 +664,9 @@ int dipb_mash_dist_matrix(dipb_mash* m, dipb_matrix** out) {
     DIPB_CUDA(cudaSetDevice(c->device));
     dipb_matrix* M = new dipb_matrix();
     M->ctx = c; M->n = m->n;
+    ctx_retain(c);
     size_t bytes = (size_t)m->n * m->n * sizeof(double);
-    if (pool_alloc(c, (void**)&M->d, bytes) != cudaSuccess) { set_error("dipb_mash_dist_matrix: allocation of %zu bytes failed", bytes); delete M; return DIPB_E_NOMEM; }
+    if (pool_alloc(c, (void**)&M->d, bytes) != cudaSuccess) { set_error("dipb_mash_dist_matrix: allocation of %zu bytes failed", bytes); M->d = nullptr; dipb_matrix_free(M); return DIPB_E_NOMEM; }
     int rc = timer_begin(c);
     MashTileParams p{};
     p.sk = m->sketches; p.n = m->n; p.s = m->s; p.k = m->k; p.tri = 1; p.r0 = 0; p.r1 = m->n; p.ncols = m->n;
@@ -664,7 +677,7 @@ int dipb_mash_dist_matrix(dipb_mash* m, dipb_matrix** out) {
         c->launches++;
         rc = timer_end(c, DIPB_T_MASH_DIST);
     }
-    if (rc) { pool_free(c, M->d); delete M; return rc; }
+    if (rc) { dipb_matrix_free(M); return rc; }
     *out = M;
     return 0;
 }

@@ -236,31 +236,37 @@ __global__ void nj_init_kernel(NJState* st, int* realID, int n) {
     }
 }
 
-int nj_run(dipb_matrix* m, int algo, int32_t* child0, int32_t* child1, double* len0, double* len1) {
-    dipb_ctx* c = m->ctx;
-    const int n = m->n;
-    if (n < 2) { set_error("dipb_nj: need at least 2 sequences"); return DIPB_E_ARG; }
-    const bool auto_algo = algo == DIPB_NJ_AUTO;
-    if (auto_algo) algo = nj_cluster_fits(n) ? DIPB_NJ_CLUSTER : DIPB_NJ_PRUNED;
-    if (algo == DIPB_NJ_CLUSTER && !nj_cluster_fits(n)) { set_error("dipb_nj: %d tips do not fit the cluster kernel's shared memory", n); return DIPB_E_ARG; }
-    const size_t ld = (size_t)n;
+namespace {
+struct NJBuffers {      // device temporaries of one dipb_nj call; freed on every path by nj_run
     double *U = nullptr, *u = nullptr, *partial = nullptr, *l0 = nullptr, *l1 = nullptr;
-    int *realID = nullptr;
+    int* realID = nullptr;
     int32_t *c0 = nullptr, *c1 = nullptr;
     NJState* st = nullptr;
     Cand* bb = nullptr;
+};
+}  // namespace
+
+static int nj_run_impl(dipb_matrix* m, int algo, const bool auto_algo, NJBuffers& b, int32_t* child0, int32_t* child1, double* len0, double* len1) {
+    dipb_ctx* c = m->ctx;
+    const int n = m->n;
+    const size_t ld = (size_t)n;
     const int scan_grid = c->num_sms * 4;
     const int upd_grid = (n + 1023) / 1024;
-    DIPB_CUDA(pool_alloc(c, (void**)&U, sizeof(double) * n));
-    DIPB_CUDA(pool_alloc(c, (void**)&u, sizeof(double) * n));
-    DIPB_CUDA(pool_alloc(c, (void**)&partial, sizeof(double) * (upd_grid + 1)));
-    DIPB_CUDA(pool_alloc(c, (void**)&l0, sizeof(double) * n));
-    DIPB_CUDA(pool_alloc(c, (void**)&l1, sizeof(double) * n));
-    DIPB_CUDA(pool_alloc(c, (void**)&c0, sizeof(int32_t) * n));
-    DIPB_CUDA(pool_alloc(c, (void**)&c1, sizeof(int32_t) * n));
-    DIPB_CUDA(pool_alloc(c, (void**)&realID, sizeof(int) * n));
-    DIPB_CUDA(pool_alloc(c, (void**)&st, sizeof(NJState)));
-    DIPB_CUDA(pool_alloc(c, (void**)&bb, sizeof(Cand) * scan_grid));
+    DIPB_CUDA(pool_alloc(c, (void**)&b.U, sizeof(double) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&b.u, sizeof(double) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&b.partial, sizeof(double) * (upd_grid + 1)));
+    DIPB_CUDA(pool_alloc(c, (void**)&b.l0, sizeof(double) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&b.l1, sizeof(double) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&b.c0, sizeof(int32_t) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&b.c1, sizeof(int32_t) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&b.realID, sizeof(int) * n));
+    DIPB_CUDA(pool_alloc(c, (void**)&b.st, sizeof(NJState)));
+    DIPB_CUDA(pool_alloc(c, (void**)&b.bb, sizeof(Cand) * scan_grid));
+    double *U = b.U, *u = b.u, *partial = b.partial, *l0 = b.l0, *l1 = b.l1;
+    int* realID = b.realID;
+    int32_t *c0 = b.c0, *c1 = b.c1;
+    NJState* st = b.st;
+    Cand* bb = b.bb;
     int rc = timer_begin(c);
     if (rc) return rc;
     nj_init_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(st, realID, n);
@@ -295,19 +301,33 @@ int nj_run(dipb_matrix* m, int algo, int32_t* child0, int32_t* child1, double* l
     rc = timer_end(c, DIPB_T_NJ);
     if (rc) return rc;
     NJState hs;
-    DIPB_CUDA(cudaMemcpy(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost));
+    DIPB_CUDA(cudaMemcpyAsync(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+    DIPB_CUDA(cudaMemcpyAsync(child0, c0, sizeof(int32_t) * (n - 1), cudaMemcpyDeviceToHost, c->stream));
+    DIPB_CUDA(cudaMemcpyAsync(child1, c1, sizeof(int32_t) * (n - 1), cudaMemcpyDeviceToHost, c->stream));
+    DIPB_CUDA(cudaMemcpyAsync(len0, l0, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost, c->stream));
+    DIPB_CUDA(cudaMemcpyAsync(len1, l1, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost, c->stream));
+    DIPB_CUDA(cudaStreamSynchronize(c->stream));
     if (!done) {
         c->nj_rows_scanned = hs.rows_scanned;
         c->nj_iterations = hs.iters;
         c->nj_bytes_scanned = 0;
     }
-    DIPB_CUDA(cudaMemcpy(child0, c0, sizeof(int32_t) * (n - 1), cudaMemcpyDeviceToHost));
-    DIPB_CUDA(cudaMemcpy(child1, c1, sizeof(int32_t) * (n - 1), cudaMemcpyDeviceToHost));
-    DIPB_CUDA(cudaMemcpy(len0, l0, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost));
-    DIPB_CUDA(cudaMemcpy(len1, l1, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost));
-    pool_free(c, U); pool_free(c, u); pool_free(c, partial); pool_free(c, l0); pool_free(c, l1); pool_free(c, c0); pool_free(c, c1);
-    pool_free(c, realID); pool_free(c, st); pool_free(c, bb);
     return 0;
+}
+
+int nj_run(dipb_matrix* m, int algo, int32_t* child0, int32_t* child1, double* len0, double* len1) {
+    dipb_ctx* c = m->ctx;
+    const int n = m->n;
+    if (n < 2) { set_error("dipb_nj: need at least 2 sequences"); return DIPB_E_ARG; }
+    const bool auto_algo = algo == DIPB_NJ_AUTO;
+    if (auto_algo) algo = nj_cluster_fits(n) ? DIPB_NJ_CLUSTER : DIPB_NJ_PRUNED;
+    if (algo == DIPB_NJ_CLUSTER && !nj_cluster_fits(n)) { set_error("dipb_nj: %d tips do not fit the cluster kernel's shared memory", n); return DIPB_E_ARG; }
+    NJBuffers b;
+    const int rc = nj_run_impl(m, algo, auto_algo, b, child0, child1, len0, len1);
+    if (rc) cudaStreamSynchronize(c->stream);   // a failed run may still have work queued on these buffers
+    pool_free(c, b.U); pool_free(c, b.u); pool_free(c, b.partial); pool_free(c, b.l0); pool_free(c, b.l1); pool_free(c, b.c0); pool_free(c, b.c1);
+    pool_free(c, b.realID); pool_free(c, b.st); pool_free(c, b.bb);
+    return rc;
 }
 
 }  // namespace dipb

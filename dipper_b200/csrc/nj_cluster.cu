@@ -839,8 +839,9 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
         std::vector<double2> hbl(iters);
         std::vector<int> rid(n), hc0(n), hc1(n);
         std::vector<double> hl0(n), hl1(n);
-        DIPB_CUDA(cudaMemcpy(hxy.data(), log_xy, sizeof(int2) * iters, cudaMemcpyDeviceToHost));
-        DIPB_CUDA(cudaMemcpy(hbl.data(), log_bl, sizeof(double2) * iters, cudaMemcpyDeviceToHost));
+        DIPB_CUDA(cudaMemcpyAsync(hxy.data(), log_xy, sizeof(int2) * iters, cudaMemcpyDeviceToHost, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(hbl.data(), log_bl, sizeof(double2) * iters, cudaMemcpyDeviceToHost, c->stream));
+        DIPB_CUDA(cudaStreamSynchronize(c->stream));
         for (int i = 0; i < n; i++) rid[i] = i;
         int id = n;
         for (int it = 0; it < iters; it++) {
@@ -849,15 +850,18 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
             hc1[it] = rid[yy]; hl1[it] = hbl[it].y;
             rid[xx] = id++; rid[yy] = rid[act - 1];
         }
-        DIPB_CUDA(cudaMemcpy(c0, hc0.data(), sizeof(int32_t) * iters, cudaMemcpyHostToDevice));
-        DIPB_CUDA(cudaMemcpy(c1, hc1.data(), sizeof(int32_t) * iters, cudaMemcpyHostToDevice));
-        DIPB_CUDA(cudaMemcpy(l0, hl0.data(), sizeof(double) * iters, cudaMemcpyHostToDevice));
-        DIPB_CUDA(cudaMemcpy(l1, hl1.data(), sizeof(double) * iters, cudaMemcpyHostToDevice));
-        DIPB_CUDA(cudaMemcpy(realID, rid.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        // uploads ride the context's stream (nj_finish_kernel reads realID there); the host vectors live until the sync
+        DIPB_CUDA(cudaMemcpyAsync(c0, hc0.data(), sizeof(int32_t) * iters, cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(c1, hc1.data(), sizeof(int32_t) * iters, cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(l0, hl0.data(), sizeof(double) * iters, cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(l1, hl1.data(), sizeof(double) * iters, cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(realID, rid.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaStreamSynchronize(c->stream));
     }
     lap(3);
     CStats hs;
-    DIPB_CUDA(cudaMemcpy(&hs, stats, sizeof(hs), cudaMemcpyDeviceToHost));
+    DIPB_CUDA(cudaMemcpyAsync(&hs, stats, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+    DIPB_CUDA(cudaStreamSynchronize(c->stream));
     c->nj_rows_scanned = hs.rows_scanned;
     c->nj_iterations = hs.iters;
     c->nj_bytes_scanned = hs.bytes_scanned;

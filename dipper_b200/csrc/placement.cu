@@ -221,9 +221,7 @@ __global__ void place_backbone_kernel(int* head, int* e, int* nxt, int* belong, 
     for (int i = 0; i < B; i++) bfs_closest(head, nxt, e, len, cdis, cid, i, q_node, q_from, q_dis, &s_tail, nullptr, 0, 0x7fffffff);
 }
 
-int tree_alloc(dipb_ctx* c, int n, dipb_tree** out) {
-    dipb_tree* t = new dipb_tree();
-    t->ctx = c; t->n = n;
+static int tree_alloc_impl(dipb_ctx* c, int n, dipb_tree* t) {
     size_t N = (size_t)n;
     DIPB_CUDA(cudaMalloc(&t->head, 2 * N * sizeof(int)));
     DIPB_CUDA(cudaMalloc(&t->e, 8 * N * sizeof(int)));
@@ -236,6 +234,14 @@ int tree_alloc(dipb_ctx* c, int n, dipb_tree** out) {
     long long total = 8LL * n;
     place_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(t->head, t->e, t->nxt, t->belong, t->len, t->cid, t->cdis, t->rev, n);
     DIPB_KERNEL_CHECK(c);
+    return 0;
+}
+int tree_alloc(dipb_ctx* c, int n, dipb_tree** out) {
+    dipb_tree* t = new dipb_tree();
+    t->ctx = c; t->n = n;
+    ctx_retain(c);
+    const int rc = tree_alloc_impl(c, n, t);
+    if (rc) { dipb_tree_free(t); return rc; }
     *out = t;
     return 0;
 }
@@ -360,9 +366,8 @@ int dipb_place_kclosest(dipb_ctx* c, const dipb_dist_source* src, int n, dipb_tr
     rc = place_scratch_alloc(c, n, &sc);
     if (!rc) rc = place_from_scratch(c, src, n, n, t, &sc);
     place_scratch_free(c, &sc);
+    if (!rc) rc = timer_end(c, DIPB_T_PLACE);
     if (rc) { dipb_tree_free(t); return rc; }
-    rc = timer_end(c, DIPB_T_PLACE);
-    if (rc) return rc;
     *out = t;
     return 0;
 }
@@ -376,28 +381,33 @@ int dipb_place_add(dipb_ctx* c, const dipb_dist_source* src, int n, int backbone
     int rc = check_source(src, n);
     if (rc) return rc;
     DIPB_CUDA(cudaSetDevice(c->device));
+    // rooted binary backbone: exactly 4B-4 directed slots in use (src/placement_close_k.cu:887)
+    for (int q = 0; q < 4 * backbone - 4; q++)
+        if (h_belong[q] < 0 || h_e[q] < 0) { set_error("dipb_place_add: backbone slot %d is unused; a rooted binary backbone has 4B-4 = %d slots", q, 4 * backbone - 4); return DIPB_E_ARG; }
+    if ((size_t)(4 * backbone - 4) < 8 * (size_t)n && h_belong[4 * backbone - 4] >= 0) { set_error("dipb_place_add: backbone has more than 4B-4 slots (not a rooted binary tree)"); return DIPB_E_ARG; }
     rc = timer_begin(c);
     if (rc) return rc;
     dipb_tree* t = nullptr;
     rc = tree_alloc(c, n, &t);
     if (rc) return rc;
     size_t N = (size_t)n;
-    DIPB_CUDA(cudaMemcpyAsync(t->head, h_head, 2 * N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    DIPB_CUDA(cudaMemcpyAsync(t->e, h_e, 8 * N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    DIPB_CUDA(cudaMemcpyAsync(t->nxt, h_nxt, 8 * N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    DIPB_CUDA(cudaMemcpyAsync(t->belong, h_belong, 8 * N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    DIPB_CUDA(cudaMemcpyAsync(t->len, h_len, 8 * N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     PlaceScratch sc;
-    rc = place_scratch_alloc(c, n, &sc);
-    if (rc) return rc;
-    // rooted binary backbone: 4B-4 slots (src/placement_close_k.cu:887)
-    place_backbone_kernel<<<1, PL_THREADS, 0, c->stream>>>(t->head, t->e, t->nxt, t->belong, t->len, t->cid, t->cdis, t->rev, 4 * backbone - 4, backbone, sc.ps, sc.q_node, sc.q_from, sc.q_dis);
-    DIPB_KERNEL_CHECK(c);
-    rc = place_run(c, src, n, backbone, n, t, &sc);
+    auto body = [&]() -> int {
+        DIPB_CUDA(cudaMemcpyAsync(t->head, h_head, 2 * N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(t->e, h_e, 8 * N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(t->nxt, h_nxt, 8 * N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(t->belong, h_belong, 8 * N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        DIPB_CUDA(cudaMemcpyAsync(t->len, h_len, 8 * N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        int r = place_scratch_alloc(c, n, &sc);
+        if (r) return r;
+        place_backbone_kernel<<<1, PL_THREADS, 0, c->stream>>>(t->head, t->e, t->nxt, t->belong, t->len, t->cid, t->cdis, t->rev, 4 * backbone - 4, backbone, sc.ps, sc.q_node, sc.q_from, sc.q_dis);
+        DIPB_KERNEL_CHECK(c);
+        return place_run(c, src, n, backbone, n, t, &sc);
+    };
+    rc = body();
     place_scratch_free(c, &sc);
+    if (!rc) rc = timer_end(c, DIPB_T_PLACE);
     if (rc) { dipb_tree_free(t); return rc; }
-    rc = timer_end(c, DIPB_T_PLACE);
-    if (rc) return rc;
     *out = t;
     return 0;
 }
@@ -430,6 +440,7 @@ void dipb_tree_free(dipb_tree* t) {
     cudaSetDevice(t->ctx->device);
     cudaFree(t->head); cudaFree(t->e); cudaFree(t->nxt); cudaFree(t->belong); cudaFree(t->rev);
     cudaFree(t->len); cudaFree(t->cid); cudaFree(t->cdis);
+    ctx_release(t->ctx);
     delete t;
 }
 

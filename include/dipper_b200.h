@@ -50,7 +50,13 @@ typedef struct dipb_tree dipb_tree;
 /* ---- context ------------------------------------------------------------ */
 /* replaces cudaSetDevice(1) in src/tree_generation.cu:240-245 (device is a parameter) */
 int dipb_init(int device, dipb_ctx **out);
+/* Drops the creator's reference.  Every child handle (msa, mash, matrix, tree, D&C state) holds its own
+ * reference on the context, so children may be freed AFTER dipb_destroy, in any order: the stream and the
+ * context go away with the last reference (the reference's structs are global statics that are never torn
+ * down, src/mash_placement.cuh:287-300).  A second dipb_destroy on the same context is ignored. */
 void dipb_destroy(dipb_ctx *ctx);
+/* live references on the context (1 = only the creator's); for tests */
+int dipb_ctx_refs(const dipb_ctx *ctx);
 const char *dipb_last_error(void);
 const char *dipb_version(void);
 /* device-side duration (CUDA events on the context's stream) of the most recent call

@@ -100,3 +100,14 @@ def test_reference_backbone_file_parses():
     B = kp.initializeDeviceArrays(nwk)
     # 1000 leaves, first leaf T9326 idx 0, T342 idx 1
     assert B == 1000 and kp.backbone_names[0] == "T9326" and kp.backbone_names[1] == "T342"
+
+
+def test_backbone_loader_rejects_non_binary_trees():
+    """dipb_place_add walks exactly 4B-4 slots (rooted binary backbone, src/placement_close_k.cu:887):
+    an unrooted (trifurcating root) or unary-node Newick must be refused, not walked out of bounds."""
+    for bad in ("(A:0.1,B:0.2,(C:0.3,D:0.1):0.2);", "((A:0.1,B:0.2):0.3);"):
+        kp = api.KPlacementDeviceArrays(None)
+        kp.allocateDeviceArrays(8)
+        with pytest.raises(api.DipperError) as e:
+            kp.initializeDeviceArrays(bad)
+        assert "rooted binary" in str(e.value)
