@@ -554,6 +554,7 @@ int dipb_dc_assign(dipb_dc_state* st, int q0, int q1, int32_t* h_cluster) {
     }
     int rc = 0;
     const bool prof = getenv("DIPB_PLACE_PROFILE") != nullptr;
+    const bool ref_b17 = getenv("DIPB_DC_REF_B17") && atoi(getenv("DIPB_DC_REF_B17")) != 0;
     double t_dist = 0, t_assign = 0;
     auto t_mark = std::chrono::steady_clock::now();
     for (int a0 = q0; a0 < q1 && !rc; a0 += qb) {
@@ -564,6 +565,15 @@ int dipb_dc_assign(dipb_dc_state* st, int q0, int q1, int32_t* h_cluster) {
             rows = buf; ldr = ld;
             rc = src->msa ? msa_block(src->msa, src->dist_type, a0, a1, B, buf, ld) : dipb_mash_dist_block(src->mash, a0, a1, B, buf, ld);
             if (rc) break;
+            // Parity switch, off by default.  The reference AS SHIPPED never computes d(query, backbone tip B-1) for
+            // aligned input (defect B17: `idx>=ed-st`, src/divide_and_conquer/msa.cu:334) and scores with what d_dist[B-1]
+            // held before, the zero of a fresh allocation.  DIPB_DC_REF_B17=1 reproduces that, so that the result can be
+            // compared slot for slot with the reference's own objects (tests/test_ref_parity.py).
+            if (src->msa && ref_b17 && cudaMemset2DAsync(buf + (B - 1), ld * sizeof(double), 0, sizeof(double), (size_t)(a1 - a0), c->stream) != cudaSuccess) {
+                set_error("dipb_dc_assign: memset failed");
+                rc = DIPB_E_CUDA;
+                break;
+            }
         }
         if (prof) { cudaStreamSynchronize(c->stream); const auto now = std::chrono::steady_clock::now(); t_dist += std::chrono::duration<double, std::milli>(now - t_mark).count(); t_mark = now; }
         if (transposed) {

@@ -153,3 +153,37 @@ def write_phylip(path, names_, D, lower=True):
         for i in range(n):
             vals = D[i, :i] if lower else D[i]
             f.write(names_[i] + (" " if len(vals) else "") + " ".join("%.6f" % v for v in vals) + "\n")
+
+
+def tree_with_queries(newick_text, n_queries, seed=1, scale=1.0, query_bl=None):
+    """Yule-style extension of a given rooted tree (the reference's only fixture, dataset/t2.backbone.nwk, in
+    BASELINE config 4b): every query tip is attached in the middle of a random existing edge.  Returns the
+    `tree` tuple evolve() takes, plus (backbone_leaf_nodes, backbone_leaf_names, query_nodes); branch lengths
+    are multiplied by `scale` (the fixture's alisim-regime lengths give almost identical sequences at a few
+    thousand sites)."""
+    from . import newick as _nw
+    children, length, name = _nw.parse(newick_text)
+    children = [list(c) for c in children]
+    parent = [-1] * len(children)
+    for v, ch in enumerate(children):
+        for c in ch:
+            parent[c] = v
+    bl = [float(x) * scale for x in length]
+    bb_leaves = [v for v in range(len(children)) if not children[v]]
+    bb_names = [name[v] for v in bb_leaves]
+    rng = np.random.default_rng(seed)
+    mean = float(np.mean([bl[v] for v in range(1, len(bl))])) if query_bl is None else query_bl
+    qnodes = []
+    for _ in range(n_queries):
+        v = int(rng.integers(1, len(children)))          # edge above v (never the root)
+        p = parent[v]
+        m, q = len(children), len(children) + 1         # new internal node, new tip
+        children += [[v, q], []]
+        parent += [p, m]
+        bl += [bl[v] * 0.5, max(float(rng.exponential(mean)), 1e-6)]
+        bl[v] *= 0.5
+        children[p][children[p].index(v)] = m
+        parent[v] = m
+        qnodes.append(q)
+    leaves = bb_leaves + qnodes
+    return (np.array(parent), np.array(bl), children, leaves), bb_leaves, bb_names, qnodes

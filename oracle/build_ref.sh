@@ -13,6 +13,16 @@ NVCC=/usr/local/cuda/bin/nvcc
 FLAGS="-gencode arch=compute_100a,code=sm_100a -rdc=true --extended-lambda -std=c++17 -O3 -w -ccbin /usr/bin/g++ -I$HERE/stubs -I$REF/src"
 SRCS="src/MSA.cu src/mash.cu src/neighborJoining.cu src/placement_close_k.cu src/placement.cu src/matrix_reader.cu src/tree.cpp"
 pids=""
+# the divide-and-conquer twins (same base names as the files above: objects get a dc_ prefix);
+# DC/mash.cpp and DC/placement_close_k.cpp need real TBB and nothing in the kernel objects calls them
+DCSRCS="src/divide_and_conquer/placement_close_k.cu src/divide_and_conquer/msa.cu src/divide_and_conquer/mash.cu"
+for s in $DCSRCS; do
+  o="$OUT/dc_$(basename ${s%.*}).o"
+  if [ ! -f "$o" ] || [ "$REF/$s" -nt "$o" ]; then
+    ( $NVCC $FLAGS -x cu -dc "$REF/$s" -o "$o" ) &
+    pids="$pids $!"
+  fi
+done
 for s in $SRCS; do
   o="$OUT/$(basename ${s%.*}).o"
   if [ ! -f "$o" ] || [ "$REF/$s" -nt "$o" ]; then

@@ -1032,7 +1032,13 @@ static void bfs_in_cluster(orc_ptree *t, int x, int cluster_eid, const int *mask
 
 /* findBackboneTreeDC + findClustersDC + findClusterTreeDC, DC/placement_close_k.cu:731-1535.
  * cluster_out[n]: winning backbone slot of every tip >= B (-1 for backbone tips). */
+static orc_ptree *orc_dc2(int n, int B, orc_pair_fn pair, orc_pair_fn pair_stage2, void *ctx, int32_t *cluster_out);
 ORC_API orc_ptree *orc_dc(int n, int B, orc_pair_fn pair, void *ctx, int32_t *cluster_out) {
+    return orc_dc2(n, B, pair, pair, ctx, cluster_out);
+}
+/* pair_stage2: the distance provider of the cluster-assignment stage.  It equals `pair` in the intended algorithm;
+ * the "as shipped" checks (orc_dc_matrix_as_shipped) pass a provider that reproduces reference defect B17. */
+static orc_ptree *orc_dc2(int n, int B, orc_pair_fn pair, orc_pair_fn pair_stage2, void *ctx, int32_t *cluster_out) {
     orc_ptree *t = orc_ptree_new(n);   /* node_off = n = totalNumSequences */
     double *dis = (double *)calloc((size_t)n, sizeof(double));
     /* stage 1: backbone = tips 0..B-1 */
@@ -1053,7 +1059,7 @@ ORC_API orc_ptree *orc_dc(int n, int B, orc_pair_fn pair, void *ctx, int32_t *cl
     int nslots = 4 * B - 4;
     for (int j = 0; j < n; j++) cluster_out[j] = -1;
     for (int j = B; j < n; j++) {
-        for (int q = 0; q < B; q++) dis[q] = pair(ctx, j, q);
+        for (int q = 0; q < B; q++) dis[q] = pair_stage2(ctx, j, q);
         int slot; double frac, add;
         orc_ptree_best_edge(t, dis, nslots, &slot, &frac, &add);
         cluster_out[j] = slot;
@@ -1102,4 +1108,26 @@ static double mat_pair(void *c, int row, int col) {
 ORC_API orc_ptree *orc_dc_matrix(const double *D, int n, int B, int32_t *cluster_out) {
     mat_ctx c = {D, n};
     return orc_dc(n, B, mat_pair, &c, cluster_out);
+}
+
+/* The reference AS SHIPPED for aligned input (defect B17): the cluster-assignment distance kernel
+ * MSADistConstructionRangeForClusteringDC (src/divide_and_conquer/msa.cu:321-335) returns for idx >= ed-st with
+ * ed = B-1, so d(query, backbone tip B-1) is never computed and calculateBranchLengthDC reads what d_dist[B-1]
+ * still holds: nothing has written it before (findBackboneTreeDC writes idx < rowId <= B-2), i.e. the zero of a
+ * fresh cudaMalloc.  `stale` is that value.  Used ONLY to show that the restatement reproduces the reference's
+ * own output once its defect is switched on (tests/test_oracle.py); the product follows the intended rule
+ * (what the Mash twin, src/divide_and_conquer/mash.cu:499, does). */
+typedef struct { const double *D; int n, B; double stale; } mat_ctx_b17;
+static double mat_pair_b17(void *c, int row, int col) {
+    mat_ctx_b17 *m = (mat_ctx_b17 *)c;
+    if (col == m->B - 1) return m->stale;
+    return m->D[(size_t)row * m->n + col];
+}
+static double mat_pair_b17_plain(void *c, int row, int col) {
+    mat_ctx_b17 *m = (mat_ctx_b17 *)c;
+    return m->D[(size_t)row * m->n + col];
+}
+ORC_API orc_ptree *orc_dc_matrix_as_shipped(const double *D, int n, int B, double stale, int32_t *cluster_out) {
+    mat_ctx_b17 c = {D, n, B, stale};
+    return orc_dc2(n, B, mat_pair_b17_plain, mat_pair_b17, &c, cluster_out);
 }

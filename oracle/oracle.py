@@ -69,6 +69,8 @@ def lib():
         L.orc_ptree_load_backbone.argtypes = [C.c_void_p, C.c_int, i32p, i32p, i32p, f64p, C.c_int]
         L.orc_dc_matrix.argtypes = [f64p, C.c_int, C.c_int, i32p]
         L.orc_dc_matrix.restype = C.c_void_p
+        L.orc_dc_matrix_as_shipped.argtypes = [f64p, C.c_int, C.c_int, C.c_double, i32p]
+        L.orc_dc_matrix_as_shipped.restype = C.c_void_p
         L.orc_ptree_newick.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
         L.orc_ptree_newick.restype = C.c_void_p
         for nm, ty in (("head", C.c_int), ("e", C.c_int), ("nxt", C.c_int), ("belong", C.c_int),
@@ -254,6 +256,15 @@ def place_add(D, B, root, child_off, child_idx, parent, bl):
                                   np.ascontiguousarray(bl, np.float64), B)
     lib().orc_place_add_matrix(t.h, D, n, B)
     return t
+
+
+def dc_as_shipped(D, B, stale=0.0):
+    """The reference's aligned D&C with its defect B17 switched on (see orc_dc_matrix_as_shipped): checker of the
+    restatement against the reference's own output, never the product rule."""
+    D = np.ascontiguousarray(D, np.float64)
+    n = D.shape[0]
+    cl = np.zeros(n, np.int32)
+    return PTree(lib().orc_dc_matrix_as_shipped(D, n, B, float(stale), cl), n), cl
 
 
 def dc(D, B):

@@ -10,7 +10,7 @@
 // instead of a time-seeded shuffle; for Mash + NJ the missing allocateDeviceArrays +
 // sketchConstructionOnGpu calls are inserted (reference bug, tree_generation.cu:576-587).
 //
-// usage: dipper_ref <mode> <input.bin> <out_prefix> [dist_type] [k]
+// usage: dipper_ref <mode> <input.bin> <out_prefix> [dist_type] [k] [backbone.nwk | backbone_size]
 //   input.bin: int64 n, int64 bits (4 = aligned 4-bit, 2 = unaligned 2-bit),
 //              uint64 len[n], then each sequence's packed words back to back.
 //   modes: msa_rows   -> <out>.rows   lower-triangle distances (row i: i doubles)
@@ -21,6 +21,19 @@
 //          mash_rows  -> <out>.rows
 //          mash_nj    -> <out>.nwk
 //          mash_place -> <out>.nwk
+//          msa_add / mash_add -> <out>.nwk   add-tips (-m 1 --add): argv[6] = backbone Newick file; input.bin holds the
+//                        backbone tips first, in the leaf order of the Newick (src/tree_generation.cu:271-282 idMap),
+//                        then the queries; drives initializeDeviceArrays(Tree*) + addQuery
+//                        (src/placement_close_k.cu:126-264,858-990); <out>.arrays = int32 head[2n], e[8n], nxt[8n],
+//                        belong[8n], double len[8n]
+//          msa_dc / mash_dc  -> <out>.nwk, <out>.clusters (int32 clusterID[n], -1 for backbone tips), <out>.arrays:
+//                        divide and conquer (-m 3), argv[6] = backbone size (default n/20,
+//                        src/tree_generation.cu:425,545); drives findBackboneTreeDC / findClustersDC /
+//                        findClusterTreeDC (src/divide_and_conquer/placement_close_k.cu:731-1535) with
+//                        MSADeviceArraysDC / MashDeviceArraysDC (src/divide_and_conquer/msa.cu, mash.cu)
+//          msa_dc_rows -> <out>.rows  rows through MSADeviceArraysDC::distConstructionOnGpuForBackboneDC with the
+//                        whole input as backbone: the well-formed twins of the six distance models
+//                        (src/divide_and_conquer/msa.cu:219-264; src/MSA.cu:239-265 is broken for models 3-6)
 //   every mode prints one JSON line with wall-clock phase times (cudaDeviceSynchronize
 //   on both sides) to stdout.
 #include <chrono>
@@ -43,6 +56,7 @@ int main(int argc, char** argv) {
     std::string mode = argv[1], in = argv[2], out = argv[3];
     int distType = argc > 4 ? atoi(argv[4]) : 2;
     int k = argc > 5 ? atoi(argv[5]) : 15;
+    std::string extra = argc > 6 ? argv[6] : "";
     if (cudaSetDevice(0) != cudaSuccess) { fprintf(stderr, "no CUDA device\n"); return 3; }
     FILE* f = fopen(in.c_str(), "rb");
     if (!f) { fprintf(stderr, "cannot open %s\n", in.c_str()); return 2; }
@@ -67,6 +81,78 @@ int main(int argc, char** argv) {
     double t_alloc = 0, t_sketch = 0, t_dist = 0, t_tree = 0;
     cudaDeviceSynchronize();
     auto t0 = Clock::now();
+    auto dump_arrays = [&](const char* suffix, int* d_head, int* d_e, int* d_nxt, int* d_belong, double* d_len) {
+        std::vector<int> hh(2 * n), he(8 * n), hn(8 * n), hb(8 * n);
+        std::vector<double> hl(8 * n);
+        cudaMemcpy(hh.data(), d_head, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost);
+        cudaMemcpy(he.data(), d_e, sizeof(int) * 8 * n, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hn.data(), d_nxt, sizeof(int) * 8 * n, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hb.data(), d_belong, sizeof(int) * 8 * n, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hl.data(), d_len, sizeof(double) * 8 * n, cudaMemcpyDeviceToHost);
+        FILE* o = fopen((out + suffix).c_str(), "wb");
+        fwrite(hh.data(), 4, hh.size(), o); fwrite(he.data(), 4, he.size(), o); fwrite(hn.data(), 4, hn.size(), o);
+        fwrite(hb.data(), 4, hb.size(), o); fwrite(hl.data(), 8, hl.size(), o);
+        fclose(o);
+    };
+    if (mode == "msa_dc" || mode == "mash_dc" || mode == "msa_dc_rows") {
+        // ---- divide and conquer structs (src/tree_generation.cu:422-449 aligned, :541-575 unaligned)
+        const bool rows_only = mode == "msa_dc_rows";
+        int B = rows_only ? (int)n : (extra.empty() ? (int)(n / 20) : atoi(extra.c_str()));
+        params.batchSize = B;
+        params.backboneSize = B;
+        if (msa) MashPlacement::msaDeviceArraysDC.allocateDeviceArraysDC(seqs, lens.data(), n, params);
+        else MashPlacement::mashDeviceArraysDC.allocateDeviceArraysDC(seqs, lens.data(), n, params);
+        t_alloc = ms_since(t0);
+        if (!msa) {
+            t0 = Clock::now();
+            MashPlacement::mashDeviceArraysDC.sketchConstructionOnGpuDC(params, seqs, lens.data(), n);
+            t_sketch = ms_since(t0);
+        }
+        if (rows_only) {
+            double* d_row;
+            cudaMalloc(&d_row, sizeof(double) * n);
+            std::vector<double> h(n);
+            FILE* o = fopen((out + ".rows").c_str(), "wb");
+            t0 = Clock::now();
+            for (int i = 1; i < n; i++) {
+                MashPlacement::msaDeviceArraysDC.distConstructionOnGpuForBackboneDC(params, i, d_row);
+                cudaMemcpy(h.data(), d_row, sizeof(double) * i, cudaMemcpyDeviceToHost);
+                fwrite(h.data(), 8, i, o);
+            }
+            t_dist = ms_since(t0);
+            fclose(o);
+        } else {
+            std::ofstream os(out + ".nwk");
+            auto& kp = MashPlacement::kplacementDeviceArraysDC;
+            kp.allocateDeviceArraysDC(B, n);
+            t0 = Clock::now();
+            kp.findBackboneTreeDC(params, MashPlacement::mashDeviceArraysDC, MashPlacement::matrixReader,
+                                  MashPlacement::msaDeviceArraysDC, MashPlacement::kplacementDeviceArraysHostDC);
+            t_dist = ms_since(t0);   // "dist_ms" = backbone stage in this mode
+            t0 = Clock::now();
+            kp.findClustersDC(params, MashPlacement::mashDeviceArraysDC, MashPlacement::matrixReader,
+                              MashPlacement::msaDeviceArraysDC, MashPlacement::kplacementDeviceArraysHostDC);
+            t_sketch += ms_since(t0);   // "sketch_ms" (+) = cluster assignment stage in this mode
+            {
+                std::vector<int> cl(n, -1);
+                for (int64_t j = B; j < n; j++) cl[j] = MashPlacement::kplacementDeviceArraysHostDC.clusterID[j];
+                FILE* o = fopen((out + ".clusters").c_str(), "wb");
+                fwrite(cl.data(), 4, cl.size(), o);
+                fclose(o);
+            }
+            t0 = Clock::now();
+            kp.findClusterTreeDC(params, MashPlacement::mashDeviceArraysDC, MashPlacement::matrixReader,
+                                 MashPlacement::msaDeviceArraysDC, MashPlacement::kplacementDeviceArraysHostDC);
+            t_tree = ms_since(t0);
+            kp.printTreeDC(names, os);
+            dump_arrays(".arrays", kp.d_head, kp.d_e, kp.d_nxt, kp.d_belong, kp.d_len);
+        }
+        cudaError_t e = cudaDeviceSynchronize();
+        printf("{\"impl\": \"reference-cuda\", \"mode\": \"%s\", \"n\": %lld, \"backbone\": %d, \"alloc_ms\": %.3f, \"assign_ms\": %.3f, "
+               "\"backbone_ms\": %.3f, \"clusters_ms\": %.3f, \"cuda_status\": \"%s\"}\n",
+               mode.c_str(), (long long)n, B, t_alloc, t_sketch, t_dist, t_tree, cudaGetErrorString(e));
+        return e == cudaSuccess ? 0 : 4;
+    }
     if (msa) MashPlacement::msaDeviceArrays.allocateDeviceArrays(seqs, lens.data(), n, params);
     else MashPlacement::mashDeviceArrays.allocateDeviceArrays(seqs, lens.data(), n, params);
     t_alloc = ms_since(t0);
@@ -114,6 +200,29 @@ int main(int argc, char** argv) {
                                                                 MashPlacement::matrixReader, MashPlacement::msaDeviceArrays);
         t_tree = ms_since(t0);
         MashPlacement::kplacementDeviceArrays.printTree(names, os);
+    } else if (mode == "msa_add" || mode == "mash_add") {
+        // src/tree_generation.cu:252-332: Tree(newick, #seqs), leaves numbered by order of appearance; the caller
+        // already ordered input.bin that way (idMap), queries follow the backbone tips
+        std::ifstream tf(extra);
+        if (!tf) { fprintf(stderr, "cannot open backbone tree %s\n", extra.c_str()); return 2; }
+        std::string nwk;
+        std::getline(tf, nwk);
+        Tree* t = new Tree(nwk, (size_t)n);
+        const int B = (int)t->m_numLeaves;
+        for (auto& kv : t->allNodes)
+            if (kv.second->children.empty() && kv.second->idx < B) names[kv.second->idx] = kv.first;
+        for (int64_t i = B; i < n; i++) names[i] = "Q" + std::to_string(i - B + 1);
+        std::ofstream os(out + ".nwk");
+        auto& kp = MashPlacement::kplacementDeviceArrays;
+        kp.allocateDeviceArrays(n, B);
+        t0 = Clock::now();
+        kp.initializeDeviceArrays(t);
+        t_dist = ms_since(t0);      // "dist_ms" = backbone load in this mode
+        t0 = Clock::now();
+        kp.addQuery(params, MashPlacement::mashDeviceArrays, MashPlacement::matrixReader, MashPlacement::msaDeviceArrays);
+        t_tree = ms_since(t0);
+        kp.printTree(names, os);
+        dump_arrays(".arrays", kp.d_head, kp.d_e, kp.d_nxt, kp.d_belong, kp.d_len);
     } else if (mode == "msa_place_exact" || mode == "mash_place_exact") {
         std::ofstream os(out + ".nwk");
         MashPlacement::placementDeviceArrays.allocateDeviceArrays(n);

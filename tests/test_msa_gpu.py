@@ -92,6 +92,8 @@ def test_golden_fixtures_through_cuda(ctx):
     import glob, os
     for fn in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*msa*.npz"))):
         z = np.load(fn)
+        if str(z["kind"]) not in ("msa", "ref_msa"):
+            continue                       # D&C / add-tips fixtures: tests/test_ref_golden_gpu.py
         P, L = z["packed"], int(z["seq_len"])
         msa = upload(ctx, P, L)
         if str(z["kind"]) == "ref_msa":

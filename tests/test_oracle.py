@@ -249,6 +249,89 @@ def test_golden_fixtures(oracle):
             assert np.allclose(D[low], z["rows"][low], rtol=1e-6, atol=0), fn
             assert oracle.place_all(D).newick(names) == str(z["place_newick"]), fn
             assert oracle.place_exact(D).newick(names) == str(z["place_exact_newick"]), fn
+        elif kind == "ref_models":
+            # the six distance models, rows from the reference's well-formed DC twins (src/divide_and_conquer/msa.cu:219-264)
+            P, L = z["packed"], int(z["seq_len"])
+            low = np.tril_indices(P.shape[0], -1)
+            for t in range(1, 7):
+                D = oracle.msa_dist_matrix(P, L, t)
+                assert np.allclose(D[low], z["rows_%d" % t][low], rtol=1e-6, atol=0), (fn, t)
+        elif kind == "ref_dc_msa":
+            # aligned D&C as the reference ships it: defect B17 on (see orc_dc_matrix_as_shipped) -> identical output
+            P, L, B = z["packed"], int(z["seq_len"]), int(z["backbone"])
+            n = P.shape[0]
+            D = oracle.msa_dist_matrix(P, L, 2)
+            t, cl = oracle.dc_as_shipped(D, B, 0.0)
+            assert np.array_equal(cl, z["clusters"]), fn
+            _same_slot_arrays(t.arrays(), z, n, fn)
+            assert t.newick(synth.names(n)) == str(z["newick"]), fn
+            # the intended rule (what the Mash twin does and the product follows) differs from the shipped one only in
+            # queries whose candidate lists see backbone tip B-1
+            _, cl2 = oracle.dc(D, B)
+            assert 0 < np.count_nonzero(cl2 != cl) < 0.05 * (n - B), fn
+        elif kind == "ref_dc_mash":
+            B = int(z["backbone"])
+            sk = oracle.sketch_all(z["flat"], z["offsets"], z["lens"], int(z["k"]), int(z["s"]))
+            n = sk.shape[0]
+            t, cl = oracle.dc(oracle.mash_dist_matrix(sk, int(z["k"])), B)
+            assert np.array_equal(cl, z["clusters"]), fn
+            _same_slot_arrays(t.arrays(), z, n, fn)
+            assert t.newick(synth.names(n)) == str(z["newick"]), fn
+        elif kind in ("ref_add_msa", "ref_add_t2"):
+            # add-tips (initializeDeviceArrays(Tree*) + addQuery, src/placement_close_k.cu:126-264,858-990)
+            from dipper_b200 import api
+            P, L, B = z["packed"], int(z["seq_len"]), int(z["backbone"])
+            n = P.shape[0]
+            bb = str(z["backbone_newick"]) if "backbone_newick" in z else open(os.path.join(GOLD, "t2.backbone.nwk")).readline().strip()
+            kp = api.KPlacementDeviceArrays(None)
+            kp.allocateDeviceArrays(n)
+            assert kp.initializeDeviceArrays(bb) == B
+            root, off, flat, parent, bl = _backbone_tables(bb, n)
+            t = oracle.place_add(oracle.msa_dist_matrix(P, L, 2), B, root, off, flat, parent, bl)
+            _same_slot_arrays(t.arrays(), z, n, fn)
+            names = kp.backbone_names + ["Q%d" % (i + 1) for i in range(n - B)]
+            assert t.newick(names) == str(z["newick"]), fn
+
+
+def _same_slot_arrays(a, z, n, fn):
+    ns = 4 * n - 4
+    assert np.array_equal(a["head"][: 2 * n], z["head"][: 2 * n]), fn
+    for k in ("e", "nxt", "belong"):
+        assert np.array_equal(a[k][:ns], z[k][:ns]), (fn, k)
+    assert np.allclose(a["len"][:ns], z["len"][:ns], rtol=0, atol=1e-12), fn   # libm vs libdevice log: <= 1 ulp of a distance
+
+
+def _backbone_tables(nwk, total):
+    """Newick -> the node tables orc_ptree_load_backbone takes (leaf ids by order of appearance, internal ids
+    total, total+1, ... in order of '(', src/tree.cpp:308-341)."""
+    children, length, name = newick.parse(nwk)
+    nn = len(children)
+    idx = [0] * nn
+    leaf = 0
+    k = 0
+    # parse() numbers nodes in order of appearance: node 0 = root = first '(', internal nodes in order of '('
+    for v in range(nn):
+        if children[v]:
+            idx[v] = total + k
+            k += 1
+        else:
+            idx[v] = leaf
+            leaf += 1
+    size = 2 * total + 2
+    parent = np.full(size, -1, np.int32)
+    bl = np.zeros(size, np.float64)
+    ch = [[] for _ in range(size)]
+    for v in range(nn):
+        for c in children[v]:
+            parent[idx[c]] = idx[v]
+            bl[idx[c]] = float(np.float32(length[c]))
+            ch[idx[v]].append(idx[c])
+    off = np.zeros(size + 1, np.int32)
+    flat = []
+    for v in range(size):
+        off[v + 1] = off[v] + len(ch[v])
+        flat += ch[v]
+    return idx[0], off, np.array(flat if flat else [0], np.int32), parent, bl
 
 
 def test_exact_placement_oracle_recovers_an_additive_tree(oracle):

@@ -128,3 +128,150 @@ def test_msa_exact_placement_tree_vs_reference_cuda(ctx, oracle, tmp_path):
     assert nwk == ref_nwk      # same slots, same adjacency order, same %g text
     D = msa.distMatrix(prm).to_host()
     assert oracle.place_exact(D).newick(synth.names(n)) == ref_nwk   # pins the oracle restatement
+
+
+def _read_arrays(path, n):
+    raw = np.fromfile(path, np.uint8)
+    o = 0
+    out = {}
+    for k, cnt, dt in (("head", 2 * n, np.int32), ("e", 8 * n, np.int32), ("nxt", 8 * n, np.int32), ("belong", 8 * n, np.int32),
+                       ("len", 8 * n, np.float64)):
+        nb = cnt * np.dtype(dt).itemsize
+        out[k] = raw[o:o + nb].view(dt).copy()
+        o += nb
+    return out
+
+
+def _same_tree_arrays(kp, ref, n):
+    a = kp.export()
+    ns = 4 * n - 4
+    assert np.array_equal(a["head"][: 2 * n], ref["head"][: 2 * n])
+    for k in ("e", "nxt", "belong"):
+        assert np.array_equal(a[k][:ns], ref[k][:ns]), k
+    assert np.allclose(a["len"][:ns], ref["len"][:ns], rtol=0, atol=1e-12)
+
+
+def _singleton_at_B(cl, B):
+    """see tools/make_ref_golden.py: keeps reference defect B12 (tip id == B read from the wrong buffer) without effect"""
+    cnt = np.bincount(cl[B:], minlength=int(cl.max()) + 1)
+    return next(q for q in range(B, len(cl)) if cnt[cl[q]] == 1)
+
+
+@pytest.mark.parametrize("dist_type", [3, 4, 5, 6])
+def test_msa_rows_models_3_to_6_vs_reference_cuda(ctx, oracle, tmp_path, dist_type):
+    """TN / K2P / Tamura / Jin-Nei: rows of the reference's well-formed DC twins (src/divide_and_conquer/msa.cu:219-264;
+    src/MSA.cu:239-265 indexes out of bounds) vs our bit-plane kernel and the oracle.  Tolerance 1e-6 relative
+    (north star): nvcc may contract the Tajima-Nei / Tamura products into FMAs differently."""
+    n, L = 150, 3000
+    codes, P, _ = make_msa(n, L, seed=48, gap_cols=0.05)
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "o")
+    write_bin(inp, P, [L] * n, 4)
+    run_ref("msa_dc_rows", inp, out, dist_type)
+    ref = np.fromfile(out + ".rows", np.float64)
+    msa = api.MSADeviceArrays(ctx)
+    msa.allocateDeviceArrays(P, np.full(n, L, np.uint64), n, api.Param(in_="m"))
+    D = msa.distMatrix(api.Param(distanceType=dist_type, in_="m")).to_host()
+    mine = np.concatenate([D[i, :i] for i in range(1, n)])
+    ok = np.isfinite(ref)
+    assert ok.mean() > 0.99
+    assert np.allclose(mine[ok], ref[ok], rtol=1e-6, atol=0)
+    orc = oracle.msa_dist_matrix(P, L, dist_type)
+    assert np.allclose(np.concatenate([orc[i, :i] for i in range(1, n)])[ok], ref[ok], rtol=1e-6, atol=0)
+
+
+def test_dc_aligned_vs_reference_cuda(ctx, oracle, tmp_path, monkeypatch):
+    """-m 3 on aligned input vs findBackboneTreeDC / findClustersDC / findClusterTreeDC of the reference's own objects
+    (src/divide_and_conquer/placement_close_k.cu:731-1535).  The reference as shipped carries defect B17 (stale
+    d(query, tip B-1) in the assignment stage); DIPB_DC_REF_B17=1 switches the same behaviour on here so that all
+    cluster ids and slot arrays can be compared exactly; the default (intended) rule is checked against the oracle."""
+    n, L, B = 2000, 2000, 100
+    codes, P, _ = make_msa(n, L, seed=61)
+    D0 = oracle.msa_dist_matrix(P, L, 2)
+    _, cl0 = oracle.dc_as_shipped(D0, B, 0.0)
+    q = _singleton_at_B(cl0, B)
+    P[[B, q]] = P[[q, B]]
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "o")
+    write_bin(inp, P, [L] * n, 4)
+    run_ref("msa_dc", inp, out, 2, 15, B)
+    ref_cl = np.fromfile(out + ".clusters", np.int32)
+    ref = _read_arrays(out + ".arrays", n)
+    prm = api.Param(distanceType=2, in_="m")
+    msa = api.MSADeviceArrays(ctx)
+    msa.allocateDeviceArrays(P, np.full(n, L, np.uint64), n, prm)
+    monkeypatch.setenv("DIPB_DC_REF_B17", "1")
+    kp = api.KPlacementDeviceArrays(ctx)
+    kp.allocateDeviceArrays(n)
+    kp.findTreeDC(prm, backboneSize=B, msaDeviceArrays=msa)
+    assert np.array_equal(kp.clusterID, ref_cl)
+    _same_tree_arrays(kp, ref, n)
+    assert kp.printTree(synth.names(n)) == open(out + ".nwk").read()
+    # the oracle with the defect on reproduces the reference too (pins orc_dc)
+    D = msa.distMatrix(prm).to_host()
+    ot, ocl = oracle.dc_as_shipped(D, B, 0.0)
+    assert np.array_equal(ocl, ref_cl) and ot.newick(synth.names(n)) == open(out + ".nwk").read()
+    # default = intended rule: equal to the oracle's intended rule, a few queries near tip B-1 differ from the reference
+    monkeypatch.delenv("DIPB_DC_REF_B17")
+    kp2 = api.KPlacementDeviceArrays(ctx)
+    kp2.allocateDeviceArrays(n)
+    kp2.findTreeDC(prm, backboneSize=B, msaDeviceArrays=msa)
+    _, icl = oracle.dc(D, B)
+    assert np.array_equal(kp2.clusterID, icl)
+    assert np.count_nonzero(icl != ref_cl) < 0.05 * (n - B)
+
+
+def test_dc_mash_vs_reference_cuda(ctx, oracle, tmp_path):
+    """-m 3 on unaligned input vs the reference's own DC objects (src/divide_and_conquer/mash.cu + placement_close_k.cu)."""
+    n, B = 300, 60
+    codes, _ = synth.evolve(n, 3000, seed=62, regime="tiefree", gap_cols=0.01)
+    seqs = synth.unaligned(codes)
+    flat, offs, lens = synth.flatten2(seqs)
+    _, cl0 = oracle.dc(oracle.mash_dist_matrix(oracle.sketch_all(flat, offs, lens, 15, 1000), 15), B)
+    q = _singleton_at_B(cl0, B)
+    seqs[B], seqs[q] = seqs[q], seqs[B]
+    packed = [synth.pack2_np(s) for s in seqs]
+    lens = np.array([len(s) for s in seqs], np.uint64)
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "o")
+    write_bin(inp, packed, lens, 2)
+    run_ref("mash_dc", inp, out, 1, 15, B)
+    ref_cl = np.fromfile(out + ".clusters", np.int32)
+    ref = _read_arrays(out + ".arrays", n)
+    prm = api.Param(kmerSize=15, sketchSize=1000, in_="r")
+    m = api.MashDeviceArrays(ctx)
+    m.allocateDeviceArrays(packed, lens, n, prm)
+    m.sketchConstructionOnGpu()
+    kp = api.KPlacementDeviceArrays(ctx)
+    kp.allocateDeviceArrays(n)
+    kp.findTreeDC(prm, backboneSize=B, mashDeviceArrays=m)
+    assert np.array_equal(kp.clusterID, ref_cl)
+    _same_tree_arrays(kp, ref, n)
+    assert kp.printTree(synth.names(n)) == open(out + ".nwk").read()
+
+
+def test_add_tips_onto_t2_backbone_vs_reference_cuda(ctx, oracle, tmp_path):
+    """BASELINE config 4b: -m 1 --add onto the reference's own fixture dataset/t2.backbone.nwk (1000 tips; copy under
+    tests/golden/), 2000 queries evolved on a tree that contains it; vs initializeDeviceArrays(Tree*) + addQuery of the
+    reference's objects (src/placement_close_k.cu:126-264,858-990)."""
+    bbt = open(os.path.join(ROOT, "tests", "golden", "t2.backbone.nwk")).readline().strip()
+    nq, L = 2000, 3000
+    tree, bb_leaves, bb_names, qnodes = synth.tree_with_queries(bbt, nq, seed=63, scale=50.0)
+    B = len(bb_leaves)
+    n = B + nq
+    codes, info = synth.evolve(n, L, seed=64, tree=tree, gap_cols=0.02)
+    row_of = {int(v): i for i, v in enumerate(info["order"])}
+    order = [row_of[v] for v in bb_leaves] + [row_of[v] for v in qnodes]
+    P = np.ascontiguousarray(synth.pack4_np(codes[order]))
+    inp, out, nwk = str(tmp_path / "in.bin"), str(tmp_path / "o"), str(tmp_path / "bb.nwk")
+    write_bin(inp, P, [L] * n, 4)
+    open(nwk, "w").write(bbt + "\n")
+    run_ref("msa_add", inp, out, 2, 15, nwk)
+    ref = _read_arrays(out + ".arrays", n)
+    prm = api.Param(distanceType=2, in_="m")
+    msa = api.MSADeviceArrays(ctx)
+    msa.allocateDeviceArrays(P, np.full(n, L, np.uint64), n, prm)
+    kp = api.KPlacementDeviceArrays(ctx)
+    kp.allocateDeviceArrays(n)
+    assert kp.initializeDeviceArrays(bbt) == B and kp.backbone_names == bb_names
+    kp.addQuery(prm, msaDeviceArrays=msa)
+    _same_tree_arrays(kp, ref, n)
+    names = bb_names + ["Q%d" % (i + 1) for i in range(nq)]
+    assert kp.printTree(names) == open(out + ".nwk").read()
