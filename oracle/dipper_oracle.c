@@ -1002,9 +1002,17 @@ static void insert_in_cluster(orc_ptree *t, int eid, double fracLen, double addL
 }
 
 /* updateClosestNodesInClusterDC :312-356 */
+/* Stage-3 BFS seed.  Intended: the new leaf at distance 0, coming from nowhere.  The reference seeds dis[x] / from[x]
+ * but reads dis[0] / from[0] (defect B10, src/divide_and_conquer/placement_close_k.cu:326-331) of queue arrays that
+ * findClusterTreeDC has just cudaMalloc'ed and never initialises (:1261-1275): zero-filled memory gives the intended
+ * result, recycled memory a garbage offset on every closest-list entry of stage 3.  The two globals exist only so that
+ * tests can show this is what separates a deviating reference run from the restatement. */
+static double g_stage3_seed_dis = 0.0;
+static int g_stage3_seed_from = -1;
+ORC_API void orc_dc_set_stage3_seed(double dis, int from) { g_stage3_seed_dis = dis; g_stage3_seed_from = from; }
 static void bfs_in_cluster(orc_ptree *t, int x, int cluster_eid, const int *mask_index) {
     int l = 0, r = 0;
-    t->q_id[0] = x; t->q_dis[0] = 0; t->q_from[0] = -1;
+    t->q_id[0] = x; t->q_dis[0] = g_stage3_seed_dis; t->q_from[0] = g_stage3_seed_from;
     int ed1 = t->e[cluster_eid], ed2 = t->belong[cluster_eid];
     while (l <= r) {
         int node = t->q_id[l], fb = t->q_from[l];

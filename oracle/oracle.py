@@ -71,6 +71,8 @@ def lib():
         L.orc_dc_matrix.restype = C.c_void_p
         L.orc_dc_matrix_as_shipped.argtypes = [f64p, C.c_int, C.c_int, C.c_double, i32p]
         L.orc_dc_matrix_as_shipped.restype = C.c_void_p
+        L.orc_dc_set_stage3_seed.argtypes = [C.c_double, C.c_int]
+        L.orc_dc_set_stage3_seed.restype = None
         L.orc_ptree_newick.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
         L.orc_ptree_newick.restype = C.c_void_p
         for nm, ty in (("head", C.c_int), ("e", C.c_int), ("nxt", C.c_int), ("belong", C.c_int),
@@ -258,18 +260,27 @@ def place_add(D, B, root, child_off, child_idx, parent, bl):
     return t
 
 
-def dc_as_shipped(D, B, stale=0.0):
-    """The reference's aligned D&C with its defect B17 switched on (see orc_dc_matrix_as_shipped): checker of the
-    restatement against the reference's own output, never the product rule."""
+def dc_as_shipped(D, B, stale=0.0, stage3_seed=0.0):
+    """The reference's aligned D&C with its defect B17 switched on (see orc_dc_matrix_as_shipped) and, optionally, the
+    stale stage-3 BFS seed of defect B10 (orc_dc_set_stage3_seed): checker of the restatement against the reference's
+    own output, never the product rule."""
     D = np.ascontiguousarray(D, np.float64)
     n = D.shape[0]
     cl = np.zeros(n, np.int32)
-    return PTree(lib().orc_dc_matrix_as_shipped(D, n, B, float(stale), cl), n), cl
+    lib().orc_dc_set_stage3_seed(float(stage3_seed), -1)
+    try:
+        return PTree(lib().orc_dc_matrix_as_shipped(D, n, B, float(stale), cl), n), cl
+    finally:
+        lib().orc_dc_set_stage3_seed(0.0, -1)
 
 
-def dc(D, B):
+def dc(D, B, stage3_seed=0.0):
     """Divide-and-conquer tree (DC/placement_close_k.cu:731-1535); returns (PTree, cluster ids)."""
     D = np.ascontiguousarray(D, np.float64)
     n = D.shape[0]
     cl = np.zeros(n, np.int32)
-    return PTree(lib().orc_dc_matrix(D, n, B, cl), n), cl
+    lib().orc_dc_set_stage3_seed(float(stage3_seed), -1)
+    try:
+        return PTree(lib().orc_dc_matrix(D, n, B, cl), n), cl
+    finally:
+        lib().orc_dc_set_stage3_seed(0.0, -1)

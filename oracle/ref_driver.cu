@@ -30,7 +30,8 @@
 //                        divide and conquer (-m 3), argv[6] = backbone size (default n/20,
 //                        src/tree_generation.cu:425,545); drives findBackboneTreeDC / findClustersDC /
 //                        findClusterTreeDC (src/divide_and_conquer/placement_close_k.cu:731-1535) with
-//                        MSADeviceArraysDC / MashDeviceArraysDC (src/divide_and_conquer/msa.cu, mash.cu)
+//                        MSADeviceArraysDC / MashDeviceArraysDC (src/divide_and_conquer/msa.cu, mash.cu); <out>.arrays
+//                        also carries int32 closest_id[20n], double closest_dis[20n] in these modes
 //          msa_dc_rows -> <out>.rows  rows through MSADeviceArraysDC::distConstructionOnGpuForBackboneDC with the
 //                        whole input as backbone: the well-formed twins of the six distance models
 //                        (src/divide_and_conquer/msa.cu:219-264; src/MSA.cu:239-265 is broken for models 3-6)
@@ -44,6 +45,9 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "mash_placement.cuh"
+
+// defined (external linkage) in src/divide_and_conquer/placement_close_k.cu:1113-1134; used by the mash_dc_probe mode only
+__global__ void rearrangeHashListInClusterDC(int numSequences, int sketchSize, uint64_t* original, uint64_t* target);
 
 using Clock = std::chrono::high_resolution_clock;
 static double ms_since(Clock::time_point t0) {
@@ -81,7 +85,8 @@ int main(int argc, char** argv) {
     double t_alloc = 0, t_sketch = 0, t_dist = 0, t_tree = 0;
     cudaDeviceSynchronize();
     auto t0 = Clock::now();
-    auto dump_arrays = [&](const char* suffix, int* d_head, int* d_e, int* d_nxt, int* d_belong, double* d_len) {
+    auto dump_arrays = [&](const char* suffix, int* d_head, int* d_e, int* d_nxt, int* d_belong, double* d_len, int* d_cid = nullptr,
+                           double* d_cdis = nullptr) {
         std::vector<int> hh(2 * n), he(8 * n), hn(8 * n), hb(8 * n);
         std::vector<double> hl(8 * n);
         cudaMemcpy(hh.data(), d_head, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost);
@@ -92,8 +97,56 @@ int main(int argc, char** argv) {
         FILE* o = fopen((out + suffix).c_str(), "wb");
         fwrite(hh.data(), 4, hh.size(), o); fwrite(he.data(), 4, he.size(), o); fwrite(hn.data(), 4, hn.size(), o);
         fwrite(hb.data(), 4, hb.size(), o); fwrite(hl.data(), 8, hl.size(), o);
+        if (d_cid && d_cdis) {   // closest-leaf lists, 5 per slot for the first 4n slots (the structs allocate 20n entries)
+            std::vector<int> hc(20 * n);
+            std::vector<double> hd(20 * n);
+            cudaMemcpy(hc.data(), d_cid, sizeof(int) * 20 * n, cudaMemcpyDeviceToHost);
+            cudaMemcpy(hd.data(), d_cdis, sizeof(double) * 20 * n, cudaMemcpyDeviceToHost);
+            fwrite(hc.data(), 4, hc.size(), o); fwrite(hd.data(), 8, hd.size(), o);
+        }
         fclose(o);
     };
+    if (mode == "mash_dc_probe") {
+        // Diagnostic: the stage-3 distance call of findClusterTreeDC in isolation.  argv[6] = backbone size, argv[7] =
+        // probe file: int32 nb, batch[nb] (tips of one stage-3 batch, in order), int32 r (row tip = batch position),
+        // int32 m, ids[m], maps[m] (leaf ids and their d_leafMap entries).  Prints d(row tip, ids[k]) as computed by
+        // transferMashClusterInfoDC's steps + MashDeviceArraysDC::distSpecialIDConstructionOnGpuDC.
+        int B = atoi(extra.c_str());
+        params.batchSize = B; params.backboneSize = B;
+        auto& md = MashPlacement::mashDeviceArraysDC;
+        md.allocateDeviceArraysDC(seqs, lens.data(), n, params);
+        md.sketchConstructionOnGpuDC(params, seqs, lens.data(), n);
+        FILE* pf = fopen(argv[7], "rb");
+        int nb = 0, r = 0, m = 0;
+        fread(&nb, 4, 1, pf);
+        std::vector<int> batch(nb);
+        fread(batch.data(), 4, nb, pf);
+        fread(&r, 4, 1, pf); fread(&m, 4, 1, pf);
+        std::vector<int> ids(m), maps(m);
+        fread(ids.data(), 4, m, pf); fread(maps.data(), 4, m, pf);
+        fclose(pf);
+        std::vector<uint64_t> local((size_t)B * 1000, 0);
+        for (int l = 0; l < nb; l++) memcpy(local.data() + (size_t)l * 1000, md.h_hashList + (size_t)batch[l] * 1000, 8000);
+        cudaMemcpy(md.d_hashListConst, local.data(), local.size() * 8, cudaMemcpyHostToDevice);
+        uint64_t* tmp;
+        cudaMalloc(&tmp, local.size() * 8);
+        rearrangeHashListInClusterDC<<<1024, 1024>>>(B, 1000, md.d_hashListConst, tmp);
+        std::swap(md.d_hashListConst, tmp);
+        cudaFree(tmp);
+        int *d_id, *d_map;
+        double* d_dist;
+        cudaMalloc(&d_id, 4 * m); cudaMalloc(&d_map, 4 * m); cudaMalloc(&d_dist, 8 * n);
+        cudaMemset(d_dist, 0, 8 * n);
+        cudaMemcpy(d_id, ids.data(), 4 * m, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_map, maps.data(), 4 * m, cudaMemcpyHostToDevice);
+        md.distSpecialIDConstructionOnGpuDC(params, r, d_dist, m, d_id, d_map);
+        std::vector<double> hd(n);
+        cudaMemcpy(hd.data(), d_dist, 8 * n, cudaMemcpyDeviceToHost);
+        printf("{\"probe\": [");
+        for (int k = 0; k < m; k++) printf("%s%.17g", k ? ", " : "", hd[ids[k]]);
+        printf("], \"cuda_status\": \"%s\"}\n", cudaGetErrorString(cudaDeviceSynchronize()));
+        return 0;
+    }
     if (mode == "msa_dc" || mode == "mash_dc" || mode == "msa_dc_rows") {
         // ---- divide and conquer structs (src/tree_generation.cu:422-449 aligned, :541-575 unaligned)
         const bool rows_only = mode == "msa_dc_rows";
@@ -145,7 +198,7 @@ int main(int argc, char** argv) {
                                  MashPlacement::msaDeviceArraysDC, MashPlacement::kplacementDeviceArraysHostDC);
             t_tree = ms_since(t0);
             kp.printTreeDC(names, os);
-            dump_arrays(".arrays", kp.d_head, kp.d_e, kp.d_nxt, kp.d_belong, kp.d_len);
+            dump_arrays(".arrays", kp.d_head, kp.d_e, kp.d_nxt, kp.d_belong, kp.d_len, kp.d_closest_id, kp.d_closest_dis);
         }
         cudaError_t e = cudaDeviceSynchronize();
         printf("{\"impl\": \"reference-cuda\", \"mode\": \"%s\", \"n\": %lld, \"backbone\": %d, \"alloc_ms\": %.3f, \"assign_ms\": %.3f, "

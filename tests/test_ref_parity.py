@@ -135,15 +135,29 @@ def _read_arrays(path, n):
     o = 0
     out = {}
     for k, cnt, dt in (("head", 2 * n, np.int32), ("e", 8 * n, np.int32), ("nxt", 8 * n, np.int32), ("belong", 8 * n, np.int32),
-                       ("len", 8 * n, np.float64)):
+                       ("len", 8 * n, np.float64), ("cid", 20 * n, np.int32), ("cdis", 20 * n, np.float64)):
         nb = cnt * np.dtype(dt).itemsize
+        if o + nb > raw.size:
+            break                      # closest lists are only dumped by the D&C modes
         out[k] = raw[o:o + nb].view(dt).copy()
         o += nb
     return out
 
 
+def _stage3_seed(ref, B):
+    """Reference defect B10 in its D&C twin: the stage-3 closest-leaf BFS reads dis[0] / from[0] of queue arrays that
+    findClusterTreeDC cudaMalloc's and never initialises (src/divide_and_conquer/placement_close_k.cu:326-331,
+    1261-1275).  Zero-filled memory gives the intended result (seed 0); recycled memory adds the stale value to every
+    closest-list distance of stage 3.  The value is visible in the reference's own output: the first placed tip's
+    slot tip->middle (index 4B-4+2) lists the tip itself at that distance."""
+    return float(ref["cdis"][(4 * B - 4 + 2) * 5])
+
+
 def _same_tree_arrays(kp, ref, n):
-    a = kp.export()
+    _same_arrays(kp.export(), ref, n)
+
+
+def _same_arrays(a, ref, n):
     ns = 4 * n - 4
     assert np.array_equal(a["head"][: 2 * n], ref["head"][: 2 * n])
     for k in ("e", "nxt", "belong"):
@@ -184,7 +198,9 @@ def test_dc_aligned_vs_reference_cuda(ctx, oracle, tmp_path, monkeypatch):
     (src/divide_and_conquer/placement_close_k.cu:731-1535).  The reference as shipped carries defect B17 (stale
     d(query, tip B-1) in the assignment stage); DIPB_DC_REF_B17=1 switches the same behaviour on here so that all
     cluster ids and slot arrays can be compared exactly; the default (intended) rule is checked against the oracle."""
-    n, L, B = 2000, 2000, 100
+    # (the reference exits when a cluster reaches the backbone size, src/divide_and_conquer/placement_close_k.cu:1334-1337;
+    # with its stale distance to tip B-1 that tip attracts many queries, so the backbone is taken large here)
+    n, L, B = 2000, 2000, 400
     codes, P, _ = make_msa(n, L, seed=61)
     D0 = oracle.msa_dist_matrix(P, L, 2)
     _, cl0 = oracle.dc_as_shipped(D0, B, 0.0)
@@ -203,12 +219,19 @@ def test_dc_aligned_vs_reference_cuda(ctx, oracle, tmp_path, monkeypatch):
     kp.allocateDeviceArrays(n)
     kp.findTreeDC(prm, backboneSize=B, msaDeviceArrays=msa)
     assert np.array_equal(kp.clusterID, ref_cl)
-    _same_tree_arrays(kp, ref, n)
-    assert kp.printTree(synth.names(n)) == open(out + ".nwk").read()
-    # the oracle with the defect on reproduces the reference too (pins orc_dc)
+    # the oracle with the reference's defects on reproduces the reference run (pins orc_dc): B17 and, when this run's
+    # stage-3 queue memory was not zero-filled, the stale BFS seed B10 (see _stage3_seed)
     D = msa.distMatrix(prm).to_host()
-    ot, ocl = oracle.dc_as_shipped(D, B, 0.0)
-    assert np.array_equal(ocl, ref_cl) and ot.newick(synth.names(n)) == open(out + ".nwk").read()
+    seed = _stage3_seed(ref, B)
+    ot, ocl = oracle.dc_as_shipped(D, B, 0.0, stage3_seed=seed)
+    assert np.array_equal(ocl, ref_cl)
+    _same_arrays(ot.arrays(), ref, n)
+    assert ot.newick(synth.names(n)) == open(out + ".nwk").read()
+    if seed == 0.0:      # memory was clean: the product (B17 switch on) must equal the reference slot for slot
+        _same_tree_arrays(kp, ref, n)
+        assert kp.printTree(synth.names(n)) == open(out + ".nwk").read()
+    ot0, _ = oracle.dc_as_shipped(D, B, 0.0)
+    _same_tree_arrays(kp, ot0.arrays(), n)
     # default = intended rule: equal to the oracle's intended rule, a few queries near tip B-1 differ from the reference
     monkeypatch.delenv("DIPB_DC_REF_B17")
     kp2 = api.KPlacementDeviceArrays(ctx)
@@ -243,8 +266,18 @@ def test_dc_mash_vs_reference_cuda(ctx, oracle, tmp_path):
     kp.allocateDeviceArrays(n)
     kp.findTreeDC(prm, backboneSize=B, mashDeviceArrays=m)
     assert np.array_equal(kp.clusterID, ref_cl)
-    _same_tree_arrays(kp, ref, n)
-    assert kp.printTree(synth.names(n)) == open(out + ".nwk").read()
+    D = m.distMatrix().to_host()
+    seed = _stage3_seed(ref, B)
+    ot, ocl = oracle.dc(D, B, stage3_seed=seed)          # the reference run incl. its stale BFS seed, if any
+    assert np.array_equal(ocl, ref_cl)
+    _same_arrays(ot.arrays(), ref, n)
+    assert ot.newick(synth.names(n)) == open(out + ".nwk").read()
+    if seed == 0.0:
+        _same_tree_arrays(kp, ref, n)
+        assert kp.printTree(synth.names(n)) == open(out + ".nwk").read()
+    ot0, _ = oracle.dc(D, B)
+    _same_tree_arrays(kp, ot0.arrays(), n)
+    assert kp.printTree(synth.names(n)) == ot0.newick(synth.names(n))
 
 
 def test_add_tips_onto_t2_backbone_vs_reference_cuda(ctx, oracle, tmp_path):
