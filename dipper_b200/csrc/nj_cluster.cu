@@ -18,14 +18,26 @@
 // rewrote (v: new node x, f: the node moved into y), and scans its own column chunks of every selected row
 // (u of those columns is local).  D lives in global memory and is read with ld.global.cg.
 //
-// Iteration (4 cluster barriers; everything a peer needs after a barrier was pushed into its shared memory
+// Iteration (3 cluster barriers; everything a peer needs after a barrier was pushed into its shared memory
 // before it -- measured: pulling the same word from one CTA by 512 warps serialises for ~1500 cycles):
 //   D  every CTA reduces the published CTA winners to the same (x, y); rank 0 logs the merge
-//   A  owners update rows x, y (move `last` into y), U, u; push chunk sums and max u-drift           | barrier
-//   B1 U[x] (canonical sum order), C += drift; ring the helpers; re-evaluate carried candidates      | barrier
-//   B2 ub = min over CTAs; owners fold the new column into K and select rows with lb <= ub           | barrier
-//   C  every CTA stages the selected rows (index, u, v, f) in shared memory, scans its column chunks of them,
-//      combines per-row minima in shared memory, pushes them to the row owners' K; publishes its winner  | barrier
+//   A  owners update rows x, y (move `last` into y), U (double buffered), u; push chunk sums and max u-drift;
+//      the carried candidates are re-evaluated with the post-merge u of their two ends, which every CTA derives
+//      itself from the pre-merge U (the other buffer) and rows x, y -- so the upper bound travels with the drift  | barrier
+//   B  U[x] (canonical sum order), C += drift, ub = min over CTAs; ring the helpers; owners fold the new column
+//      into K and select rows with lb <= ub                                                             | barrier
+//   C  every CTA stages the selected rows (index, u, v, f) in shared memory and scans, of its column chunks of
+//      them, only the UNITS whose own lower-bound key reaches ub (see Kb below); combines per-row minima in shared
+//      memory, pushes them to the row owners' K; publishes its winner                                    | barrier
+//
+// Unit keys (Kb).  A scan unit = UC column chunks of one row in one CTA (UC * 32 columns, UC * 256 bytes of D).
+// Kb[row][cta][part] holds, like the row keys, (min over the unit's columns of d - u_j) + C at evaluation time,
+// rounded down to fp32: a lower bound that drifts with C.  A selected row is no longer read as a whole (240 KB at
+// 30 000 tips): each CTA reads its `parts` keys of the row and loads only the units that can still hold a
+// candidate <= ub -- typically the unit of the runner-up that made the row's bound reach ub, 2 KB.  Units that are
+// skipped contribute their key to the row's runner-up bound K2.  The new column of a merge (and the column that
+// receives the moved last row) is folded into the unit keys of every row by the helper clusters together with the
+// column stores (red.global.min), the scan patches those two columns itself for the merge in flight.
 #include <cooperative_groups.h>
 #include <chrono>
 #include <cstdlib>
@@ -43,7 +55,8 @@ namespace {
 constexpr int MAXW = 32;      // warps per CTA at most
 constexpr int CPOOL = 128;    // carried candidate pairs per CTA
 constexpr int MAXCS = 16;
-constexpr int TILE = 512;     // selected rows staged in shared memory at a time
+constexpr int TILE = 256;     // selected rows staged in shared memory at a time
+constexpr int MAXPARTS = 32;  // units per row and CTA at most (the staged qualification mask is one word)
 constexpr unsigned long long KMAX = 0xffffffffffffffffull;
 constexpr unsigned int K32MAX = 0xffffffffu;   // row keys are order-preserving fp32, rounded DOWN (a lower bound stays one);
                                                // 32-bit min is a native shared-memory atomic, local and remote
@@ -54,15 +67,17 @@ struct CRec {                 // a CTA's best candidate of one scan
     int i, j;
 };
 
+struct NJMsg { double ux, uy, C, pad; };   // u of the new node, u of the node moved into y, drift sum: what a key needs
 struct NJCtl {                     // main cluster -> helper clusters doorbell (global memory)
-    unsigned long long bell;       // one word, one plain store: [seq:13 | x:17 | y:17 | n:17]; all ones = quit.
+    unsigned long long bell;       // one word, one release store: [seq:13 | x:17 | y:17 | n:17]; all ones = quit.
                                    // x: new node, y: slot that received the old last row when y < n, seq: merge number
     unsigned int done;             // helper CTAs that finished, cumulative
     unsigned int pad;
+    NJMsg msg[8];                  // payload of merge seq in msg[seq & 7], written before the bell
 };
 
 struct CStats {
-    unsigned long long rows_scanned, bytes_scanned, iters;
+    unsigned long long rows_scanned, bytes_scanned, iters, units_scanned;
     unsigned long long cyc[24];
     unsigned long long t_ns, t_cycles;   // whole main loop: globaltimer ns and SM cycles (their ratio is the SM clock)
 };
@@ -138,7 +153,7 @@ __device__ __forceinline__ int warp_best_lane(double t, int i, int j, int n) {
 
 // bytes of dynamic shared memory for LS owned rows per CTA and `chunks` 32-row chunks in total
 inline size_t cluster_smem_bytes(int LS, int chunks) {
-    return sizeof(double) * ((size_t)5 * LS + chunks + 2) + sizeof(unsigned int) * (size_t)3 * LS + (size_t)TILE * (3 * 8 + 8 + 4 + 4);
+    return sizeof(double) * ((size_t)6 * LS + chunks + 2) + sizeof(unsigned int) * (size_t)3 * LS + (size_t)TILE * (3 * 8 + 8 + 4 + 4 + 4);
 }
 
 }  // namespace
@@ -147,12 +162,12 @@ template <int CS, int CT, int UC, bool PROF>   // UC: column chunks per scan uni
 __global__ void __launch_bounds__(CT, 1)
 nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ U0, const double* __restrict__ u0,
                   int* __restrict__ sel_rows, CStats* stats, int2* __restrict__ log_xy, double2* __restrict__ log_bl,
-                  int n_total, int LS, double dmax, NJCtl* ctl, int HC) {
+                  int n_total, int LS, double dmax, NJCtl* ctl, int HC, unsigned int* __restrict__ Kb, int PARTS, int dbg, double slack_merges) {
     if (blockIdx.x >= CS) {
         // ---- helper clusters (the other GPCs): transpose rows x and y of each published merge into columns x and
-        // y.  These 2n scattered 8-byte stores per merge are request-rate bound on one GPC's L2 port when the
-        // main cluster issues them itself (~1 us per 1000 tips); spread over the other GPCs they are off the
-        // critical path.
+        // y, and fold those two new columns into the unit keys of every row.  These 2n scattered 8-byte stores (and
+        // 2n 4-byte minima) per merge are request-rate bound on one GPC's L2 port when the main cluster issues them
+        // itself (~1 us per 1000 tips); spread over the other GPCs they are off the critical path.
         const int hc = (int)blockIdx.x - CS, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
         __shared__ unsigned long long s_msg;
         unsigned long long seen = 0;
@@ -172,12 +187,23 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             if (q == KMAX) return;
             seen = q;
             const int x = (int)((q >> 34) & 0x1ffffu), y = (int)((q >> 17) & 0x1ffffu), n = (int)(q & 0x1ffffu);
+            const NJMsg* mp = &ctl->msg[(q >> 51) & 7];
+            const double ux = __ldcg(&mp->ux), uy = __ldcg(&mp->uy), Cm = __ldcg(&mp->C);
+            const size_t kx = (size_t)((x >> 5) % CS) * PARTS + ((x >> 5) / CS) / UC;    // unit of column x within a row's keys
+            const size_t ky = (size_t)((y >> 5) % CS) * PARTS + ((y >> 5) / CS) / UC;
+            const size_t krow = (size_t)CS * PARTS;
             const int nch = (n + 31) >> 5;
             for (int c = hc + w * HC; c < nch; c += HC * (CT / 32)) {
                 const int i = c * 32 + lane;
                 if (i < n && i != x && i != y) {
-                    D[(size_t)i * ld + x] = __ldcg(&D[(size_t)x * ld + i]);
-                    if (y < n) D[(size_t)i * ld + y] = __ldcg(&D[(size_t)y * ld + i]);
+                    const double vx = __ldcg(&D[(size_t)x * ld + i]);
+                    D[(size_t)i * ld + x] = vx;
+                    atomicMin(&Kb[(size_t)i * krow + kx], key_of((vx - ux) + Cm));
+                    if (y < n) {
+                        const double fy = __ldcg(&D[(size_t)y * ld + i]);
+                        D[(size_t)i * ld + y] = fy;
+                        atomicMin(&Kb[(size_t)i * krow + ky], key_of((fy - uy) + Cm));
+                    }
                 }
             }
             __threadfence();
@@ -190,10 +216,12 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     constexpr int NW = CT / 32;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int chunks_total = (n_total + 31) >> 5;
+    const size_t krow = (size_t)CS * PARTS;            // unit keys per row
+    unsigned int* const Kmine = Kb + (size_t)rank * PARTS;   // + row * krow + part
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* U_s = reinterpret_cast<double*>(smem_raw);   // [LS] row sums of owned rows
-    double* u_s = U_s + LS;                              // [LS] U / (n - 2)
+    double* U_s = reinterpret_cast<double*>(smem_raw);   // [2][LS] row sums of owned rows; buffer `cur` is valid, A writes the other
+    double* u_s = U_s + 2 * LS;                          // [LS] U / (n - 2)
     double* v_s = u_s + LS;                              // [LS] distance to the newest node x
     double* f_s = v_s + LS;                              // [LS] distance to the node moved into slot y
     double* da_s = f_s + LS;                             // [LS] distance to the tracked best partner a (exact, constant while both live)
@@ -204,18 +232,19 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     unsigned long long* t_best = reinterpret_cast<unsigned long long*>(t_f + TILE);   // (key of the row minimum << 32) | its column
     unsigned int* t_k2 = reinterpret_cast<unsigned int*>(t_best + TILE);              // key of the runner-up
     int* t_row = reinterpret_cast<int*>(t_k2 + TILE);
+    unsigned int* t_qm = reinterpret_cast<unsigned int*>(t_row + TILE);               // bit p: unit p of this CTA must be scanned
     // Lower-bound keys of owned rows.  K1 bounds the tracked best partner a_s (whose exact value can be re-evaluated
     // from da_s and u[a]), K2 every other column; both are (value + C) at evaluation time, so `dec(K) - C` stays a
     // lower bound while u drifts.
-    unsigned int* K1_s = reinterpret_cast<unsigned int*>(t_row + TILE);
+    unsigned int* K1_s = t_qm + TILE;
     unsigned int* K2_s = K1_s + LS;
     int* a_s = reinterpret_cast<int*>(K2_s + LS);
 
     __shared__ CRec recs[MAXCS];            // winners published by every CTA of the cluster
     __shared__ CRec wrec[MAXW];
     __shared__ double drift_all[MAXCS], ubmin_all[MAXCS];   // pushed by the peers
-    __shared__ double s_red[MAXW], s_blk[128 + 16];         // s_blk: one sum per 1024-row block (n <= 131 072)
-    __shared__ double s_total, s_C;
+    __shared__ double s_red[MAXW], s_red2[MAXW], s_blk[128 + 16];   // s_blk: one sum per 1024-row block (n <= 131 072)
+    __shared__ double s_total, s_C, s_uy;   // s_uy (rank 0's copy): u of the node moved into slot y, pushed by its owner
     __shared__ unsigned int s_sel;          // selected-row counter (rank 0's copy is the live one)
     __shared__ int s_list[TILE];            // first TILE selected rows, in rank 0's copy (the rest spill to sel_rows in global
                                             // memory; a list that was just written by 16 SMs reads back slowly from L2)
@@ -223,19 +252,22 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     __shared__ double pool_d[CPOOL];        // d of a carried pair never changes while both ends survive
     __shared__ double pool_t[CPOOL];        // its value at the last re-evaluation: new candidates replace worse ones only
     __shared__ int s_pool_head, s_nsel;
+    __shared__ unsigned int s_nunits;          // live scan units of the staged tile
+    __shared__ unsigned short s_ulist[TILE * 12];   // (staged row << 5) | unit, in no particular order
     __shared__ unsigned long long s_cyc[24];   // rank 0, thread 0: cycles per phase (DIPB_NJ_PROFILE)
 
     // ---- load owned state
     for (int s = tid; s < LS; s += CT) {
         const int i = ((s >> 5) * CS + rank) * 32 + (s & 31);
         U_s[s] = i < n_total ? U0[i] : 0.0;
+        U_s[LS + s] = 0.0;
         u_s[s] = i < n_total ? u0[i] : 0.0;
         v_s[s] = 0.0; f_s[s] = 0.0;
         K1_s[s] = K32MAX; K2_s[s] = K32MAX; a_s[s] = -1; da_s[s] = 0.0;
     }
     if (tid == 0) t_row[0] = 0;
-    for (int p = tid; p < CPOOL; p += CT) { pool_i[p] = -1; pool_j[p] = -1; }
-    if (tid == 0) { s_pool_head = 0; s_sel = 0; }
+    for (int p = tid; p < CPOOL; p += CT) { pool_i[p] = -1; pool_j[p] = -1; pool_t[p] = 1e300; }
+    if (tid == 0) { s_pool_head = 0; s_sel = 0; s_uy = 0.0; }
     if (tid < 24) s_cyc[tid] = 0;
     __syncthreads();
     cluster.sync();
@@ -246,7 +278,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     double dxy = 0.0;
     bool first = true;
     int iter = 0;
-    unsigned long long my_rows = 0, my_bytes = 0;
+    int cur = 0;                              // valid U buffer
+    unsigned long long my_rows = 0, my_units = 0;
     unsigned int* sel0 = cluster.map_shared_rank(&s_sel, 0);
 
     // Partner records: the CTA whose slice holds a scanned row's minimum (its key equals the combined K1) tells the
@@ -284,13 +317,41 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     } while (0)
 
     while (n > 2) {
-        double ub = 1e300;
+        double ub = 1e300, ux = 0.0;
+        const double margin = 1e-9 * (4.0 * dmax + fabs(C));   // refreshed below once C has moved
+        double marg = margin;
         if (!first) {
             // ------------------------------------------------------------ A: merge update by row owners
             CL_MARK(0);
             const int last = n - 1;
             const double den_new = (double)(n - 3);
             const int nchunk = (last + 31) >> 5;               // chunks holding rows < last
+            const double* Uo = U_s + cur * LS;                  // pre-merge sums (read by every CTA through DSMEM)
+            double* Un = U_s + (cur ^ 1) * LS;                  // post-merge sums
+            // carried candidates of this CTA, re-evaluated exactly with the post-merge u of their ends (none touches x;
+            // an end in slot y is the node that lived in `last`): same expressions as the owners use below
+            // (done by the last four warps: they own one chunk less of the update below than the first ones)
+            double pv = 1e300;
+            const int ptid = tid - (CT - CPOOL);
+            if (ptid >= 0 && n > 3 && pool_i[ptid] >= 0) {
+                double un2[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int p = e == 0 ? pool_i[ptid] : pool_j[ptid];
+                    const int src = p == y ? last : p;
+                    const double a = __ldcg(&D[(size_t)x * ld + src]), b = __ldcg(&D[(size_t)y * ld + src]);
+                    double Ui = ld_peer_f64(&Uo[((src >> 5) / CS) * 32 + (src & 31)], (src >> 5) % CS);
+                    const double val = (a + b - dxy) * 0.5;
+                    Ui += -a - b + val;
+                    un2[e] = Ui / den_new;
+                }
+                pv = (pool_d[ptid] - un2[0]) - un2[1];
+            }
+            if (ptid >= 0) {
+                pool_t[ptid] = pv;
+                pv = warp_min_f64(pv);
+                if (lane == 0) s_red2[w - (NW - CPOOL / 32)] = pv;
+            }
             double dmx = -1e300;
             for (int lw = w; lw * CS + rank < nchunk; lw += NW) {
                 const int i = (lw * CS + rank) * 32 + lane;
@@ -302,55 +363,65 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     const int src = isy ? last : i;
                     const double a = __ldcg(&D[(size_t)x * ld + src]), b = __ldcg(&D[(size_t)y * ld + src]);
                     const double far = __ldcg(&D[(size_t)last * ld + i]);
-                    double Ui = U_s[s], uo = u_s[s];
+                    double Ui = Uo[s], uo = u_s[s];
                     if (isy) {
                         const int lo = (last >> 5) % CS, ls = ((last >> 5) / CS) * 32 + (last & 31);
-                        Ui = ld_peer_f64(&U_s[ls], lo);
+                        Ui = ld_peer_f64(&Uo[ls], lo);
                         uo = ld_peer_f64(&u_s[ls], lo);
                     }
                     const double val = (a + b - dxy) * 0.5;
                     Ui += -a - b + val;
-                    U_s[s] = Ui;
-                    D[(size_t)x * ld + i] = val;         // rows x and y: coalesced, visible after the next barrier
-                    if (isy) D[(size_t)y * ld + x] = val;
-                    else D[(size_t)y * ld + i] = far;
-                    f_s[s] = far;                        // columns x and y of row i are written by the helper clusters
+                    Un[s] = Ui;
+                    f_s[s] = far;                        // rows x and y of D are written from v_s / f_s after the barrier (phase B)
                     slot = val;
                     if (n > 3) {
                         const double un = Ui / den_new;
                         dmx = fmax(dmx, un - uo);
                         u_s[s] = un;
+                        if (isy) st_peer_f64(&s_uy, 0, un);      // the helpers' key fold needs it (rank 0 rings the bell)
                     }
-                }
+                } else if (i == x) Un[s] = 0.0;            // replaced by the canonical sum in phase B
                 v_s[s] = slot;
                 // canonical block sum, level 1: this chunk's stride-halving tree, pushed to every CTA
                 const double csum = __shfl_sync(0xffffffffu, warp_tree_sum(slot), 0);
                 if (lane < CS) st_peer_f64(&cs_all[lw * CS + rank], lane, csum);
             }
+            // unit keys of the row that moves from `last` into slot y: every CTA copies its own units
+            if (y < last && tid >= CT - 32 && lane < PARTS) Kmine[(size_t)y * krow + lane] = __ldcg(&Kmine[(size_t)last * krow + lane]);
             dmx = warp_max_f64(dmx);
             if (lane == 0) s_red[w] = dmx;
             __syncthreads();
             if (w == 0) {
                 const double m = warp_max_f64(lane < NW ? s_red[lane] : -1e300);
-                if (lane < CS) st_peer_f64(&drift_all[rank], lane, m);
+                double pm = s_red2[0];
+#pragma unroll
+                for (int q = 1; q < CPOOL / 32; q++) pm = fmin(pm, s_red2[q]);
+                if (lane < CS) { st_peer_f64(&drift_all[rank], lane, m); st_peer_f64(&ubmin_all[rank], lane, pm); }
             }
+            cur ^= 1;
             CL_MARK(1);
             cluster.sync();
             CL_MARK(2);
 
-            // ------------------------------------------------------------ B1: U[x], drift, carried candidates
+            // ------------------------------------------------------------ B: U[x], drift, upper bound, fold, select
+            // Rows x and y of D, from the values phase A left in v_s / f_s.  Not written in phase A itself: there every CTA
+            // still reads the pre-merge rows x and y for the ends of its carried candidates.  Coalesced; visible to the
+            // scan (and, through the bell rung after the next barrier, to the helpers that transpose them into columns).
+            for (int lw = w; lw * CS + rank < nchunk; lw += NW) {
+                const int i = (lw * CS + rank) * 32 + lane;
+                const int s = lw * 32 + lane;
+                if (i < last && i != x) {
+                    const double val = v_s[s];
+                    D[(size_t)x * ld + i] = val;
+                    if (i == y) D[(size_t)y * ld + x] = val;
+                    else D[(size_t)y * ld + i] = f_s[s];
+                }
+            }
             n = last;
             if (n <= 2) {
                 // last merge: nj_finish_kernel reads D[0][1], a column entry when x == 1
                 if (rank == 0 && tid < n && tid != x && tid != y) D[(size_t)tid * ld + x] = v_s[tid];
                 break;
-            }
-            if (HC > 0 && rank == 0 && tid == 0) {
-                // rows x and y are complete and fenced (every thread ran MEMBAR.GPU before the barrier), so the bell is
-                // one relaxed store; merge numbers differ in the low 13 bits between consecutive merges
-                const unsigned long long q = ((unsigned long long)(iter & 0x1fff) << 51) | ((unsigned long long)x << 34) |
-                                             ((unsigned long long)y << 17) | (unsigned long long)n;
-                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->bell), "l"(q) : "memory");
             }
             {
                 // canonical sum, level 2: 1024-row blocks (32 chunk sums, stride-halving tree), then blocks ascending
@@ -374,48 +445,35 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     for (int q = 1; q < CS; q++) drift = fmax(drift, drift_all[q]);
                     s_total = acc;
                     s_C = C + drift;
+                    if (HC > 0 && rank == 0) {
+                        // payload of this merge's bell (rung after the next barrier, whose fence publishes it)
+                        NJMsg* mp = &ctl->msg[iter & 7];
+                        mp->ux = acc / (double)(n - 2); mp->uy = s_uy; mp->C = C + drift;
+                    }
                 }
                 __syncthreads();
             }
             CL_MARK(3);
             const double total = s_total;
-            const double ux = total / (double)(n - 2);
+            ux = total / (double)(n - 2);
             C = s_C;
+            marg = 1e-9 * (4.0 * dmax + fabs(C));
             if (((x >> 5) % CS) == rank && tid == 0) {
                 const int sx = ((x >> 5) / CS) * 32 + (x & 31);
-                U_s[sx] = total;
+                U_s[cur * LS + sx] = total;
                 u_s[sx] = ux;
+                // the moved row's unit key of the new column (its other units were copied in phase A; row y is not among
+                // the rows the helpers fold)
+                if (y < n) atomicMin(&Kmine[(size_t)y * krow + ((x >> 5) / CS) / UC],
+                                     key_of((ld_peer_f64(&v_s[((y >> 5) / CS) * 32 + (y & 31)], (y >> 5) % CS) - ux) + C));
             }
-            // carried candidates of this CTA, re-evaluated exactly with the post-merge u (none touches x or y)
-            if (tid < CPOOL) {
-                double pv = 1e300;
-                if (pool_i[tid] >= 0) {
-                    const int pi = pool_i[tid], pj = pool_j[tid];
-                    const double upi = ld_peer_f64(&u_s[((pi >> 5) / CS) * 32 + (pi & 31)], (pi >> 5) % CS);
-                    const double upj = ld_peer_f64(&u_s[((pj >> 5) / CS) * 32 + (pj & 31)], (pj >> 5) % CS);
-                    pv = (pool_d[tid] - upi) - upj;
-                }
-                pool_t[tid] = pv;
-                pv = warp_min_f64(pv);
-                if (lane == 0) s_red[w] = pv;
-            }
-            __syncthreads();
-            if (w == 0) {
-                double m = s_red[0];
-#pragma unroll
-                for (int q = 1; q < CPOOL / 32; q++) m = fmin(m, s_red[q]);
-                if (lane < CS) st_peer_f64(&ubmin_all[rank], lane, m);
-            }
-            CL_MARK(4);
-            cluster.sync();
-            CL_MARK(5);
-
-            // ------------------------------------------------------------ B2: upper bound, fold column x, select
             ub = ubmin_all[0];
 #pragma unroll
             for (int q = 1; q < CS; q++) ub = fmin(ub, ubmin_all[q]);
+            if (dbg & 2) ub = 1e300;
+            CL_MARK(4);
+            CL_MARK(5);
             {
-                const double margin = 1e-9 * (4.0 * dmax + fabs(C));
                 const int nch = (n + 31) >> 5;
                 for (int lw = w; lw * CS + rank < nch; lw += NW) {
                     const int i = (lw * CS + rank) * 32 + lane;
@@ -441,18 +499,18 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                             if (kc < k2) k2 = kc;
                             // stage 1: both keys as drifting lower bounds (no memory traffic)
                             const unsigned int km = k1 < k2 ? k1 : k2;
-                            take = !(((double)dec_f32(km) - C) - u_s[s] - margin > ub);
+                            take = !(((double)dec_f32(km) - C) - u_s[s] - marg > ub);
                             if (take && a >= 0) {
                                 // stage 2: the tracked partner exactly (its d never changes, u[a] from its owner)
                                 const double e1 = da_s[s] - ld_peer_f64(&u_s[((a >> 5) / CS) * 32 + (a & 31)], (a >> 5) % CS);
                                 k1 = key_of(e1 + C);
                                 const double rest = (double)dec_f32(k2) - C;
-                                take = !((e1 < rest ? e1 : rest) - u_s[s] - margin > ub);
+                                take = !((e1 < rest ? e1 : rest) - u_s[s] - marg > ub);
                             }
                             if (PROF && rank == 0 && take) {
                                 // why rows are rescanned (rank 0's rows only): 12 no tracked partner, 13 partner itself is
                                 // a contender, 14 the runner-up bound has drifted down to the upper bound
-                                const int why = a < 0 ? 12 : ((da_s[s] - ld_peer_f64(&u_s[((a >> 5) / CS) * 32 + (a & 31)], (a >> 5) % CS)) - u_s[s] - margin > ub ? 14 : 13);
+                                const int why = a < 0 ? 12 : ((da_s[s] - ld_peer_f64(&u_s[((a >> 5) / CS) * 32 + (a & 31)], (a >> 5) % CS)) - u_s[s] - marg > ub ? 14 : 13);
                                 atomicAdd(&s_cyc[why], 1ull);
                             }
                             if (take) { k1 = K32MAX; k2 = K32MAX; a = -1; }   // reset, the scan lowers them
@@ -493,17 +551,25 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
         cluster.sync();
         CL_MARK(7);
 
-        // ---------------------------------------------------------------- C: scan own column chunks of the selected rows
+        // ---------------------------------------------------------------- C: scan the qualifying units of the selected rows
         {
-            if (tid == 0) s_nsel = (int)*sel0;
+            if (tid == 0) { s_nsel = (int)*sel0; s_nunits = 0; }
             const bool merged = !first;
             const bool ymoved = merged && y < n;               // false when y was the last slot: nothing moved into it
-            // Without helper clusters the main cluster writes columns x and y itself; the stores ride behind the
-            // loads of the scan units, one chunk (64 scattered stores) per warp and unit.
+            if (HC > 0 && merged && rank == 0 && tid == 0) {
+                // rows x and y and the payload are complete and fenced (every thread ran MEMBAR.GPU before the barrier), so
+                // the bell is one relaxed store; merge numbers differ in the low 13 bits between consecutive merges
+                const unsigned long long q = ((unsigned long long)(iter & 0x1fff) << 51) | ((unsigned long long)x << 34) |
+                                             ((unsigned long long)y << 17) | (unsigned long long)n;
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->bell), "l"(q) : "memory");
+            }
+            // Without helper clusters the main cluster writes columns x and y (and folds them into the unit keys) itself;
+            // the stores ride behind the loads of the scan units, one chunk (64 scattered stores) per warp and unit.
             const int st_nch = (merged && HC == 0) ? (n + 31) >> 5 : 0;
             int st_lw = w;
             __syncthreads();
             const int nsel = s_nsel;
+            if (rank == 0 && tid == 0) my_rows += (unsigned long long)nsel;
             const int nch = (n + 31) >> 5;
             const int lch = nch > rank ? (nch - rank + CS - 1) / CS : 0;      // local chunks holding columns < n
             const int parts = (lch + UC - 1) / UC;
@@ -512,31 +578,75 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             // v / f of the row, not from D (the helpers may still be writing them)
             const int xlw = (merged && ((x >> 5) % CS) == rank) ? (x >> 5) / CS : -1000000;
             const int ylw = (ymoved && ((y >> 5) % CS) == rank) ? (y >> 5) / CS : -1000000;
+            const double uy_loc = ylw >= 0 ? u_s[ylw * 32 + (y & 31)] : 0.0;
+            // Units are refreshed a little EARLY: a unit whose bound will reach ub within about `slack_merges` merges at
+            // the average drift so far is read now, while its row is staged anyway.  Without this every unit drifts to
+            // the threshold on its own and costs its row a selection of its own (measured: 129 selected rows per merge
+            // instead of 13); with it a row comes back when its runner-up does, as with whole-row rescans.
+            const double slack = iter > 0 ? slack_merges * (fabs(C) / (double)iter) : 0.0;   // (C may be negative: never tighten)
+            const size_t kxg = (size_t)((x >= 0 ? x >> 5 : 0) % CS) * PARTS + ((x >= 0 ? x >> 5 : 0) / CS) / UC;
+            const size_t kyg = (size_t)((y >= 0 ? y >> 5 : 0) % CS) * PARTS + ((y >= 0 ? y >> 5 : 0) / CS) / UC;
             double bt = 1e300, bd = 0.0, bui = 0.0, buj = 0.0;
             int bi = -1, bj = -1;
             for (int t0 = 0; t0 < nsel || (t0 == 0 && st_nch > 0); t0 += TILE) {
                 const int tn = nsel - t0 < TILE ? nsel - t0 : TILE;
-                // stage the tile: row index, u, v, f of the row (owner's shared memory), empty combined minimum
+                if (t0 > 0) {                       // (the first tile's counter was reset before the barrier above)
+                    __syncthreads();
+                    if (tid == 0) s_nunits = 0;
+                    __syncthreads();
+                }
+                // stage the tile: row index, u, v, f of the row (owner's shared memory), empty combined minimum, and from
+                // this CTA's unit keys of the row which units must be read and what the others bound
                 for (int k = tid; k < tn; k += CT) {
                     const int r = t0 + k < TILE ? ld_peer_s32(&s_list[t0 + k], 0) : __ldcg(&sel_rows[t0 + k]);
                     const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
+                    const bool all = first || r == x || (dbg & 1);
+                    const unsigned int* kp = Kmine + (size_t)r * krow;
+                    unsigned int kq[12];
+                    if (!all) {
+#pragma unroll
+                        for (int p = 0; p < 12; p++) kq[p] = p < parts ? __ldcg(&kp[p]) : K32MAX;
+                    }
+                    const double ur = ld_peer_f64(&u_s[rs], ro), vr = ld_peer_f64(&v_s[rs], ro), fr = ld_peer_f64(&f_s[rs], ro);
                     t_row[k] = r;
-                    t_u[k] = ld_peer_f64(&u_s[rs], ro);
-                    t_v[k] = ld_peer_f64(&v_s[rs], ro);
-                    t_f[k] = ld_peer_f64(&f_s[rs], ro);
+                    t_u[k] = ur; t_v[k] = vr; t_f[k] = fr;
                     t_best[k] = KMAX;
-                    t_k2[k] = K32MAX;
+                    unsigned int qm = 0, rest = K32MAX;
+                    if (all) qm = parts >= 32 ? 0xffffffffu : ((1u << parts) - 1u);
+                    else {
+                        const bool patch = merged && r != y;        // (row y's keys were completed by the owner of column x)
+                        const int xp = (patch && xlw >= 0) ? xlw / UC : -1, yp = (patch && ylw >= 0) ? ylw / UC : -1;
+                        const unsigned int kxv = xp >= 0 ? key_of((vr - ux) + C) : K32MAX;
+                        const unsigned int kyv = yp >= 0 ? key_of((fr - uy_loc) + C) : K32MAX;
+                        auto unit = [&](int p, unsigned int kv) {
+                            if (p == xp && kxv < kv) kv = kxv;      // the merge in flight: the helpers' fold may not have landed
+                            if (p == yp && kyv < kv) kv = kyv;
+                            if (((double)dec_f32(kv) - C) - ur - marg > ub + slack) rest = kv < rest ? kv : rest;
+                            else qm |= 1u << p;
+                        };
+#pragma unroll
+                        for (int p = 0; p < 12; p++) if (p < parts) unit(p, kq[p]);
+                        for (int p = 12; p < parts; p++) unit(p, __ldcg(&kp[p]));
+                    }
+                    t_qm[k] = qm;
+                    t_k2[k] = rest;
+                    if (qm) {
+                        // live units go to a compact list so that every warp gets about the same number of them
+                        unsigned int pos = atomicAdd(&s_nunits, (unsigned int)__popc(qm));
+                        for (unsigned int m = qm; m; m &= m - 1u) s_ulist[pos++] = (unsigned short)((k << 5) | (__ffs(m) - 1));
+                    }
                 }
                 __syncthreads();
                 CL_MARK(8);
-                const int units = tn > 0 ? tn * parts : 0;
+                const int units = (int)s_nunits;
                 // one pass = one scan unit (UC column chunks of one selected row) + one chunk of column stores; a warp
                 // that has run out of one of the two keeps going with the other (a dead unit loads nothing)
                 for (int un = w; un < units || st_lw * CS + rank < st_nch; un += NW) {
                     const bool live = un < units;
-                    const int k = live ? un / pdiv : 0;
+                    const unsigned int ent = live ? s_ulist[un] : 0u;
+                    const int k = (int)(ent >> 5), part = (int)(ent & 31u);
                     const int r = t_row[k];
-                    const int lw0 = live ? (un % pdiv) * UC : lch;
+                    const int lw0 = live ? part * UC : lch;
                     const double* row = D + (size_t)r * ld;
                     double dv[UC];
 #pragma unroll
@@ -547,11 +657,18 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     if (st_lw * CS + rank < st_nch) {
                         const int i = (st_lw * CS + rank) * 32 + lane;
                         if (i < n && i != x && i != y) {
-                            D[(size_t)i * ld + x] = v_s[st_lw * 32 + lane];
-                            if (ymoved) D[(size_t)i * ld + y] = f_s[st_lw * 32 + lane];
+                            const double vx = v_s[st_lw * 32 + lane];
+                            D[(size_t)i * ld + x] = vx;
+                            atomicMin(&Kb[(size_t)i * krow + kxg], key_of((vx - ux) + C));
+                            if (ymoved) {
+                                const double fy = f_s[st_lw * 32 + lane];
+                                D[(size_t)i * ld + y] = fy;
+                                atomicMin(&Kb[(size_t)i * krow + kyg], key_of((fy - ld_peer_f64(&u_s[((y >> 5) / CS) * 32 + (y & 31)], (y >> 5) % CS)) + C));
+                            }
                         }
                         st_lw += NW;
                     }
+                    if (!live) continue;
                     const double ur = t_u[k];
                     const bool patch = merged && r != x && r != y;
                     const int xq = (patch && lane == (x & 31)) ? xlw - lw0 : -1;
@@ -571,13 +688,15 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         if (mv < lm1) { lm2 = lm1; lm1 = mv; lq = q; } else lm2 = fmin(lm2, mv);
                         if (t < ut) { ut = t; ud = d; uuj = uj; uq = q; }
                     }
-                    if (ut < 10000.0 && (ut < bt || (ut == bt && bi != r && tie_before(r, ((lw0 + uq) * CS + rank) * 32 + lane, bi, bj, n)))) {
+                    // (units of one row may reach a lane in any order now: ties within the row go through the reference order too)
+                    if (ut < 10000.0 && (ut < bt || (ut == bt && tie_before(r, ((lw0 + uq) * CS + rank) * 32 + lane, bi, bj, n)))) {
                         bt = ut; bi = r; bj = ((lw0 + uq) * CS + rank) * 32 + lane; bd = ud; bui = ur; buj = uuj;
                     }
-                    // row minimum and runner-up of this unit -> the CTA's (minimum, column) and runner-up of the row.  An
+                    // unit minimum and runner-up -> the unit's key, the CTA's (minimum, column) and runner-up of the row.  An
                     // atomic that loses to (or displaces) the standing minimum demotes the loser to the runner-up.
                     const unsigned int key1 = lm1 < 1e299 ? key_of(lm1 + C) : K32MAX;
                     const unsigned int k1w = __reduce_min_sync(0xffffffffu, key1);
+                    if (lane == 0) Kmine[(size_t)r * krow + part] = k1w;
                     if (k1w != K32MAX) {
                         const int wl = __ffs(__ballot_sync(0xffffffffu, key1 == k1w)) - 1;
                         const int jw = __shfl_sync(0xffffffffu, ((lw0 + lq) * CS + rank) * 32 + lane, wl);
@@ -590,21 +709,21 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                             atomicMin(&t_k2[k], demoted < k2w ? demoted : k2w);
                         }
                     }
-                    if (lane == 0 && live && lw0 == 0 && rank == 0) { my_rows++; my_bytes += (unsigned long long)n * 8ull; }
+                    if (lane == 0) my_units++;
                 }
                 __syncthreads();
                 CL_MARK(9);
-                // this CTA's minimum of each staged row goes to the row owner's key
+                // this CTA's minimum of each staged row goes to the row owner's key; skipped units only bound the runner-up
                 for (int k = tid; k < tn; k += CT) {
                     const unsigned int k1 = (unsigned int)(t_best[k] >> 32);
+                    const unsigned int k2 = t_k2[k];
+                    const int r = t_row[k];
+                    const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
                     if (k1 != K32MAX) {
-                        const int r = t_row[k];
-                        const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
                         const unsigned int old = atom_peer_min_u32(&K1_s[rs], ro, k1);
                         const unsigned int demoted = k1 < old ? old : k1;
-                        const unsigned int k2 = t_k2[k];
                         red_peer_min_u32(&K2_s[rs], ro, demoted < k2 ? demoted : k2);
-                    }
+                    } else if (k2 != K32MAX) red_peer_min_u32(&K2_s[rs], ro, k2);
                 }
                 if (nsel > TILE) {
                     // rare (first search, bursts): one extra cluster barrier per tile so that every tile gets its records
@@ -719,14 +838,20 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
         stats->t_ns = ns_end - ns_begin;
         stats->t_cycles = (unsigned long long)(clock64() - cyc_begin);
     }
-    if (rank == 0 && lane == 0 && my_rows) { atomicAdd(&stats->rows_scanned, my_rows); atomicAdd(&stats->bytes_scanned, my_bytes); }
+    if (lane == 0 && (my_units || my_rows)) {
+        atomicAdd(&stats->units_scanned, my_units);
+        atomicAdd(&stats->bytes_scanned, my_units * (unsigned long long)(UC * 256));
+        if (my_rows) atomicAdd(&stats->rows_scanned, my_rows);
+    }
     cluster.sync();   // no CTA may exit while peers can still read its shared memory
 }
 
 template <int CS, int CT, int UC, bool PROF>
-static int launch_cluster(dipb_ctx* c, int n, void** args, int* LS_out, int* HC, int max_helper_clusters, bool* ok) {
+static int launch_cluster(dipb_ctx* c, int n, void** args, int* LS_out, int* HC, int* PARTS, int max_helper_clusters, bool* ok) {
     const int chunks = (n + 31) / 32;
     const int LS = ((chunks + CS - 1) / CS) * 32;
+    *PARTS = ((chunks + CS - 1) / CS + UC - 1) / UC;      // scan units per row and CTA
+    if (*PARTS > MAXPARTS) { *ok = false; return 0; }
     const size_t smem = cluster_smem_bytes(LS, chunks);
     auto kern = nj_cluster_kernel<CS, CT, UC, PROF>;
     *ok = false;
@@ -766,7 +891,8 @@ bool nj_cluster_fits(int n) {
     // device cannot co-schedule 16 CTAs and the 8-CTA layout is too large, nj_cluster_loop reports DIPB_E_UNSUPPORTED
     const int chunks = (n + 31) / 32;
     const int LS = ((chunks + 15) / 16) * 32;
-    return n < 131072 && cluster_smem_bytes(LS, chunks) <= 200u * 1024u;   // (the doorbell packs indices in 17 bits)
+    // (the doorbell packs indices in 17 bits; the unit list of a staged tile holds 12 units per row: 49 152 tips)
+    return n < 131072 && cluster_smem_bytes(LS, chunks) <= 200u * 1024u && (LS / 32 + 7) / 8 <= 12;
 }
 
 int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* c0, int32_t* c1, double* l0, double* l1) {
@@ -784,6 +910,11 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     NJCtl* ctl = nullptr;
     int2* log_xy = nullptr;
     double2* log_bl = nullptr;
+    unsigned int* Kb = nullptr;
+    // unit keys: n rows x (CS * PARTS) keys; CS * PARTS <= chunks / UC + 2 * CS for either cluster size (UC >= 4)
+    const size_t kb_bytes = sizeof(unsigned int) * (size_t)n * ((size_t)((n + 31) / 32) / 4 + 32);
+    DIPB_CUDA(pool_alloc(c, (void**)&Kb, kb_bytes));
+    DIPB_CUDA(cudaMemsetAsync(Kb, 0xff, kb_bytes, c->stream));
     DIPB_CUDA(pool_alloc(c, (void**)&sel, sizeof(int) * n));
     DIPB_CUDA(pool_alloc(c, (void**)&stats, sizeof(CStats)));
     DIPB_CUDA(pool_alloc(c, (void**)&ctl, sizeof(NJCtl)));
@@ -809,25 +940,27 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     const int want = force ? atoi(force) : 16;
     const char* hp = getenv("DIPB_NJ_HELPERS");      // helper clusters for the column stores (default: all that fit, at most 7)
     const int max_helpers = hp ? atoi(hp) : 7;
-    int used = 0, HC = 0, LS = 0;
+    int used = 0, HC = 0, LS = 0, PARTS = 0;
     bool ok = false;
     int rc = 0;
-    void* args[] = {&Dp, &ld, &U, &u, &sel, &stats, &log_xy, &log_bl, &n_total, &LS, &dmax, &ctl, &HC};
+    int dbg = getenv("DIPB_NJ_DBG") ? atoi(getenv("DIPB_NJ_DBG")) : 0;   // bit 0: every unit of a selected row is read (full rescans)
+    double slack_merges = getenv("DIPB_NJ_SLACK") ? atof(getenv("DIPB_NJ_SLACK")) : 256.0;
+    void* args[] = {&Dp, &ld, &U, &u, &sel, &stats, &log_xy, &log_bl, &n_total, &LS, &dmax, &ctl, &HC, &Kb, &PARTS, &dbg, &slack_merges};
     // 1024 threads, 8 loads in flight per lane: measured best of {512, 1024} x {8, 16} (profiles/r1_nj_cluster_tuning.json)
     const char* e_uc = getenv("DIPB_NJ_UC");
     const int uc = e_uc ? atoi(e_uc) : 8;
     if (want >= 16) {
-        if (profile) rc = launch_cluster<16, 1024, 8, true>(c, n, args, &LS, &HC, max_helpers, &ok);
-        else if (uc == 4) rc = launch_cluster<16, 1024, 4, false>(c, n, args, &LS, &HC, max_helpers, &ok);
-        else rc = launch_cluster<16, 1024, 8, false>(c, n, args, &LS, &HC, max_helpers, &ok);
+        if (profile) rc = launch_cluster<16, 1024, 8, true>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok);
+        else if (uc == 4) rc = launch_cluster<16, 1024, 4, false>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok);
+        else rc = launch_cluster<16, 1024, 8, false>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok);
         used = 16;
     }
     if (!rc && !ok) {
-        rc = profile ? launch_cluster<8, 1024, 8, true>(c, n, args, &LS, &HC, max_helpers, &ok) : launch_cluster<8, 1024, 8, false>(c, n, args, &LS, &HC, max_helpers, &ok);
+        rc = profile ? launch_cluster<8, 1024, 8, true>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok) : launch_cluster<8, 1024, 8, false>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok);
         used = 8;
     }
     if (!rc && !ok) { set_error("nj_cluster: no cluster configuration fits this device"); rc = DIPB_E_UNSUPPORTED; }
-    if (rc) { pool_free(c, sel); pool_free(c, stats); pool_free(c, ctl); pool_free(c, log_xy); pool_free(c, log_bl); return rc; }
+    if (rc) { pool_free(c, sel); pool_free(c, stats); pool_free(c, ctl); pool_free(c, log_xy); pool_free(c, log_bl); pool_free(c, Kb); return rc; }
     c->launches++;
     lap(1);
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -866,21 +999,21 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     c->nj_iterations = hs.iters;
     c->nj_bytes_scanned = hs.bytes_scanned;
     if (profile) {
-        const char* nm[12] = {"D pick + pool", "A update + push", "barrier 1", "B1 canonical sum", "B1 pool eval + push", "barrier 2",
-                              "B2 fold + select", "barrier 3", "C stage tile", "C scan units", "C keys + reduce + publish", "barrier 4"};
+        const char* nm[12] = {"D pick + pool", "A update + pool eval + push", "barrier 1", "B canonical sum + bell", "B upper bound", "(unused)",
+                              "B fold + select", "barrier 2", "C stage tile + unit keys", "C scan units", "C keys + reduce + publish", "barrier 3"};
         fprintf(stderr, "[nj_cluster] main loop: %.1f ms, %.3f G cycles -> SM clock %.0f MHz while it ran\n", hs.t_ns * 1e-6, hs.t_cycles * 1e-9,
                 hs.t_ns ? 1e3 * (double)hs.t_cycles / (double)hs.t_ns : 0.0);
         fprintf(stderr, "[nj_cluster] rescans of rank 0's rows: %llu without a tracked partner, %llu partner is a contender, %llu runner-up bound reached ub\n",
                 hs.cyc[12], hs.cyc[13], hs.cyc[14]);
         double tot = 0;
         for (int k = 0; k < 12; k++) tot += (double)hs.cyc[k];
-        fprintf(stderr, "[nj_cluster] n=%d cluster=%d helper_ctas=%d iters=%llu rows_scanned=%llu (%.1f/iter)\n", n, used, HC, hs.iters,
-                hs.rows_scanned, hs.iters ? (double)hs.rows_scanned / hs.iters : 0.0);
+        fprintf(stderr, "[nj_cluster] n=%d cluster=%d helper_ctas=%d iters=%llu rows_selected=%llu (%.1f/iter) units_scanned=%llu (%.1f/iter, %d per full row)\n", n, used, HC, hs.iters,
+                hs.rows_scanned, hs.iters ? (double)hs.rows_scanned / hs.iters : 0.0, hs.units_scanned, hs.iters ? (double)hs.units_scanned / hs.iters : 0.0, used * PARTS);
         for (int k = 0; k < 12; k++)
             fprintf(stderr, "[nj_cluster]   %-26s %8.0f cyc/iter  %5.1f%%\n", nm[k], hs.iters ? hs.cyc[k] / (double)hs.iters : 0.0,
                     tot > 0 ? 100.0 * hs.cyc[k] / tot : 0.0);
     }
-    pool_free(c, sel); pool_free(c, stats); pool_free(c, ctl); pool_free(c, log_xy); pool_free(c, log_bl);
+    pool_free(c, sel); pool_free(c, stats); pool_free(c, ctl); pool_free(c, log_xy); pool_free(c, log_bl); pool_free(c, Kb);
     lap(4);
     if (profile) fprintf(stderr, "[nj_cluster] host ms: alloc+scale %.1f, launch %.1f, kernel wait %.1f, replay %.1f, profile print + frees %.1f\n", t_host[0], t_host[1], t_host[2], t_host[3], t_host[4]);
     return 0;
