@@ -67,18 +67,20 @@ struct CRec {                 // a CTA's best candidate of one scan
     int i, j;
 };
 
-struct NJMsg { double ux, uy, C, pad; };   // u of the new node, u of the node moved into y, drift sum: what a key needs
 struct NJCtl {                     // main cluster -> helper clusters doorbell (global memory)
-    unsigned long long bell;       // one word, one release store: [seq:13 | x:17 | y:17 | n:17]; all ones = quit.
+    unsigned long long bell;       // one word, one plain store: [seq:13 | x:17 | y:17 | n:17]; all ones = quit.
                                    // x: new node, y: slot that received the old last row when y < n, seq: merge number
     unsigned int done;             // helper CTAs that finished, cumulative
     unsigned int pad;
-    NJMsg msg[8];                  // payload of merge seq in msg[seq & 7], written before the bell
+    // What the helpers need for the unit-key fold is only known a little later than the bell (after the canonical sum):
+    // u of the new node (rounded up), u of the node moved into y (rounded up), drift sum C (rounded down), each as
+    // (merge number << 32) | fp32 bits.  A word is its own arrival flag: no fence, no second doorbell.
+    unsigned long long pw[3];
 };
 
 struct CStats {
     unsigned long long rows_scanned, bytes_scanned, iters, units_scanned;
-    unsigned long long cyc[24];
+    unsigned long long cyc[32];
     unsigned long long t_ns, t_cycles;   // whole main loop: globaltimer ns and SM cycles (their ratio is the SM clock)
 };
 
@@ -129,6 +131,14 @@ __device__ __forceinline__ int ld_peer_s32(const int* p, int rank) {
     return v;
 }
 __device__ __forceinline__ unsigned int key_of(double v) { return enc_f32(__double2float_rd(v)); }
+// a / d, correctly rounded, from r = RN(1 / d): q = RN(a r), rem = a - q d (exact in the FMA), RN(q + rem r) is the IEEE quotient
+// (Markstein 1990; d = n - 3 is a small integer, no overflow or underflow on this path).  Bit-identical to the division the
+// reference and the oracle perform, at 3 instructions per row instead of the ~14 of a division; checked against a / d for
+// every d <= 140 000 on 56 M operands (tools/experiments/markstein_div.c) and by the bit-exact tree tests.
+__device__ __forceinline__ double div_rn(double a, double d, double r) {
+    const double q = __dmul_rn(a, r);
+    return __fma_rn(__fma_rn(-q, d, a), r, q);
+}
 
 // ---- candidate order (reference scan order, nj_bound.cuh), out of line: exact ties are rare
 __device__ __noinline__ bool tie_before(int ia, int ja, int ib, int jb, int n) {
@@ -162,7 +172,7 @@ template <int CS, int CT, int UC, bool PROF>   // UC: column chunks per scan uni
 __global__ void __launch_bounds__(CT, 1)
 nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ U0, const double* __restrict__ u0,
                   int* __restrict__ sel_rows, CStats* stats, int2* __restrict__ log_xy, double2* __restrict__ log_bl,
-                  int n_total, int LS, double dmax, NJCtl* ctl, int HC, unsigned int* __restrict__ Kb, int PARTS, int dbg, double slack_merges) {
+                  int n_total, int LS, double dmax, NJCtl* ctl, int HC, unsigned int* __restrict__ Kb, int PARTS, int dbg, double slack_merges, double* __restrict__ R) {
     if (blockIdx.x >= CS) {
         // ---- helper clusters (the other GPCs): transpose rows x and y of each published merge into columns x and
         // y, and fold those two new columns into the unit keys of every row.  These 2n scattered 8-byte stores (and
@@ -170,7 +180,9 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
         // itself (~1 us per 1000 tips); spread over the other GPCs they are off the critical path.
         const int hc = (int)blockIdx.x - CS, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
         __shared__ unsigned long long s_msg;
+        __shared__ float s_pw[3];
         unsigned long long seen = 0;
+        unsigned int hit = 0;
         for (;;) {
             if (tid == 0) {
                 unsigned long long q;
@@ -187,24 +199,50 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             if (q == KMAX) return;
             seen = q;
             const int x = (int)((q >> 34) & 0x1ffffu), y = (int)((q >> 17) & 0x1ffffu), n = (int)(q & 0x1ffffu);
-            const NJMsg* mp = &ctl->msg[(q >> 51) & 7];
-            const double ux = __ldcg(&mp->ux), uy = __ldcg(&mp->uy), Cm = __ldcg(&mp->C);
-            const size_t kx = (size_t)((x >> 5) % CS) * PARTS + ((x >> 5) / CS) / UC;    // unit of column x within a row's keys
-            const size_t ky = (size_t)((y >> 5) % CS) * PARTS + ((y >> 5) / CS) / UC;
-            const size_t krow = (size_t)CS * PARTS;
+            hit++;                                                  // merges are published one by one: this is merge number `hit`
+            const double* Rx = R + (size_t)(hit & 1) * 2 * ld;      // the new rows x and y as phase A left them (scratch)
+            const double* Ry = Rx + ld;
+            const bool ymoved = y < n;
+            // key rows of the units that hold columns x and y (Kb is [cta][part][row]: this fold is coalesced over the rows)
+            const size_t KLD = (size_t)((n_total + 31) & ~31);
+            unsigned int* const Kx = Kb + ((size_t)((x >> 5) % CS) * PARTS + ((x >> 5) / CS) / UC) * KLD;
+            unsigned int* const Ky = Kb + ((size_t)((y >> 5) % CS) * PARTS + ((y >> 5) / CS) / UC) * KLD;
             const int nch = (n + 31) >> 5;
+            // 1. rows and columns x, y of D
+            double vx[2], fy[2];
+            int cnt = 0;
             for (int c = hc + w * HC; c < nch; c += HC * (CT / 32)) {
                 const int i = c * 32 + lane;
-                if (i < n && i != x && i != y) {
-                    const double vx = __ldcg(&D[(size_t)x * ld + i]);
-                    D[(size_t)i * ld + x] = vx;
-                    atomicMin(&Kb[(size_t)i * krow + kx], key_of((vx - ux) + Cm));
-                    if (y < n) {
-                        const double fy = __ldcg(&D[(size_t)y * ld + i]);
-                        D[(size_t)i * ld + y] = fy;
-                        atomicMin(&Kb[(size_t)i * krow + ky], key_of((fy - uy) + Cm));
+                double v = 0.0, f = 0.0;
+                if (i < n) {
+                    if (i != x) { v = __ldcg(&Rx[i]); D[(size_t)x * ld + i] = v; if (!(dbg & 8)) D[(size_t)i * ld + x] = v; }
+                    if (ymoved && i != y) { f = __ldcg(&Ry[i]); D[(size_t)y * ld + i] = f; if (!(dbg & 8)) D[(size_t)i * ld + y] = f; }
+                }
+                if (cnt < 2) { vx[cnt] = v; fy[cnt] = f; }
+                cnt++;
+            }
+            // 2. the two new columns folded into the unit keys of every other row, once the payload has arrived
+            if (tid == 0) {
+                unsigned long long a0, a1, a2;
+                do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a0) : "l"(&ctl->pw[0]) : "memory"); } while ((unsigned int)(a0 >> 32) != hit);
+                do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a1) : "l"(&ctl->pw[1]) : "memory"); } while ((unsigned int)(a1 >> 32) != hit);
+                do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a2) : "l"(&ctl->pw[2]) : "memory"); } while ((unsigned int)(a2 >> 32) != hit);
+                s_pw[0] = __uint_as_float((unsigned int)a0); s_pw[1] = __uint_as_float((unsigned int)a1); s_pw[2] = __uint_as_float((unsigned int)a2);
+            }
+            __syncthreads();
+            const double ux = (double)s_pw[0], uy = (double)s_pw[1], Cm = (double)s_pw[2];
+            cnt = 0;
+            for (int c = hc + w * HC; c < nch; c += HC * (CT / 32)) {
+                const int i = c * 32 + lane;
+                if (i < n && i != x && i != y && !(dbg & 4)) {
+                    const double v = cnt < 2 ? vx[cnt < 2 ? cnt : 0] : __ldcg(&Rx[i]);
+                    atomicMin(&Kx[i], key_of((v - ux) + Cm));
+                    if (ymoved) {
+                        const double f = cnt < 2 ? fy[cnt < 2 ? cnt : 0] : __ldcg(&Ry[i]);
+                        atomicMin(&Ky[i], key_of((f - uy) + Cm));
                     }
                 }
+                cnt++;
             }
             __threadfence();
             __syncthreads();
@@ -216,8 +254,10 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     constexpr int NW = CT / 32;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int chunks_total = (n_total + 31) >> 5;
-    const size_t krow = (size_t)CS * PARTS;            // unit keys per row
-    unsigned int* const Kmine = Kb + (size_t)rank * PARTS;   // + row * krow + part
+    // unit keys, [cta][part][row] (row stride KLD): the per-merge fold of a new column into one unit of EVERY row touches
+    // one contiguous key row (120 KB at 30 000 tips) instead of one cache line per row (7.7 MB), so the keys stay in L2
+    const size_t KLD = (size_t)((n_total + 31) & ~31);
+    unsigned int* const Kmine = Kb + (size_t)rank * PARTS * KLD;   // + part * KLD + row
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* U_s = reinterpret_cast<double*>(smem_raw);   // [2][LS] row sums of owned rows; buffer `cur` is valid, A writes the other
@@ -246,15 +286,13 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     __shared__ double s_red[MAXW], s_red2[MAXW], s_blk[128 + 16];   // s_blk: one sum per 1024-row block (n <= 131 072)
     __shared__ double s_total, s_C, s_uy;   // s_uy (rank 0's copy): u of the node moved into slot y, pushed by its owner
     __shared__ unsigned int s_sel;          // selected-row counter (rank 0's copy is the live one)
-    __shared__ int s_list[TILE];            // first TILE selected rows, in rank 0's copy (the rest spill to sel_rows in global
-                                            // memory; a list that was just written by 16 SMs reads back slowly from L2)
     __shared__ int pool_i[CPOOL], pool_j[CPOOL];
     __shared__ double pool_d[CPOOL];        // d of a carried pair never changes while both ends survive
     __shared__ double pool_t[CPOOL];        // its value at the last re-evaluation: new candidates replace worse ones only
     __shared__ int s_pool_head, s_nsel;
     __shared__ unsigned int s_nunits;          // live scan units of the staged tile
     __shared__ unsigned short s_ulist[TILE * 12];   // (staged row << 5) | unit, in no particular order
-    __shared__ unsigned long long s_cyc[24];   // rank 0, thread 0: cycles per phase (DIPB_NJ_PROFILE)
+    __shared__ unsigned long long s_cyc[32];   // rank 0, thread 0: cycles per phase (DIPB_NJ_PROFILE)
 
     // ---- load owned state
     for (int s = tid; s < LS; s += CT) {
@@ -268,7 +306,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     if (tid == 0) t_row[0] = 0;
     for (int p = tid; p < CPOOL; p += CT) { pool_i[p] = -1; pool_j[p] = -1; pool_t[p] = 1e300; }
     if (tid == 0) { s_pool_head = 0; s_sel = 0; s_uy = 0.0; }
-    if (tid < 24) s_cyc[tid] = 0;
+    if (tid < 32) s_cyc[tid] = 0;
     __syncthreads();
     cluster.sync();
 
@@ -285,8 +323,9 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     // Partner records: the CTA whose slice holds a scanned row's minimum (its key equals the combined K1) tells the
     // owner the column and the exact distance, so that the owner can re-evaluate that pair exactly instead of
     // rescanning the row while only the bound has drifted.  Runs after a cluster barrier that follows the key flush.
-    auto partner_records = [&](int tn, bool merged, int x, int y, int n) {
-        for (int k = tid; k < tn; k += CT) {
+    auto partner_records = [&](int tn, bool merged, int x, int y, int n, int iter) {
+        for (int k = w; k < tn; k += NW) {        // one warp per row (divergent DSMEM targets serialise within a warp)
+            if (lane != 0) continue;
             const unsigned long long best = t_best[k];
             const unsigned int k1 = (unsigned int)(best >> 32);
             if (k1 == K32MAX) continue;
@@ -297,6 +336,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             double da;
             if (merged && r != x && r != y && j1 == x) da = t_v[k];
             else if (merged && r != x && r != y && j1 == y && y < n) da = t_f[k];
+            else if (merged && r == x) da = __ldcg(&R[(size_t)(iter & 1) * 2 * ld + j1]);          // (rows x, y: scratch, see phase A)
+            else if (merged && r == y && y < n) da = __ldcg(&R[((size_t)(iter & 1) * 2 + 1) * ld + j1]);
             else da = __ldcg(&D[(size_t)r * ld + j1]);
             st_peer_s32(&a_s[rs], ro, j1);
             st_peer_f64(&da_s[rs], ro, da);
@@ -325,77 +366,108 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             CL_MARK(0);
             const int last = n - 1;
             const double den_new = (double)(n - 3);
+            const double rden = 1.0 / den_new;
             const int nchunk = (last + 31) >> 5;               // chunks holding rows < last
+            double* const Rx = R + (size_t)(iter & 1) * 2 * ld;  // scratch rows of this merge
+            double* const Ry = Rx + ld;
             const double* Uo = U_s + cur * LS;                  // pre-merge sums (read by every CTA through DSMEM)
             double* Un = U_s + (cur ^ 1) * LS;                  // post-merge sums
             // carried candidates of this CTA, re-evaluated exactly with the post-merge u of their ends (none touches x;
-            // an end in slot y is the node that lived in `last`): same expressions as the owners use below
-            // (done by the last four warps: they own one chunk less of the update below than the first ones)
-            double pv = 1e300;
-            const int ptid = tid - (CT - CPOOL);
-            if (ptid >= 0 && n > 3 && pool_i[ptid] >= 0) {
-                double un2[2];
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int p = e == 0 ? pool_i[ptid] : pool_j[ptid];
-                    const int src = p == y ? last : p;
-                    const double a = __ldcg(&D[(size_t)x * ld + src]), b = __ldcg(&D[(size_t)y * ld + src]);
-                    double Ui = ld_peer_f64(&Uo[((src >> 5) / CS) * 32 + (src & 31)], (src >> 5) % CS);
-                    const double val = (a + b - dxy) * 0.5;
-                    Ui += -a - b + val;
-                    un2[e] = Ui / den_new;
-                }
-                pv = (pool_d[ptid] - un2[0]) - un2[1];
-            }
-            if (ptid >= 0) {
-                pool_t[ptid] = pv;
-                pv = warp_min_f64(pv);
-                if (lane == 0) s_red2[w - (NW - CPOOL / 32)] = pv;
+            // an end in slot y is the node that lived in `last`): same expressions as the owners use below.  Four candidates
+            // per warp, one lane per (candidate, end); the loads are issued here and consumed after the update loop.
+            constexpr int PCW = CPOOL / (CT / 32);              // candidates per warp (4 at 1024 threads)
+            static_assert(PCW * (CT / 32) == CPOOL && 2 * PCW <= 32, "pool layout: PCW candidates per warp, two lanes each");
+            double p_a = 0.0, p_b = 0.0, p_U = 0.0;
+            const int pc = w * PCW + (lane >> 1);               // candidate of this lane (lanes 0 .. 2 PCW - 1)
+            const int pend = (lane < 2 * PCW && n > 3 && pool_i[pc] >= 0) ? ((lane & 1) ? pool_j[pc] : pool_i[pc]) : -1;
+            if (pend >= 0) {
+                const int src = pend == y ? last : pend;
+                p_a = __ldcg(&D[(size_t)x * ld + src]); p_b = __ldcg(&D[(size_t)y * ld + src]);
+                p_U = ld_peer_f64(&Uo[((src >> 5) / CS) * 32 + (src & 31)], (src >> 5) % CS);
             }
             double dmx = -1e300;
-            for (int lw = w; lw * CS + rank < nchunk; lw += NW) {
-                const int i = (lw * CS + rank) * 32 + lane;
-                const int s = lw * 32 + lane;
-                double slot = 0.0;
-                if (i < last && i != x) {
-                    // slot y receives the node that lived in row `last`: same formulas, sources taken from `last`
-                    const bool isy = (i == y);
-                    const int src = isy ? last : i;
-                    const double a = __ldcg(&D[(size_t)x * ld + src]), b = __ldcg(&D[(size_t)y * ld + src]);
-                    const double far = __ldcg(&D[(size_t)last * ld + i]);
-                    double Ui = Uo[s], uo = u_s[s];
-                    if (isy) {
-                        const int lo = (last >> 5) % CS, ls = ((last >> 5) / CS) * 32 + (last & 31);
-                        Ui = ld_peer_f64(&Uo[ls], lo);
-                        uo = ld_peer_f64(&u_s[ls], lo);
+            // A warp owns chunks lw = w, w + NW, ... (two at 30 000 tips): the loads of up to AB of them are issued before any
+            // is consumed -- one exposed memory round trip per merge instead of one per chunk (measured 5.4 k -> cycles below)
+            constexpr int AB = CT >= 1024 ? 3 : (CT >= 512 ? 4 : 8);
+            for (int lwb = w; lwb * CS + rank < nchunk; lwb += NW * AB) {
+                double la[AB], lb[AB], lf[AB];
+#pragma unroll
+                for (int c = 0; c < AB; c++) {
+                    const int lw = lwb + c * NW;
+                    const int i = (lw * CS + rank) * 32 + lane;
+                    la[c] = lb[c] = lf[c] = 0.0;
+                    if (lw * CS + rank < nchunk && i < last && i != x) {
+                        const int src = i == y ? last : i;
+                        la[c] = __ldcg(&D[(size_t)x * ld + src]); lb[c] = __ldcg(&D[(size_t)y * ld + src]);
+                        lf[c] = __ldcg(&D[(size_t)last * ld + i]);
                     }
-                    const double val = (a + b - dxy) * 0.5;
-                    Ui += -a - b + val;
-                    Un[s] = Ui;
-                    f_s[s] = far;                        // rows x and y of D are written from v_s / f_s after the barrier (phase B)
-                    slot = val;
-                    if (n > 3) {
-                        const double un = Ui / den_new;
-                        dmx = fmax(dmx, un - uo);
-                        u_s[s] = un;
-                        if (isy) st_peer_f64(&s_uy, 0, un);      // the helpers' key fold needs it (rank 0 rings the bell)
-                    }
-                } else if (i == x) Un[s] = 0.0;            // replaced by the canonical sum in phase B
-                v_s[s] = slot;
-                // canonical block sum, level 1: this chunk's stride-halving tree, pushed to every CTA
-                const double csum = __shfl_sync(0xffffffffu, warp_tree_sum(slot), 0);
-                if (lane < CS) st_peer_f64(&cs_all[lw * CS + rank], lane, csum);
+                }
+                if (PROF && lwb == w) { CL_MARK(18); asm volatile("" ::"d"(la[0]), "d"(lb[0]), "d"(lf[0])); CL_MARK(19); }
+#pragma unroll
+                for (int c = 0; c < AB; c++) {
+                    const int lw = lwb + c * NW;
+                    if (!(lw * CS + rank < nchunk)) break;
+                    const int i = (lw * CS + rank) * 32 + lane;
+                    const int s = lw * 32 + lane;
+                    double slot = 0.0;
+                    if (i < last && i != x) {
+                        // slot y receives the node that lived in row `last`: same formulas, sources taken from `last`
+                        const bool isy = (i == y);
+                        const double a = la[c], b = lb[c], far = lf[c];
+                        double Ui = Uo[s], uo = u_s[s];
+                        if (isy) {
+                            const int lo = (last >> 5) % CS, ls = ((last >> 5) / CS) * 32 + (last & 31);
+                            Ui = ld_peer_f64(&Uo[ls], lo);
+                            uo = ld_peer_f64(&u_s[ls], lo);
+                        }
+                        const double val = (a + b - dxy) * 0.5;
+                        Ui += -a - b + val;
+                        Un[s] = Ui;
+                        f_s[s] = far;
+                        // the new rows x and y go to a scratch pair, not into D: phase A must not write D, because every CTA
+                        // still reads the pre-merge rows x and y for the ends of its carried candidates; the helpers copy the
+                        // scratch rows into D (rows and columns), the scan of this merge reads them from the scratch
+                        Rx[i] = val;
+                        if (isy) Ry[x] = val; else Ry[i] = far;
+                        slot = val;
+                        if (n > 3) {
+                            const double un = div_rn(Ui, den_new, rden);
+                            dmx = fmax(dmx, un - uo);
+                            u_s[s] = un;
+                            if (isy) st_peer_f64(&s_uy, 0, un);      // the helpers' key fold needs it (rank 0 rings the bell)
+                        }
+                    } else if (i == x) Un[s] = 0.0;            // replaced by the canonical sum in phase B
+                    v_s[s] = slot;
+                    // canonical block sum, level 1: this chunk's stride-halving tree, pushed to every CTA
+                    const double csum = __shfl_sync(0xffffffffu, warp_tree_sum(slot), 0);
+                    if (lane < CS) st_peer_f64(&cs_all[lw * CS + rank], lane, csum);
+                }
             }
+            CL_MARK(20);
             // unit keys of the row that moves from `last` into slot y: every CTA copies its own units
-            if (y < last && tid >= CT - 32 && lane < PARTS) Kmine[(size_t)y * krow + lane] = __ldcg(&Kmine[(size_t)last * krow + lane]);
+            if (y < last && tid >= CT - 32 && lane < PARTS) Kmine[(size_t)lane * KLD + y] = __ldcg(&Kmine[(size_t)lane * KLD + last]);
+            {
+                double un = 0.0;
+                if (pend >= 0) {
+                    const double val = (p_a + p_b - dxy) * 0.5;
+                    p_U += -p_a - p_b + val;
+                    un = div_rn(p_U, den_new, rden);
+                }
+                const double uo2 = __shfl_xor_sync(0xffffffffu, un, 1);
+                double pv = 1e300;
+                if (pend >= 0 && !(lane & 1)) pv = (pool_d[pc] - un) - uo2;
+                if (lane < 2 * PCW && !(lane & 1)) pool_t[pc] = pv;
+                pv = warp_min_f64(pv);
+                if (lane == 0) s_red2[w] = pv;
+            }
             dmx = warp_max_f64(dmx);
             if (lane == 0) s_red[w] = dmx;
+            CL_MARK(21);
             __syncthreads();
+            CL_MARK(22);
             if (w == 0) {
                 const double m = warp_max_f64(lane < NW ? s_red[lane] : -1e300);
-                double pm = s_red2[0];
-#pragma unroll
-                for (int q = 1; q < CPOOL / 32; q++) pm = fmin(pm, s_red2[q]);
+                const double pm = warp_min_f64(lane < NW ? s_red2[lane] : 1e300);
                 if (lane < CS) { st_peer_f64(&drift_all[rank], lane, m); st_peer_f64(&ubmin_all[rank], lane, pm); }
             }
             cur ^= 1;
@@ -404,24 +476,18 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             CL_MARK(2);
 
             // ------------------------------------------------------------ B: U[x], drift, upper bound, fold, select
-            // Rows x and y of D, from the values phase A left in v_s / f_s.  Not written in phase A itself: there every CTA
-            // still reads the pre-merge rows x and y for the ends of its carried candidates.  Coalesced; visible to the
-            // scan (and, through the bell rung after the next barrier, to the helpers that transpose them into columns).
-            for (int lw = w; lw * CS + rank < nchunk; lw += NW) {
-                const int i = (lw * CS + rank) * 32 + lane;
-                const int s = lw * 32 + lane;
-                if (i < last && i != x) {
-                    const double val = v_s[s];
-                    D[(size_t)x * ld + i] = val;
-                    if (i == y) D[(size_t)y * ld + x] = val;
-                    else D[(size_t)y * ld + i] = f_s[s];
-                }
-            }
             n = last;
             if (n <= 2) {
-                // last merge: nj_finish_kernel reads D[0][1], a column entry when x == 1
-                if (rank == 0 && tid < n && tid != x && tid != y) D[(size_t)tid * ld + x] = v_s[tid];
+                // last merge: nj_finish_kernel reads D[0][1] = distance of the two nodes left (slots 0 and 1; x is one of them)
+                if (rank == 0 && tid == 0) D[1] = x == 0 ? v_s[1] : v_s[0];
                 break;
+            }
+            if (HC > 0 && rank == 0 && tid == 32) {
+                // the scratch rows are complete and fenced (every thread ran MEMBAR.GPU before the barrier), so the bell is
+                // one relaxed store; merge numbers differ in the low 13 bits between consecutive merges
+                const unsigned long long q = ((unsigned long long)(iter & 0x1fff) << 51) | ((unsigned long long)x << 34) |
+                                             ((unsigned long long)y << 17) | (unsigned long long)n;
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->bell), "l"(q) : "memory");
             }
             {
                 // canonical sum, level 2: 1024-row blocks (32 chunk sums, stride-halving tree), then blocks ascending
@@ -446,9 +512,14 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     s_total = acc;
                     s_C = C + drift;
                     if (HC > 0 && rank == 0) {
-                        // payload of this merge's bell (rung after the next barrier, whose fence publishes it)
-                        NJMsg* mp = &ctl->msg[iter & 7];
-                        mp->ux = acc / (double)(n - 2); mp->uy = s_uy; mp->C = C + drift;
+                        // what the helpers' key fold needs, each word tagged with the merge number (see NJCtl)
+                        const unsigned long long tag = (unsigned long long)(unsigned int)iter << 32;
+                        const unsigned long long w0 = tag | __float_as_uint(__double2float_ru(acc / (double)(n - 2)));
+                        const unsigned long long w1 = tag | __float_as_uint(__double2float_ru(s_uy));
+                        const unsigned long long w2 = tag | __float_as_uint(__double2float_rd(C + drift));
+                        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->pw[0]), "l"(w0) : "memory");
+                        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->pw[1]), "l"(w1) : "memory");
+                        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->pw[2]), "l"(w2) : "memory");
                     }
                 }
                 __syncthreads();
@@ -464,7 +535,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 u_s[sx] = ux;
                 // the moved row's unit key of the new column (its other units were copied in phase A; row y is not among
                 // the rows the helpers fold)
-                if (y < n) atomicMin(&Kmine[(size_t)y * krow + ((x >> 5) / CS) / UC],
+                if (y < n) atomicMin(&Kmine[(size_t)(((x >> 5) / CS) / UC) * KLD + y],
                                      key_of((ld_peer_f64(&v_s[((y >> 5) / CS) * 32 + (y & 31)], (y >> 5) % CS) - ux) + C));
             }
             ub = ubmin_all[0];
@@ -525,8 +596,18 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         if (lane == 0) base = atomicAdd(sel0, (unsigned int)__popc(bal));
                         base = __shfl_sync(0xffffffffu, base, 0);
                         if (take) {
+                            // a selected row goes, with its u, v, f, straight into every CTA's staging arrays: the scan phase
+                            // then starts from local shared memory (pulling the list from rank 0 and the row state from the
+                            // owners cost two dependent DSMEM round trips, the first one 16 CTAs deep on one SM)
                             const unsigned int pos = base + __popc(bal & ((1u << lane) - 1u));
-                            if (pos < (unsigned int)TILE) st_peer_s32(&s_list[pos], 0, i); else sel_rows[pos] = i;
+                            if (pos < (unsigned int)TILE) {
+                                const double us = i == x ? ux : u_s[s], vs = v_s[s], fs = f_s[s];
+#pragma unroll 4
+                                for (int q = 0; q < CS; q++) {
+                                    st_peer_s32(&t_row[pos], q, i);
+                                    st_peer_f64(&t_u[pos], q, us); st_peer_f64(&t_v[pos], q, vs); st_peer_f64(&t_f[pos], q, fs);
+                                }
+                            } else sel_rows[pos] = i;
                         }
                     }
                 }
@@ -543,32 +624,42 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (take) {
                     const unsigned int pos = base + __popc(bal & ((1u << lane) - 1u));
-                    if (pos < (unsigned int)TILE) st_peer_s32(&s_list[pos], 0, i); else sel_rows[pos] = i;
+                    if (pos < (unsigned int)TILE) {
+                        const double us = u_s[lw * 32 + lane];
+                        for (int q = 0; q < CS; q++) {
+                            st_peer_s32(&t_row[pos], q, i);
+                            st_peer_f64(&t_u[pos], q, us); st_peer_f64(&t_v[pos], q, 0.0); st_peer_f64(&t_f[pos], q, 0.0);
+                        }
+                    } else sel_rows[pos] = i;
                 }
             }
         }
         CL_MARK(6);
         cluster.sync();
         CL_MARK(7);
+        if (PROF && rank == 0 && tid == 0) {
+            // probe: how long does one global load of a fixed, L2-resident word take right after the barrier?
+            unsigned int pv_;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(pv_) : "l"(&ctl->pad) : "memory");
+            asm volatile("" ::"r"(pv_));
+            CL_MARK(24);
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(pv_) : "l"(&ctl->pad) : "memory");
+            asm volatile("" ::"r"(pv_));
+            CL_MARK(25);
+        }
 
         // ---------------------------------------------------------------- C: scan the qualifying units of the selected rows
         {
             if (tid == 0) { s_nsel = (int)*sel0; s_nunits = 0; }
             const bool merged = !first;
             const bool ymoved = merged && y < n;               // false when y was the last slot: nothing moved into it
-            if (HC > 0 && merged && rank == 0 && tid == 0) {
-                // rows x and y and the payload are complete and fenced (every thread ran MEMBAR.GPU before the barrier), so
-                // the bell is one relaxed store; merge numbers differ in the low 13 bits between consecutive merges
-                const unsigned long long q = ((unsigned long long)(iter & 0x1fff) << 51) | ((unsigned long long)x << 34) |
-                                             ((unsigned long long)y << 17) | (unsigned long long)n;
-                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->bell), "l"(q) : "memory");
-            }
             // Without helper clusters the main cluster writes columns x and y (and folds them into the unit keys) itself;
             // the stores ride behind the loads of the scan units, one chunk (64 scattered stores) per warp and unit.
             const int st_nch = (merged && HC == 0) ? (n + 31) >> 5 : 0;
             int st_lw = w;
             __syncthreads();
             const int nsel = s_nsel;
+            CL_MARK(17);
             if (rank == 0 && tid == 0) my_rows += (unsigned long long)nsel;
             const int nch = (n + 31) >> 5;
             const int lch = nch > rank ? (nch - rank + CS - 1) / CS : 0;      // local chunks holding columns < n
@@ -579,13 +670,15 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             const int xlw = (merged && ((x >> 5) % CS) == rank) ? (x >> 5) / CS : -1000000;
             const int ylw = (ymoved && ((y >> 5) % CS) == rank) ? (y >> 5) / CS : -1000000;
             const double uy_loc = ylw >= 0 ? u_s[ylw * 32 + (y & 31)] : 0.0;
+            const double* const Rxs = R + (size_t)(iter & 1) * 2 * ld;
+            const double* const Rys = Rxs + ld;
             // Units are refreshed a little EARLY: a unit whose bound will reach ub within about `slack_merges` merges at
             // the average drift so far is read now, while its row is staged anyway.  Without this every unit drifts to
             // the threshold on its own and costs its row a selection of its own (measured: 129 selected rows per merge
             // instead of 13); with it a row comes back when its runner-up does, as with whole-row rescans.
             const double slack = iter > 0 ? slack_merges * (fabs(C) / (double)iter) : 0.0;   // (C may be negative: never tighten)
-            const size_t kxg = (size_t)((x >= 0 ? x >> 5 : 0) % CS) * PARTS + ((x >= 0 ? x >> 5 : 0) / CS) / UC;
-            const size_t kyg = (size_t)((y >= 0 ? y >> 5 : 0) % CS) * PARTS + ((y >= 0 ? y >> 5 : 0) / CS) / UC;
+            unsigned int* const Kxg = Kb + ((size_t)((x >= 0 ? x >> 5 : 0) % CS) * PARTS + ((x >= 0 ? x >> 5 : 0) / CS) / UC) * KLD;
+            unsigned int* const Kyg = Kb + ((size_t)((y >= 0 ? y >> 5 : 0) % CS) * PARTS + ((y >= 0 ? y >> 5 : 0) / CS) / UC) * KLD;
             double bt = 1e300, bd = 0.0, bui = 0.0, buj = 0.0;
             int bi = -1, bj = -1;
             for (int t0 = 0; t0 < nsel || (t0 == 0 && st_nch > 0); t0 += TILE) {
@@ -595,126 +688,150 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     if (tid == 0) s_nunits = 0;
                     __syncthreads();
                 }
-                // stage the tile: row index, u, v, f of the row (owner's shared memory), empty combined minimum, and from
-                // this CTA's unit keys of the row which units must be read and what the others bound
-                for (int k = tid; k < tn; k += CT) {
-                    const int r = t0 + k < TILE ? ld_peer_s32(&s_list[t0 + k], 0) : __ldcg(&sel_rows[t0 + k]);
+                // stage the tile, one WARP per row (a warp whose 32 lanes gather from 32 different CTAs' shared memory pays for
+                // them one after the other: ~1000 cycles per instruction; measured 8 k cycles for 34 rows staged by 34 threads):
+                // row index, u, v, f of the row (owner's shared memory), empty combined minimum, and from this CTA's unit keys of
+                // the row (lane p: unit p) which units must be read and what the others bound
+                for (int k = w * 2 + (lane >> 4); k - (lane >> 4) < tn; k += 2 * NW) {
+                    // half warp per row: lane hl of the half handles unit hl (parts <= 12)
+                    const int hl = lane & 15;
+                    const unsigned int hmask = 0xffffu << (lane & 16);
+                    const bool have = k < tn;
+                    // the first tile was pushed into t_row / t_u / t_v / t_f by the row owners (phase B); later tiles (first
+                    // search, bursts) come from the spill list in global memory and the owners' shared memory
+                    int r = 0;
+                    if (have) r = t0 == 0 ? t_row[k] : __ldcg(&sel_rows[t0 + k]);
                     const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
                     const bool all = first || r == x || (dbg & 1);
-                    const unsigned int* kp = Kmine + (size_t)r * krow;
-                    unsigned int kq[12];
-                    if (!all) {
-#pragma unroll
-                        for (int p = 0; p < 12; p++) kq[p] = p < parts ? __ldcg(&kp[p]) : K32MAX;
-                    }
-                    const double ur = ld_peer_f64(&u_s[rs], ro), vr = ld_peer_f64(&v_s[rs], ro), fr = ld_peer_f64(&f_s[rs], ro);
-                    t_row[k] = r;
-                    t_u[k] = ur; t_v[k] = vr; t_f[k] = fr;
-                    t_best[k] = KMAX;
-                    unsigned int qm = 0, rest = K32MAX;
-                    if (all) qm = parts >= 32 ? 0xffffffffu : ((1u << parts) - 1u);
+                    unsigned int kv = K32MAX;
+                    if (have && !all && hl < parts) kv = __ldcg(&Kmine[(size_t)hl * KLD + r]);
+                    double ur, vr, fr;
+                    if (t0 == 0) { ur = have ? t_u[k] : 0.0; vr = have ? t_v[k] : 0.0; fr = have ? t_f[k] : 0.0; }
                     else {
+                        double g = 0.0;
+                        if (have && hl < 3) g = ld_peer_f64(hl == 0 ? &u_s[rs] : (hl == 1 ? &v_s[rs] : &f_s[rs]), ro);
+                        ur = __shfl_sync(0xffffffffu, g, 0, 16); vr = __shfl_sync(0xffffffffu, g, 1, 16); fr = __shfl_sync(0xffffffffu, g, 2, 16);
+                    }
+                    if (PROF && k == 0) { CL_MARK(15); asm volatile("" ::"r"(kv)); CL_MARK(16); }
+                    bool q = have && hl < parts;
+                    if (!all) {
                         const bool patch = merged && r != y;        // (row y's keys were completed by the owner of column x)
-                        const int xp = (patch && xlw >= 0) ? xlw / UC : -1, yp = (patch && ylw >= 0) ? ylw / UC : -1;
-                        const unsigned int kxv = xp >= 0 ? key_of((vr - ux) + C) : K32MAX;
-                        const unsigned int kyv = yp >= 0 ? key_of((fr - uy_loc) + C) : K32MAX;
-                        auto unit = [&](int p, unsigned int kv) {
-                            if (p == xp && kxv < kv) kv = kxv;      // the merge in flight: the helpers' fold may not have landed
-                            if (p == yp && kyv < kv) kv = kyv;
-                            if (((double)dec_f32(kv) - C) - ur - marg > ub + slack) rest = kv < rest ? kv : rest;
-                            else qm |= 1u << p;
-                        };
-#pragma unroll
-                        for (int p = 0; p < 12; p++) if (p < parts) unit(p, kq[p]);
-                        for (int p = 12; p < parts; p++) unit(p, __ldcg(&kp[p]));
+                        // the merge in flight: the helpers' fold of the two new columns may not have landed
+                        if (patch && xlw >= 0 && hl == xlw / UC) { const unsigned int kxv = key_of((vr - ux) + C); if (kxv < kv) kv = kxv; }
+                        if (patch && ylw >= 0 && hl == ylw / UC) { const unsigned int kyv = key_of((fr - uy_loc) + C); if (kyv < kv) kv = kyv; }
+                        q = q && !(((double)dec_f32(kv) - C) - ur - marg > ub + slack);
                     }
-                    t_qm[k] = qm;
-                    t_k2[k] = rest;
-                    if (qm) {
-                        // live units go to a compact list so that every warp gets about the same number of them
-                        unsigned int pos = atomicAdd(&s_nunits, (unsigned int)__popc(qm));
-                        for (unsigned int m = qm; m; m &= m - 1u) s_ulist[pos++] = (unsigned short)((k << 5) | (__ffs(m) - 1));
+                    const unsigned int qm = (__ballot_sync(0xffffffffu, q) >> (lane & 16)) & 0xffffu;
+                    const unsigned int rest = __reduce_min_sync(hmask, (have && hl < parts && !q) ? kv : K32MAX);
+                    unsigned int base = 0;
+                    if (have && hl == 0) {
+                        if (t0 > 0) { t_row[k] = r; t_u[k] = ur; t_v[k] = vr; t_f[k] = fr; }
+                        t_best[k] = KMAX;
+                        t_qm[k] = qm;
+                        t_k2[k] = rest;
+                        if (qm) base = atomicAdd(&s_nunits, (unsigned int)__popc(qm));   // live units go to a compact list
                     }
+                    base = __shfl_sync(0xffffffffu, base, 0, 16);
+                    if (q) s_ulist[base + __popc(qm & ((1u << hl) - 1u))] = (unsigned short)((k << 5) | hl);
+                    if (PROF && k == 0) CL_MARK(23);
                 }
                 __syncthreads();
                 CL_MARK(8);
                 const int units = (int)s_nunits;
                 // one pass = one scan unit (UC column chunks of one selected row) + one chunk of column stores; a warp
                 // that has run out of one of the two keeps going with the other (a dead unit loads nothing)
-                for (int un = w; un < units || st_lw * CS + rank < st_nch; un += NW) {
-                    const bool live = un < units;
-                    const unsigned int ent = live ? s_ulist[un] : 0u;
-                    const int k = (int)(ent >> 5), part = (int)(ent & 31u);
-                    const int r = t_row[k];
-                    const int lw0 = live ? part * UC : lch;
-                    const double* row = D + (size_t)r * ld;
-                    double dv[UC];
+                // A warp keeps the loads of up to SB list entries in flight before it reduces any of them (one exposed memory
+                // round trip per pass; at 512 threads 22 units per CTA and merge are one pass of 16 warps x 2).
+                constexpr int SB = CT >= 1024 ? 1 : 2;
+                for (int un0 = w; un0 < units || st_lw * CS + rank < st_nch; un0 += NW * SB) {
+                    bool live[SB];
+                    int uk[SB], upart[SB], ur_[SB];
+                    double dv[SB][UC];
 #pragma unroll
-                    for (int q = 0; q < UC; q++) {
-                        const int j = ((lw0 + q) * CS + rank) * 32 + lane;
-                        dv[q] = (live && j < n && j != r) ? __ldcg(&row[j]) : 1e300;   // 1e300: never a candidate
+                    for (int b2 = 0; b2 < SB; b2++) {
+                        const int un = un0 + b2 * NW;
+                        live[b2] = un < units;
+                        const unsigned int ent = live[b2] ? s_ulist[un] : 0u;
+                        uk[b2] = (int)(ent >> 5); upart[b2] = (int)(ent & 31u);
+                        const int r = t_row[uk[b2]];
+                        ur_[b2] = r;
+                        const int lw0 = live[b2] ? upart[b2] * UC : lch;
+                        // rows x and y of this merge are still on their way into D (helpers): read them from the scratch pair
+                        const double* row = (merged && r == x) ? Rxs : ((ymoved && r == y) ? Rys : D + (size_t)r * ld);
+#pragma unroll
+                        for (int q = 0; q < UC; q++) {
+                            const int j = ((lw0 + q) * CS + rank) * 32 + lane;
+                            dv[b2][q] = (live[b2] && j < n && j != r) ? __ldcg(&row[j]) : 1e300;   // 1e300: never a candidate
+                        }
                     }
                     if (st_lw * CS + rank < st_nch) {
                         const int i = (st_lw * CS + rank) * 32 + lane;
-                        if (i < n && i != x && i != y) {
+                        if (i < n && i != x) {
                             const double vx = v_s[st_lw * 32 + lane];
-                            D[(size_t)i * ld + x] = vx;
-                            atomicMin(&Kb[(size_t)i * krow + kxg], key_of((vx - ux) + C));
-                            if (ymoved) {
-                                const double fy = f_s[st_lw * 32 + lane];
-                                D[(size_t)i * ld + y] = fy;
-                                atomicMin(&Kb[(size_t)i * krow + kyg], key_of((fy - ld_peer_f64(&u_s[((y >> 5) / CS) * 32 + (y & 31)], (y >> 5) % CS)) + C));
-                            }
+                            D[(size_t)i * ld + x] = vx; D[(size_t)x * ld + i] = vx;
+                            if (i != y) atomicMin(&Kxg[i], key_of((vx - ux) + C));
+                        }
+                        if (ymoved && i < n && i != y) {
+                            // (i == x: the moved node's distance to the new node is v of row y, which the scratch row holds)
+                            const double fy = i == x ? __ldcg(&Rys[x]) : f_s[st_lw * 32 + lane];
+                            D[(size_t)i * ld + y] = fy; D[(size_t)y * ld + i] = fy;
+                            if (i != x) atomicMin(&Kyg[i], key_of((fy - ld_peer_f64(&u_s[((y >> 5) / CS) * 32 + (y & 31)], (y >> 5) % CS)) + C));
                         }
                         st_lw += NW;
                     }
-                    if (!live) continue;
-                    const double ur = t_u[k];
-                    const bool patch = merged && r != x && r != y;
-                    const int xq = (patch && lane == (x & 31)) ? xlw - lw0 : -1;
-                    const int yq = (patch && lane == (y & 31)) ? ylw - lw0 : -1;
-                    // A lane's columns of one row differ by multiples of 32 * CS (a multiple of 256), so the reference
-                    // order within the row is plain ascending j: the first strict minimum is the right one.
-                    double lm1 = 1e300, lm2 = 1e300, ut = 1e300, ud = 0.0, uuj = 0.0;   // lm1/lm2: two smallest d - u_j
-                    int uq = 0, lq = 0;
 #pragma unroll
-                    for (int q = 0; q < UC; q++) {
-                        double d = dv[q];
-                        if (q == xq) d = t_v[k];
-                        if (q == yq) d = t_f[k];
-                        const double uj = u_s[(lw0 + q < lch ? lw0 + q : 0) * 32 + lane];   // (dead columns carry d = 1e300)
-                        const double t = (d - ur) - uj;
-                        const double mv = d - uj;
-                        if (mv < lm1) { lm2 = lm1; lm1 = mv; lq = q; } else lm2 = fmin(lm2, mv);
-                        if (t < ut) { ut = t; ud = d; uuj = uj; uq = q; }
-                    }
-                    // (units of one row may reach a lane in any order now: ties within the row go through the reference order too)
-                    if (ut < 10000.0 && (ut < bt || (ut == bt && tie_before(r, ((lw0 + uq) * CS + rank) * 32 + lane, bi, bj, n)))) {
-                        bt = ut; bi = r; bj = ((lw0 + uq) * CS + rank) * 32 + lane; bd = ud; bui = ur; buj = uuj;
-                    }
-                    // unit minimum and runner-up -> the unit's key, the CTA's (minimum, column) and runner-up of the row.  An
-                    // atomic that loses to (or displaces) the standing minimum demotes the loser to the runner-up.
-                    const unsigned int key1 = lm1 < 1e299 ? key_of(lm1 + C) : K32MAX;
-                    const unsigned int k1w = __reduce_min_sync(0xffffffffu, key1);
-                    if (lane == 0) Kmine[(size_t)r * krow + part] = k1w;
-                    if (k1w != K32MAX) {
-                        const int wl = __ffs(__ballot_sync(0xffffffffu, key1 == k1w)) - 1;
-                        const int jw = __shfl_sync(0xffffffffu, ((lw0 + lq) * CS + rank) * 32 + lane, wl);
-                        const unsigned int key2 = lane == wl ? (lm2 < 1e299 ? key_of(lm2 + C) : K32MAX) : key1;
-                        const unsigned int k2w = __reduce_min_sync(0xffffffffu, key2);
-                        if (lane == 0) {
-                            const unsigned long long mine = ((unsigned long long)k1w << 32) | (unsigned int)jw;
-                            const unsigned long long old = atomicMin(&t_best[k], mine);
-                            const unsigned int demoted = mine < old ? (unsigned int)(old >> 32) : k1w;
-                            atomicMin(&t_k2[k], demoted < k2w ? demoted : k2w);
+                    for (int b2 = 0; b2 < SB; b2++) {
+                        if (!live[b2]) continue;
+                        const int k = uk[b2], part = upart[b2], r = ur_[b2], lw0 = part * UC;
+                        const double ur = t_u[k];
+                        const bool patch = merged && r != x && r != y;
+                        const int xq = (patch && lane == (x & 31)) ? xlw - lw0 : -1;
+                        const int yq = (patch && lane == (y & 31)) ? ylw - lw0 : -1;
+                        // A lane's columns of one unit differ by multiples of 32 * CS (a multiple of 256), so the reference
+                        // order within the unit is plain ascending j: the first strict minimum is the right one.
+                        double lm1 = 1e300, lm2 = 1e300, ut = 1e300, ud = 0.0, uuj = 0.0;   // lm1/lm2: two smallest d - u_j
+                        int uq = 0, lq = 0;
+#pragma unroll
+                        for (int q = 0; q < UC; q++) {
+                            double d = dv[b2][q];
+                            if (q == xq) d = t_v[k];
+                            if (q == yq) d = t_f[k];
+                            const double uj = u_s[(lw0 + q < lch ? lw0 + q : 0) * 32 + lane];   // (dead columns carry d = 1e300)
+                            const double t = (d - ur) - uj;
+                            const double mv = d - uj;
+                            if (mv < lm1) { lm2 = lm1; lm1 = mv; lq = q; } else lm2 = fmin(lm2, mv);
+                            if (t < ut) { ut = t; ud = d; uuj = uj; uq = q; }
                         }
+                        // (units of one row may reach a lane in any order: ties within the row go through the reference order too)
+                        if (ut < 10000.0 && (ut < bt || (ut == bt && tie_before(r, ((lw0 + uq) * CS + rank) * 32 + lane, bi, bj, n)))) {
+                            bt = ut; bi = r; bj = ((lw0 + uq) * CS + rank) * 32 + lane; bd = ud; bui = ur; buj = uuj;
+                        }
+                        // unit minimum and runner-up -> the unit's key, the CTA's (minimum, column) and runner-up of the row.  An
+                        // atomic that loses to (or displaces) the standing minimum demotes the loser to the runner-up.
+                        const unsigned int key1 = lm1 < 1e299 ? key_of(lm1 + C) : K32MAX;
+                        const unsigned int k1w = __reduce_min_sync(0xffffffffu, key1);
+                        if (lane == 0) Kmine[(size_t)part * KLD + r] = k1w;
+                        if (k1w != K32MAX) {
+                            const int wl = __ffs(__ballot_sync(0xffffffffu, key1 == k1w)) - 1;
+                            const int jw = __shfl_sync(0xffffffffu, ((lw0 + lq) * CS + rank) * 32 + lane, wl);
+                            const unsigned int key2 = lane == wl ? (lm2 < 1e299 ? key_of(lm2 + C) : K32MAX) : key1;
+                            const unsigned int k2w = __reduce_min_sync(0xffffffffu, key2);
+                            if (lane == 0) {
+                                const unsigned long long mine = ((unsigned long long)k1w << 32) | (unsigned int)jw;
+                                const unsigned long long old = atomicMin(&t_best[k], mine);
+                                const unsigned int demoted = mine < old ? (unsigned int)(old >> 32) : k1w;
+                                atomicMin(&t_k2[k], demoted < k2w ? demoted : k2w);
+                            }
+                        }
+                        if (lane == 0) my_units++;
                     }
-                    if (lane == 0) my_units++;
                 }
                 __syncthreads();
                 CL_MARK(9);
                 // this CTA's minimum of each staged row goes to the row owner's key; skipped units only bound the runner-up
-                for (int k = tid; k < tn; k += CT) {
+                // (one warp per row, see the staging loop)
+                for (int k = w; k < tn; k += NW) {
+                    if (lane != 0) continue;
                     const unsigned int k1 = (unsigned int)(t_best[k] >> 32);
                     const unsigned int k2 = t_k2[k];
                     const int r = t_row[k];
@@ -728,7 +845,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 if (nsel > TILE) {
                     // rare (first search, bursts): one extra cluster barrier per tile so that every tile gets its records
                     cluster.sync();
-                    partner_records(tn, merged, x, y, n);
+                    partner_records(tn, merged, x, y, n, iter);
                     __syncthreads();
                 }
             }
@@ -772,7 +889,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 } while ((int)(dn - want) < 0);
             }
             // partner records of a selection that fitted one tile (larger selections did this per tile in phase C)
-            if (s_nsel <= TILE) partner_records(s_nsel, !first, x, y, n);
+            if (s_nsel <= TILE) partner_records(s_nsel, !first, x, y, n, iter);
             if (w == 0) {
                 const int src = lane < CS ? lane : 0;
                 const int ci = lane < CS ? recs[src].i : -1;
@@ -832,7 +949,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     if (rank == 0 && tid == 0) {
         if (HC > 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->bell), "l"(KMAX) : "memory");
         stats->iters = (unsigned long long)iter;
-        for (int k = 0; k < 24; k++) stats->cyc[k] = s_cyc[k];
+        for (int k = 0; k < 32; k++) stats->cyc[k] = s_cyc[k];
         unsigned long long ns_end;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
         stats->t_ns = ns_end - ns_begin;
@@ -892,7 +1009,7 @@ bool nj_cluster_fits(int n) {
     const int chunks = (n + 31) / 32;
     const int LS = ((chunks + 15) / 16) * 32;
     // (the doorbell packs indices in 17 bits; the unit list of a staged tile holds 12 units per row: 49 152 tips)
-    return n < 131072 && cluster_smem_bytes(LS, chunks) <= 200u * 1024u && (LS / 32 + 7) / 8 <= 12;
+    return n < 131072 && cluster_smem_bytes(LS, chunks) <= 200u * 1024u && (LS / 32 + 7) / 8 <= 12;   // (half-warp staging: at most 16 units per row and CTA)
 }
 
 int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* c0, int32_t* c1, double* l0, double* l1) {
@@ -911,10 +1028,13 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     int2* log_xy = nullptr;
     double2* log_bl = nullptr;
     unsigned int* Kb = nullptr;
+    double* R = nullptr;              // scratch rows x and y of the merge in flight, double buffered by merge parity
     // unit keys: n rows x (CS * PARTS) keys; CS * PARTS <= chunks / UC + 2 * CS for either cluster size (UC >= 4)
-    const size_t kb_bytes = sizeof(unsigned int) * (size_t)n * ((size_t)((n + 31) / 32) / 4 + 32);
+    const size_t kb_bytes = sizeof(unsigned int) * (size_t)((n + 31) & ~31) * ((size_t)((n + 31) / 32) / 4 + 32);
     DIPB_CUDA(pool_alloc(c, (void**)&Kb, kb_bytes));
     DIPB_CUDA(cudaMemsetAsync(Kb, 0xff, kb_bytes, c->stream));
+    DIPB_CUDA(pool_alloc(c, (void**)&R, sizeof(double) * 4 * (size_t)n));
+    DIPB_CUDA(cudaMemsetAsync(R, 0, sizeof(double) * 4 * (size_t)n, c->stream));
     DIPB_CUDA(pool_alloc(c, (void**)&sel, sizeof(int) * n));
     DIPB_CUDA(pool_alloc(c, (void**)&stats, sizeof(CStats)));
     DIPB_CUDA(pool_alloc(c, (void**)&ctl, sizeof(NJCtl)));
@@ -944,15 +1064,18 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     bool ok = false;
     int rc = 0;
     int dbg = getenv("DIPB_NJ_DBG") ? atoi(getenv("DIPB_NJ_DBG")) : 0;   // bit 0: every unit of a selected row is read (full rescans)
-    double slack_merges = getenv("DIPB_NJ_SLACK") ? atof(getenv("DIPB_NJ_SLACK")) : 256.0;
-    void* args[] = {&Dp, &ld, &U, &u, &sel, &stats, &log_xy, &log_bl, &n_total, &LS, &dmax, &ctl, &HC, &Kb, &PARTS, &dbg, &slack_merges};
+    double slack_merges = getenv("DIPB_NJ_SLACK") ? atof(getenv("DIPB_NJ_SLACK")) : 1024.0;
+    void* args[] = {&Dp, &ld, &U, &u, &sel, &stats, &log_xy, &log_bl, &n_total, &LS, &dmax, &ctl, &HC, &Kb, &PARTS, &dbg, &slack_merges, &R};
     // 1024 threads, 8 loads in flight per lane: measured best of {512, 1024} x {8, 16} (profiles/r1_nj_cluster_tuning.json)
     const char* e_uc = getenv("DIPB_NJ_UC");
     const int uc = e_uc ? atoi(e_uc) : 8;
+    const char* e_ct = getenv("DIPB_NJ_THREADS");    // threads per CTA: 256, 512 (default) or 1024
+    const int ct = e_ct ? atoi(e_ct) : 512;
+    (void)uc;
     if (want >= 16) {
-        if (profile) rc = launch_cluster<16, 1024, 8, true>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok);
-        else if (uc == 4) rc = launch_cluster<16, 1024, 4, false>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok);
-        else rc = launch_cluster<16, 1024, 8, false>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok);
+        if (ct >= 1024) rc = profile ? launch_cluster<16, 1024, 8, true>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok) : launch_cluster<16, 1024, 8, false>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok);
+        else if (ct >= 512) rc = profile ? launch_cluster<16, 512, 8, true>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok) : launch_cluster<16, 512, 8, false>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok);
+        else rc = profile ? launch_cluster<16, 256, 8, true>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok) : launch_cluster<16, 256, 8, false>(c, n, args, &LS, &HC, &PARTS, max_helpers, &ok);
         used = 16;
     }
     if (!rc && !ok) {
@@ -960,7 +1083,7 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
         used = 8;
     }
     if (!rc && !ok) { set_error("nj_cluster: no cluster configuration fits this device"); rc = DIPB_E_UNSUPPORTED; }
-    if (rc) { pool_free(c, sel); pool_free(c, stats); pool_free(c, ctl); pool_free(c, log_xy); pool_free(c, log_bl); pool_free(c, Kb); return rc; }
+    if (rc) { pool_free(c, sel); pool_free(c, stats); pool_free(c, ctl); pool_free(c, log_xy); pool_free(c, log_bl); pool_free(c, Kb); pool_free(c, R); return rc; }
     c->launches++;
     lap(1);
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -999,6 +1122,11 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     c->nj_iterations = hs.iters;
     c->nj_bytes_scanned = hs.bytes_scanned;
     if (profile) {
+        fprintf(stderr, "[nj_cluster]   stage detail (rank 0 warp 0): to first sync %.0f, key load issued %.0f, key arrived %.0f, unit test + list %.0f cyc/iter (then the CTA barrier)\n",
+                hs.cyc[17] / (double)hs.iters, hs.cyc[15] / (double)hs.iters, hs.cyc[16] / (double)hs.iters, hs.cyc[23] / (double)hs.iters);
+        fprintf(stderr, "[nj_cluster]   A detail (rank 0 warp 0): loads issued %.0f, loads arrived %.0f, chunks processed %.0f, pool + drift %.0f, wait for the CTA %.0f cyc/iter\n",
+                hs.cyc[18] / (double)hs.iters, hs.cyc[19] / (double)hs.iters, hs.cyc[20] / (double)hs.iters, hs.cyc[21] / (double)hs.iters, hs.cyc[22] / (double)hs.iters);
+        fprintf(stderr, "[nj_cluster]   probe after barrier 2: first load of a fixed word %.0f, second %.0f cyc\n", hs.cyc[24] / (double)hs.iters, hs.cyc[25] / (double)hs.iters);
         const char* nm[12] = {"D pick + pool", "A update + pool eval + push", "barrier 1", "B canonical sum + bell", "B upper bound", "(unused)",
                               "B fold + select", "barrier 2", "C stage tile + unit keys", "C scan units", "C keys + reduce + publish", "barrier 3"};
         fprintf(stderr, "[nj_cluster] main loop: %.1f ms, %.3f G cycles -> SM clock %.0f MHz while it ran\n", hs.t_ns * 1e-6, hs.t_cycles * 1e-9,
@@ -1013,7 +1141,7 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
             fprintf(stderr, "[nj_cluster]   %-26s %8.0f cyc/iter  %5.1f%%\n", nm[k], hs.iters ? hs.cyc[k] / (double)hs.iters : 0.0,
                     tot > 0 ? 100.0 * hs.cyc[k] / tot : 0.0);
     }
-    pool_free(c, sel); pool_free(c, stats); pool_free(c, ctl); pool_free(c, log_xy); pool_free(c, log_bl); pool_free(c, Kb);
+    pool_free(c, sel); pool_free(c, stats); pool_free(c, ctl); pool_free(c, log_xy); pool_free(c, log_bl); pool_free(c, Kb); pool_free(c, R);
     lap(4);
     if (profile) fprintf(stderr, "[nj_cluster] host ms: alloc+scale %.1f, launch %.1f, kernel wait %.1f, replay %.1f, profile print + frees %.1f\n", t_host[0], t_host[1], t_host[2], t_host[3], t_host[4]);
     return 0;
