@@ -3,23 +3,24 @@
 
 Workload (config C3, BASELINE.json configs[2]): synthetic aligned MSA, 30 000 tips x
 30 000 sites, JC distance matrix (-d 2) then conventional NJ (-m 2).  One "step" = one
-full pass: packed sequences -> fp64 distance matrix -> NJ tree.
+full pass: packed sequences -> int8 operand expansion -> fp64 distance matrix -> NJ tree.
 
   value   whole-job pairs/s with the packed sequences already resident in HBM: K steps between two
-          barriers + synchronize, max over ranks ("phases" are CUDA-event times inside the library)
-  e2e     same metric through the public C ABI from HOST buffers: H2D of the 4-bit
-          sequences + repack + distances + NJ + D2H of the tree, wall-clocked
-  roofline  the NJ kernel (dominant: ~93 % of the step) against the measured HBM copy
-          bandwidth; algorithmic bytes = the reference's full-scan cost sum_n (n^2+4n)*8
-           -- the pruned exact search reads ~1/250 of that, so it exceeds 1.0
-          of the yard-stick; "bytes_read" / "frac_on_bytes_read" give the bytes it really
-          reads (it is latency bound: ~23 us per merge, 4 cluster barriers each)
+          barriers + synchronize, max over ranks ("phases" are CUDA-event times inside the library).  The
+          tensor-core operand expansion is paid in EVERY step (dipb_msa_drop_operands before it).
+  e2e     same metric through the public C ABI from HOST (pinned) buffers: H2D of the 4-bit
+          sequences + repack + expansion + distances + NJ + D2H of the tree, wall-clocked
+  roofline  the NJ kernel (dominant: ~90 % of the step) against the measured HBM copy bandwidth on the
+          bytes the kernel itself reads and writes (it is latency / issue bound: frac ~ 0.03); the
+          reference's full-scan cost sum_n (n^2+4n)*8 B (SURVEY.md 8d yard-stick) is reported separately as
+          "speedup_vs_fullscan_bytes", not as a roofline
   dist_kernel  the tcgen05 int8 distance kernel against the tensor roofline (int8 dense
-          peak taken as 2x the measured bf16 peak) with its ncu DRAM traffic
+          peak taken as 2x the measured bf16 peak); traffic from the committed ncu capture
   cpu_baseline  the OpenMP oracle port on a bounded sample (rank 0, N=1 only)
 
-`--impl reference` runs the reference's own CUDA objects (oracle/_ref/dipper_ref; the
-reference has no CPU path) on a bounded sample of the same workload.
+`--impl reference` runs the reference's own CUDA objects (oracle/_ref/dipper_ref; the reference has no CPU
+path) on the SAME workload (30 000 tips): one job takes ~55 s there, so the number of timed
+jobs is bounded by a time budget (stated in the line) instead of the driver's step count.
 Multi-GPU (torchrun): the distance matrix is row-block sharded over ranks and gathered
 onto rank 0 (NCCL send/recv of the row blocks + a mirror kernel), NJ runs on rank 0 (BASELINE.json configs[2]).
 """
@@ -39,6 +40,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "pairwise distances/sec (JC distance matrix + NJ tree, whole job)"
 UNIT = "pairs/s"
+
+
+def workload_config(n, L):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": "C3: aligned MSA %d tips x %d sites, JC distance matrix + neighbor joining, one tree per step" % (n, L),
+            "inputs": "larger than L2 (%.0f MB packed sequences, %.1f GB fp64 matrix)" % (n * ((L + 15) // 16) * 8 / 1e6, n * n * 8 / 1e9),
+            "timing": "every step builds everything from the packed sequences (no cached operands)"}
 
 
 def measured_peaks():
@@ -147,42 +155,57 @@ def write_ref_bin(path, P, L):
 
 
 def run_reference(args):
-    """The reference's own CUDA objects on a bounded sample (rank 0 only)."""
+    """The reference's own CUDA objects on the same workload (rank 0 only).  A job takes ~55 s at 30 000 tips, so the
+    timed jobs are bounded by --ref-budget seconds (at least one), whatever --steps says; one small warm-up job absorbs
+    CUDA initialisation."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     exe = os.path.join(ROOT, "oracle", "_ref", "dipper_ref")
+    n, L = args.tips, args.sites
     base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True}
+            "warmup": args.warmup, "higher_is_better": True, "config": workload_config(n, L)}
     if not os.path.exists(exe):
         print(json.dumps(dict(base, unavailable="oracle/_ref/dipper_ref not built (reference sources absent at build time)")))
         return
-    n, L = args.ref_tips, args.sites
-    P = gen_data(n, L, args.seed)
     tmp = tempfile.mkdtemp(prefix="dipb_ref_")
-    inp = os.path.join(tmp, "in.bin")
-    write_ref_bin(inp, P, L)
-    times = []
-    for it in range(args.warmup + args.steps):
-        p = subprocess.run([exe, "msa_nj", inp, os.path.join(tmp, "o"), "2"], capture_output=True, text=True)
+
+    def job(P, tag):
+        inp = os.path.join(tmp, tag + ".bin")
+        write_ref_bin(inp, P, L)
+        t0 = time.time()
+        p = subprocess.run([exe, "msa_nj", inp, os.path.join(tmp, tag), "2"], capture_output=True, text=True)
+        os.remove(inp)
         if p.returncode != 0:
-            print(json.dumps(dict(base, unavailable="dipper_ref failed: " + p.stderr[-200:].replace("\n", " "))))
-            return
+            raise RuntimeError("dipper_ref failed: " + p.stderr[-200:].replace("\n", " "))
         j = json.loads(p.stdout.strip().splitlines()[-1])
-        if it >= args.warmup:
-            times.append((j["dist_ms"], j["tree_ms"], j["alloc_ms"]))
+        return j["dist_ms"], j["tree_ms"], j["alloc_ms"], time.time() - t0
+
+    try:
+        job(gen_data(min(n, 3000), L, args.seed + 1), "warm")
+        P = gen_data(n, L, args.seed)
+        times, t_begin = [], time.time()
+        while len(times) < args.steps:
+            times.append(job(P, "job"))
+            per_job = (time.time() - t_begin) / len(times)
+            if time.time() - t_begin + per_job > args.ref_budget:
+                break
+    except RuntimeError as e:
+        print(json.dumps(dict(base, unavailable=str(e))))
+        return
     t = np.array(times)
     dist_ms, nj_ms = float(t[:, 0].mean()), float(t[:, 1].mean())
     pairs = n * (n - 1) / 2
     val = pairs / ((dist_ms + nj_ms) / 1e3)
-    sample = "%d tips x %d sites (bounded sample of the 30000-tip workload), reference CUDA objects on 1 B200" % (n, L)
-    print(json.dumps(dict(base, value=val, ms_per_step=dist_ms + nj_ms, scaling="strong", vs_baseline=None,
+    sample = ("the full workload, %d tips x %d sites; %d timed job(s) of the %d requested steps fit the %d s budget "
+              "(+ one 3000-tip warm-up job); reference CUDA objects on 1 B200, device phases dist %.1f s + NJ %.1f s"
+              % (n, L, len(times), args.steps, args.ref_budget, dist_ms / 1e3, nj_ms / 1e3))
+    print(json.dumps(dict(base, value=val, ms_per_step=dist_ms + nj_ms, steps_timed=len(times), scaling="strong", vs_baseline=None,
                           dtype="int32 counts + f64", data="synthetic",
-                          config={"workload": "C3 sample: aligned MSA %d tips x %d sites, JC matrix + NJ" % (n, L),
-                                  "inputs": "larger than L2"},
-                          phases={"dist_ms": dist_ms, "nj_ms": nj_ms, "alloc_ms": float(t[:, 2].mean())},
+                          phases={"dist_ms": dist_ms, "nj_ms": nj_ms, "alloc_ms": float(t[:, 2].mean()), "wall_s_per_job": float(t[:, 3].mean())},
                           cpu_baseline={"value": val, "unit": UNIT, "cores": 0, "kind": "reference", "sample": sample},
-                          e2e={"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})))
+                          e2e={"value": pairs / float(t[:, 3].mean()), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                               "note": "wall clock of the whole dipper_ref process incl. reading its input file"})))
 
 
 def cpu_baseline(args, L):
@@ -207,8 +230,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tips", type=int, default=30000)
     ap.add_argument("--sites", type=int, default=30000)
-    ap.add_argument("--ref-tips", type=int, default=12000)
-    ap.add_argument("--cpu-tips", type=int, default=2000)
+    ap.add_argument("--ref-budget", type=int, default=170, help="seconds of timed reference jobs (--impl reference)")
+    ap.add_argument("--cpu-tips", type=int, default=6000)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--nj-algo", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -255,6 +278,7 @@ def main():
     def one_step(msa, timed):
         """resident-input step: distances (sharded) -> reduce -> NJ on rank 0. Returns (dist_ms, comm_ms, nj_ms)."""
         r0, r1 = shard(rank)
+        msa.dropOperands()                # the int8 expansion is part of every step
         if world == 1:
             M = msa.distMatrix(prm)
         else:
@@ -358,39 +382,57 @@ def main():
 
     if rank == 0:
         peak, peak_bf16, peak_src = measured_peaks()
-        nj_bytes = nj_algorithmic_bytes(n)
-        ach = nj_bytes / (nj_ms / 1e3) / 1e9
-        scanned = nj_stats.get("rows_scanned", 0)
-        # bytes the pruned search really touches: rescanned rows + per merge 5 row reads/writes and 2 column writes
         m = np.arange(3, n + 1, dtype=np.float64)
-        bytes_read = float(nj_stats.get("bytes_scanned", 0)) + float((7 * m * 8).sum())
+        # Bytes the NJ kernel itself moves, per merge with m active rows: phase A reads rows x, y, last
+        # (3m x 8), writes the two scratch rows (2m x 8); the helper clusters read them (2m x 8), write rows and columns
+        # x, y of D (4m x 8) and fold the two new columns into the unit keys (2m x 4 B read-modify-write); plus the scan
+        # units the search really loads (counted by the kernel).
+        nj_kernel_bytes = float(nj_stats.get("bytes_scanned", 0)) + float((104.0 * m).sum())
+        nj_ach = nj_kernel_bytes / (nj_ms / 1e3) / 1e9
+        fullscan_bytes = nj_algorithmic_bytes(n)
         tc_ops = dist_tensor_ops(n, L)
         tc_ach = tc_ops / (d_ms / 1e3) / 1e12 / max(world, 1)
+
+        def ncu_traffic(fn):
+            """dram read + write bytes of one launch from a committed ncu summary (profiles/), else None."""
+            try:
+                mt = json.load(open(os.path.join(ROOT, "profiles", fn)))["metrics"]
+                tot = 0.0
+                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v, u = mt[k].split()[:2]
+                    tot += float(v) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+                return tot
+            except Exception:
+                return None
+
         out = {
             "metric": METRIC, "value": pairs / (step_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int8 dot products -> int32 counts -> f64", "data": "synthetic",
-            "config": {"workload": "C3: aligned MSA %d tips x %d sites, JC distance matrix (row-block sharded over %d GPU) + single-GPU NJ" % (n, L, world),
-                       "inputs": "larger than L2 (450 MB packed sequences, 3.6 GB int8 operands, 7.2 GB fp64 matrix)", "nj_algo": args.nj_algo},
+            "config": workload_config(n, L),
+            "sharding": "distance row blocks over %d GPU(s), gathered on rank 0; NJ on rank 0 (BASELINE configs[2])" % world,
             "phases": {"dist_ms": d_ms, "reduce_ms": c_ms, "nj_ms": nj_ms,
                        "dist_pairs_per_sec": pairs / (d_ms / 1e3), "nj_wall_s": nj_ms / 1e3,
-                       "nj_us_per_merge": nj_ms * 1e3 / max(n - 2, 1)},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "nj_cluster_kernel (one launch = all %d merges)" % (n - 2),
-                         "algorithmic_bytes": nj_bytes,
-                         "definition": "SURVEY.md 8(d) yard-stick = bytes of the reference's full scan, sum_m (m^2+4m)*8; the exact pruned search "
-                                       "skips rows whose lower bound exceeds the best candidate, so frac > 1",
-                         "rows_rescanned": scanned, "bytes_read": bytes_read,
-                         "achieved_on_bytes_read": bytes_read / (nj_ms / 1e3) / 1e9,
-                         "frac_on_bytes_read": bytes_read / (nj_ms / 1e3) / 1e9 / peak,
-                         "note": "latency bound, not bandwidth bound: 4 cluster barriers and ~10 dependent shared/L2 round trips per merge "
-                                 "(profiles/r1_nj_cluster_phases.txt); ncu collects no DRAM counters for this cluster launch"},
-            "dist_kernel": {"kernel": "msa_tc2_kernel (tcgen05.mma.cta_group::2.kind::i8, 256x256 tiles per CTA pair)", "bound": "tensor", "achieved": tc_ach,
-                            "peak": 2.0 * peak_bf16, "unit": "TOP/s", "frac": tc_ach / (2.0 * peak_bf16),
-                            "peak_definition": "int8 dense = 2 x measured bf16 dense burst (%s)" % peak_src,
-                            "algorithmic_ops": tc_ops, "traffic": 255.4e9,
-                            "traffic_source": "profiles/r1_ncu_tc_cluster_30k.json (dram read+write, one launch): 71x the 3.6 GB of operands -- "
-                                              "L2/DRAM bound on operand re-streaming, tensor pipe 48 % active",
+                       "nj_us_per_merge": nj_ms * 1e3 / max(n - 2, 1),
+                       "note": "dist_ms includes the int8 operand expansion of every step"},
+            "roofline": {"bound": "hbm", "achieved": nj_ach, "peak": peak, "unit": "GB/s", "frac": nj_ach / peak,
+                         "traffic": ncu_traffic("r2_ncu_nj_cluster_30k.json"), "peak_source": peak_src,
+                         "kernel": "nj_cluster_kernel (one launch = all %d merges; %.0f %% of the step)" % (n - 2, 100.0 * nj_ms / step_ms),
+                         "algorithmic_bytes": nj_kernel_bytes,
+                         "definition": "bytes the kernel itself reads and writes: per merge 104 B per active row (rows x, y, last in; scratch rows, "
+                                       "rows and columns x, y of D, unit-key folds out) + the scan units actually loaded (kernel counter)",
+                         "rows_selected": nj_stats.get("rows_scanned", 0), "scan_bytes": float(nj_stats.get("bytes_scanned", 0)),
+                         "speedup_vs_fullscan_bytes": fullscan_bytes / nj_kernel_bytes,
+                         "fullscan_bytes": fullscan_bytes,
+                         "note": "not bandwidth bound: a chain of 3 cluster barriers per merge whose phases are instruction-issue and "
+                                 "latency bound (profiles/r2_nj_cluster_phases.txt); fullscan_bytes = SURVEY.md 8(d) yard-stick "
+                                 "(what the reference's search reads), kept apart from the roofline"},
+            "dist_kernel": {"kernel": "msa_tc2_kernel (tcgen05.mma.cta_group::2.kind::i8, 256x256 tiles per CTA pair) + msa_tc_expand_kernel", "bound": "tensor",
+                            "achieved": tc_ach, "peak": 2.0 * peak_bf16, "unit": "TOP/s", "frac": tc_ach / (2.0 * peak_bf16),
+                            "peak_definition": "int8 dense = 2 x measured bf16 dense burst (%s); no measured int8 peak exists" % peak_src,
+                            "algorithmic_ops": tc_ops, "traffic": ncu_traffic("r2_ncu_tc2_30k.json") or ncu_traffic("r1_ncu_tc2_30k.json"),
+                            "traffic_source": "profiles/r2_ncu_tc2_30k.json if present, else r1_ncu_tc2_30k.json (dram read + write of one msa_tc2_kernel launch)",
+                            "algorithmic_bytes": float(n) * ((L + 15) // 16) * 8 + float(n) * n * 8,
                             "bitplane_equivalent_Tops": dist_algorithmic_intops(n, L) / (d_ms / 1e3) / 1e12 / max(world, 1)},
             "e2e": {"value": pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(P.nbytes + lens.nbytes),
                     "d2h_bytes_per_step": int((n - 1) * 24), "seconds": e2e_s, "host_buffers": "pinned"},

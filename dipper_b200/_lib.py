@@ -42,6 +42,7 @@ SIGNATURES = {
     "dipb_msa_upload": (C.c_int, [vp, C.POINTER(C.c_void_p), u64p, C.c_size_t, vpp]),
     "dipb_msa_upload_flat": (C.c_int, [vp, u64p, C.c_size_t, C.c_uint64, vpp]),
     "dipb_msa_free": (None, [vp]),
+    "dipb_msa_drop_operands": (C.c_int, [vp]),
     "dipb_msa_dist_row": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "dipb_msa_dist_row_host": (C.c_int, [vp, C.c_int, C.c_int, f64p]),
     "dipb_msa_dist_block": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]),
@@ -97,6 +98,7 @@ SIGNATURES = {
     "dipb_fasta_word_offsets": (C.POINTER(C.c_uint64), [vp]),
     "dipb_fasta_words": (C.POINTER(C.c_uint64), [vp]),
     "dipb_fasta_close": (None, [vp]),
+    "dipb_phylip_write": (C.c_int, [C.c_char_p, C.c_int, f64p, C.POINTER(C.c_char_p), C.c_int]),
     "dipb_backbone_from_newick": (C.c_int, [C.c_char_p, C.c_int, i32p, i32p, i32p, i32p, f64p, vpp]),
 }
 

@@ -159,6 +159,10 @@ class MSADeviceArrays:
             check(lib().dipb_msa_dist_matrix_rows(self.h, params.distanceType, row_begin, row_end, C.byref(h)))
         return Matrix(self.ctx, h)
 
+    def dropOperands(self):
+        """Release the tensor-core operand expansion (rebuilt by the next p / JC matrix or row block)."""
+        check(lib().dipb_msa_drop_operands(self.h))
+
     def deallocateDeviceArrays(self):
         if self.h:
             lib().dipb_msa_free(self.h)

@@ -163,6 +163,15 @@ void dipb_msa_free(dipb_msa* m) {
     delete m;
 }
 
+int dipb_msa_drop_operands(dipb_msa* m) {
+    if (!m) { set_error("dipb_msa_drop_operands: null msa"); return DIPB_E_ARG; }
+    DIPB_CUDA(cudaSetDevice(m->ctx->device));
+    pool_free(m->ctx, m->tc_S); pool_free(m->ctx, m->tc_V); pool_free(m->ctx, m->tc_Sx); pool_free(m->ctx, m->tc_Vx);
+    m->tc_S = m->tc_V = m->tc_Sx = m->tc_Vx = nullptr;
+    m->tc_rows = m->tc_have = m->tc_xrows = 0;
+    return 0;
+}
+
 int dipb_msa_dist_row(dipb_msa* m, int dist_type, int row, double* d_out) {
     if (!m || !d_out) { set_error("dipb_msa_dist_row: bad argument"); return DIPB_E_ARG; }
     if (row < 0 || row >= m->n) { set_error("dipb_msa_dist_row: row %d out of range", row); return DIPB_E_ARG; }

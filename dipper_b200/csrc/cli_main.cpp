@@ -41,6 +41,7 @@ static void usage() {
         "  -O, --output-file arg    Output file path\n"
         "Optional Options:\n"
         "  -o, --output-format arg  t - phylogenetic tree in Newick format (default)\n"
+        "                           d - distance matrix in PHYLIP format (lower-triangular; -i r / -i m)\n"
         "  -m, --algorithm arg      0 - default mode (NJ < 30000 <= placement < 1000000 <= divide-and-conquer)\n"
         "                           1 - force placement, 2 - force conventional NJ, 3 - force divide-and-conquer\n"
         "  -p, --placement-mode arg 0 - exact mode, 1 - k-closest mode (default)\n"
@@ -173,7 +174,8 @@ int main(int argc, char** argv) {
         usage();
         return 1;
     }
-    if (out_fmt != "t" || (in != "r" && in != "m" && in != "d")) { printf("Invalid input-output combinations!!!!!\n"); return 1; }
+    if ((out_fmt != "t" && out_fmt != "d") || (in != "r" && in != "m" && in != "d")) { printf("Invalid input-output combinations!!!!!\n"); return 1; }
+    if (out_fmt == "d" && (in == "d" || add)) { std::cerr << "-o d needs sequence input (-i r or -i m) and no --add\n"; return 1; }
     std::ofstream output_(output.c_str());
     if (!output_) { std::cerr << "ERROR: cant open output file: " << output << "\n"; return 1; }
 
@@ -323,7 +325,20 @@ int main(int argc, char** argv) {
     if (aligned) std::cerr << "Allocated in: " << ms_since(t_alloc) << " ms\n";
 
     auto t_tree = Clock::now();
-    if (add) {
+    if (out_fmt == "d") {
+        // -o d (documented by the reference, docs/index.md:114, not implemented there): lower-triangular PHYLIP
+        output_.close();
+        dipb_matrix* M = nullptr;
+        if (aligned) CHECK(dipb_msa_dist_matrix(msa, (int)dist_type, &M));
+        else CHECK(dipb_mash_dist_matrix(mash, &M));
+        std::vector<double> D(n * n);
+        CHECK(dipb_matrix_to_host(M, D.data()));
+        dipb_matrix_free(M);
+        std::vector<const char*> nm(n);
+        for (size_t i = 0; i < n; i++) nm[i] = names[i].c_str();
+        CHECK(dipb_phylip_write(output.c_str(), (int)n, D.data(), nm.data(), 1));
+        std::cerr << "Distance matrix written in: " << ms_since(t_tree) << " ms\n";
+    } else if (add) {
         dipb_tree* T = nullptr;
         CHECK(dipb_place_add(ctx, &src, (int)n, backbone, bb_head.data(), bb_e.data(), bb_nxt.data(), bb_belong.data(), bb_len.data(), &T));
         if (write_tree(T, names, output_)) return 1;

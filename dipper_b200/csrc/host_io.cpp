@@ -298,6 +298,29 @@ char* dipb_tree_newick(int n_nodes, int root_node, const int32_t* head, const in
 
 void dipb_free_str(char* s) { free(s); }
 
+int dipb_phylip_write(const char* path, int n, const double* D, const char* const* names, int lower) {
+    if (!path || !D || !names || n < 1) { dipb::set_error("dipb_phylip_write: bad argument"); return DIPB_E_ARG; }
+    FILE* f = fopen(path, "w");
+    if (!f) { dipb::set_error("dipb_phylip_write: cannot open %s", path); return DIPB_E_ARG; }
+    std::vector<char> buf((size_t)1 << 22);
+    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    fprintf(f, "%d\n", n);
+    std::string line;
+    char num[40];
+    for (int i = 0; i < n; i++) {
+        line.assign(names[i]);
+        const int cols = lower ? i : n;
+        for (int j = 0; j < cols; j++) {
+            const int k = snprintf(num, sizeof num, " %.9g", D[(size_t)i * n + j]);
+            line.append(num, (size_t)k);
+        }
+        line.push_back('\n');
+        if (fwrite(line.data(), 1, line.size(), f) != line.size()) { fclose(f); dipb::set_error("dipb_phylip_write: write failed"); return DIPB_E_ARG; }
+    }
+    if (fclose(f) != 0) { dipb::set_error("dipb_phylip_write: close failed"); return DIPB_E_ARG; }
+    return 0;
+}
+
 int dipb_backbone_from_newick(const char* newick, int total_leaves, int32_t* head, int32_t* e, int32_t* nxt,
                               int32_t* belong, double* len, char** leaf_names_out) {
     if (!newick || total_leaves < 2 || !head || !e || !nxt || !belong || !len) {

@@ -55,6 +55,13 @@ void dipb_free_str(char *s);
 int dipb_backbone_from_newick(const char *newick, int total_leaves, int32_t *head, int32_t *e, int32_t *nxt,
                               int32_t *belong, double *len, char **leaf_names_out);
 
+/* -o d: distance matrix in PHYLIP format.  The reference documents the option ("coming soon", docs/index.md:114) but
+ * does not implement it; the text written here is what its own reader accepts (MatrixReader, src/matrix_reader.cu:15-44:
+ * first line n, then one line per taxon: name, then the distances to the taxa before it (lower = 1) or to all taxa
+ * (lower = 0), parsed there with stof).  Values are written with 9 significant digits (round-trips through float32).
+ * D is the dense n x n matrix, row-major.  Returns 0 or a negative DIPB_E_* code. */
+int dipb_phylip_write(const char *path, int n, const double *D, const char *const *names, int lower);
+
 #ifdef __cplusplus
 }
 #endif

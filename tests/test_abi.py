@@ -111,3 +111,24 @@ def test_backbone_loader_rejects_non_binary_trees():
         with pytest.raises(api.DipperError) as e:
             kp.initializeDeviceArrays(bad)
         assert "rooted binary" in str(e.value)
+
+
+def test_phylip_writer_round_trips_through_the_reference_reader_rule(tmp_path):
+    """-o d (docs/index.md:114): what dipb_phylip_write emits is what MatrixReader (src/matrix_reader.cu:15-44) reads:
+    n, then `name v0 v1 ...` rows whose values survive a float32 parse."""
+    rng = np.random.default_rng(7)
+    n = 9
+    D = rng.random((n, n))
+    D = np.tril(D, -1) + np.tril(D, -1).T
+    names = ["tx%d" % i for i in range(n)]
+    for lower in (1, 0):
+        path = str(tmp_path / ("m%d.phy" % lower))
+        rc = _lib.lib().dipb_phylip_write(path.encode(), n, np.ascontiguousarray(D), _lib.names_array(names), lower)
+        assert rc == 0
+        lines = open(path).read().splitlines()
+        assert int(lines[0]) == n and len(lines) == n + 1
+        for i in range(n):
+            tok = lines[1 + i].split()
+            assert tok[0] == names[i] and len(tok) == 1 + (i if lower else n)
+            got = np.array([np.float32(t) for t in tok[1:1 + i]], np.float32)
+            assert np.array_equal(got, D[i, :i].astype(np.float32))

@@ -105,3 +105,22 @@ def test_cli_errors(tmp_path):
     assert p.returncode == 1 and "cant open file" in p.stderr
     p = subprocess.run([EXE, "-h"], capture_output=True, text=True)
     assert p.returncode == 0 and "--input-format" in p.stderr
+
+
+def test_output_format_d_writes_a_matrix_the_cli_reads_back(ctx, oracle, tmp_path):
+    """-o d (docs/index.md:114, not implemented by the reference): PHYLIP out, then -i d in -> the same tree as -i m."""
+    n, L = 90, 1500
+    codes, P, _ = make_msa(n, L, seed=66)
+    names = synth.names(n)
+    fa, phy, t1, t2 = (str(tmp_path / x) for x in ("a.fa", "m.phy", "a.nwk", "b.nwk"))
+    synth.write_fasta(fa, names, synth.codes_to_strings(codes))
+    run("-i", "m", "-I", fa, "-O", phy, "-o", "d", "-d", 2, "--no-shuffle")
+    lines = open(phy).read().splitlines()
+    assert int(lines[0]) == n and [ln.split()[0] for ln in lines[1:]] == names
+    D = oracle.msa_dist_matrix(P, L, 2)
+    row = np.array([float(t) for t in lines[1 + 40].split()[1:]])
+    assert len(row) == 40 and np.allclose(row, D[40, :40], rtol=1e-6, atol=0)
+    run("-i", "m", "-I", fa, "-O", t1, "-d", 2, "-m", 2, "--no-shuffle")
+    run("-i", "d", "-I", phy, "-O", t2, "-m", 2)
+    a, b = open(t1).read(), open(t2).read()
+    assert newick.rf_distance(a, b) == 0 and newick.max_branch_diff(a, b) < 1e-5     # (values pass through float32 on the way back)
