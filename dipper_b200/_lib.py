@@ -83,6 +83,7 @@ SIGNATURES = {
     "dipb_dc_finish": (C.c_int, [vp, vpp]),
     "dipb_tree_export": (C.c_int, [vp, i32p, i32p, i32p, i32p, f64p]),
     "dipb_tree_export_closest": (C.c_int, [vp, i32p, f64p]),
+    "dipb_tree_device_arrays": (C.c_int, [vp, vpp, vpp, vpp, vpp, vpp, vpp, vpp]),
     "dipb_tree_n": (C.c_int, [vp]),
     "dipb_tree_free": (None, [vp]),
     # dipper_host.h

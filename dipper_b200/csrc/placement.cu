@@ -433,6 +433,19 @@ int dipb_tree_export_closest(dipb_tree* t, int32_t* cid, double* cdis) {
     return 0;
 }
 
+int dipb_tree_device_arrays(dipb_tree* t, int32_t** head, int32_t** e, int32_t** nxt, int32_t** belong, double** len, int32_t** closest_id,
+                            double** closest_dis) {
+    if (!t) { set_error("dipb_tree_device_arrays: null tree"); return DIPB_E_ARG; }
+    if (head) *head = t->head;
+    if (e) *e = t->e;
+    if (nxt) *nxt = t->nxt;
+    if (belong) *belong = t->belong;
+    if (len) *len = t->len;
+    if (closest_id) *closest_id = t->cid;
+    if (closest_dis) *closest_dis = t->cdis;
+    return 0;
+}
+
 int dipb_tree_n(const dipb_tree* t) { return t ? t->n : 0; }
 
 void dipb_tree_free(dipb_tree* t) {

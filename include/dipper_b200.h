@@ -204,6 +204,11 @@ int dipb_dc_cluster_ids(dipb_ctx *ctx, int32_t *h_out, int n);
 int dipb_tree_export(dipb_tree *t, int32_t *head, int32_t *e, int32_t *nxt, int32_t *belong, double *len);
 /* closest lists, for parity tests: cid[40n], cdis[40n] */
 int dipb_tree_export_closest(dipb_tree *t, int32_t *cid, double *cdis);
+/* The device arrays themselves -- the reference exposes them as public fields of its structs (d_head, d_e, d_nxt,
+ * d_belong, d_len, d_closest_id, d_closest_dis; src/mash_placement.cuh:167-197): head[2n], e/nxt/belong[8n], len[8n],
+ * closest lists 5 per slot [40n].  Owned by the tree; valid until dipb_tree_free. */
+int dipb_tree_device_arrays(dipb_tree *t, int32_t **head, int32_t **e, int32_t **nxt, int32_t **belong, double **len,
+                            int32_t **closest_id, double **closest_dis);
 int dipb_tree_n(const dipb_tree *t);
 void dipb_tree_free(dipb_tree *t);
 

@@ -34,3 +34,15 @@ for p in $pids; do wait $p; done
 $NVCC $FLAGS -dc "$HERE/ref_driver.cu" -o "$OUT/ref_driver.o"
 $NVCC -gencode arch=compute_100a,code=sm_100a -rdc=true -ccbin /usr/bin/g++ -o "$OUT/dipper_ref" "$OUT"/*.o
 echo "build_ref: built $OUT/dipper_ref"
+# The drop-in test: the SAME main (ref_driver.cu), the reference's unmodified mash_placement.cuh / tree.cpp /
+# matrix_reader.cu, but the struct API implemented by integration/mash_placement_b200.cpp on libdipper_b200.so.
+LIB="$HERE/../dipper_b200"
+if [ -f "$LIB/libdipper_b200.so" ]; then
+  mkdir -p "$OUT/shim"
+  $NVCC $FLAGS -DDIPPER_REF_SHIM -dc "$HERE/ref_driver.cu" -o "$OUT/shim/ref_driver.o"
+  $NVCC $FLAGS -x cu -dc "$HERE/../integration/mash_placement_b200.cpp" -o "$OUT/shim/mash_placement_b200.o"
+  $NVCC -gencode arch=compute_100a,code=sm_100a -rdc=true -ccbin /usr/bin/g++ -o "$OUT/dipper_ref_b200" \
+      "$OUT/shim/ref_driver.o" "$OUT/shim/mash_placement_b200.o" "$OUT/tree.o" "$OUT/matrix_reader.o" \
+      -L"$LIB" -ldipper_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../../dipper_b200'
+  echo "build_ref: built $OUT/dipper_ref_b200 (reference main + shim + libdipper_b200.so)"
+fi

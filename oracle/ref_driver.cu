@@ -46,9 +46,19 @@
 #include <cuda_runtime.h>
 #include "mash_placement.cuh"
 
+// -DDIPPER_REF_SHIM: the same main linked against integration/mash_placement_b200.cpp + libdipper_b200.so instead of
+// the reference's kernel objects (oracle/_ref/dipper_ref_b200, tests/test_shim_gpu.py); only the probe mode, which
+// reaches into the reference's internals, is left out.
+#ifndef DIPPER_REF_SHIM
 // defined (external linkage) in src/divide_and_conquer/placement_close_k.cu:1113-1134; used by the mash_dc_probe mode only
 __global__ void rearrangeHashListInClusterDC(int numSequences, int sketchSize, uint64_t* original, uint64_t* target);
+#endif
 
+#ifdef DIPPER_REF_SHIM
+#define DIPPER_DRIVER_IMPL "reference-main+libdipper_b200"
+#else
+#define DIPPER_DRIVER_IMPL "reference-cuda"
+#endif
 using Clock = std::chrono::high_resolution_clock;
 static double ms_since(Clock::time_point t0) {
     cudaDeviceSynchronize();
@@ -106,6 +116,7 @@ int main(int argc, char** argv) {
         }
         fclose(o);
     };
+#ifndef DIPPER_REF_SHIM
     if (mode == "mash_dc_probe") {
         // Diagnostic: the stage-3 distance call of findClusterTreeDC in isolation.  argv[6] = backbone size, argv[7] =
         // probe file: int32 nb, batch[nb] (tips of one stage-3 batch, in order), int32 r (row tip = batch position),
@@ -147,6 +158,7 @@ int main(int argc, char** argv) {
         printf("], \"cuda_status\": \"%s\"}\n", cudaGetErrorString(cudaDeviceSynchronize()));
         return 0;
     }
+#endif
     if (mode == "msa_dc" || mode == "mash_dc" || mode == "msa_dc_rows") {
         // ---- divide and conquer structs (src/tree_generation.cu:422-449 aligned, :541-575 unaligned)
         const bool rows_only = mode == "msa_dc_rows";
@@ -201,7 +213,7 @@ int main(int argc, char** argv) {
             dump_arrays(".arrays", kp.d_head, kp.d_e, kp.d_nxt, kp.d_belong, kp.d_len, kp.d_closest_id, kp.d_closest_dis);
         }
         cudaError_t e = cudaDeviceSynchronize();
-        printf("{\"impl\": \"reference-cuda\", \"mode\": \"%s\", \"n\": %lld, \"backbone\": %d, \"alloc_ms\": %.3f, \"assign_ms\": %.3f, "
+        printf("{\"impl\": \"" DIPPER_DRIVER_IMPL "\", \"mode\": \"%s\", \"n\": %lld, \"backbone\": %d, \"alloc_ms\": %.3f, \"assign_ms\": %.3f, "
                "\"backbone_ms\": %.3f, \"clusters_ms\": %.3f, \"cuda_status\": \"%s\"}\n",
                mode.c_str(), (long long)n, B, t_alloc, t_sketch, t_dist, t_tree, cudaGetErrorString(e));
         return e == cudaSuccess ? 0 : 4;
@@ -289,7 +301,7 @@ int main(int argc, char** argv) {
         return 2;
     }
     cudaError_t e = cudaDeviceSynchronize();
-    printf("{\"impl\": \"reference-cuda\", \"mode\": \"%s\", \"n\": %lld, \"alloc_ms\": %.3f, \"sketch_ms\": %.3f, "
+    printf("{\"impl\": \"" DIPPER_DRIVER_IMPL "\", \"mode\": \"%s\", \"n\": %lld, \"alloc_ms\": %.3f, \"sketch_ms\": %.3f, "
            "\"dist_ms\": %.3f, \"tree_ms\": %.3f, \"cuda_status\": \"%s\"}\n",
            mode.c_str(), (long long)n, t_alloc, t_sketch, t_dist, t_tree, cudaGetErrorString(e));
     return e == cudaSuccess ? 0 : 4;

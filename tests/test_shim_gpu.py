@@ -1,0 +1,137 @@
+"""The drop-in boundary, compiled: oracle/_ref/dipper_ref_b200 is the reference-side main (oracle/ref_driver.cu) and the
+reference's UNMODIFIED src/mash_placement.cuh, tree.cpp and matrix_reader.cu, linked against
+integration/mash_placement_b200.cpp + libdipper_b200.so instead of the reference's nine kernel files.  Every mode is run
+through both binaries (dipper_ref = the reference's own objects) on the same input and the outputs are diffed."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from dipper_b200 import newick, synth
+from conftest import make_msa, ROOT
+from test_ref_parity import write_bin, _read_arrays, _singleton_at_B, _stage3_seed
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(ROOT, "oracle", "_ref", "dipper_ref")
+SHIM = os.path.join(ROOT, "oracle", "_ref", "dipper_ref_b200")
+
+
+def both(mode, inp, tmp, *extra, env=None):
+    if not (os.path.exists(REF) and os.path.exists(SHIM)):
+        pytest.skip("oracle/_ref binaries not built (reference not mounted at build time)")
+    outs = []
+    for exe, tag in ((REF, "ref"), (SHIM, "b200")):
+        out = str(tmp / (tag + "_" + mode))
+        e = dict(os.environ)
+        if exe == SHIM and env:
+            e.update(env)
+        p = subprocess.run([exe, mode, inp, out, *map(str, extra)], capture_output=True, text=True, timeout=600, env=e)
+        assert p.returncode == 0, (exe, p.stderr[-1500:])
+        j = json.loads(p.stdout.strip().splitlines()[-1])
+        assert j["impl"] == ("reference-cuda" if exe == REF else "reference-main+libdipper_b200")
+        outs.append(out)
+    return outs
+
+
+def _same_arrays(a, b, n):
+    ns = 4 * n - 4
+    assert np.array_equal(a["head"][: 2 * n], b["head"][: 2 * n])
+    for k in ("e", "nxt", "belong"):
+        assert np.array_equal(a[k][:ns], b[k][:ns]), k
+    assert np.allclose(a["len"][:ns], b["len"][:ns], rtol=0, atol=1e-12)
+
+
+@pytest.fixture(scope="module")
+def aligned(tmp_path_factory):
+    n, L = 240, 2500
+    codes, P, _ = make_msa(n, L, seed=81, gap_cols=0.04)
+    d = tmp_path_factory.mktemp("shim_msa")
+    inp = str(d / "in.bin")
+    write_bin(inp, P, [L] * n, 4)
+    return n, L, P, inp
+
+
+@pytest.fixture(scope="module")
+def unaligned(tmp_path_factory):
+    n = 96
+    codes, _ = synth.evolve(n, 3000, seed=82, regime="tiefree", gap_cols=0.01)
+    seqs = synth.unaligned(codes)
+    d = tmp_path_factory.mktemp("shim_mash")
+    inp = str(d / "in.bin")
+    write_bin(inp, [synth.pack2_np(s) for s in seqs], [len(s) for s in seqs], 2)
+    return n, seqs, inp
+
+
+@pytest.mark.parametrize("dist_type", [1, 2])
+def test_shim_aligned_rows(aligned, tmp_path, dist_type):
+    n, L, P, inp = aligned
+    a, b = both("msa_rows", inp, tmp_path, dist_type)
+    assert np.array_equal(np.fromfile(a + ".rows", np.float64), np.fromfile(b + ".rows", np.float64))      # bit-equal rows
+
+
+@pytest.mark.parametrize("dist_type", [3, 4, 5, 6])
+def test_shim_aligned_rows_other_models(aligned, tmp_path, dist_type):
+    n, L, P, inp = aligned
+    a, b = both("msa_dc_rows", inp, tmp_path, dist_type)
+    ra, rb = np.fromfile(a + ".rows", np.float64), np.fromfile(b + ".rows", np.float64)
+    ok = np.isfinite(ra)
+    assert np.allclose(rb[ok], ra[ok], rtol=1e-6, atol=0)
+
+
+def test_shim_nj_and_placement_trees(aligned, tmp_path):
+    n, L, P, inp = aligned
+    a, b = both("msa_nj", inp, tmp_path, 2)
+    ta, tb = open(a + ".nwk").read(), open(b + ".nwk").read()
+    assert newick.rf_distance(ta, tb) == 0 and newick.max_branch_diff(ta, tb) < 1e-5     # (the reference's U is summed atomically)
+    for mode in ("msa_place", "msa_place_exact"):
+        a, b = both(mode, inp, tmp_path, 2)
+        assert open(a + ".nwk").read() == open(b + ".nwk").read(), mode                 # text-identical
+
+
+def test_shim_mash_sketches_rows_trees(unaligned, tmp_path):
+    n, seqs, inp = unaligned
+    a, b = both("mash_sketch", inp, tmp_path, 1, 15)
+    assert np.array_equal(np.fromfile(a + ".sk", np.uint64), np.fromfile(b + ".sk", np.uint64))
+    a, b = both("mash_rows", inp, tmp_path, 1, 15)
+    assert np.array_equal(np.fromfile(a + ".rows", np.float64), np.fromfile(b + ".rows", np.float64))
+    a, b = both("mash_place", inp, tmp_path, 1, 15)
+    assert open(a + ".nwk").read() == open(b + ".nwk").read()
+    a, b = both("mash_nj", inp, tmp_path, 1, 15)
+    ta, tb = open(a + ".nwk").read(), open(b + ".nwk").read()
+    assert newick.rf_distance(ta, tb) == 0 and newick.max_branch_diff(ta, tb) < 1e-5
+
+
+def test_shim_add_tips(aligned, tmp_path):
+    n, L, P, inp = aligned
+    B = 100
+    bb_in = str(tmp_path / "bb.bin")
+    write_bin(bb_in, P[:B], [L] * B, 4)
+    a, _ = both("msa_place", bb_in, tmp_path, 2)
+    bb = open(a + ".nwk").read().strip()
+    _, _, nm = newick.parse(bb)
+    order = [int(x[1:]) - 1 for x in nm if x] + list(range(B, n))
+    add_in, nwk = str(tmp_path / "add.bin"), str(tmp_path / "bb.nwk")
+    write_bin(add_in, np.ascontiguousarray(P[order]), [L] * n, 4)
+    open(nwk, "w").write(bb + "\n")
+    a, b = both("msa_add", add_in, tmp_path, 2, 15, nwk)
+    assert open(a + ".nwk").read() == open(b + ".nwk").read()
+    _same_arrays(_read_arrays(a + ".arrays", n), _read_arrays(b + ".arrays", n), n)
+
+
+def test_shim_divide_and_conquer(oracle, tmp_path):
+    n, L, B = 900, 1500, 180
+    codes, P, _ = make_msa(n, L, seed=83)
+    _, cl0 = oracle.dc_as_shipped(oracle.msa_dist_matrix(P, L, 2), B, 0.0)
+    q = _singleton_at_B(cl0, B)                 # keeps reference defect B12 without effect (see tools/make_ref_golden.py)
+    P[[B, q]] = P[[q, B]]
+    inp = str(tmp_path / "dc.bin")
+    write_bin(inp, P, [L] * n, 4)
+    # DIPB_DC_REF_B17: the reference as shipped scores with a stale distance to backbone tip B-1 (defect B17, dc.cu)
+    a, b = both("msa_dc", inp, tmp_path, 2, 15, B, env={"DIPB_DC_REF_B17": "1"})
+    assert np.array_equal(np.fromfile(a + ".clusters", np.int32), np.fromfile(b + ".clusters", np.int32))
+    ra, rb = _read_arrays(a + ".arrays", n), _read_arrays(b + ".arrays", n)
+    if _stage3_seed(ra, B) == 0.0:              # (reference defect B10: a stale stage-3 BFS seed changes its own result)
+        _same_arrays(ra, rb, n)
+        assert open(a + ".nwk").read() == open(b + ".nwk").read()
