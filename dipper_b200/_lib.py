@@ -86,6 +86,15 @@ SIGNATURES = {
     "dipb_tree_device_arrays": (C.c_int, [vp, vpp, vpp, vpp, vpp, vpp, vpp, vpp]),
     "dipb_tree_n": (C.c_int, [vp]),
     "dipb_tree_free": (None, [vp]),
+    "dipb_multi_init": (C.c_int, [i32p, C.c_int, vpp]),
+    "dipb_multi_destroy": (None, [vp]),
+    "dipb_multi_devices": (C.c_int, [vp]),
+    "dipb_multi_ctx": (vp, [vp, C.c_int]),
+    "dipb_multi_elapsed_ms": (C.c_double, [vp, C.c_int]),
+    "dipb_multi_msa_upload_flat": (C.c_int, [vp, u64p, C.c_size_t, C.c_uint64]),
+    "dipb_multi_msa_dist_matrix": (C.c_int, [vp, C.c_int, vpp]),
+    "dipb_multi_dc": (C.c_int, [vp, C.c_int, C.c_int, vpp]),
+    "dipb_multi_dc_cluster_ids": (C.c_int, [vp, i32p, C.c_int]),
     # dipper_host.h
     "dipb_pack4": (None, [C.c_char_p, C.c_size_t, u64p]),
     "dipb_pack2": (None, [C.c_char_p, C.c_size_t, u64p]),

@@ -496,3 +496,57 @@ def pack2(seq):
     out = np.zeros((len(b) + 31) // 32, np.uint64)
     lib().dipb_pack2(b, len(b), out)
     return out
+
+
+class MultiDevice:
+    """Several GPUs of one box in ONE process (dipb_multi_*, csrc/multi.cu): one context and one host thread per device,
+    shards exchanged by peer copies.  The reference is single GPU (src/tree_generation.cu:240)."""
+
+    def __init__(self, devices):
+        devs = np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        check(lib().dipb_multi_init(devs, len(devs), C.byref(h)))
+        self.h, self.devices, self.n = h, list(devices), 0
+
+    def context(self, d=0):
+        c = Context.__new__(Context)
+        c.h, c.device = C.c_void_p(lib().dipb_multi_ctx(self.h, d)), self.devices[d]
+        c.close = lambda: None          # owned by the multi-device handle
+        return c
+
+    def allocateDeviceArrays(self, flat, seq_len):
+        flat = np.ascontiguousarray(flat, np.uint64)
+        self.n = flat.shape[0]
+        check(lib().dipb_multi_msa_upload_flat(self.h, flat, self.n, int(seq_len)))
+
+    def distMatrix(self, params):
+        h = C.c_void_p()
+        check(lib().dipb_multi_msa_dist_matrix(self.h, params.distanceType, C.byref(h)))
+        return Matrix(self.context(0), h)
+
+    def findTreeDC(self, params, backboneSize=None):
+        """-m 3 with stage 2 split over the devices; returns a KPlacementDeviceArrays holding the tree (device 0)."""
+        B = self.n // 20 if backboneSize is None else backboneSize
+        h = C.c_void_p()
+        check(lib().dipb_multi_dc(self.h, params.distanceType, B, C.byref(h)))
+        kp = KPlacementDeviceArrays(self.context(0))
+        kp.allocateDeviceArrays(self.n)
+        kp.h = h
+        cl = np.zeros(self.n, np.int32)
+        check(lib().dipb_multi_dc_cluster_ids(self.h, cl, self.n))
+        kp.clusterID = cl
+        return kp
+
+    def elapsed_ms(self, what):
+        return float(lib().dipb_multi_elapsed_ms(self.h, what))
+
+    def close(self):
+        if self.h:
+            lib().dipb_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

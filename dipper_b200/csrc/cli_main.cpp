@@ -45,6 +45,7 @@ static void usage() {
         "  -m, --algorithm arg      0 - default mode (NJ < 30000 <= placement < 1000000 <= divide-and-conquer)\n"
         "                           1 - force placement, 2 - force conventional NJ, 3 - force divide-and-conquer\n"
         "  -p, --placement-mode arg 0 - exact mode, 1 - k-closest mode (default)\n"
+        "      --devices a,b,..     several GPUs of this box for aligned input: NJ matrix row blocks / -m 3 queries\n"
         "  -k, --kmer-size arg      K-mer size, 2-32 (default: 15)\n"
         "  -s, --sketch-size arg    Sketch size (default: 1000)\n"
         "  -d, --distance-type arg  1 - uncorrected (default, as the reference ships), 2 - JC, 3 - Tajima-Nei,\n"
@@ -135,12 +136,13 @@ int main(int argc, char** argv) {
     std::string in = "r", out_fmt = "t", algo = "0", placemode = "1", input, output, tree_file;
     long k = 15, sketch = 1000, dist_type = 1, device = 0;
     bool add = false, shuffle = true, have_seed = false, help = false;
+    std::vector<int> devices;
     unsigned long seed = 0;
     static option opts[] = {{"input-format", 1, 0, 'i'}, {"input-file", 1, 0, 'I'}, {"output-file", 1, 0, 'O'},
                             {"output-format", 1, 0, 'o'}, {"algorithm", 1, 0, 'm'}, {"placement-mode", 1, 0, 'p'},
                             {"kmer-size", 1, 0, 'k'}, {"sketch-size", 1, 0, 's'}, {"distance-type", 1, 0, 'd'},
                             {"add", 0, 0, 'a'}, {"input-tree", 1, 0, 't'}, {"help", 0, 0, 'h'},
-                            {"device", 1, 0, 1000}, {"seed", 1, 0, 1001}, {"no-shuffle", 0, 0, 1002}, {0, 0, 0, 0}};
+                            {"device", 1, 0, 1000}, {"seed", 1, 0, 1001}, {"no-shuffle", 0, 0, 1002}, {"devices", 1, 0, 1003}, {0, 0, 0, 0}};
     int c;
     auto to_long = [](const char* s, long dflt) { char* e; long v = strtol(s, &e, 10); return (e == s) ? dflt : v; };
     while ((c = getopt_long(argc, argv, "i:I:O:o:m:p:k:s:d:at:h", opts, nullptr)) != -1) {
@@ -160,6 +162,10 @@ int main(int argc, char** argv) {
             case 1000: device = to_long(optarg, 0); break;
             case 1001: seed = strtoul(optarg, nullptr, 10); have_seed = true; break;
             case 1002: shuffle = false; break;
+            case 1003: {   // --devices 0,1,2,3: several GPUs of this box (aligned input: NJ matrix and -m 3)
+                for (const char* q = optarg; *q;) { char* e2; long v = strtol(q, &e2, 10); if (e2 == q) break; devices.push_back((int)v); q = *e2 == ',' ? e2 + 1 : e2; }
+                break;
+            }
             default: usage(); return 1;
         }
     }
@@ -179,6 +185,7 @@ int main(int argc, char** argv) {
     std::ofstream output_(output.c_str());
     if (!output_) { std::cerr << "ERROR: cant open output file: " << output << "\n"; return 1; }
 
+    if (!devices.empty()) device = devices[0];
     dipb_ctx* ctx = nullptr;
     if (dipb_init((int)device, &ctx) != 0) { std::cerr << "Failed to set CUDA device: " << dipb_last_error() << std::endl; return -1; }
     const int placement_thr = 30000, dc_thr = 1000000;
@@ -306,6 +313,36 @@ int main(int argc, char** argv) {
     }
     std::cerr << "Input in: " << ms_since(t_input) << " ms\n";
 
+    if (devices.size() > 1 && aligned && !add && out_fmt == "t" &&
+        (algo == "2" || algo == "3" || (algo == "0" && (n < (size_t)placement_thr || n >= (size_t)dc_thr)))) {
+        // several GPUs, one process (csrc/multi.cu): distance row blocks or D&C queries sharded, tree on devices[0]
+        for (size_t i = 1; i < n; i++) if (lens[i] != lens[0]) { std::cerr << "dipper: aligned input requires equal sequence lengths\n"; return 1; }
+        const size_t comp = (lens[0] + 15) / 16;
+        std::vector<uint64_t> flat(n * comp);
+        parallel_for(n, [&](size_t i) { memcpy(flat.data() + i * comp, ptrs[i], comp * sizeof(uint64_t)); });
+        dipb_multi* md = nullptr;
+        CHECK(dipb_multi_init(devices.data(), (int)devices.size(), &md));
+        CHECK(dipb_multi_msa_upload_flat(md, flat.data(), n, lens[0]));
+        auto t_tree2 = Clock::now();
+        if (algo == "3" || (algo == "0" && n >= (size_t)dc_thr)) {
+            std::cerr << "Using divide-and-conquer mode on " << devices.size() << " devices\n";
+            dipb_tree* T = nullptr;
+            CHECK(dipb_multi_dc(md, (int)dist_type, (int)(n / 20), &T));
+            if (write_tree(T, names, output_)) return 1;
+            dipb_tree_free(T);
+        } else {
+            std::cerr << "Using conventional NJ, distance matrix on " << devices.size() << " devices\n";
+            dipb_matrix* M = nullptr;
+            CHECK(dipb_multi_msa_dist_matrix(md, (int)dist_type, &M));
+            if (write_nj(M, names, output_)) return 1;
+            dipb_matrix_free(M);
+        }
+        std::cerr << "Tree Created in: " << ms_since(t_tree2) << " ms\n";
+        dipb_multi_destroy(md);
+        if (fa) dipb_fasta_close(fa);
+        dipb_destroy(ctx);
+        return 0;
+    }
     auto t_alloc = Clock::now();
     dipb_msa* msa = nullptr;
     dipb_mash* mash = nullptr;

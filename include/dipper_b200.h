@@ -212,6 +212,25 @@ int dipb_tree_device_arrays(dipb_tree *t, int32_t **head, int32_t **e, int32_t *
 int dipb_tree_n(const dipb_tree *t);
 void dipb_tree_free(dipb_tree *t);
 
+/* ---- several GPUs of one box, one process -------------------------------------------------------------------
+ * The reference is single GPU (device 1 hard-coded, src/tree_generation.cu:240-245).  Here one dipb_ctx per device is
+ * driven by one host thread each; shards are exchanged with peer copies over NVLink:
+ *   dipb_multi_msa_dist_matrix  row blocks balanced by triangle area, gathered (lower trapezoids only) and mirrored
+ *                               on devices[0]: the matrix NJDeviceArrays::getDismatrix builds (src/neighborJoining.cu:35-85)
+ *   dipb_multi_dc               -m 3 with the queries of the cluster-assignment stage split over the devices
+ *                               (src/divide_and_conquer/placement_close_k.cu:937-1113); the tree ends on devices[0]
+ * dipb_multi_elapsed_ms(what): host wall clock of the last call: 0 sharded compute, 1 gather, 2 the rest, 3 total. */
+typedef struct dipb_multi dipb_multi;
+int dipb_multi_init(const int *devices, int n_devices, dipb_multi **out);
+void dipb_multi_destroy(dipb_multi *m);
+int dipb_multi_devices(const dipb_multi *m);
+dipb_ctx *dipb_multi_ctx(dipb_multi *m, int d);
+double dipb_multi_elapsed_ms(const dipb_multi *m, int what);
+int dipb_multi_msa_upload_flat(dipb_multi *m, const uint64_t *flat, size_t n, uint64_t seq_len);
+int dipb_multi_msa_dist_matrix(dipb_multi *m, int dist_type, dipb_matrix **out);
+int dipb_multi_dc(dipb_multi *m, int dist_type, int backbone, dipb_tree **out);
+int dipb_multi_dc_cluster_ids(const dipb_multi *m, int32_t *h_out, int n);
+
 #ifdef __cplusplus
 }
 #endif
