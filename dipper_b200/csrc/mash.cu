@@ -499,11 +499,7 @@ static int mash_launch(dipb_mash* m, MashTileParams p) {
     const size_t rk_smem = (size_t)(m->s + MR_PAD) * (MR_TA + MR_TB) * sizeof(uint32_t);
     if (!(er && atoi(er) == 0) && (size_t)m->n * m->s < 0xFFFFFFFFull && rk_smem <= 227 * 1024) {
         if (!m->ranks) { int rc = mash_build_ranks(m); if (rc) return rc; }
-        static size_t attr_rk = 0;
-        if (rk_smem > attr_rk) {
-            DIPB_CUDA(cudaFuncSetAttribute(mash_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rk_smem));
-            attr_rk = rk_smem;
-        }
+        DIPB_CUDA(cudaFuncSetAttribute(mash_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rk_smem));   // (per device)
         const int tiles_y = (rows + MR_TB - 1) / MR_TB, tiles_x = (ncols + MR_TA - 1) / MR_TA;
         const long long tiles = (long long)tiles_y * tiles_x;
         const int grid = (int)(tiles < (long long)c->num_sms * 4 ? tiles : (long long)c->num_sms * 4);
@@ -514,12 +510,8 @@ static int mash_launch(dipb_mash* m, MashTileParams p) {
     // ---- 64-bit hashes
     size_t smem = (size_t)(MD_TA + MD_TB) * m->s * 8 + 64;
     if (smem > 227 * 1024) { set_error("mash distance: sketch size %d does not fit shared memory tiles", m->s); return DIPB_E_ARG; }
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        DIPB_CUDA(cudaFuncSetAttribute(mash_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DIPB_CUDA(cudaFuncSetAttribute(mash_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    DIPB_CUDA(cudaFuncSetAttribute(mash_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // (per device)
+    DIPB_CUDA(cudaFuncSetAttribute(mash_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const char* ew = getenv("DIPB_MASH_WARP");   // 1: merge-path warp-per-pair kernel (measured equal to the thread-per-pair one: both sit on
     const bool warp_merge = m->s <= 1024 && ew && atoi(ew) == 1;   // the shared-memory wavefronts of random 8-byte reads)
     int tiles_y = (rows + MD_TB - 1) / MD_TB, tiles_x = (ncols + MD_TA - 1) / MD_TA;

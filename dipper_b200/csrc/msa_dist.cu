@@ -265,11 +265,8 @@ static int launch_generic(dipb_msa* m, TileParams p, long long tiles) {
     dipb_ctx* c = m->ctx;
     int grid = (int)(tiles < c->num_sms ? tiles : c->num_sms);
     if (grid < 1) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DIPB_CUDA(cudaFuncSetAttribute(msa_tile_kernel<FN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSA_SMEM_BYTES));
-        attr_set = true;
-    }
+    // (per device and cheap: set on every launch, several devices / host threads may use the library, csrc/multi.cu)
+    DIPB_CUDA(cudaFuncSetAttribute(msa_tile_kernel<FN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSA_SMEM_BYTES));
     msa_tile_kernel<FN, false><<<grid, MSA_THREADS, MSA_SMEM_BYTES, c->stream>>>(p, tiles);
     DIPB_KERNEL_CHECK(c);
     return 0;
@@ -293,11 +290,7 @@ static int launch_fast(dipb_msa* m, TileParams p, long long tiles) {
     dipb_ctx* c = m->ctx;
     int grid = (int)(tiles < c->num_sms ? tiles : c->num_sms);
     if (grid < 1) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DIPB_CUDA(cudaFuncSetAttribute(msa_tile_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSA_SMEM_BYTES));
-        attr_set = true;
-    }
+    DIPB_CUDA(cudaFuncSetAttribute(msa_tile_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSA_SMEM_BYTES));
     msa_tile_kernel<0, true><<<grid, MSA_THREADS, MSA_SMEM_BYTES, c->stream>>>(p, tiles);
     DIPB_KERNEL_CHECK(c);
     return 0;

@@ -35,6 +35,28 @@ struct dipb_multi {
 
 using namespace dipb;
 
+// Device 0 pulls rows [r0, r1) of a peer's matrix (entries below the diagonal only) straight out of the peer's memory
+// over NVLink and writes them twice: in place and mirrored above the diagonal.  32 x 32 tiles through shared memory so
+// that both the peer reads and the two local writes are coalesced.  (A pitched cudaMemcpy3DPeerAsync of the same
+// trapezoid ran at 36 GB/s; this kernel is bound by the NVLink read.)
+__global__ void gather_mirror_kernel(const double* __restrict__ src, double* __restrict__ dst, int n, int r0, int r1) {
+    __shared__ double tile[32][33];
+    const int i0 = r0 + blockIdx.y * 32, j0 = blockIdx.x * 32;
+    if (j0 > i0 + 31) return;                       // tile entirely above the diagonal
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int k = ty; k < 32; k += 8) {
+        const int i = i0 + k, j = j0 + tx;
+        double v = 0.0;
+        if (i < r1 && j < i) { v = src[(size_t)i * n + j]; dst[(size_t)i * n + j] = v; }
+        tile[k][tx] = v;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int j = j0 + k, i = i0 + tx;          // write dst[j][i], coalesced along i
+        if (i < r1 && j < i) dst[(size_t)j * n + i] = tile[tx][k];
+    }
+}
+
 namespace {
 // run fn(d) on one host thread per device; the first failure (lowest device) wins and its message is re-raised here
 int on_all(dipb_multi* m, const std::function<int(int)>& fn) {
@@ -83,8 +105,23 @@ int dipb_multi_init(const int* devices, int n_devices, dipb_multi** out) {
         if (can) {
             cudaSetDevice(devices[0]);
             cudaError_t e = cudaDeviceEnablePeerAccess(devices[d], 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error("dipb_multi_init: peer access %d -> %d: %s", devices[0], devices[d], cudaGetErrorString(e)); }
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error("dipb_multi_init: peer access %d -> %d: %s", devices[0], devices[d], cudaGetErrorString(e)); for (auto* x : m->ctx) dipb_destroy(x); delete m; return DIPB_E_CUDA; }
             cudaGetLastError();
+        } else { set_error("dipb_multi_init: device %d cannot access device %d (no NVLink / PCIe peer path)", devices[0], devices[d]); for (auto* x : m->ctx) dipb_destroy(x); delete m; return DIPB_E_UNSUPPORTED; }
+    }
+    // matrices come from the stream-ordered pool of each device (cudaMallocAsync): pool memory is private to its device
+    // until access is granted, whatever cudaDeviceEnablePeerAccess says
+    for (int d = 1; d < n_devices; d++) {
+        cudaMemPool_t pool;
+        cudaMemAccessDesc desc = {};
+        desc.location.type = cudaMemLocationTypeDevice;
+        desc.location.id = devices[0];
+        desc.flags = cudaMemAccessFlagsProtReadWrite;
+        if (cudaDeviceGetDefaultMemPool(&pool, devices[d]) != cudaSuccess || cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) {
+            set_error("dipb_multi_init: cannot open the memory pool of device %d to device %d: %s", devices[d], devices[0], cudaGetErrorString(cudaGetLastError()));
+            for (auto* x : m->ctx) dipb_destroy(x);
+            delete m;
+            return DIPB_E_CUDA;
         }
     }
     m->msa.assign(n_devices, nullptr);
@@ -127,30 +164,22 @@ int dipb_multi_msa_dist_matrix(dipb_multi* m, int dist_type, dipb_matrix** out) 
     });
     auto t1 = std::chrono::steady_clock::now();
     if (!rc) {
-        // device 0 pulls the trapezoid rows [r0, r1) x columns [0, r1) of every peer (all copies in flight together)
+        // device 0 pulls the rows of every peer below the diagonal and mirrors them on the way in
         dipb_ctx* c0 = m->ctx[0];
         cudaSetDevice(c0->device);
         for (int d = 1; d < nd && !rc; d++) {
             int r0, r1;
             row_shard(n, nd, d, &r0, &r1);
             if (r1 <= r0) continue;
-            cudaMemcpy3DPeerParms p = {};
-            p.srcDevice = m->ctx[d]->device; p.dstDevice = c0->device;
-            p.srcPtr = make_cudaPitchedPtr(M[d]->d + (size_t)r0 * n, (size_t)n * sizeof(double), (size_t)n * sizeof(double), (size_t)(r1 - r0));
-            p.dstPtr = make_cudaPitchedPtr(M[0]->d + (size_t)r0 * n, (size_t)n * sizeof(double), (size_t)n * sizeof(double), (size_t)(r1 - r0));
-            p.extent = make_cudaExtent((size_t)r1 * sizeof(double), (size_t)(r1 - r0), 1);
-            if (cudaMemcpy3DPeerAsync(&p, c0->stream) != cudaSuccess) { set_error("dipb_multi_msa_dist_matrix: peer copy from device %d: %s", m->ctx[d]->device, cudaGetErrorString(cudaGetLastError())); rc = DIPB_E_CUDA; }
+            dim3 grid((r1 + 31) / 32, (r1 - r0 + 31) / 32), block(32, 8);
+            gather_mirror_kernel<<<grid, block, 0, c0->stream>>>(M[d]->d, M[0]->d, n, r0, r1);
+            c0->launches++;
+            if (cudaGetLastError() != cudaSuccess) { set_error("dipb_multi_msa_dist_matrix: gather from device %d failed to launch", m->ctx[d]->device); rc = DIPB_E_CUDA; }
         }
         if (!rc && cudaStreamSynchronize(c0->stream) != cudaSuccess) { set_error("dipb_multi_msa_dist_matrix: gather failed: %s", cudaGetErrorString(cudaGetLastError())); rc = DIPB_E_CUDA; }
     }
     auto t2 = std::chrono::steady_clock::now();
-    if (!rc && nd > 1) {
-        int r0, r1;
-        row_shard(n, nd, 0, &r0, &r1);
-        rc = dipb_matrix_mirror_rows(M[0], r1, n);      // device 0 mirrored its own block in the kernel epilogue
-        if (!rc) rc = dipb_sync(m->ctx[0]);
-    }
-    auto t3 = std::chrono::steady_clock::now();
+    auto t3 = t2;
     for (int d = 1; d < nd; d++) if (M[d]) { cudaSetDevice(m->ctx[d]->device); dipb_matrix_free(M[d]); }
     cudaSetDevice(m->ctx[0]->device);
     if (rc) { if (M[0]) dipb_matrix_free(M[0]); return rc; }
