@@ -508,7 +508,15 @@ int dipb_dc_assign(dipb_dc_state* st, int q0, int q1, int32_t* h_cluster) {
     }
     while ((size_t)qb * ld * sizeof(double) > cap && qb > 128) qb /= 2;
     double* buf = nullptr;
-    if (!src->matrix) DIPB_CUDA(pool_alloc(c, (void**)&buf, (size_t)qb * ld * sizeof(double)));
+    if (!src->matrix && pool_alloc(c, (void**)&buf, (size_t)qb * ld * sizeof(double)) != cudaSuccess) {
+        size_t fb = 0, tb = 0;
+        cudaGetLastError();
+        cudaMemGetInfo(&fb, &tb);
+        set_error("dipb_dc_assign: device %d: no memory for a %zu MB distance block (%d queries x %zu); %zu MB of %zu MB free",
+                  c->device, (size_t)qb * ld * sizeof(double) >> 20, qb, ld, fb >> 20, tb >> 20);
+        pool_free(c, d_cluster);
+        return DIPB_E_NOMEM;
+    }
     // transposed block T[leaf][query] + per-(query, slot range) minima (DIPB_DC_ASSIGN_T=0: the row-major kernel)
     const char* et = getenv("DIPB_DC_ASSIGN_T");
     const bool transposed = !(et && atoi(et) == 0);

@@ -29,6 +29,11 @@ int dipb_dc_finish(dipb_dc_state* st, dipb_tree** out);
 struct dipb_multi {
     std::vector<dipb_ctx*> ctx;
     std::vector<dipb_msa*> msa;
+    // row blocks of the peers for the matrix gather: plain cudaMalloc memory (peer readable once peer access is on;
+    // memory of the stream-ordered pools is private to its device, and a pool opened to a peer with cudaMemPoolSetAccess
+    // refused to grow while that peer was busy), kept across calls
+    std::vector<double*> block;
+    std::vector<size_t> block_bytes;
     std::vector<int32_t> clusters;      // cluster ids of the last dipb_multi_dc (test hook)
     double t_ms[4] = {0, 0, 0, 0};      // last call: compute (max over devices), gather, mirror, total
 };
@@ -39,7 +44,7 @@ using namespace dipb;
 // over NVLink and writes them twice: in place and mirrored above the diagonal.  32 x 32 tiles through shared memory so
 // that both the peer reads and the two local writes are coalesced.  (A pitched cudaMemcpy3DPeerAsync of the same
 // trapezoid ran at 36 GB/s; this kernel is bound by the NVLink read.)
-__global__ void gather_mirror_kernel(const double* __restrict__ src, double* __restrict__ dst, int n, int r0, int r1) {
+__global__ void gather_mirror_kernel(const double* __restrict__ src, size_t lds, double* __restrict__ dst, int n, int r0, int r1) {
     __shared__ double tile[32][33];
     const int i0 = r0 + blockIdx.y * 32, j0 = blockIdx.x * 32;
     if (j0 > i0 + 31) return;                       // tile entirely above the diagonal
@@ -47,7 +52,7 @@ __global__ void gather_mirror_kernel(const double* __restrict__ src, double* __r
     for (int k = ty; k < 32; k += 8) {
         const int i = i0 + k, j = j0 + tx;
         double v = 0.0;
-        if (i < r1 && j < i) { v = src[(size_t)i * n + j]; dst[(size_t)i * n + j] = v; }
+        if (i < r1 && j < i) { v = src[(size_t)(i - r0) * lds + j]; dst[(size_t)i * n + j] = v; }   // src row 0 = matrix row r0
         tile[k][tx] = v;
     }
     __syncthreads();
@@ -109,22 +114,9 @@ int dipb_multi_init(const int* devices, int n_devices, dipb_multi** out) {
             cudaGetLastError();
         } else { set_error("dipb_multi_init: device %d cannot access device %d (no NVLink / PCIe peer path)", devices[0], devices[d]); for (auto* x : m->ctx) dipb_destroy(x); delete m; return DIPB_E_UNSUPPORTED; }
     }
-    // matrices come from the stream-ordered pool of each device (cudaMallocAsync): pool memory is private to its device
-    // until access is granted, whatever cudaDeviceEnablePeerAccess says
-    for (int d = 1; d < n_devices; d++) {
-        cudaMemPool_t pool;
-        cudaMemAccessDesc desc = {};
-        desc.location.type = cudaMemLocationTypeDevice;
-        desc.location.id = devices[0];
-        desc.flags = cudaMemAccessFlagsProtReadWrite;
-        if (cudaDeviceGetDefaultMemPool(&pool, devices[d]) != cudaSuccess || cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) {
-            set_error("dipb_multi_init: cannot open the memory pool of device %d to device %d: %s", devices[d], devices[0], cudaGetErrorString(cudaGetLastError()));
-            for (auto* x : m->ctx) dipb_destroy(x);
-            delete m;
-            return DIPB_E_CUDA;
-        }
-    }
     m->msa.assign(n_devices, nullptr);
+    m->block.assign(n_devices, nullptr);
+    m->block_bytes.assign(n_devices, 0);
     *out = m;
     return 0;
 }
@@ -133,6 +125,7 @@ void dipb_multi_destroy(dipb_multi* m) {
     if (!m) return;
     for (size_t d = 0; d < m->ctx.size(); d++) {
         if (m->msa[d]) dipb_msa_free(m->msa[d]);
+        if (m->block[d]) { cudaSetDevice(m->ctx[d]->device); cudaFree(m->block[d]); }
         dipb_destroy(m->ctx[d]);
     }
     delete m;
@@ -153,12 +146,26 @@ int dipb_multi_msa_upload_flat(dipb_multi* m, const uint64_t* flat, size_t n, ui
 int dipb_multi_msa_dist_matrix(dipb_multi* m, int dist_type, dipb_matrix** out) {
     if (!m || !out || !m->msa[0]) { set_error("dipb_multi_msa_dist_matrix: upload the sequences first"); return DIPB_E_STATE; }
     const int nd = (int)m->ctx.size(), n = m->msa[0]->n;
-    std::vector<dipb_matrix*> M(nd, nullptr);
+    dipb_matrix* M0 = nullptr;
+    std::vector<size_t> lds(nd, 0);
     auto t0 = std::chrono::steady_clock::now();
     int rc = on_all(m, [&](int d) {
         int r0, r1;
         row_shard(n, nd, d, &r0, &r1);
-        int r = dipb_msa_dist_matrix_rows(m->msa[d], dist_type, r0, r1, &M[d]);
+        int r = 0;
+        if (d == 0) r = dipb_msa_dist_matrix_rows(m->msa[0], dist_type, 0, nd > 1 ? r1 : n, &M0);   // full matrix, own rows mirrored
+        else if (r1 > r0) {
+            // rows [r0, r1) x columns [0, r1) as a rectangular block in peer-readable memory
+            lds[d] = (size_t)((r1 + 127) / 128 * 128);
+            const size_t need = (size_t)(r1 - r0) * lds[d] * sizeof(double);
+            if (need > m->block_bytes[d]) {
+                if (m->block[d]) cudaFree(m->block[d]);
+                m->block[d] = nullptr; m->block_bytes[d] = 0;
+                if (cudaMalloc(&m->block[d], need) != cudaSuccess) { set_error("dipb_multi_msa_dist_matrix: %zu MB row block: %s", need >> 20, cudaGetErrorString(cudaGetLastError())); return (int)DIPB_E_NOMEM; }
+                m->block_bytes[d] = need;
+            }
+            r = dipb_msa_dist_block(m->msa[d], dist_type, r0, r1, r1, m->block[d], lds[d]);
+        }
         if (!r) r = dipb_sync(m->ctx[d]);
         return r;
     });
@@ -172,7 +179,7 @@ int dipb_multi_msa_dist_matrix(dipb_multi* m, int dist_type, dipb_matrix** out) 
             row_shard(n, nd, d, &r0, &r1);
             if (r1 <= r0) continue;
             dim3 grid((r1 + 31) / 32, (r1 - r0 + 31) / 32), block(32, 8);
-            gather_mirror_kernel<<<grid, block, 0, c0->stream>>>(M[d]->d, M[0]->d, n, r0, r1);
+            gather_mirror_kernel<<<grid, block, 0, c0->stream>>>(m->block[d], lds[d], M0->d, n, r0, r1);
             c0->launches++;
             if (cudaGetLastError() != cudaSuccess) { set_error("dipb_multi_msa_dist_matrix: gather from device %d failed to launch", m->ctx[d]->device); rc = DIPB_E_CUDA; }
         }
@@ -180,12 +187,11 @@ int dipb_multi_msa_dist_matrix(dipb_multi* m, int dist_type, dipb_matrix** out) 
     }
     auto t2 = std::chrono::steady_clock::now();
     auto t3 = t2;
-    for (int d = 1; d < nd; d++) if (M[d]) { cudaSetDevice(m->ctx[d]->device); dipb_matrix_free(M[d]); }
     cudaSetDevice(m->ctx[0]->device);
-    if (rc) { if (M[0]) dipb_matrix_free(M[0]); return rc; }
+    if (rc) { if (M0) dipb_matrix_free(M0); return rc; }
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     m->t_ms[0] = ms(t0, t1); m->t_ms[1] = ms(t1, t2); m->t_ms[2] = ms(t2, t3); m->t_ms[3] = ms(t0, t3);
-    *out = M[0];
+    *out = M0;
     return 0;
 }
 
