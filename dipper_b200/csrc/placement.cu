@@ -34,7 +34,7 @@ struct PlQueue {
 };
 __device__ void bfs_closest(const int* head, const int* nxt, const int* e, const double* len, double* cdis, int* cid,
                             int x, int* q_node, int* q_from, double* q_dis, unsigned int* s_tail, PlShared* prof,
-                            int leaf_limit, int split_node_min) {
+                            int leaf_limit, int split_node_min, const PlDirty* dirty = nullptr, const int* rev = nullptr) {
     __shared__ unsigned int lo, hi;
     __shared__ PlQueue q;
     if (threadIdx.x == 0) {
@@ -53,10 +53,21 @@ __device__ void bfs_closest(const int* head, const int* nxt, const int* e, const
             // The slots of a node never change after it is created: a leaf (id < leaf_limit) has one, an inner node made
             // by split_edge (id >= split_node_min) has head, head - 2, head - 3 (c3, c1, c0); only nodes of a loaded
             // backbone need the linked list.
-            int s = head[node];
-            if (node < leaf_limit) { if (k > 0) continue; }
-            else if (node >= split_node_min) s -= (k == 0 ? 0 : k + 1);
-            else for (int j = 0; j < k && s != -1; j++) s = nxt[s];
+            // Tip p >= first_split_tip owns slots 4p-4 .. 4p-1 (c0: middle->x, c1: middle->y, c2: p->middle, c3: middle->p) and
+            // made the inner node p + leaf_limit - 1, so its slots follow from the node number: no head[] round trip per
+            // BFS level.  Only the first two leaves and the nodes of a loaded backbone go through the lists.
+            int s;
+            const int first_tip_ = split_node_min == 0x7fffffff ? 0x7fffffff : split_node_min - leaf_limit + 1;
+            if (node < leaf_limit) {
+                if (k > 0) continue;
+                s = node >= first_tip_ ? 4 * node - 2 : head[node];
+            } else if (node >= split_node_min) {
+                const int p4 = 4 * (node - leaf_limit + 1);
+                s = k == 0 ? p4 - 1 : (k == 1 ? p4 - 3 : p4 - 4);
+            } else {
+                s = head[node];
+                for (int j = 0; j < k && s != -1; j++) s = nxt[s];
+            }
             if (s == -1) continue;
             // one round trip for everything the slot needs: target node, length, the 5-entry list
             const int to = e[s];
@@ -76,6 +87,7 @@ __device__ void bfs_closest(const int* head, const int* nxt, const int* e, const
                     if (j > at) { cdis[s * KC5 + j] = cd[j - 1]; cid[s * KC5 + j] = ci[j - 1]; }
                     else if (j == at) { cdis[s * KC5 + j] = d; cid[s * KC5 + j] = x; }
                 }
+                if (dirty) pl_mark_dirty(*dirty, node > to ? s : rev[s]);   // the edge's candidate slot is the one with belong > e
                 const unsigned int pos = atomicAdd(s_tail, 1u);
                 const double nd = d + ls;
                 if (pos < PL_QCAP) { q.node[pos] = to; q.from[pos] = node; q.dis[pos] = nd; }
@@ -174,6 +186,176 @@ place_batch_kernel(int* head, int* e, int* nxt, int* belong, double* len, int* c
         pl_grid_barrier(&ps->bar_counter, G, gen);
         PL_MARK(3);
     }
+}
+
+// ---- speculative batches (experiment, DIPB_PLACE_SPEC=1) --------------------------------------------------------------
+// The per-tip kernel above synchronises the whole grid twice per tip (3.5 k + 2.2 k cycles of software barrier) around
+// 6-8 k cycles of scoring, and then one CTA works alone for 20 k cycles.  Here a batch of T tips is scored at once
+// against the tree AS IT IS WHEN THE BATCH STARTS (all SMs, slot data read once per four tips), and then ONE CTA places
+// the tips in order without any grid-wide step: the score of a slot only changes when an insertion touches its edge
+// (the split edge, the four new slots, the slots whose closest-leaf list the BFS updates: ~20 per tip), those slots are
+// collected in a dirty list and re-scored exactly for every later tip of the batch; the best untouched slot of a tip is
+// the one the batch scoring found -- unless that very slot has been touched, in which case the batch ends early and a
+// new one starts at this tip.  Same winner, same tie-break (smallest slot among equal pendant lengths), same arrays.
+constexpr int PSQ = 4;   // tips per CTA in the batch scoring
+__global__ void __launch_bounds__(256)
+place_spec_score_kernel(const int* __restrict__ e, const int* __restrict__ belong, const double* __restrict__ len,
+                        const int* __restrict__ cid, const double* __restrict__ cdis, const int* __restrict__ rev, int nslots,
+                        const double* __restrict__ rows, size_t ld, int row_base, int t0, int T, PlCand* __restrict__ part) {
+    __shared__ PlCand sb[PSQ][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = blockIdx.x, slice = blockIdx.y, nslices = gridDim.y;
+    const double* dis[PSQ];
+    double badd[PSQ];
+    int bslot[PSQ];
+#pragma unroll
+    for (int j = 0; j < PSQ; j++) {
+        const int t = t0 + min(g * PSQ + j, T - 1);
+        dis[j] = rows + (size_t)(t - row_base) * ld;
+        badd[j] = 2.0; bslot[j] = 0;
+    }
+    for (int q = slice * 256 + threadIdx.x; q < nslots; q += nslices * 256) {
+        if (!(belong[q] > e[q])) continue;
+        const int r = rev[q];
+        int iq[KC5], ir[KC5];
+        double dq[KC5], dr[KC5];
+#pragma unroll
+        for (int k = 0; k < KC5; k++) { iq[k] = cid[q * KC5 + k]; dq[k] = cdis[q * KC5 + k]; ir[k] = cid[r * KC5 + k]; dr[k] = cdis[r * KC5 + k]; }
+        const double L = len[q];
+#pragma unroll
+        for (int j = 0; j < PSQ; j++) {
+            double d1 = 0, d2 = 0;
+#pragma unroll
+            for (int k = 0; k < KC5; k++) {
+                if (iq[k] != -1) { const double v = dis[j][iq[k]] - dq[k]; if (v > d1) d1 = v; }
+                if (ir[k] != -1) { const double v = dis[j][ir[k]] - dr[k]; if (v > d2) d2 = v; }
+            }
+            double a = (d1 + d2 - L) / 2;
+            if (a < 0) a = 0;
+            d1 -= a; d2 -= a;
+            if (d1 < 0) d1 = 0;
+            if (d2 < 0) d2 = 0;
+            if (d1 > L) a += d1 - L;
+            if (d2 > L) a += d2 - L;
+            if (a < badd[j] || (a == badd[j] && q < bslot[j])) { badd[j] = a; bslot[j] = q; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < PSQ; j++) {
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const double oa = __shfl_xor_sync(0xffffffffu, badd[j], s);
+            const int os = __shfl_xor_sync(0xffffffffu, bslot[j], s);
+            if (oa < badd[j] || (oa == badd[j] && os < bslot[j])) { badd[j] = oa; bslot[j] = os; }
+        }
+        if (lane == 0) { sb[j][w].add = badd[j]; sb[j][w].slot = bslot[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < PSQ && g * PSQ + (int)threadIdx.x < T) {
+        const int j = threadIdx.x;
+        PlCand b = sb[j][0];
+        for (int k = 1; k < 8; k++)
+            if (sb[j][k].add < b.add || (sb[j][k].add == b.add && sb[j][k].slot < b.slot)) b = sb[j][k];
+        b.frac = 0.0;
+        part[(size_t)slice * T + g * PSQ + j] = b;     // (add >= 2: no candidate in this slice)
+    }
+}
+
+__global__ void __launch_bounds__(PL_THREADS)
+place_spec_seq_kernel(int* head, int* e, int* nxt, int* belong, double* len, int* cid, double* cdis, int* rev,
+                      const double* __restrict__ rows, size_t ld, int row_base, int t0, int T, int node_off, PlShared* ps,
+                      const PlCand* __restrict__ part, int nslices, int* q_node, int* q_from, double* q_dis, PlDirty dirty,
+                      int* next_out, int first_split_tip, int profile) {
+    __shared__ PlCand sb[PL_THREADS / 32];
+    __shared__ PlCand s_clean;
+    __shared__ unsigned int s_tail;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    long long tm = clock64();
+#define PS_MARK(k)                                                                  \
+    do {                                                                            \
+        if (profile && tid == 0) {                                                  \
+            const long long now__ = clock64();                                      \
+            ps->cyc[k] += (unsigned long long)(now__ - tm);                         \
+            tm = now__;                                                             \
+        }                                                                           \
+    } while (0)
+    auto better = [](double a, int s, double oa, int os) { return oa < a || (oa == a && os < s); };
+    for (int t = t0; t < t0 + T; t++) {
+        const double* dis = rows + (size_t)(t - row_base) * ld;
+        // best slot of the batch scoring: first minimum over the slices
+        if (w == 0) {
+            double a = 2.0; int sl = 0;
+            for (int s = lane; s < nslices; s += 32) {
+                const PlCand c = part[(size_t)s * T + (t - t0)];
+                if (c.add < 2.0 && better(a, sl, c.add, c.slot)) { a = c.add; sl = c.slot; }
+            }
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const double oa = __shfl_xor_sync(0xffffffffu, a, s);
+                const int os = __shfl_xor_sync(0xffffffffu, sl, s);
+                if (better(a, sl, oa, os)) { a = oa; sl = os; }
+            }
+            if (lane == 0) { s_clean.add = a; s_clean.slot = a < 2.0 ? sl : 0; }
+        }
+        __syncthreads();
+        const int cs = s_clean.slot;
+        const unsigned int nd = *reinterpret_cast<volatile unsigned int*>(dirty.count);
+        if ((cs != 0 && __ldcg(&dirty.flag[cs]) == dirty.gen) || nd + 64u > (unsigned int)dirty.cap) {
+            // the batch's answer for this tip is stale (or the dirty list is about to overflow): a new batch starts here
+            if (tid == 0) *next_out = t;
+            return;
+        }
+        PS_MARK(0);
+        double badd = 2.0, bfrac = 0.0;
+        int bslot = 0;
+        if (tid == 0 && cs != 0) {
+            double f, a;
+            score_slot(dis, cid, cdis, len, rev, cs, f, a);
+            if (a < 2.0) { badd = a; bfrac = f; bslot = cs; }
+        }
+        for (unsigned int k = tid; k < nd; k += PL_THREADS) {
+            const int q = __ldcg(&dirty.list[k]);
+            if (__ldcg(&belong[q]) > __ldcg(&e[q])) {
+                double f, a;
+                score_slot(dis, cid, cdis, len, rev, q, f, a);
+                if (a < badd || (a == badd && q < bslot)) { badd = a; bfrac = f; bslot = q; }
+            }
+        }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const double oa = __shfl_xor_sync(0xffffffffu, badd, s), of = __shfl_xor_sync(0xffffffffu, bfrac, s);
+            const int os = __shfl_xor_sync(0xffffffffu, bslot, s);
+            if (oa < badd || (oa == badd && os < bslot)) { badd = oa; bfrac = of; bslot = os; }
+        }
+        if (lane == 0) { sb[w].add = badd; sb[w].frac = bfrac; sb[w].slot = bslot; }
+        __syncthreads();
+        PS_MARK(1);
+        if (profile && tid == 0) ps->bfs_nodes += nd;      // (dirty slots re-scored)
+        if (w == 0) {
+            PlCand b = sb[0];
+            for (int k = 1; k < PL_THREADS / 32; k++)
+                if (sb[k].add < b.add || (sb[k].add == b.add && sb[k].slot < b.slot)) b = sb[k];
+            if (!(b.add < 2.0)) { b.add = 2.0; b.frac = 0.0; b.slot = 0; }   // the (0,0,2) tuple at position 0 wins
+            const int idx = ps->idx;
+            const int xe = b.slot, ye = rev[xe];
+            split_edge_warp(head, nxt, e, len, cdis, cid, belong, rev, b.slot, b.frac, b.add, t, idx, node_off);
+            if (lane == 0) {
+                ps->idx = idx + 4;
+                // the three edges the split made: x - middle (xe / c0), y - middle (ye / c1), tip - middle (c2 / c3);
+                // middle is the newest node, so the slots leaving it (c0, c1, c3) are the candidates
+                pl_mark_dirty(dirty, idx); pl_mark_dirty(dirty, idx + 1); pl_mark_dirty(dirty, idx + 3);
+                pl_mark_dirty(dirty, xe); pl_mark_dirty(dirty, ye);      // (no longer candidates: their stamp ends a batch that chose them)
+            }
+            __threadfence_block();
+        }
+        __syncthreads();
+        PS_MARK(5);
+        bfs_closest(head, nxt, e, len, cdis, cid, t, q_node, q_from, q_dis, &s_tail, nullptr, node_off, first_split_tip + node_off - 1, &dirty, rev);
+        __threadfence();
+        __syncthreads();
+        PS_MARK(2);
+    }
+    if (tid == 0) *next_out = t0 + T;
 }
 
 __global__ void place_init_kernel(int* head, int* e, int* nxt, int* belong, double* len, int* cid, double* cdis, int* rev,
@@ -291,18 +473,81 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int 
     int profile = getenv("DIPB_PLACE_PROFILE") ? 1 : 0;
     DIPB_CUDA(cudaMemsetAsync(&sc->ps->bar_counter, 0, sizeof(unsigned int), c->stream));
     DIPB_CUDA(cudaMemsetAsync(sc->ps->cyc, 0, sizeof(unsigned long long) * 8, c->stream));
+    // DIPB_PLACE_SPEC=1: speculative batches (see place_spec_seq_kernel) instead of the per-tip cooperative kernel.  Exact
+    // (same arrays, tests/test_placement_gpu.py runs both) but NOT faster as it stands, so it is off by default: at 30 000
+    // tips 70 % of the 64-tip batches end early (35 tips per batch), the batch scoring costs as much per placed tip as the
+    // per-tip scoring it replaces (3.2 us), and the sequential kernel spends 11.7 k cycles per tip re-scoring 388 dirty
+    // slots on one SM plus 17.9 k on the split (five returning atomics for the dirty marks) and 21.7 k on the BFS:
+    // 29.9 k tips/s against 43-51 k for the per-tip kernel (profiles/r2_placement_experiments.json).
+    const char* esp = getenv("DIPB_PLACE_SPEC");
+    const bool spec = esp && atoi(esp) != 0;
+    const char* etb = getenv("DIPB_PLACE_BATCH");
+    const int TB = etb && atoi(etb) > 0 ? atoi(etb) : 64;
+    constexpr int DCAP = 1 << 16;
+    int *dflag = nullptr, *dlist = nullptr, *dnext = nullptr;
+    unsigned int* dcount = nullptr;
+    PlCand* part = nullptr;
+    int max_slices = 0, dgen = 0;
+    long long n_batches = 0, n_early = 0;
+    double t_score = 0;
+    if (spec) {
+        DIPB_CUDA(pool_alloc(c, (void**)&dflag, sizeof(int) * 8 * (size_t)n_alloc));
+        DIPB_CUDA(cudaMemsetAsync(dflag, 0, sizeof(int) * 8 * (size_t)n_alloc, c->stream));
+        DIPB_CUDA(pool_alloc(c, (void**)&dlist, sizeof(int) * DCAP));
+        DIPB_CUDA(pool_alloc(c, (void**)&dcount, sizeof(unsigned int) * 2));
+        dnext = reinterpret_cast<int*>(dcount + 1);
+        max_slices = 2 * G;
+        DIPB_CUDA(pool_alloc(c, (void**)&part, sizeof(PlCand) * (size_t)max_slices * TB));
+    }
     for (int i0 = first_tip; i0 < end && !rc; i0 += batch) {
         int i1 = i0 + batch < end ? i0 + batch : end;
         const double* rows; int row_base; size_t ldr;
         rc = place_fetch_rows(src, i0, i1, buf, ld, &rows, &row_base, &ldr);
         if (rc) break;
         int node_off = n_alloc;
-        void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &t->cid, &t->cdis, &t->rev, &rows, &ldr, &row_base,
-                        &i0, &i1, &node_off, &sc->ps, &cb, &sc->q_node, &sc->q_from, &sc->q_dis, &gen0, &profile, &first_tip};
-        cudaError_t e = cudaLaunchCooperativeKernel((void*)place_batch_kernel, dim3(G), dim3(PL_THREADS), args, 0, c->stream);
-        if (e != cudaSuccess) { set_error("placement: cooperative launch failed: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; break; }
-        c->launches++;
-        gen0 += 2u * (unsigned int)(i1 - i0);
+        if (!spec) {
+            void* args[] = {&t->head, &t->e, &t->nxt, &t->belong, &t->len, &t->cid, &t->cdis, &t->rev, &rows, &ldr, &row_base,
+                            &i0, &i1, &node_off, &sc->ps, &cb, &sc->q_node, &sc->q_from, &sc->q_dis, &gen0, &profile, &first_tip};
+            cudaError_t e = cudaLaunchCooperativeKernel((void*)place_batch_kernel, dim3(G), dim3(PL_THREADS), args, 0, c->stream);
+            if (e != cudaSuccess) { set_error("placement: cooperative launch failed: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; break; }
+            c->launches++;
+            gen0 += 2u * (unsigned int)(i1 - i0);
+            continue;
+        }
+        for (int t0 = i0; t0 < i1 && !rc;) {
+            const int T = t0 + TB < i1 ? TB : i1 - t0;
+            const int nslots = 4 * t0 - 4;
+            const int groups = (T + PSQ - 1) / PSQ;
+            // enough CTAs to fill the GPU, at least ~8 candidate slots per thread and slice
+            int nslices = (2 * G + groups - 1) / groups;
+            const int by_work = (nslots / 2 + 256 * 8 - 1) / (256 * 8);
+            if (nslices > by_work) nslices = by_work < 1 ? 1 : by_work;
+            if (nslices > max_slices) nslices = max_slices;
+            if (profile) cudaEventRecord(c->ev0, c->stream);
+            place_spec_score_kernel<<<dim3(groups, nslices), 256, 0, c->stream>>>(t->e, t->belong, t->len, t->cid, t->cdis, t->rev, nslots, rows, ldr, row_base, t0, T, part);
+            if (profile) cudaEventRecord(c->ev1, c->stream);
+            DIPB_CUDA(cudaMemsetAsync(dcount, 0, sizeof(unsigned int), c->stream));
+            PlDirty dirty{dflag, dlist, dcount, ++dgen, DCAP};
+            place_spec_seq_kernel<<<1, PL_THREADS, 0, c->stream>>>(t->head, t->e, t->nxt, t->belong, t->len, t->cid, t->cdis, t->rev, rows, ldr, row_base, t0, T,
+                                                                   node_off, sc->ps, part, nslices, sc->q_node, sc->q_from, sc->q_dis, dirty, dnext, first_tip, profile);
+            c->launches += 2;
+            int next = 0;
+            if (cudaMemcpyAsync(&next, dnext, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+                set_error("placement: batch [%d, %d) failed: %s", t0, t0 + T, cudaGetErrorString(cudaGetLastError()));
+                rc = DIPB_E_CUDA;
+                break;
+            }
+            if (next <= t0 || next > t0 + T) { set_error("placement: batch [%d, %d) made no progress (next = %d)", t0, t0 + T, next); rc = DIPB_E_STATE; break; }
+            n_batches++;
+            if (next < t0 + T) n_early++;
+            if (profile) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); t_score += ms; }
+            t0 = next;
+        }
+    }
+    if (spec) {
+        if (profile) fprintf(stderr, "[placement] speculative batches of %d tips: %lld batches, %lld ended early (%.1f tips per batch); batch scoring kernels %.1f ms in total\n", TB, n_batches, n_early,
+                             n_batches ? (double)(end - first_tip) / (double)n_batches : 0.0, t_score);
+        pool_free(c, dflag); pool_free(c, dlist); pool_free(c, dcount); pool_free(c, part);
     }
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (!rc && e != cudaSuccess) { set_error("placement: %s", cudaGetErrorString(e)); rc = DIPB_E_CUDA; }
@@ -310,7 +555,9 @@ static int place_run(dipb_ctx* c, const dipb_dist_source* src, int n_alloc, int 
         PlShared hs;
         if (cudaMemcpy(&hs, sc->ps, sizeof(hs), cudaMemcpyDeviceToHost) == cudaSuccess) {
             const double tips = (double)(end - first_tip);
-            fprintf(stderr, "[placement] tips %d..%d: cycles per tip (CTA 0): score %.0f, barrier 1 %.0f, argmin %.0f, split %.0f, BFS %.0f, barrier 2 %.0f; BFS levels %.1f, queue entries %.1f per tip\n",
+            if (spec) fprintf(stderr, "[placement] sequential kernel, cycles per tip: batch answer + staleness check %.0f, dirty re-scoring %.0f (%.0f slots), split %.0f, BFS %.0f\n",
+                              hs.cyc[0] / tips, hs.cyc[1] / tips, hs.bfs_nodes / tips, hs.cyc[5] / tips, hs.cyc[2] / tips);
+            else fprintf(stderr, "[placement] tips %d..%d: cycles per tip (CTA 0): score %.0f, barrier 1 %.0f, argmin %.0f, split %.0f, BFS %.0f, barrier 2 %.0f; BFS levels %.1f, queue entries %.1f per tip\n",
                     first_tip, end, hs.cyc[0] / tips, hs.cyc[1] / tips, hs.cyc[4] / tips, hs.cyc[5] / tips, hs.cyc[2] / tips, hs.cyc[3] / tips, hs.bfs_levels / tips, hs.bfs_nodes / tips);
         }
     }

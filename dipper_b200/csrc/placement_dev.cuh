@@ -34,6 +34,21 @@ struct PlShared {
     unsigned long long bfs_levels, bfs_nodes;
 };
 
+// Candidate slots whose score has changed since the current speculative batch started (placement.cu, place_run): a
+// generation stamp per slot plus a compact list.
+struct PlDirty {
+    int* flag;            // [8n] generation of the batch that last touched the slot's edge
+    int* list;            // [cap]
+    unsigned int* count;
+    int gen, cap;
+};
+__device__ __forceinline__ void pl_mark_dirty(const PlDirty& d, int cand) {
+    if (atomicExch(&d.flag[cand], d.gen) != d.gen) {
+        const unsigned int pos = atomicAdd(d.count, 1u);
+        if (pos < (unsigned int)d.cap) d.list[pos] = cand;
+    }
+}
+
 __device__ __forceinline__ void pl_grid_barrier(unsigned int* counter, unsigned int nblocks, unsigned int& gen) {
     gen++;
     __syncthreads();
