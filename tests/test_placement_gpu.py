@@ -135,3 +135,33 @@ def test_add_tips_onto_backbone(ctx, oracle):
     compare_trees(kp, ot, n, 4 * n - 4)
     new_names = [names[i] for i in order]
     assert kp.printTree(new_names) == ot.newick(new_names)
+
+
+@pytest.mark.parametrize("case", ["tiefree", "alisim", "add"])
+def test_speculative_batch_path_is_exact(ctx, oracle, monkeypatch, case):
+    """DIPB_PLACE_SPEC=1 (batch scoring + one-CTA sequential phase, placement.cu): same arrays as the oracle, including
+    tie-heavy data and add-tips onto a loaded backbone.  Off by default (not faster), kept exact."""
+    monkeypatch.setenv("DIPB_PLACE_SPEC", "1")
+    monkeypatch.setenv("DIPB_PLACE_BATCH", "16")
+    if case == "add":
+        n, B = 260, 120
+        codes, P, _ = make_msa(n, 1200, seed=29)
+        D = oracle.msa_dist_matrix(P, 1200, 2)
+        names = synth.names(n)
+        bb = oracle.place_all(np.ascontiguousarray(D[:B, :B])).newick(names[:B])
+        root, off, flat, parent, bl, leaf_names = _backbone_struct(bb, n)
+        order = [names.index(x) for x in leaf_names] + list(range(B, n))
+        Dp = np.ascontiguousarray(D[np.ix_(order, order)])
+        kp = api.KPlacementDeviceArrays(ctx)
+        kp.allocateDeviceArrays(n)
+        assert kp.initializeDeviceArrays(bb) == B
+        kp.addQuery(api.Param(in_="d"), matrix=api.Matrix.from_host(ctx, Dp))
+        compare_trees(kp, oracle.place_add(Dp, B, root, off, flat, parent, bl), n, 4 * n - 4)
+        return
+    n = 700 if case == "tiefree" else 300
+    codes, P, _ = make_msa(n, 1000, seed=207, regime=case, gap_cols=0.0, gap_runs=False)
+    D = oracle.msa_dist_matrix(P, 1000, 2 if case == "tiefree" else 1)
+    kp = api.KPlacementDeviceArrays(ctx)
+    kp.allocateDeviceArrays(n)
+    kp.findPlacementTree(api.Param(in_="d"), matrix=api.Matrix.from_host(ctx, D))
+    compare_trees(kp, oracle.place_all(D), n, 4 * n - 4)
