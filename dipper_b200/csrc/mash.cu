@@ -345,11 +345,13 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mash_warp_kernel(MashTileParams
 // position, and at most two lanes meet on a row-list bank -- the thread-per-pair kernel above spends ~5.5 shared-memory
 // wavefronts per step on random 8-byte reads.  A few extra rows of 0xFFFFFFFF after each list replace the index clamps.
 constexpr int MR_TA = 32;   // column sketches ("A" lists) per tile = lanes
-constexpr int MR_TB = 16;   // row sketches ("B" lists) per tile = warps
-constexpr int MR_THREADS = MR_TB * 32;
 constexpr int MR_PAD = 6;   // 0xFFFFFFFF rows after each list
 
-__global__ void __launch_bounds__(MR_THREADS, 1) mash_rank_kernel(MashTileParams p, const uint32_t* __restrict__ rk, long long num_tiles, int tiles_x) {
+// MR_TB = row sketches ("B" lists) per tile = warps: 24 when the tile fits shared memory (s <= 1031: 6 warps per scheduler hide
+// more of the compare -> select -> load chain than 4), else 16
+template <int MR_TB>
+__global__ void __launch_bounds__(MR_TB * 32, 1) mash_rank_kernel(MashTileParams p, const uint32_t* __restrict__ rk, long long num_tiles, int tiles_x) {
+    constexpr int MR_THREADS = MR_TB * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int s = p.s;
     uint32_t* sA = reinterpret_cast<uint32_t*>(smem_raw);          // [(s + MR_PAD)][32]
@@ -376,20 +378,19 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mash_rank_kernel(MashTileParams
                     sA[(size_t)(2 * h + 1) * MR_TA + lane] = v.y;
                 }
             }
-            // rows: lanes 0-15 / 16-31 = sketch, alternate element pairs
-            const int qb = lane & 15, r = row0 + qb;
-            if (r < p.r1) {
-                const uint2* src = reinterpret_cast<const uint2*>(rk + (size_t)r * s);
-#pragma unroll 8
-                for (int h = wid * 2 + (lane >> 4); h < half; h += 2 * MR_TB) {
-                    const uint2 v = __ldg(src + h);
+            // rows: consecutive threads = consecutive sketches of one element pair (conflict-free stores)
+#pragma unroll 4
+            for (int e = tid; e < MR_TB * half; e += MR_THREADS) {
+                const int qb = e % MR_TB, h = e / MR_TB, r = row0 + qb;
+                if (r < p.r1) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(rk + (size_t)r * s) + h);
                     sB[(size_t)(2 * h) * MR_TB + qb] = v.x;
                     sB[(size_t)(2 * h + 1) * MR_TB + qb] = v.y;
                 }
             }
         }
         __syncthreads();
-        const int ib = (lane + wid) & (MR_TB - 1);
+        const int ib = (lane + wid) % MR_TB;
         const int i = row0 + ib, j = col0 + lane;
         const int jlim = p.tri ? i : p.ncols;
         if (i < p.r1 && j < jlim && j < p.n) {
@@ -398,12 +399,12 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mash_rank_kernel(MashTileParams
             // critical path; an exhausted B list reads 0xFFFFFFFF (> every rank).  Every step consumes one element, so
             // inter = steps - uni.
             uint32_t pa = (uint32_t)__cvta_generic_to_shared(sA + lane), pb = (uint32_t)__cvta_generic_to_shared(sB + ib);
+            int uni = 0, steps = 0;
             uint32_t av, an, bv, bn;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(av) : "r"(pa));
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(an) : "r"(pa + MR_TA * 4));
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bv) : "r"(pb));
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bn) : "r"(pb + MR_TB * 4));
-            int uni = 0, steps = 0;
             // The element loaded in a step is committed at the top of the NEXT step (warps issue in order: consuming it in
             // the same step would park the warp on the load).  It becomes "next" then and "current" one step later at the
             // earliest, so nothing is compared before it has arrived.  Four steps per loop trip: the steps past the one
@@ -496,14 +497,21 @@ static int mash_launch(dipb_mash* m, MashTileParams p) {
     if (rows <= 0 || ncols <= 0) return 0;
     // ---- rank-compressed, interleaved tiles (default)
     const char* er = getenv("DIPB_MASH_RANKS");   // 0: keep the 64-bit hashes (first versions, kept for comparison)
-    const size_t rk_smem = (size_t)(m->s + MR_PAD) * (MR_TA + MR_TB) * sizeof(uint32_t);
+    const char* etb = getenv("DIPB_MASH_TB");     // 16: force the 16-row tile (comparison)
+    int TB = ((size_t)(m->s + MR_PAD) * (MR_TA + 24) * sizeof(uint32_t) <= 227 * 1024 && !(etb && atoi(etb) == 16)) ? 24 : 16;
+    const size_t rk_smem = (size_t)(m->s + MR_PAD) * (MR_TA + TB) * sizeof(uint32_t);
     if (!(er && atoi(er) == 0) && (size_t)m->n * m->s < 0xFFFFFFFFull && rk_smem <= 227 * 1024) {
         if (!m->ranks) { int rc = mash_build_ranks(m); if (rc) return rc; }
-        DIPB_CUDA(cudaFuncSetAttribute(mash_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rk_smem));   // (per device)
-        const int tiles_y = (rows + MR_TB - 1) / MR_TB, tiles_x = (ncols + MR_TA - 1) / MR_TA;
+        const int tiles_y = (rows + TB - 1) / TB, tiles_x = (ncols + MR_TA - 1) / MR_TA;
         const long long tiles = (long long)tiles_y * tiles_x;
         const int grid = (int)(tiles < (long long)c->num_sms * 4 ? tiles : (long long)c->num_sms * 4);
-        mash_rank_kernel<<<grid, MR_THREADS, rk_smem, c->stream>>>(p, m->ranks, tiles, tiles_x);
+        auto go = [&](auto kern, int threads) -> int {
+            DIPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rk_smem));   // (per device)
+            kern<<<grid, threads, rk_smem, c->stream>>>(p, m->ranks, tiles, tiles_x);
+            return 0;
+        };
+        const int rc = TB == 24 ? go(mash_rank_kernel<24>, 24 * 32) : go(mash_rank_kernel<16>, 16 * 32);
+        if (rc) return rc;
         DIPB_KERNEL_CHECK(c);
         return 0;
     }
