@@ -55,7 +55,7 @@ namespace {
 constexpr int MAXW = 32;      // warps per CTA at most
 constexpr int CPOOL = 128;    // carried candidate pairs per CTA
 constexpr int MAXCS = 16;
-constexpr int TILE = 256;     // selected rows staged in shared memory at a time
+constexpr int TILE = 128;     // selected rows staged in shared memory at a time
 constexpr int MAXPARTS = 32;  // units per row and CTA at most (the staged qualification mask is one word)
 constexpr unsigned long long KMAX = 0xffffffffffffffffull;
 constexpr unsigned int K32MAX = 0xffffffffu;   // row keys are order-preserving fp32, rounded DOWN (a lower bound stays one);
@@ -91,6 +91,14 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
     const unsigned int ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
     return ((unsigned long long)mh << 32) | ml;
 }
+// minimum over each HALF of the warp.  redux.sync with two 16-lane masks costs ~175 cycles on sm_100a (the halves are
+// serialised on a slow path; tools/experiments/warp_ops_latency.cu), a full-mask one 22: two full-mask ops, each half's
+// lanes standing aside in the other's.
+__device__ __forceinline__ unsigned int half_min_u32(unsigned int v, int lane) {
+    const unsigned int lo = __reduce_min_sync(0xffffffffu, lane < 16 ? v : 0xffffffffu);
+    const unsigned int hi = __reduce_min_sync(0xffffffffu, lane < 16 ? 0xffffffffu : v);
+    return lane < 16 ? lo : hi;
+}
 __device__ __forceinline__ double warp_min_f64(double v) { return dec_f64(warp_min_u64(enc_f64(v))); }
 __device__ __forceinline__ double warp_max_f64(double v) { return -warp_min_f64(-v); }
 
@@ -114,13 +122,8 @@ __device__ __forceinline__ unsigned int ld_peer_u32(const unsigned int* p, int r
 __device__ __forceinline__ void st_peer_f64(double* p, int rank, double v) {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(peer_addr(p, rank)), "d"(v) : "memory");
 }
-__device__ __forceinline__ void red_peer_min_u32(unsigned int* p, int rank, unsigned int v) {
-    asm volatile("red.shared::cluster.min.u32 [%0], %1;" ::"r"(peer_addr(p, rank)), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int atom_peer_min_u32(unsigned int* p, int rank, unsigned int v) {
-    unsigned int old;
-    asm volatile("atom.shared::cluster.min.u32 %0, [%1], %2;" : "=r"(old) : "r"(peer_addr(p, rank)), "r"(v) : "memory");
-    return old;
+__device__ __forceinline__ void st_peer_v4(uint4* p, int rank, unsigned int a, unsigned int b, unsigned int c, unsigned int d) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(peer_addr(p, rank)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void st_peer_s32(int* p, int rank, int v) {
     asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(peer_addr(p, rank)), "r"(v) : "memory");
@@ -163,7 +166,8 @@ __device__ __forceinline__ int warp_best_lane(double t, int i, int j, int n) {
 
 // bytes of dynamic shared memory for LS owned rows per CTA and `chunks` 32-row chunks in total
 inline size_t cluster_smem_bytes(int LS, int chunks) {
-    return sizeof(double) * ((size_t)6 * LS + chunks + 2) + sizeof(unsigned int) * (size_t)3 * LS + (size_t)TILE * (3 * 8 + 8 + 4 + 4 + 4);
+    return sizeof(double) * ((size_t)6 * LS + chunks + 2) + sizeof(unsigned int) * (size_t)3 * LS + (size_t)TILE * (3 * 8 + 8 + 4 + 4 + 4) +
+           (size_t)TILE * MAXCS * 16;   // + the result slots
 }
 
 }  // namespace
@@ -260,7 +264,10 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     unsigned int* const Kmine = Kb + (size_t)rank * PARTS * KLD;   // + part * KLD + row
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* U_s = reinterpret_cast<double*>(smem_raw);   // [2][LS] row sums of owned rows; buffer `cur` is valid, A writes the other
+    // result slots of the staged tile: slot_s[k][q] = what CTA q found in its slice of staged row k (key of its minimum, its
+    // column, key of its runner-up), written by CTA q into the shared memory of the row's OWNER with one 16-byte store
+    uint4* slot_s = reinterpret_cast<uint4*>(smem_raw);
+    double* U_s = reinterpret_cast<double*>(smem_raw + (size_t)TILE * MAXCS * 16);   // [2][LS] row sums of owned rows; buffer `cur` is valid, A writes the other
     double* u_s = U_s + 2 * LS;                          // [LS] U / (n - 2)
     double* v_s = u_s + LS;                              // [LS] distance to the newest node x
     double* f_s = v_s + LS;                              // [LS] distance to the node moved into slot y
@@ -289,7 +296,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     __shared__ int pool_i[CPOOL], pool_j[CPOOL];
     __shared__ double pool_d[CPOOL];        // d of a carried pair never changes while both ends survive
     __shared__ double pool_t[CPOOL];        // its value at the last re-evaluation: new candidates replace worse ones only
-    __shared__ int s_pool_head, s_nsel;
+    __shared__ int s_nsel;
     __shared__ unsigned int s_nunits;          // live scan units of the staged tile
     __shared__ unsigned short s_ulist[TILE * 12];   // (staged row << 5) | unit, in no particular order
     __shared__ unsigned long long s_cyc[32];   // rank 0, thread 0: cycles per phase (DIPB_NJ_PROFILE)
@@ -305,7 +312,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     }
     if (tid == 0) t_row[0] = 0;
     for (int p = tid; p < CPOOL; p += CT) { pool_i[p] = -1; pool_j[p] = -1; pool_t[p] = 1e300; }
-    if (tid == 0) { s_pool_head = 0; s_sel = 0; s_uy = 0.0; }
+    if (tid == 0) { s_sel = 0; s_uy = 0.0; }
     if (tid < 32) s_cyc[tid] = 0;
     __syncthreads();
     cluster.sync();
@@ -320,27 +327,51 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     unsigned long long my_rows = 0, my_units = 0;
     unsigned int* sel0 = cluster.map_shared_rank(&s_sel, 0);
 
-    // Partner records: the CTA whose slice holds a scanned row's minimum (its key equals the combined K1) tells the
-    // owner the column and the exact distance, so that the owner can re-evaluate that pair exactly instead of
-    // rescanning the row while only the bound has drifted.  Runs after a cluster barrier that follows the key flush.
-    auto partner_records = [&](int tn, bool merged, int x, int y, int n, int iter) {
-        for (int k = w; k < tn; k += NW) {        // one warp per row (divergent DSMEM targets serialise within a warp)
-            if (lane != 0) continue;
-            const unsigned long long best = t_best[k];
-            const unsigned int k1 = (unsigned int)(best >> 32);
-            if (k1 == K32MAX) continue;
-            const int r = t_row[k];
+    // Resolve (runs at the OWNER of a staged row, after the cluster barrier that follows the slot pushes): the row's
+    // minimum over the CS slices becomes its tracked partner (K1, a, exact distance da: re-evaluated exactly later instead
+    // of rescanning the row while only the bound has drifted), everything else bounds the runner-up K2.  No cross-CTA
+    // round trip: the slots are local.  Half a warp per row, lane q reads slot q.  A selection that fitted one tile is
+    // resolved in phase A of the NEXT merge, in the shadow of its row loads (`defer`; nothing reads K1 / K2 / a / da before
+    // that merge's selection); the tiles of a longer one right after their scan.
+    const double* pend_ptr = nullptr;
+    int pend_rs = -1;
+    unsigned int done_early = 0;
+    double rden = 0.0;                        // 1 / (n - 3): reciprocal of the next merge's divisor, computed inside barrier 2
+    int pool_head = 0;                        // rotating insertion point of the candidate pool (same in every thread)
+    auto resolve = [&](int tn, bool merged, int x, int y, int n, int iter, bool defer) {
+        for (int k = w * 2 + (lane >> 4); k - (lane >> 4) < tn; k += 2 * NW) {
+            const int hl = lane & 15;
+            const bool have = k < tn;
+            const int r = have ? t_row[k] : 0;
             const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
-            if (ld_peer_u32(&K1_s[rs], ro) != k1) continue;
-            const int j1 = (int)(unsigned int)best;
+            const bool mine = have && ro == rank;
+            uint4 e = make_uint4(K32MAX, 0xffffffffu, K32MAX, 0u);
+            if (mine && hl < CS) e = slot_s[k * MAXCS + hl];
+            const unsigned int k1m = half_min_u32(e.x, lane);
+            const unsigned int j1m = half_min_u32(e.x == k1m ? e.y : 0xffffffffu, lane);
+            const bool win = e.x == k1m && e.y == j1m;
+            const unsigned int k2m = half_min_u32(win ? e.z : (e.x < e.z ? e.x : e.z), lane);
+            if (!mine || hl != 0) continue;
+            K1_s[rs] = k1m; K2_s[rs] = k2m;
+            if (k1m == K32MAX) continue;                   // nothing scanned: a_s stays -1 (reset by the selection)
+            const int j1 = (int)j1m;
+            a_s[rs] = j1;
+            if (defer) {
+                // (phase A: D is complete, the pick has waited for the helpers.)  The first row of a lane is only recorded and
+                // loaded behind phase A's row loads; more than one row per lane is rare (> 30 selected rows)
+                if (pend_rs < 0) { pend_rs = rs; pend_ptr = &D[(size_t)r * ld + j1]; }
+                else da_s[rs] = __ldcg(&D[(size_t)r * ld + j1]);
+                continue;
+            }
+            // between the tiles of a long selection the helpers may still be writing D: columns x and y of an old row come
+            // from v / f of the row, rows x and y from the scratch pair
             double da;
             if (merged && r != x && r != y && j1 == x) da = t_v[k];
             else if (merged && r != x && r != y && j1 == y && y < n) da = t_f[k];
-            else if (merged && r == x) da = __ldcg(&R[(size_t)(iter & 1) * 2 * ld + j1]);          // (rows x, y: scratch, see phase A)
+            else if (merged && r == x) da = __ldcg(&R[(size_t)(iter & 1) * 2 * ld + j1]);
             else if (merged && r == y && y < n) da = __ldcg(&R[((size_t)(iter & 1) * 2 + 1) * ld + j1]);
             else da = __ldcg(&D[(size_t)r * ld + j1]);
-            st_peer_s32(&a_s[rs], ro, j1);
-            st_peer_f64(&da_s[rs], ro, da);
+            da_s[rs] = da;
         }
     };
 
@@ -366,7 +397,6 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             CL_MARK(0);
             const int last = n - 1;
             const double den_new = (double)(n - 3);
-            const double rden = 1.0 / den_new;
             const int nchunk = (last + 31) >> 5;               // chunks holding rows < last
             double* const Rx = R + (size_t)(iter & 1) * 2 * ld;  // scratch rows of this merge
             double* const Ry = Rx + ld;
@@ -385,6 +415,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 p_a = __ldcg(&D[(size_t)x * ld + src]); p_b = __ldcg(&D[(size_t)y * ld + src]);
                 p_U = ld_peer_f64(&Uo[((src >> 5) / CS) * 32 + (src & 31)], (src >> 5) % CS);
             }
+            double pend_da = 0.0;
+            bool resolved = false;
             double dmx = -1e300;
             // A warp owns chunks lw = w, w + NW, ... (two at 30 000 tips): the loads of up to AB of them are issued before any
             // is consumed -- one exposed memory round trip per merge instead of one per chunk (measured 5.4 k -> cycles below)
@@ -402,7 +434,14 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         lf[c] = __ldcg(&D[(size_t)last * ld + i]);
                     }
                 }
-                if (PROF && lwb == w) { CL_MARK(18); asm volatile("" ::"d"(la[0]), "d"(lb[0]), "d"(lf[0])); CL_MARK(19); }
+                if (PROF && lwb == w) { CL_MARK(18); }
+                if (!resolved) {
+                    // the previous scan's results, in the shadow of the loads just issued (see `resolve`)
+                    if (s_nsel <= TILE) resolve(s_nsel, true, -1, -1, n, iter, true);
+                    if (pend_rs >= 0) pend_da = __ldcg(pend_ptr);
+                    resolved = true;
+                }
+                if (PROF && lwb == w) { CL_MARK(19); }
 #pragma unroll
                 for (int c = 0; c < AB; c++) {
                     const int lw = lwb + c * NW;
@@ -444,6 +483,11 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 }
             }
             CL_MARK(20);
+            if (!resolved) {           // (a warp without chunks)
+                if (s_nsel <= TILE) resolve(s_nsel, true, -1, -1, n, iter, true);
+                if (pend_rs >= 0) pend_da = __ldcg(pend_ptr);
+            }
+            if (pend_rs >= 0) { da_s[pend_rs] = pend_da; pend_rs = -1; }
             // unit keys of the row that moves from `last` into slot y: every CTA copies its own units
             if (y < last && tid >= CT - 32 && lane < PARTS) Kmine[(size_t)lane * KLD + y] = __ldcg(&Kmine[(size_t)lane * KLD + last]);
             {
@@ -514,7 +558,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     if (HC > 0 && rank == 0) {
                         // what the helpers' key fold needs, each word tagged with the merge number (see NJCtl)
                         const unsigned long long tag = (unsigned long long)(unsigned int)iter << 32;
-                        const unsigned long long w0 = tag | __float_as_uint(__double2float_ru(acc / (double)(n - 2)));
+                        const unsigned long long w0 = tag | __float_as_uint(__double2float_ru(div_rn(acc, (double)(n - 2), rden)));
                         const unsigned long long w1 = tag | __float_as_uint(__double2float_ru(s_uy));
                         const unsigned long long w2 = tag | __float_as_uint(__double2float_rd(C + drift));
                         asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->pw[0]), "l"(w0) : "memory");
@@ -526,7 +570,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             }
             CL_MARK(3);
             const double total = s_total;
-            ux = total / (double)(n - 2);
+            ux = div_rn(total, (double)(n - 2), rden);   // (correctly rounded, see div_rn)
             C = s_C;
             marg = 1e-9 * (4.0 * dmax + fabs(C));
             if (((x >> 5) % CS) == rank && tid == 0) {
@@ -635,7 +679,13 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             }
         }
         CL_MARK(6);
-        cluster.sync();
+        {
+            // barrier 2, split: the reciprocal the next merge divides by (a ~130-cycle dependent chain) is computed between
+            // arrive and wait instead of in front of phase A's loads and of the new row's u in phase B
+            auto tok = cluster.barrier_arrive();
+            rden = 1.0 / (double)(n - 3);
+            cluster.barrier_wait(std::move(tok));
+        }
         CL_MARK(7);
         if (PROF && rank == 0 && tid == 0) {
             // probe: how long does one global load of a fixed, L2-resident word take right after the barrier?
@@ -676,7 +726,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             // the average drift so far is read now, while its row is staged anyway.  Without this every unit drifts to
             // the threshold on its own and costs its row a selection of its own (measured: 129 selected rows per merge
             // instead of 13); with it a row comes back when its runner-up does, as with whole-row rescans.
-            const double slack = iter > 0 ? slack_merges * (fabs(C) / (double)iter) : 0.0;   // (C may be negative: never tighten)
+            const double slack = iter > 0 ? (double)((float)slack_merges * __fdividef((float)fabs(C), (float)iter)) : 0.0;   // (a heuristic: fp32 is plenty; C may be negative: never tighten)
             unsigned int* const Kxg = Kb + ((size_t)((x >= 0 ? x >> 5 : 0) % CS) * PARTS + ((x >= 0 ? x >> 5 : 0) / CS) / UC) * KLD;
             unsigned int* const Kyg = Kb + ((size_t)((y >= 0 ? y >> 5 : 0) % CS) * PARTS + ((y >= 0 ? y >> 5 : 0) / CS) / UC) * KLD;
             double bt = 1e300, bd = 0.0, bui = 0.0, buj = 0.0;
@@ -695,7 +745,6 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 for (int k = w * 2 + (lane >> 4); k - (lane >> 4) < tn; k += 2 * NW) {
                     // half warp per row: lane hl of the half handles unit hl (parts <= 12)
                     const int hl = lane & 15;
-                    const unsigned int hmask = 0xffffu << (lane & 16);
                     const bool have = k < tn;
                     // the first tile was pushed into t_row / t_u / t_v / t_f by the row owners (phase B); later tiles (first
                     // search, bursts) come from the spill list in global memory and the owners' shared memory
@@ -722,7 +771,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         q = q && !(((double)dec_f32(kv) - C) - ur - marg > ub + slack);
                     }
                     const unsigned int qm = (__ballot_sync(0xffffffffu, q) >> (lane & 16)) & 0xffffu;
-                    const unsigned int rest = __reduce_min_sync(hmask, (have && hl < parts && !q) ? kv : K32MAX);
+                    const unsigned int rest = half_min_u32((have && hl < parts && !q) ? kv : K32MAX, lane);
                     unsigned int base = 0;
                     if (have && hl == 0) {
                         if (t0 > 0) { t_row[k] = r; t_u[k] = ur; t_v[k] = vr; t_f[k] = fr; }
@@ -828,27 +877,23 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 }
                 __syncthreads();
                 CL_MARK(9);
-                // this CTA's minimum of each staged row goes to the row owner's key; skipped units only bound the runner-up
-                // (one warp per row, see the staging loop)
+                // what this CTA found for each staged row goes to the row owner's slot (one warp per row, see the staging loop)
                 for (int k = w; k < tn; k += NW) {
                     if (lane != 0) continue;
-                    const unsigned int k1 = (unsigned int)(t_best[k] >> 32);
-                    const unsigned int k2 = t_k2[k];
+                    const unsigned long long best = t_best[k];
                     const int r = t_row[k];
-                    const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
-                    if (k1 != K32MAX) {
-                        const unsigned int old = atom_peer_min_u32(&K1_s[rs], ro, k1);
-                        const unsigned int demoted = k1 < old ? old : k1;
-                        red_peer_min_u32(&K2_s[rs], ro, demoted < k2 ? demoted : k2);
-                    } else if (k2 != K32MAX) red_peer_min_u32(&K2_s[rs], ro, k2);
+                    st_peer_v4(&slot_s[k * MAXCS + rank], (r >> 5) % CS, (unsigned int)(best >> 32), (unsigned int)best, t_k2[k], 0u);
                 }
                 if (nsel > TILE) {
-                    // rare (first search, bursts): one extra cluster barrier per tile so that every tile gets its records
+                    // rare (first search, bursts): two extra cluster barriers per tile -- the owners resolve this tile before
+                    // anyone pushes the next one
                     cluster.sync();
-                    partner_records(tn, merged, x, y, n, iter);
-                    __syncthreads();
+                    resolve(tn, merged, x, y, n, iter, false);
+                    cluster.sync();
                 }
             }
+            // helpers' progress, sampled here and looked at in the pick (see there)
+            if (HC > 0 && lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done_early) : "l"(&ctl->done) : "memory");
             // the next merge reads row n - 1 (it moves into the freed slot): pull my chunks of it into L2 now
             if (n > 3 && lane < 2) {
                 const int pch = (n - 1 + 31) >> 5;
@@ -879,69 +924,77 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
 
         // ---------------------------------------------------------------- D: pick (identical in every CTA)
         {
-            if (HC > 0 && tid == 32 && iter > 0) {
-                // the next update reads whole rows: the helpers must have finished the columns of the previous merge
-                // (one thread of warp 1 polls while the other warps pick the pair; the __syncthreads below publish it)
+            // No CTA barrier in this stretch (each costs ~350 cycles here): every warp checks the helpers, finds the winner and
+            // keeps its own pool slots by itself, and phase A follows without a join.
+            if (HC > 0 && iter > 0 && lane == 0) {
+                // the next update reads whole rows: the helpers must have finished the columns of the previous merge.  The
+                // counter was sampled before barrier 3 (a global round trip that would otherwise sit here); only if the helpers
+                // were not done by then does the lane poll
                 const unsigned int want = (unsigned int)iter * (unsigned int)HC;
-                unsigned int dn;
-                do {
+                unsigned int dn = done_early;
+                while ((int)(dn - want) < 0) {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dn) : "l"(&ctl->done) : "memory");
-                } while ((int)(dn - want) < 0);
+                }
             }
-            // partner records of a selection that fitted one tile (larger selections did this per tile in phase C)
-            if (s_nsel <= TILE) partner_records(s_nsel, !first, x, y, n, iter);
-            if (w == 0) {
-                const int src = lane < CS ? lane : 0;
-                const int ci = lane < CS ? recs[src].i : -1;
-                const int wl = warp_best_lane(recs[src].t, ci, recs[src].j, n);
-                if (lane == 0) wrec[0] = recs[wl < 0 ? 0 : wl];
-            }
-            // this scan's warp winners (still in wrec[1..]) go to the pool below
-            const int mi = (tid < NW && tid > 0) ? wrec[tid].i : -1, mj = (tid < NW && tid > 0) ? wrec[tid].j : -1;
-            const double md = (tid < NW && tid > 0) ? wrec[tid].d : 0.0, mt = (tid < NW && tid > 0) ? wrec[tid].t : 1e300;
-            __syncthreads();
-            const int wi = wrec[0].i, wj = wrec[0].j;
-            const double wd = wrec[0].d, wui = wrec[0].ui, wuj = wrec[0].uj;
+            __syncwarp();
+            CL_MARK(26);
+            // the cluster's winner (recs[] is complete after barrier 3)
+            const int src = lane < CS ? lane : 0;
+            const int ci = lane < CS ? recs[src].i : -1;
+            const int wl = warp_best_lane(recs[src].t, ci, recs[src].j, n);
+            CL_MARK(29);
+            const CRec* const win = &recs[wl < 0 ? 0 : wl];
+            const int wi = win->i, wj = win->j;
+            const double wd = win->d, wui = win->ui, wuj = win->uj;
             double uxo, uyo;
             if (wi < wj) { x = wi; y = wj; uxo = wui; uyo = wuj; } else { x = wj; y = wi; uxo = wuj; uyo = wui; }
             dxy = wd;
             const int last_ = n - 1;
-            for (int p = tid; p < CPOOL; p += CT) {
-                const int pi = pool_i[p], pj = pool_j[p];
-                if (pi >= 0) {
-                    if (pi == x || pi == y || pj == x || pj == y) pool_i[p] = -1;
-                    else {
-                        if (pi == last_) pool_i[p] = y;
-                        if (pj == last_) pool_j[p] = y;
+            {
+                // candidate pool: the lane pair that re-evaluates slot pc in phase A also keeps it -- drop a pair that lost an
+                // end, rename `last`, then take this scan's winner of warp q (still in wrec[1..NW-1]; slot (pool_head + q) %
+                // CPOOL) if it is better than what the slot holds
+                constexpr int PCW = CPOOL / NW;
+                const int pc = w * PCW + (lane >> 1);
+                if (lane < 2 * PCW && !(lane & 1)) {
+                    int pi = pool_i[pc], pj = pool_j[pc];
+                    if (pi >= 0) {
+                        if (pi == x || pi == y || pj == x || pj == y) pi = -1;
+                        else {
+                            if (pi == last_) pi = y;
+                            if (pj == last_) pj = y;
+                        }
                     }
+                    const int q = (pc - pool_head + CPOOL) % CPOOL;
+                    if (q > 0 && q < NW) {
+                        const int mi = wrec[q].i, mj = wrec[q].j;
+                        const double mt = wrec[q].t;
+                        // keep the best: a slot is overwritten only by a candidate that is better than its last evaluation
+                        if (mi >= 0 && mi != x && mi != y && mj != x && mj != y && (pi < 0 || mt < pool_t[pc])) {
+                            pi = mi == last_ ? y : mi;
+                            pj = mj == last_ ? y : mj;
+                            pool_d[pc] = wrec[q].d;
+                            pool_t[pc] = mt;
+                        }
+                    }
+                    pool_i[pc] = pi; pool_j[pc] = pj;
                 }
+                __syncwarp();
             }
-            __syncthreads();
-            if (tid > 0 && tid < NW && mi >= 0 && mi != x && mi != y && mj != x && mj != y) {
-                // keep the best: a slot is overwritten only by a candidate that is better than its last evaluation
-                const int slot = (s_pool_head + tid) % CPOOL;
-                if (pool_i[slot] < 0 || mt < pool_t[slot]) {
-                    pool_i[slot] = mi == last_ ? y : mi;
-                    pool_j[slot] = mj == last_ ? y : mj;
-                    pool_d[slot] = md;
-                    pool_t[slot] = mt;
-                }
+            pool_head = (pool_head + NW) % CPOOL;
+            CL_MARK(30);
+            if (rank == 0 && tid == 0) {
+                // host step of the reference, src/neighborJoining.cu:219-237; the realID bookkeeping
+                // (:233-237) is replayed on the host from this log
+                double blX = (dxy + uxo - uyo) * 0.5;
+                double blY = dxy - blX;
+                if (blX < 0) { blY += blX; blX = 0; }
+                if (blY < 0) { blX += blY; blY = 0; }
+                log_xy[iter] = make_int2(x, y);
+                log_bl[iter] = make_double2(blX, blY);
+                s_sel = 0;   // next appended to after two more cluster barriers
             }
-            __syncthreads();
-            if (tid == 0) {
-                s_pool_head = (s_pool_head + NW) % CPOOL;
-                if (rank == 0) {
-                    // host step of the reference, src/neighborJoining.cu:219-237; the realID bookkeeping
-                    // (:233-237) is replayed on the host from this log
-                    double blX = (dxy + uxo - uyo) * 0.5;
-                    double blY = dxy - blX;
-                    if (blX < 0) { blY += blX; blX = 0; }
-                    if (blY < 0) { blX += blY; blY = 0; }
-                    log_xy[iter] = make_int2(x, y);
-                    log_bl[iter] = make_double2(blX, blY);
-                    s_sel = 0;   // next appended to after two more cluster barriers
-                }
-            }
+            CL_MARK(27);
             iter++;
         }
         first = false;
@@ -1124,8 +1177,10 @@ int nj_cluster_loop(dipb_matrix* m, double* U, double* u, int* realID, int32_t* 
     if (profile) {
         fprintf(stderr, "[nj_cluster]   stage detail (rank 0 warp 0): to first sync %.0f, key load issued %.0f, key arrived %.0f, unit test + list %.0f cyc/iter (then the CTA barrier)\n",
                 hs.cyc[17] / (double)hs.iters, hs.cyc[15] / (double)hs.iters, hs.cyc[16] / (double)hs.iters, hs.cyc[23] / (double)hs.iters);
-        fprintf(stderr, "[nj_cluster]   A detail (rank 0 warp 0): loads issued %.0f, loads arrived %.0f, chunks processed %.0f, pool + drift %.0f, wait for the CTA %.0f cyc/iter\n",
+        fprintf(stderr, "[nj_cluster]   A detail (rank 0 warp 0): loads issued %.0f, resolve %.0f, chunks processed %.0f, pool + drift %.0f, wait for the CTA %.0f cyc/iter\n",
                 hs.cyc[18] / (double)hs.iters, hs.cyc[19] / (double)hs.iters, hs.cyc[20] / (double)hs.iters, hs.cyc[21] / (double)hs.iters, hs.cyc[22] / (double)hs.iters);
+        fprintf(stderr, "[nj_cluster]   pick detail (rank 0 thread 0): helpers done %.0f, winner of the cluster %.0f, pool slots %.0f, log %.0f cyc/iter (the rest is in 'D pick')\n",
+                hs.cyc[26] / (double)hs.iters, hs.cyc[29] / (double)hs.iters, hs.cyc[30] / (double)hs.iters, hs.cyc[27] / (double)hs.iters);
         fprintf(stderr, "[nj_cluster]   probe after barrier 2: first load of a fixed word %.0f, second %.0f cyc\n", hs.cyc[24] / (double)hs.iters, hs.cyc[25] / (double)hs.iters);
         const char* nm[12] = {"D pick + pool", "A update + pool eval + push", "barrier 1", "B canonical sum + bell", "B upper bound", "(unused)",
                               "B fold + select", "barrier 2", "C stage tile + unit keys", "C scan units", "C keys + reduce + publish", "barrier 3"};
