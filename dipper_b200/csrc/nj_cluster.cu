@@ -577,10 +577,6 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 const int sx = ((x >> 5) / CS) * 32 + (x & 31);
                 U_s[cur * LS + sx] = total;
                 u_s[sx] = ux;
-                // the moved row's unit key of the new column (its other units were copied in phase A; row y is not among
-                // the rows the helpers fold)
-                if (y < n) atomicMin(&Kmine[(size_t)(((x >> 5) / CS) / UC) * KLD + y],
-                                     key_of((ld_peer_f64(&v_s[((y >> 5) / CS) * 32 + (y & 31)], (y >> 5) % CS) - ux) + C));
             }
             ub = ubmin_all[0];
 #pragma unroll
@@ -682,6 +678,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
         {
             // barrier 2, split: the reciprocal the next merge divides by (a ~130-cycle dependent chain) is computed between
             // arrive and wait instead of in front of phase A's loads and of the new row's u in phase B
+            // (Measured: arrive.relaxed on barriers 2 and 3 saves 0.4 us per merge -- the release is MEMBAR.ALL.GPU + ERRBAR +
+            // CGAERRBAR in SASS -- but nothing then orders the DSMEM pushes before the barrier, so it stays a release.)
             auto tok = cluster.barrier_arrive();
             rden = 1.0 / (double)(n - 3);
             cluster.barrier_wait(std::move(tok));
@@ -710,6 +708,12 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             __syncthreads();
             const int nsel = s_nsel;
             CL_MARK(17);
+            // the moved row's unit key of the new column (its other units were copied in phase A; row y is not among the rows
+            // the helpers fold).  A global atomic: issued here, not in phase B, where barrier 2's release fence would wait for
+            // it; this merge's staging patches column x into row y's keys itself (below)
+            if (ymoved && ((x >> 5) % CS) == rank && tid == 0)
+                atomicMin(&Kmine[(size_t)(((x >> 5) / CS) / UC) * KLD + y],
+                          key_of((ld_peer_f64(&v_s[((y >> 5) / CS) * 32 + (y & 31)], (y >> 5) % CS) - ux) + C));
             if (rank == 0 && tid == 0) my_rows += (unsigned long long)nsel;
             const int nch = (n + 31) >> 5;
             const int lch = nch > rank ? (nch - rank + CS - 1) / CS : 0;      // local chunks holding columns < n
@@ -764,9 +768,9 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     if (PROF && k == 0) { CL_MARK(15); asm volatile("" ::"r"(kv)); CL_MARK(16); }
                     bool q = have && hl < parts;
                     if (!all) {
-                        const bool patch = merged && r != y;        // (row y's keys were completed by the owner of column x)
-                        // the merge in flight: the helpers' fold of the two new columns may not have landed
-                        if (patch && xlw >= 0 && hl == xlw / UC) { const unsigned int kxv = key_of((vr - ux) + C); if (kxv < kv) kv = kxv; }
+                        const bool patch = merged && r != y;        // (row y has no column y)
+                        // the merge in flight: the helpers' fold of the two new columns (row y: the owner's atomic) may not have landed
+                        if (merged && xlw >= 0 && hl == xlw / UC) { const unsigned int kxv = key_of((vr - ux) + C); if (kxv < kv) kv = kxv; }
                         if (patch && ylw >= 0 && hl == ylw / UC) { const unsigned int kyv = key_of((fr - uy_loc) + C); if (kyv < kv) kv = kyv; }
                         q = q && !(((double)dec_f32(kv) - C) - ur - marg > ub + slack);
                     }
@@ -877,6 +881,9 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 }
                 __syncthreads();
                 CL_MARK(9);
+                // helpers' progress, sampled here (well ahead of barrier 3, whose release fence waits for outstanding loads)
+                // and looked at in the pick
+                if (HC > 0 && lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done_early) : "l"(&ctl->done) : "memory");
                 // what this CTA found for each staged row goes to the row owner's slot (one warp per row, see the staging loop)
                 for (int k = w; k < tn; k += NW) {
                     if (lane != 0) continue;
@@ -892,8 +899,6 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     cluster.sync();
                 }
             }
-            // helpers' progress, sampled here and looked at in the pick (see there)
-            if (HC > 0 && lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done_early) : "l"(&ctl->done) : "memory");
             // the next merge reads row n - 1 (it moves into the freed slot): pull my chunks of it into L2 now
             if (n > 3 && lane < 2) {
                 const int pch = (n - 1 + 31) >> 5;
