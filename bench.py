@@ -273,7 +273,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    tip_names = ["T%d" % (i + 1) for i in range(n)]
+    from dipper_b200._lib import names_array
+    tip_names = names_array(["T%d" % (i + 1) for i in range(n)])   # char** built once, as a C++ caller holds its names
 
     def one_step(msa, timed):
         """resident-input step: distances (sharded) -> reduce -> NJ on rank 0. Returns (dist_ms, comm_ms, nj_ms)."""

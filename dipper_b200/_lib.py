@@ -101,6 +101,7 @@ SIGNATURES = {
     "dipb_nj_newick": (vp, [C.c_int, i32p, i32p, f64p, f64p, C.POINTER(C.c_char_p)]),
     "dipb_tree_newick": (vp, [C.c_int, C.c_int, i32p, i32p, i32p, f64p, C.POINTER(C.c_char_p)]),
     "dipb_free_str": (None, [vp]),
+    "dipb_format_g": (C.c_int, [C.c_double, C.c_char_p]),
     "dipb_fasta_open": (C.c_int, [C.c_char_p, C.c_int, C.c_int, vpp]),
     "dipb_fasta_count": (C.c_size_t, [vp]),
     "dipb_fasta_name": (C.c_char_p, [vp, C.c_size_t]),
@@ -143,6 +144,10 @@ def take_str(ptr):
 
 
 def names_array(names):
+    """char** of the tip names.  A caller that builds many trees over the same tips converts once and passes the array
+    itself (the reference holds its names in C++ strings: no per-tree conversion there either)."""
+    if isinstance(names, C.Array):
+        return names
     arr = (C.c_char_p * len(names))()
     arr[:] = [x.encode() if isinstance(x, str) else x for x in names]
     return arr

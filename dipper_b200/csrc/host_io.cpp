@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cctype>
+#include <cmath>
+#include <cstdint>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -40,9 +42,68 @@ struct Code2 {   // twoBitCompressor: anything but A C G T/U packs as 0
 };
 const Code2 kCode2;
 
+// "%g" (6 significant digits; what ostream << double prints) for 1e-15 <= |v| < 1e6 and 0, digit for digit what glibc's
+// printf writes: the value is M * 2^-sh exactly, so round-half-even on M * 10^p >> sh in 128-bit integers is the correctly
+// rounded 6-digit decimal.  Returns 0 when the caller has to fall back to snprintf (other magnitudes, inf, nan).  4.4x faster
+// than snprintf; a 30 000-tip Newick string holds 60 000 branch lengths (tests/test_abi.py compares both on random values).
+static inline int fmt_g6_fast(double v, char* out) {
+    char* o = out;
+    if (v == 0.0) { if (std::signbit(v)) *o++ = '-'; *o++ = '0'; return (int)(o - out); }
+    if (!(v == v) || std::isinf(v)) return 0;
+    if (v < 0) { *o++ = '-'; v = -v; }
+    if (!(v >= 1e-15 && v < 1e6)) return 0;
+    uint64_t bits;
+    memcpy(&bits, &v, 8);
+    const int be = (int)((bits >> 52) & 0x7ff);           // normal numbers only (the range check above excludes denormals)
+    const uint64_t M = (bits & ((1ull << 52) - 1)) | (1ull << 52);   // v = M * 2^(be - 1075)
+    const int sh = 1075 - be;
+    static const uint64_t P10[23] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull,
+                                     10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull, 100000000000000ull,
+                                     1000000000000000ull, 10000000000000000ull, 100000000000000000ull, 1000000000000000000ull,
+                                     10000000000000000000ull, 0, 0, 0};
+    int X = (int)(((be - 1023) * 78913) >> 18);            // floor(log10(v)) or one less (78913 / 2^18 = log10(2)); fixed up below
+    uint64_t D = 0;
+    for (int tries = 0; tries < 3; tries++) {
+        const int p = 5 - X;                              // digits = round(v * 10^p)
+        if (p < 0 || p > 19 || sh <= 0 || sh > 120) return 0;
+        const unsigned __int128 N = (unsigned __int128)M * P10[p];
+        const unsigned __int128 q = N >> sh, rem = N & (((unsigned __int128)1 << sh) - 1), half = (unsigned __int128)1 << (sh - 1);
+        D = (uint64_t)q;
+        if (rem > half || (rem == half && (D & 1ull))) D++;
+        if (D < 100000ull) { X--; continue; }
+        if (D == 1000000ull) { D = 100000ull; X++; break; }
+        if (D > 1000000ull) { X++; continue; }
+        break;
+    }
+    if (D < 100000ull || D > 999999ull || X >= 6) return 0;
+    char dig[6];
+    for (int i = 5; i >= 0; i--) { dig[i] = (char)('0' + D % 10); D /= 10; }
+    int nd = 6;
+    while (nd > 1 && dig[nd - 1] == '0') nd--;            // %g strips trailing zeros
+    if (X < -4) {                                         // scientific
+        *o++ = dig[0];
+        if (nd > 1) { *o++ = '.'; memcpy(o, dig + 1, (size_t)(nd - 1)); o += nd - 1; }
+        *o++ = 'e'; *o++ = '-';
+        const int ax = -X;
+        *o++ = (char)('0' + ax / 10); *o++ = (char)('0' + ax % 10);
+        return (int)(o - out);
+    }
+    if (X >= 0) {
+        const int ip = X + 1;                             // digits before the point
+        for (int i = 0; i < ip; i++) *o++ = i < nd ? dig[i] : '0';
+        if (nd > ip) { *o++ = '.'; memcpy(o, dig + ip, (size_t)(nd - ip)); o += nd - ip; }
+    } else {
+        *o++ = '0'; *o++ = '.';
+        for (int i = 0; i < -X - 1; i++) *o++ = '0';
+        memcpy(o, dig, (size_t)nd); o += nd;
+    }
+    return (int)(o - out);
+}
+
 void append_g(std::string& s, double v) {
     char buf[64];
-    int n = snprintf(buf, sizeof buf, "%g", v);  // ostream<<double default formatting
+    int n = fmt_g6_fast(v, buf);
+    if (n == 0) n = snprintf(buf, sizeof buf, "%g", v);  // ostream<<double default formatting
     s.append(buf, (size_t)n);
 }
 
@@ -297,6 +358,13 @@ char* dipb_tree_newick(int n_nodes, int root_node, const int32_t* head, const in
 }
 
 void dipb_free_str(char* s) { free(s); }
+
+int dipb_format_g(double v, char* out32) {
+    int n = fmt_g6_fast(v, out32);
+    if (n == 0) n = snprintf(out32, 32, "%g", v);
+    out32[n] = 0;
+    return n;
+}
 
 int dipb_phylip_write(const char* path, int n, const double* D, const char* const* names, int lower) {
     if (!path || !D || !names || n < 1) { dipb::set_error("dipb_phylip_write: bad argument"); return DIPB_E_ARG; }

@@ -41,6 +41,7 @@
 #include <cooperative_groups.h>
 #include <chrono>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 #include "common.cuh"
 #include "nj.cuh"
@@ -711,7 +712,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             // the moved row's unit key of the new column (its other units were copied in phase A; row y is not among the rows
             // the helpers fold).  A global atomic: issued here, not in phase B, where barrier 2's release fence would wait for
             // it; this merge's staging patches column x into row y's keys itself (below)
-            if (ymoved && ((x >> 5) % CS) == rank && tid == 0)
+            if (ymoved && ((x >> 5) % CS) == rank && tid == CT - 1)
                 atomicMin(&Kmine[(size_t)(((x >> 5) / CS) / UC) * KLD + y],
                           key_of((ld_peer_f64(&v_s[((y >> 5) / CS) * 32 + (y & 31)], (y >> 5) % CS) - ux) + C));
             if (rank == 0 && tid == 0) my_rows += (unsigned long long)nsel;
@@ -811,10 +812,19 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         const int lw0 = live[b2] ? upart[b2] * UC : lch;
                         // rows x and y of this merge are still on their way into D (helpers): read them from the scratch pair
                         const double* row = (merged && r == x) ? Rxs : ((ymoved && r == y) ? Rys : D + (size_t)r * ld);
+                        // (warp-uniform) a unit that lies wholly below n and does not hold the row's own column: bare loads
+                        const bool whole = live[b2] && ((lw0 + UC - 1) * CS + rank) * 32 + 31 < n &&
+                                           !(((r >> 5) % CS) == rank && (unsigned int)(((r >> 5) / CS) - lw0) < (unsigned int)UC);
+                        if (whole) {
+                            const double* const rp = row + (lw0 * CS + rank) * 32 + lane;
 #pragma unroll
-                        for (int q = 0; q < UC; q++) {
-                            const int j = ((lw0 + q) * CS + rank) * 32 + lane;
-                            dv[b2][q] = (live[b2] && j < n && j != r) ? __ldcg(&row[j]) : 1e300;   // 1e300: never a candidate
+                            for (int q = 0; q < UC; q++) dv[b2][q] = __ldcg(rp + q * (CS * 32));
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < UC; q++) {
+                                const int j = ((lw0 + q) * CS + rank) * 32 + lane;
+                                dv[b2][q] = (live[b2] && j < n && j != r) ? __ldcg(&row[j]) : 1e300;   // 1e300: never a candidate
+                            }
                         }
                     }
                     if (st_lw * CS + rank < st_nch) {
@@ -838,26 +848,41 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         const int k = uk[b2], part = upart[b2], r = ur_[b2], lw0 = part * UC;
                         const double ur = t_u[k];
                         const bool patch = merged && r != x && r != y;
-                        const int xq = (patch && lane == (x & 31)) ? xlw - lw0 : -1;
-                        const int yq = (patch && lane == (y & 31)) ? ylw - lw0 : -1;
+                        // columns x and y of an old row come from v / f of the row (the helpers may still be writing D); only the
+                        // one or two units that hold those columns pay for the test (warp-uniform)
+                        const bool near = patch && ((unsigned int)(xlw - lw0) < (unsigned int)UC || (unsigned int)(ylw - lw0) < (unsigned int)UC);
+                        const int xq = (near && lane == (x & 31)) ? xlw - lw0 : -1;
+                        const int yq = (near && lane == (y & 31)) ? ylw - lw0 : -1;
                         // A lane's columns of one unit differ by multiples of 32 * CS (a multiple of 256), so the reference
                         // order within the unit is plain ascending j: the first strict minimum is the right one.
-                        double lm1 = 1e300, lm2 = 1e300, ut = 1e300, ud = 0.0, uuj = 0.0;   // lm1/lm2: two smallest d - u_j
+                        double lm1 = 1e300, lm2 = 1e300, ut = 1e300;   // lm1/lm2: two smallest d - u_j; ut: smallest d - u_r - u_j
                         int uq = 0, lq = 0;
+                        const double* const up = u_s + lw0 * 32 + lane;   // (chunks past lch read neighbouring arrays: their d is 1e300)
+                        auto unit_pass = [&](auto patched) {
 #pragma unroll
-                        for (int q = 0; q < UC; q++) {
-                            double d = dv[b2][q];
-                            if (q == xq) d = t_v[k];
-                            if (q == yq) d = t_f[k];
-                            const double uj = u_s[(lw0 + q < lch ? lw0 + q : 0) * 32 + lane];   // (dead columns carry d = 1e300)
-                            const double t = (d - ur) - uj;
-                            const double mv = d - uj;
-                            if (mv < lm1) { lm2 = lm1; lm1 = mv; lq = q; } else lm2 = fmin(lm2, mv);
-                            if (t < ut) { ut = t; ud = d; uuj = uj; uq = q; }
-                        }
+                            for (int q = 0; q < UC; q++) {
+                                double d = dv[b2][q];
+                                if (decltype(patched)::value) {
+                                    if (q == xq) d = t_v[k];
+                                    if (q == yq) d = t_f[k];
+                                }
+                                const double uj = up[q * 32];
+                                const double t = (d - ur) - uj;
+                                const double mv = d - uj;
+                                if (mv < lm1) { lm2 = lm1; lm1 = mv; lq = q; } else lm2 = fmin(lm2, mv);
+                                if (t < ut) { ut = t; uq = q; }
+                            }
+                        };
+                        if (near) unit_pass(std::true_type{}); else unit_pass(std::false_type{});
                         // (units of one row may reach a lane in any order: ties within the row go through the reference order too)
                         if (ut < 10000.0 && (ut < bt || (ut == bt && tie_before(r, ((lw0 + uq) * CS + rank) * 32 + lane, bi, bj, n)))) {
-                            bt = ut; bi = r; bj = ((lw0 + uq) * CS + rank) * 32 + lane; bd = ud; bui = ur; buj = uuj;
+                            // rare: fetch the winning column's d and u_j again (the loop carries only the value and the index)
+                            double ud = 0.0;
+#pragma unroll
+                            for (int q = 0; q < UC; q++) if (q == uq) ud = dv[b2][q];
+                            if (uq == xq) ud = t_v[k];
+                            if (uq == yq) ud = t_f[k];
+                            bt = ut; bi = r; bj = ((lw0 + uq) * CS + rank) * 32 + lane; bd = ud; bui = ur; buj = up[uq * 32];
                         }
                         // unit minimum and runner-up -> the unit's key, the CTA's (minimum, column) and runner-up of the row.  An
                         // atomic that loses to (or displaces) the standing minimum demotes the loser to the runner-up.
@@ -1043,7 +1068,12 @@ static int launch_cluster(dipb_ctx* c, int n, void** args, int* LS_out, int* HC,
     at[1].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return 0; }
+    const unsigned long long occ_key = ((unsigned long long)CS << 56) | ((unsigned long long)CT << 40) | ((unsigned long long)PROF << 39) | (unsigned long long)smem;
+    if (c->nj_occ_key == occ_key) nclusters = c->nj_occ_clusters;
+    else {
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return 0; }
+        c->nj_occ_key = occ_key; c->nj_occ_clusters = nclusters;
+    }
     // helper clusters spin on a doorbell of the main cluster: only as many as are co-resident with it
     int helpers = nclusters - 1 < max_helper_clusters ? nclusters - 1 : max_helper_clusters;
     if (helpers < 0) helpers = 0;

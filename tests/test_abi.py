@@ -132,3 +132,25 @@ def test_phylip_writer_round_trips_through_the_reference_reader_rule(tmp_path):
             assert tok[0] == names[i] and len(tok) == 1 + (i if lower else n)
             got = np.array([np.float32(t) for t in tok[1:1 + i]], np.float32)
             assert np.array_equal(got, D[i, :i].astype(np.float32))
+
+
+def test_branch_length_formatter_equals_printf_g():
+    """dipb_format_g (the Newick writers' number formatter) against C's "%g" (Python's % operator formats the same way)."""
+    import ctypes as C
+    import math
+    from dipper_b200._lib import lib
+    rng = np.random.default_rng(11)
+    vals = [0.0, -0.0, 1.0, 10.0, 0.1, 0.5, 0.0078125, 999999.0, 999999.5, 999999.4999, 1e6, 123456.5, 1e-4, 1e-5, 9.9999949e-5,
+            9.99999951e-5, 0.000099999949, 1.5e-10, 1e-15, 9e-16, 1e-300, 5e-324, 1e300, float("inf"), float("-inf"), 2.5e-7, -3.75e-3]
+    vals += list(rng.random(60000) * 2.0)                                     # branch-length sized
+    vals += list(np.ldexp(0.5 + rng.random(60000) * 0.5, rng.integers(-70, 30, 60000)))
+    vals += list(-np.ldexp(0.5 + rng.random(5000) * 0.5, rng.integers(-40, 10, 5000)))
+    vals += [k / 2.0 ** j for j in range(0, 30, 3) for k in range(1, 3000, 7)]     # exact decimal ties
+    vals += [(999990 + d * 0.25) * 10.0 ** x for x in range(-18, 2) for d in range(0, 44)]   # carries into the next decade
+    buf = C.create_string_buffer(40)
+    f = lib().dipb_format_g
+    for v in vals:
+        n = f(float(v), buf)
+        assert buf.value.decode() == "%g" % v and n == len(buf.value), (v, buf.value)
+    n = f(float("nan"), buf)
+    assert "nan" in buf.value.decode()
