@@ -103,6 +103,8 @@ __device__ __forceinline__ unsigned int half_min_u32(unsigned int v, int lane) {
 __device__ __forceinline__ double warp_min_f64(double v) { return dec_f64(warp_min_u64(enc_f64(v))); }
 __device__ __forceinline__ double warp_max_f64(double v) { return -warp_min_f64(-v); }
 
+// (Row / column indices are never negative where an owner or a slot is derived from them: the casts to unsigned below turn
+// the divisions by the cluster size into one shift or mask each -- the signed forms cost ~5 instructions apiece, in every warp.)
 // ---- distributed shared memory: the same variable in CTA `rank` of the cluster
 __device__ __forceinline__ unsigned int peer_addr(const void* p, int rank) {
     const unsigned int a = (unsigned int)__cvta_generic_to_shared(p);
@@ -210,8 +212,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             const bool ymoved = y < n;
             // key rows of the units that hold columns x and y (Kb is [cta][part][row]: this fold is coalesced over the rows)
             const size_t KLD = (size_t)((n_total + 31) & ~31);
-            unsigned int* const Kx = Kb + ((size_t)((x >> 5) % CS) * PARTS + ((x >> 5) / CS) / UC) * KLD;
-            unsigned int* const Ky = Kb + ((size_t)((y >> 5) % CS) * PARTS + ((y >> 5) / CS) / UC) * KLD;
+            unsigned int* const Kx = Kb + ((size_t)((int)(((unsigned int)x >> 5) % CS)) * PARTS + ((int)(((unsigned int)x >> 5) / CS)) / UC) * KLD;
+            unsigned int* const Ky = Kb + ((size_t)((int)(((unsigned int)y >> 5) % CS)) * PARTS + ((int)(((unsigned int)y >> 5) / CS)) / UC) * KLD;
             const int nch = (n + 31) >> 5;
             // 1. rows and columns x, y of D
             double vx[2], fy[2];
@@ -292,7 +294,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
     __shared__ CRec wrec[MAXW];
     __shared__ double drift_all[MAXCS], ubmin_all[MAXCS];   // pushed by the peers
     __shared__ double s_red[MAXW], s_red2[MAXW], s_blk[128 + 16];   // s_blk: one sum per 1024-row block (n <= 131 072)
-    __shared__ double s_total, s_C, s_uy;   // s_uy (rank 0's copy): u of the node moved into slot y, pushed by its owner
+    __shared__ double s_total, s_C, s_ub, s_uy;   // s_uy (rank 0's copy): u of the node moved into slot y, pushed by its owner
     __shared__ unsigned int s_sel;          // selected-row counter (rank 0's copy is the live one)
     __shared__ int pool_i[CPOOL], pool_j[CPOOL];
     __shared__ double pool_d[CPOOL];        // d of a carried pair never changes while both ends survive
@@ -344,7 +346,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             const int hl = lane & 15;
             const bool have = k < tn;
             const int r = have ? t_row[k] : 0;
-            const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
+            const int ro = (int)(((unsigned int)r >> 5) % CS), rs = ((int)(((unsigned int)r >> 5) / CS)) * 32 + (r & 31);
             const bool mine = have && ro == rank;
             uint4 e = make_uint4(K32MAX, 0xffffffffu, K32MAX, 0u);
             if (mine && hl < CS) e = slot_s[k * MAXCS + hl];
@@ -414,7 +416,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             if (pend >= 0) {
                 const int src = pend == y ? last : pend;
                 p_a = __ldcg(&D[(size_t)x * ld + src]); p_b = __ldcg(&D[(size_t)y * ld + src]);
-                p_U = ld_peer_f64(&Uo[((src >> 5) / CS) * 32 + (src & 31)], (src >> 5) % CS);
+                p_U = ld_peer_f64(&Uo[((int)(((unsigned int)src >> 5) / CS)) * 32 + (src & 31)], (int)(((unsigned int)src >> 5) % CS));
             }
             double pend_da = 0.0;
             bool resolved = false;
@@ -456,7 +458,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         const double a = la[c], b = lb[c], far = lf[c];
                         double Ui = Uo[s], uo = u_s[s];
                         if (isy) {
-                            const int lo = (last >> 5) % CS, ls = ((last >> 5) / CS) * 32 + (last & 31);
+                            const int lo = (int)(((unsigned int)last >> 5) % CS), ls = ((int)(((unsigned int)last >> 5) / CS)) * 32 + (last & 31);
                             Ui = ld_peer_f64(&Uo[ls], lo);
                             uo = ld_peer_f64(&u_s[ls], lo);
                         }
@@ -542,6 +544,20 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     const double v = warp_tree_sum(cw < nchunk ? cs_all[cw] : 0.0);
                     if (lane == 0) s_blk[b] = v;
                 }
+                if (w == NW - 1) {
+                    // drift and upper bound of the cluster (pushed by every CTA in phase A): one warp, once -- every thread
+                    // folding the 16 values itself cost ~800 cycles of issue
+                    const double dr = warp_max_f64(lane < CS ? drift_all[lane] : -1e300);
+                    const double um = warp_min_f64(lane < CS ? ubmin_all[lane] : 1e300);
+                    if (lane == 0) {
+                        s_C = C + dr;
+                        s_ub = um;
+                        if (HC > 0 && rank == 0) {
+                            const unsigned long long w2 = ((unsigned long long)(unsigned int)iter << 32) | __float_as_uint(__double2float_rd(C + dr));
+                            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->pw[2]), "l"(w2) : "memory");
+                        }
+                    }
+                }
                 __syncthreads();
                 if (tid == 0) {
                     double acc = 0.0;
@@ -552,19 +568,14 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
 #pragma unroll
                         for (int q = 0; q < 16; q++) if (b0 + q < nblk) acc += v[q];
                     }
-                    double drift = drift_all[0];
-                    for (int q = 1; q < CS; q++) drift = fmax(drift, drift_all[q]);
                     s_total = acc;
-                    s_C = C + drift;
                     if (HC > 0 && rank == 0) {
                         // what the helpers' key fold needs, each word tagged with the merge number (see NJCtl)
                         const unsigned long long tag = (unsigned long long)(unsigned int)iter << 32;
                         const unsigned long long w0 = tag | __float_as_uint(__double2float_ru(div_rn(acc, (double)(n - 2), rden)));
                         const unsigned long long w1 = tag | __float_as_uint(__double2float_ru(s_uy));
-                        const unsigned long long w2 = tag | __float_as_uint(__double2float_rd(C + drift));
                         asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->pw[0]), "l"(w0) : "memory");
                         asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->pw[1]), "l"(w1) : "memory");
-                        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&ctl->pw[2]), "l"(w2) : "memory");
                     }
                 }
                 __syncthreads();
@@ -574,14 +585,12 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             ux = div_rn(total, (double)(n - 2), rden);   // (correctly rounded, see div_rn)
             C = s_C;
             marg = 1e-9 * (4.0 * dmax + fabs(C));
-            if (((x >> 5) % CS) == rank && tid == 0) {
-                const int sx = ((x >> 5) / CS) * 32 + (x & 31);
+            if (((int)(((unsigned int)x >> 5) % CS)) == rank && tid == 0) {
+                const int sx = ((int)(((unsigned int)x >> 5) / CS)) * 32 + (x & 31);
                 U_s[cur * LS + sx] = total;
                 u_s[sx] = ux;
             }
-            ub = ubmin_all[0];
-#pragma unroll
-            for (int q = 1; q < CS; q++) ub = fmin(ub, ubmin_all[q]);
+            ub = s_ub;
             if (dbg & 2) ub = 1e300;
             CL_MARK(4);
             CL_MARK(5);
@@ -598,7 +607,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                             int a = a_s[s];
                             if (i == y && y < n) {
                                 // slot y now holds the row that lived in `last` (= n): take over its keys and partner
-                                const int lo = (n >> 5) % CS, ls = ((n >> 5) / CS) * 32 + (n & 31);
+                                const int lo = (int)(((unsigned int)n >> 5) % CS), ls = ((int)(((unsigned int)n >> 5) / CS)) * 32 + (n & 31);
                                 k1 = ld_peer_u32(&K1_s[ls], lo); k2 = ld_peer_u32(&K2_s[ls], lo);
                                 a = ld_peer_s32(&a_s[ls], lo);
                                 da_s[s] = ld_peer_f64(&da_s[ls], lo);
@@ -614,7 +623,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                             take = !(((double)dec_f32(km) - C) - u_s[s] - marg > ub);
                             if (take && a >= 0) {
                                 // stage 2: the tracked partner exactly (its d never changes, u[a] from its owner)
-                                const double e1 = da_s[s] - ld_peer_f64(&u_s[((a >> 5) / CS) * 32 + (a & 31)], (a >> 5) % CS);
+                                const double e1 = da_s[s] - ld_peer_f64(&u_s[((int)(((unsigned int)a >> 5) / CS)) * 32 + (a & 31)], (int)(((unsigned int)a >> 5) % CS));
                                 k1 = key_of(e1 + C);
                                 const double rest = (double)dec_f32(k2) - C;
                                 take = !((e1 < rest ? e1 : rest) - u_s[s] - marg > ub);
@@ -622,7 +631,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                             if (PROF && rank == 0 && take) {
                                 // why rows are rescanned (rank 0's rows only): 12 no tracked partner, 13 partner itself is
                                 // a contender, 14 the runner-up bound has drifted down to the upper bound
-                                const int why = a < 0 ? 12 : ((da_s[s] - ld_peer_f64(&u_s[((a >> 5) / CS) * 32 + (a & 31)], (a >> 5) % CS)) - u_s[s] - marg > ub ? 14 : 13);
+                                const int why = a < 0 ? 12 : ((da_s[s] - ld_peer_f64(&u_s[((int)(((unsigned int)a >> 5) / CS)) * 32 + (a & 31)], (int)(((unsigned int)a >> 5) % CS))) - u_s[s] - marg > ub ? 14 : 13);
                                 atomicAdd(&s_cyc[why], 1ull);
                             }
                             if (take) { k1 = K32MAX; k2 = K32MAX; a = -1; }   // reset, the scan lowers them
@@ -708,13 +717,17 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             int st_lw = w;
             __syncthreads();
             const int nsel = s_nsel;
+            // the unit keys of this half-warp's first staged row: a global round trip, issued before the bookkeeping below
+            const int k0 = w * 2 + (lane >> 4);
+            unsigned int kv0 = K32MAX;
+            if (k0 < nsel && k0 < TILE && (lane & 15) < PARTS) kv0 = __ldcg(&Kmine[(size_t)(lane & 15) * KLD + t_row[k0]]);
             CL_MARK(17);
             // the moved row's unit key of the new column (its other units were copied in phase A; row y is not among the rows
             // the helpers fold).  A global atomic: issued here, not in phase B, where barrier 2's release fence would wait for
             // it; this merge's staging patches column x into row y's keys itself (below)
-            if (ymoved && ((x >> 5) % CS) == rank && tid == CT - 1)
-                atomicMin(&Kmine[(size_t)(((x >> 5) / CS) / UC) * KLD + y],
-                          key_of((ld_peer_f64(&v_s[((y >> 5) / CS) * 32 + (y & 31)], (y >> 5) % CS) - ux) + C));
+            if (ymoved && ((int)(((unsigned int)x >> 5) % CS)) == rank && tid == CT - 1)
+                atomicMin(&Kmine[(size_t)(((int)(((unsigned int)x >> 5) / CS)) / UC) * KLD + y],
+                          key_of((ld_peer_f64(&v_s[((int)(((unsigned int)y >> 5) / CS)) * 32 + (y & 31)], (int)(((unsigned int)y >> 5) % CS)) - ux) + C));
             if (rank == 0 && tid == 0) my_rows += (unsigned long long)nsel;
             const int nch = (n + 31) >> 5;
             const int lch = nch > rank ? (nch - rank + CS - 1) / CS : 0;      // local chunks holding columns < n
@@ -722,8 +735,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             const int pdiv = parts > 0 ? parts : 1;
             // local chunk / lane of columns x and y when this CTA owns them: the scan takes those two columns from
             // v / f of the row, not from D (the helpers may still be writing them)
-            const int xlw = (merged && ((x >> 5) % CS) == rank) ? (x >> 5) / CS : -1000000;
-            const int ylw = (ymoved && ((y >> 5) % CS) == rank) ? (y >> 5) / CS : -1000000;
+            const int xlw = (merged && ((int)(((unsigned int)x >> 5) % CS)) == rank) ? (int)(((unsigned int)x >> 5) / CS) : -1000000;
+            const int ylw = (ymoved && ((int)(((unsigned int)y >> 5) % CS)) == rank) ? (int)(((unsigned int)y >> 5) / CS) : -1000000;
             const double uy_loc = ylw >= 0 ? u_s[ylw * 32 + (y & 31)] : 0.0;
             const double* const Rxs = R + (size_t)(iter & 1) * 2 * ld;
             const double* const Rys = Rxs + ld;
@@ -732,8 +745,9 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
             // the threshold on its own and costs its row a selection of its own (measured: 129 selected rows per merge
             // instead of 13); with it a row comes back when its runner-up does, as with whole-row rescans.
             const double slack = iter > 0 ? (double)((float)slack_merges * __fdividef((float)fabs(C), (float)iter)) : 0.0;   // (a heuristic: fp32 is plenty; C may be negative: never tighten)
-            unsigned int* const Kxg = Kb + ((size_t)((x >= 0 ? x >> 5 : 0) % CS) * PARTS + ((x >= 0 ? x >> 5 : 0) / CS) / UC) * KLD;
-            unsigned int* const Kyg = Kb + ((size_t)((y >= 0 ? y >> 5 : 0) % CS) * PARTS + ((y >= 0 ? y >> 5 : 0) / CS) / UC) * KLD;
+            // (only the helper-less mode folds the new columns here)
+            unsigned int* const Kxg = HC > 0 ? Kb : Kb + ((size_t)((x >= 0 ? x >> 5 : 0) % CS) * PARTS + ((x >= 0 ? x >> 5 : 0) / CS) / UC) * KLD;
+            unsigned int* const Kyg = HC > 0 ? Kb : Kb + ((size_t)((y >= 0 ? y >> 5 : 0) % CS) * PARTS + ((y >= 0 ? y >> 5 : 0) / CS) / UC) * KLD;
             double bt = 1e300, bd = 0.0, bui = 0.0, buj = 0.0;
             int bi = -1, bj = -1;
             for (int t0 = 0; t0 < nsel || (t0 == 0 && st_nch > 0); t0 += TILE) {
@@ -755,10 +769,10 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     // search, bursts) come from the spill list in global memory and the owners' shared memory
                     int r = 0;
                     if (have) r = t0 == 0 ? t_row[k] : __ldcg(&sel_rows[t0 + k]);
-                    const int ro = (r >> 5) % CS, rs = ((r >> 5) / CS) * 32 + (r & 31);
+                    const int ro = (int)(((unsigned int)r >> 5) % CS), rs = ((int)(((unsigned int)r >> 5) / CS)) * 32 + (r & 31);
                     const bool all = first || r == x || (dbg & 1);
                     unsigned int kv = K32MAX;
-                    if (have && !all && hl < parts) kv = __ldcg(&Kmine[(size_t)hl * KLD + r]);
+                    if (have && !all && hl < parts) kv = (t0 == 0 && k == k0) ? kv0 : __ldcg(&Kmine[(size_t)hl * KLD + r]);
                     double ur, vr, fr;
                     if (t0 == 0) { ur = have ? t_u[k] : 0.0; vr = have ? t_v[k] : 0.0; fr = have ? t_f[k] : 0.0; }
                     else {
@@ -814,7 +828,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         const double* row = (merged && r == x) ? Rxs : ((ymoved && r == y) ? Rys : D + (size_t)r * ld);
                         // (warp-uniform) a unit that lies wholly below n and does not hold the row's own column: bare loads
                         const bool whole = live[b2] && ((lw0 + UC - 1) * CS + rank) * 32 + 31 < n &&
-                                           !(((r >> 5) % CS) == rank && (unsigned int)(((r >> 5) / CS) - lw0) < (unsigned int)UC);
+                                           !(((int)(((unsigned int)r >> 5) % CS)) == rank && (unsigned int)(((int)(((unsigned int)r >> 5) / CS)) - lw0) < (unsigned int)UC);
                         if (whole) {
                             const double* const rp = row + (lw0 * CS + rank) * 32 + lane;
 #pragma unroll
@@ -838,7 +852,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                             // (i == x: the moved node's distance to the new node is v of row y, which the scratch row holds)
                             const double fy = i == x ? __ldcg(&Rys[x]) : f_s[st_lw * 32 + lane];
                             D[(size_t)i * ld + y] = fy; D[(size_t)y * ld + i] = fy;
-                            if (i != x) atomicMin(&Kyg[i], key_of((fy - ld_peer_f64(&u_s[((y >> 5) / CS) * 32 + (y & 31)], (y >> 5) % CS)) + C));
+                            if (i != x) atomicMin(&Kyg[i], key_of((fy - ld_peer_f64(&u_s[((int)(((unsigned int)y >> 5) / CS)) * 32 + (y & 31)], (int)(((unsigned int)y >> 5) % CS))) + C));
                         }
                         st_lw += NW;
                     }
@@ -914,7 +928,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     if (lane != 0) continue;
                     const unsigned long long best = t_best[k];
                     const int r = t_row[k];
-                    st_peer_v4(&slot_s[k * MAXCS + rank], (r >> 5) % CS, (unsigned int)(best >> 32), (unsigned int)best, t_k2[k], 0u);
+                    st_peer_v4(&slot_s[k * MAXCS + rank], (int)(((unsigned int)r >> 5) % CS), (unsigned int)(best >> 32), (unsigned int)best, t_k2[k], 0u);
                 }
                 if (nsel > TILE) {
                     // rare (first search, bursts): two extra cluster barriers per tile -- the owners resolve this tile before
