@@ -100,7 +100,7 @@ static int msa_create_impl(dipb_msa* m, const uint64_t* d_in, size_t n, uint64_t
     if (m->nkc < 1) m->nkc = 1;
     size_t words = (size_t)(m->npad / MSA_TS) * m->nkc * MSA_SLAB_WORDS;
     DIPB_CUDA(pool_alloc(c, (void**)&m->planes, words * sizeof(uint32_t)));
-    DIPB_CUDA(cudaMalloc(&m->nv, sizeof(int) * m->npad));
+    DIPB_CUDA(pool_alloc(c, (void**)&m->nv, sizeof(int) * m->npad));
     DIPB_CUDA(cudaMemsetAsync(m->nv, 0, sizeof(int) * m->npad, c->stream));
     return msa_repack(m, d_in, (int)((seq_len + 15) / 16));
 }
@@ -120,6 +120,8 @@ int dipb_msa_upload_flat(dipb_ctx* c, const uint64_t* flat, size_t n, uint64_t s
     DIPB_CUDA(cudaSetDevice(c->device));
     size_t comp = (seq_len + 15) / 16;
     uint64_t* d_in = nullptr;
+    // (deliberately NOT from the stream-ordered pool: a short-lived 450 MB block there splits the free 7 GB block the next
+    // matrix wants and makes the pool grow again -- measured 90-270 ms per tree instead of 1-3 ms for this pair)
     DIPB_CUDA(cudaMalloc(&d_in, n * comp * sizeof(uint64_t)));
     int rc = timer_begin(c);
     if (!rc && cudaMemcpyAsync(d_in, flat, n * comp * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
@@ -154,7 +156,7 @@ void dipb_msa_free(dipb_msa* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     pool_free(m->ctx, m->planes);
-    cudaFree(m->nv);
+    pool_free(m->ctx, m->nv);
     pool_free(m->ctx, m->tc_S);
     pool_free(m->ctx, m->tc_V);
     pool_free(m->ctx, m->tc_Sx);

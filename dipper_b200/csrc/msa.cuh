@@ -25,6 +25,7 @@ struct dipb_msa {
     int8_t* tc_S = nullptr;
     int8_t* tc_V = nullptr;
     size_t tc_ks = 0, tc_kv = 0, tc_rows = 0, tc_have = 0, tc_reserve = 0;
+    int tc_fmt = 0;              // operand encoding of the buffers below: 0 int8, 2 e2m1 (two elements per byte; tc_ks / tc_kv are BYTES per row), fixed at the first expansion
     int8_t* tc_Sx = nullptr;
     int8_t* tc_Vx = nullptr;
     size_t tc_xrows = 0;

@@ -34,7 +34,8 @@ constexpr int TC_THREADS = 192;
 // ---- operand expansion: planes -> simplex int8 (S) and validity int8 (V), K-major rows ----------
 // rows [row0, row0 + nrows) of the alignment into rows 0.. of S / V
 __global__ void msa_tc_expand_kernel(const uint32_t* __restrict__ planes, int row0, int nrows, int nkc, int w32, int8_t* __restrict__ S,
-                                     size_t ks, int8_t* __restrict__ V, size_t kv) {
+                                     size_t ks, int8_t* __restrict__ V, size_t kv, int fmt) {
+    const uint32_t pos = 0x01u, neg = 0xFFu;   // two's complement int8 (fmt 0)
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)nrows * w32) return;
     const int sd = (int)(gid / w32), w = (int)(gid % w32);
@@ -42,6 +43,29 @@ __global__ void msa_tc_expand_kernel(const uint32_t* __restrict__ planes, int ro
     const int sb = s / MSA_TS, sl = s % MSA_TS, kc = w / MSA_KC, kk = w % MSA_KC;
     const size_t base = ((size_t)sb * nkc + kc) * MSA_SLAB_WORDS + (size_t)kk * MSA_TS + sl;
     const uint32_t b0 = planes[base], b1 = planes[base + MSA_KC * MSA_TS], v = planes[base + 2 * MSA_KC * MSA_TS];
+    if (fmt == 2) {
+        // e2m1 nibbles (+1 = 0x2, -1 = 0xA, 0 = 0x0), two elements per byte, element k in the low nibble of byte k / 2 for even k:
+        // 48 bytes of S (three 16-byte runs of 32 elements) and 16 bytes of V per 32-site word
+        uint8_t* so4 = reinterpret_cast<uint8_t*>(S) + (size_t)sd * ks + (size_t)w * 48;
+        uint8_t* vo4 = reinterpret_cast<uint8_t*>(V) + (size_t)sd * kv + (size_t)w * 16;
+#pragma unroll 4
+        for (int q = 0; q < 4; q++) {
+            uint32_t e0 = 0, e1 = 0, e2 = 0, vv = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const int bit = 8 * q + t;
+                const int ok = (v >> bit) & 1, x0 = (b0 >> bit) & 1, x1 = (b1 >> bit) & 1;
+                const uint32_t n0 = ok ? (x1 ? 0xAu : 0x2u) : 0u, n1 = ok ? (x0 ? 0xAu : 0x2u) : 0u, n2 = ok ? ((x0 ^ x1) ? 0xAu : 0x2u) : 0u;
+                e0 |= n0 << (4 * t); e1 |= n1 << (4 * t); e2 |= n2 << (4 * t);
+                vv |= (ok ? 0x2u : 0u) << (4 * t);
+            }
+            reinterpret_cast<uint32_t*>(so4)[q] = e0;
+            reinterpret_cast<uint32_t*>(so4 + 16)[q] = e1;
+            reinterpret_cast<uint32_t*>(so4 + 32)[q] = e2;
+            reinterpret_cast<uint32_t*>(vo4)[q] = vv;
+        }
+        return;
+    }
     int8_t* so = S + (size_t)sd * ks + (size_t)w * 96;
     int8_t* vo = V + (size_t)sd * kv + (size_t)w * 32;
 #pragma unroll 4
@@ -52,10 +76,10 @@ __global__ void msa_tc_expand_kernel(const uint32_t* __restrict__ planes, int ro
             const int bit = 4 * q + t;
             const int ok = (v >> bit) & 1, x0 = (b0 >> bit) & 1, x1 = (b1 >> bit) & 1;
             const int c0 = ok ? 1 - 2 * x1 : 0, c1 = ok ? 1 - 2 * x0 : 0, c2 = ok ? 1 - 2 * (x0 ^ x1) : 0;
-            e0 |= (uint32_t)(uint8_t)c0 << (8 * t);
-            e1 |= (uint32_t)(uint8_t)c1 << (8 * t);
-            e2 |= (uint32_t)(uint8_t)c2 << (8 * t);
-            vv |= (uint32_t)ok << (8 * t);
+            e0 |= (c0 == 0 ? 0u : (c0 > 0 ? pos : neg)) << (8 * t);
+            e1 |= (c1 == 0 ? 0u : (c1 > 0 ? pos : neg)) << (8 * t);
+            e2 |= (c2 == 0 ? 0u : (c2 > 0 ? pos : neg)) << (8 * t);
+            vv |= (ok ? pos : 0u) << (8 * t);
         }
         reinterpret_cast<uint32_t*>(so)[q] = e0;
         reinterpret_cast<uint32_t*>(so + 32)[q] = e1;
@@ -89,6 +113,16 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
@@ -138,7 +172,10 @@ struct TcParams {
 
 // Epilogue of one 128 x 256 tile: thread (q, lane) owns row 32 q + lane of the tile; D1 in TMEM columns [0,256), D2 in
 // [256,512).  match = (D1 + D2) / 4, useful = nv_i + nv_j - D2, then p / JC in fp64 in the reference's expression order.
+template <int FMT = 0>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tmem_base, int tile_row, int tile_col, int q, int lane) {
+    // FMT 0: s32 accumulators; else f32 accumulators holding exact integers
+    auto acc = [](uint32_t r) -> int { return FMT == 0 ? (int)r : __float2int_rn(__uint_as_float(r)); };
     const int2 tl = make_int2(tile_row, tile_col);
     const int i = tl.x * TC_M + 32 * q + lane;
     const int nvi = i < p.n ? p.nv[i] : 0;
@@ -155,8 +192,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
                 for (int c = 0; c < 32; c++) {
                     const int j = j0 + c;
                     if (j < p.ncols) {
-                        const int both = (int)r2[c];
-                        const int match = ((int)r1[c] + both) >> 2;
+                        const int both = acc(r2[c]);
+                        const int match = (acc(r1[c]) + both) >> 2;
                         p.out[(size_t)(i - p.r0) * p.ld + j] = dist_p_jc(match, nvi + p.nv[j] - both, p.dist_type);
                     }
                 }
@@ -166,8 +203,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
             for (int c = 0; c < 32; c++) {
                 const int j = j0 + c;
                 if (j < i) {
-                    const int both = (int)r2[c];
-                    const int match = ((int)r1[c] + both) >> 2;
+                    const int both = acc(r2[c]);
+                    const int match = (acc(r1[c]) + both) >> 2;
                     const double d = dist_p_jc(match, nvi + p.nv[j] - both, p.dist_type);
                     p.out[(size_t)i * p.ld + j] = d;
                     p.out[(size_t)j * p.ld + i] = d;
@@ -183,7 +220,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
 // CTAs of that row and the B slab of a tile column by the CM CTAs of that column, so every CTA loads 1/CN of its A
 // slab and 1/CM of its B slab and TMA-multicasts them to the peers: (1/CN + 2/CM) / 3 of the L2 -> SM traffic of
 // independent CTAs, and sharing no longer depends on L2 residency (ncu, 1 x 1: 248 GB of DRAM reads for 3.6 GB of operands).
-template <int CM, int CN>
+template <int CM, int CN, int FMT = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__ CUtensorMap mapSB,
               const __grid_constant__ CUtensorMap mapVA, const __grid_constant__ CUtensorMap mapVB, TcParams p) {
@@ -241,7 +278,7 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* a = smem + (size_t)stage * TC_STAGE_BYTES + cc * A_PART;
                     unsigned char* b = smem + (size_t)stage * TC_STAGE_BYTES + TC_A_BYTES + cr * B_PART;
-                    mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);   // own parts + the peers' multicasts
+                    mbar_arrive_expect_tx(&full[stage], FMT == 2 ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES);   // own parts + the peers' multicasts (e2m1: packed bytes)
                     const bool sv = c >= p.ns_chunks;
                     const int kc = (sv ? c - p.ns_chunks : c) * TC_KB;
                     if (CSZ == 1) {
@@ -259,7 +296,7 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
         // ===================== MMA issuer =====================
         if (lane == 0) {
             // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 256, M = 128
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            const uint32_t idesc = (FMT == 0 ? ((2u << 4) | (1u << 7) | (1u << 10)) : ((1u << 4) | (5u << 7) | (5u << 10))) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
             uint32_t stage = 0, phase = 0, tphase = 0;
             for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
                 mbar_wait(tmem_empty, tphase ^ 1);
@@ -274,7 +311,8 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
                     const bool first_of_acc = (c == 0) || (c == p.ns_chunks);
 #pragma unroll
                     for (int k = 0; k < TC_KB / 32; k++)   // UMMA_K = 32 int8 = 32 B: advance the start address by 2 (x16 B)
-                        umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first_of_acc && k == 0) ? 0u : 1u);
+                        if (FMT == 0) umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first_of_acc && k == 0) ? 0u : 1u);
+                        else umma_f8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first_of_acc && k == 0) ? 0u : 1u);
                     // the stage is free when these MMAs have read it: tell every CTA that writes into it
                     if (CSZ == 1) umma_commit(&empty[stage]);
                     else umma_commit_mc(&empty[stage], (uint16_t)(mask_row | mask_col));
@@ -292,7 +330,7 @@ msa_tc_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__
             const int2 tl = make_int2(p.tiles[t].x * CM + cr, p.tiles[t].y * CN + cc);   // this CTA's 128 x 256 tile
             mbar_wait(tmem_full, tphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            tc_epilogue_tile(p, tmem_base, tl.x, tl.y, q, lane);
+            tc_epilogue_tile<FMT>(p, tmem_base, tl.x, tl.y, q, lane);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
@@ -351,12 +389,23 @@ __device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
+__device__ __forceinline__ void umma2_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                  "h"((uint16_t)3)
                  : "memory");
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 msa_tc2_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant__ CUtensorMap mapSB,
                const __grid_constant__ CUtensorMap mapVA, const __grid_constant__ CUtensorMap mapVB, TcParams p) {
@@ -403,7 +452,8 @@ msa_tc2_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant_
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* a = smem + (size_t)stage * T2_STAGE_BYTES;
                     const uint32_t lfull = cluster_addr(&full[stage], 0);
-                    mbar_arrive_expect_tx_cluster(lfull, T2_STAGE_BYTES);
+                    // (e2m1: the transaction counts the packed bytes that leave global memory, half of what lands in shared memory)
+                    mbar_arrive_expect_tx_cluster(lfull, FMT == 2 ? T2_STAGE_BYTES / 2 : T2_STAGE_BYTES);
                     const bool sv = c >= p.ns_chunks;
                     const int kc = (sv ? c - p.ns_chunks : c) * TC_KB;
                     tma_load_2d_pair(a, sv ? &mapVA : &mapSA, kc, arow, lfull);
@@ -416,7 +466,9 @@ msa_tc2_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant_
         // ===================== MMA issuer (leader only) =====================
         if (lane == 0 && crank == 0) {
             // D = s32, A = B = signed 8-bit, both K-major, N = 256, M = 256 (128 rows in each CTA's TMEM)
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            // (FMT 2: kind::f8f6f4, D = f32 (c_format 1), A = B = e2m1 (a/b_format 5): 4-bit in global memory, unpacked by the TMA
+            //  into 16-byte groups of 8 data + 8 padding bytes -- the same shared-memory footprint and K step as int8)
+            const uint32_t idesc = (FMT == 0 ? ((2u << 4) | (1u << 7) | (1u << 10)) : ((1u << 4) | (5u << 7) | (5u << 10))) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             uint32_t stage = 0, phase = 0, tphase = 0;
             for (int t = pair_id; t < p.num_tiles; t += num_pairs) {
                 mbar_wait(tmem_empty, tphase ^ 1);
@@ -431,7 +483,8 @@ msa_tc2_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant_
                     const bool first_of_acc = (c == 0) || (c == p.ns_chunks);
 #pragma unroll
                     for (int k = 0; k < TC_KB / 32; k++)
-                        umma2_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first_of_acc && k == 0) ? 0u : 1u);
+                        if (FMT == 0) umma2_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first_of_acc && k == 0) ? 0u : 1u);
+                        else umma2_f8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first_of_acc && k == 0) ? 0u : 1u);
                     umma2_commit(&empty[stage]);
                     if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -448,7 +501,7 @@ msa_tc2_kernel(const __grid_constant__ CUtensorMap mapSA, const __grid_constant_
             const int2 tl = p.tiles[t];
             mbar_wait(tmem_full, tphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            tc_epilogue_tile(p, tmem_base, tl.x * 2 + (int)crank, tl.y, q, lane);
+            tc_epilogue_tile<FMT>(p, tmem_base, tl.x * 2 + (int)crank, tl.y, q, lane);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(l_tmem_empty);
@@ -467,13 +520,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(EncodeTiledFn fn, CUtensorMap* m, void* base, size_t kbytes, size_t rows, int box_rows) {
-    cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
+static int make_map(EncodeTiledFn fn, CUtensorMap* m, void* base, size_t kbytes, size_t rows, int box_rows, int fmt = 0) {
+    // fmt 2: rows of packed 4-bit elements (kbytes * 2 of them); a box is still 128 elements = one 128-byte swizzle row of
+    // shared memory after the TMA's unpack (CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B)
+    cuuint64_t dims[2] = {(cuuint64_t)(fmt == 2 ? kbytes * 2 : kbytes), (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)kbytes};
     cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(m, fmt == 2 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DIPB_E_CUDA; }
     return 0;
 }
@@ -491,7 +546,7 @@ static int tc_expand(dipb_msa* m, size_t row0, size_t nrows, int8_t* S, int8_t* 
     dipb_ctx* c = m->ctx;
     const int w32 = (m->seq_len + 31) / 32;
     const long long total = (long long)nrows * w32;
-    msa_tc_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(m->planes, (int)row0, (int)nrows, m->nkc, w32, S, m->tc_ks, V, m->tc_kv);
+    msa_tc_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(m->planes, (int)row0, (int)nrows, m->nkc, w32, S, m->tc_ks, V, m->tc_kv, m->tc_fmt);
     DIPB_KERNEL_CHECK(c);
     return 0;
 }
@@ -501,9 +556,14 @@ static int tc_ensure_prefix(dipb_msa* m, size_t rows) {
     dipb_ctx* c = m->ctx;
     if (rows > (size_t)m->n) rows = (size_t)m->n;
     if (!m->tc_ks) {
+        // operand format: e2m1 (4 bits per element in HBM / L2, kind::f8f6f4, f32 accumulators: exact for these +-1 / 0 products,
+        // sums < 2^24) unless DIPB_TC_FMT=0 asks for int8 or one of the int8-only multicast cluster experiments is selected
+        const char* ef = getenv("DIPB_TC_FMT");
+        m->tc_fmt = (ef ? atoi(ef) == 2 : true) && !getenv("DIPB_MSA_TC_CLUSTER") ? 2 : 0;
         const int w32 = (m->seq_len + 31) / 32;
-        m->tc_ks = ((size_t)w32 * 96 + TC_KB - 1) / TC_KB * TC_KB;
+        m->tc_ks = ((size_t)w32 * 96 + TC_KB - 1) / TC_KB * TC_KB;     // K elements, padded to whole 128-element chunks ...
         m->tc_kv = ((size_t)w32 * 32 + TC_KB - 1) / TC_KB * TC_KB;
+        if (m->tc_fmt == 2) { m->tc_ks /= 2; m->tc_kv /= 2; }            // ... = bytes per row, two elements per byte for e2m1
     }
     const size_t full = ((size_t)m->n + 255) / 256 * 256;
     if (rows > m->tc_rows) {
@@ -578,7 +638,9 @@ static int tc_launch_c(dipb_msa* m, const TcOperands& op, TileListFn make_tiles,
         if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return DIPB_E_CUDA; }
         encode = (EncodeTiledFn)fn;
     }
-    auto kern = msa_tc_kernel<CM, CN>;
+    // (e2m1 operands: the plain 1 x 1 kernel only; the multicast cluster experiments keep int8, see tc_ensure_prefix)
+    const void* kern = (CM == 1 && CN == 1 && m->tc_fmt == 2) ? (const void*)msa_tc_kernel<1, 1, 2> : (const void*)msa_tc_kernel<CM, CN, 0>;
+    const int fmt = m->tc_fmt;
     constexpr int CSZ = CM * CN;
     DIPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     if (CSZ > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -599,19 +661,19 @@ static int tc_launch_c(dipb_msa* m, const TcOperands& op, TileListFn make_tiles,
     if (tiles.empty()) { *launched = true; return 0; }
     int rc;
     CUtensorMap mSA, mSB, mVA, mVB;
-    if ((rc = make_map(encode, &mSA, op.SA, m->tc_ks, op.rowsA, TC_M / CN)) || (rc = make_map(encode, &mSB, op.SB, m->tc_ks, op.rowsB, TC_N / CM)) ||
-        (rc = make_map(encode, &mVA, op.VA, m->tc_kv, op.rowsA, TC_M / CN)) || (rc = make_map(encode, &mVB, op.VB, m->tc_kv, op.rowsB, TC_N / CM)))
+    if ((rc = make_map(encode, &mSA, op.SA, m->tc_ks, op.rowsA, TC_M / CN, fmt)) || (rc = make_map(encode, &mSB, op.SB, m->tc_ks, op.rowsB, TC_N / CM, fmt)) ||
+        (rc = make_map(encode, &mVA, op.VA, m->tc_kv, op.rowsA, TC_M / CN, fmt)) || (rc = make_map(encode, &mVB, op.VB, m->tc_kv, op.rowsB, TC_N / CM, fmt)))
         return rc;
     int2* d_tiles = nullptr;
     DIPB_CUDA(pool_alloc(c, (void**)&d_tiles, sizeof(int2) * tiles.size()));
     DIPB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
     p.tiles = d_tiles; p.num_tiles = (int)tiles.size();
-    p.ns_chunks = (int)(m->tc_ks / TC_KB); p.nv_chunks = (int)(m->tc_kv / TC_KB);
+    p.ns_chunks = (int)(m->tc_ks * (fmt == 2 ? 2 : 1) / TC_KB); p.nv_chunks = (int)(m->tc_kv * (fmt == 2 ? 2 : 1) / TC_KB);
     p.nv = m->nv; p.n = m->n;
     const int use = p.num_tiles < nclusters ? p.num_tiles : nclusters;
     cfg.gridDim = dim3(use * CSZ);
     void* args[] = {&mSA, &mSB, &mVA, &mVB, &p};
-    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
+    cudaError_t e = cudaLaunchKernelExC(&cfg, kern, args);
     if (e != cudaSuccess) { pool_free(c, d_tiles); set_error("msa_tc: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
     c->launches++;
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -632,7 +694,8 @@ static int tc_launch_pair(dipb_msa* m, const TcOperands& op, TileListFn make_til
         if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return DIPB_E_CUDA; }
         encode = (EncodeTiledFn)fn;
     }
-    if (cudaFuncSetAttribute(msa_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const void* kern2 = m->tc_fmt == 2 ? (const void*)msa_tc2_kernel<2> : (const void*)msa_tc2_kernel<0>;
+    if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM) != cudaSuccess) { cudaGetLastError(); return 0; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = T2_SMEM; cfg.stream = c->stream;
     cudaLaunchAttribute at[1];
@@ -640,7 +703,7 @@ static int tc_launch_pair(dipb_msa* m, const TcOperands& op, TileListFn make_til
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int npairs = 0;
-    if (cudaOccupancyMaxActiveClusters(&npairs, msa_tc2_kernel, &cfg) != cudaSuccess || npairs < 1) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&npairs, kern2, &cfg) != cudaSuccess || npairs < 1) { cudaGetLastError(); return 0; }
     int sm_cols = 1;
     while ((sm_cols + 1) * (sm_cols + 1) <= npairs) sm_cols++;      // square tiles: square super-tile
     const int sm_rows = npairs / sm_cols;
@@ -649,19 +712,20 @@ static int tc_launch_pair(dipb_msa* m, const TcOperands& op, TileListFn make_til
     if (!force && (int)tiles.size() < 4 * npairs) return 0;      // too few 256 x 256 tiles to balance: 128 x 256 tiles of the 1-CTA kernel
     int rc;
     CUtensorMap mSA, mSB, mVA, mVB;
-    if ((rc = make_map(encode, &mSA, op.SA, m->tc_ks, op.rowsA, 128)) || (rc = make_map(encode, &mSB, op.SB, m->tc_ks, op.rowsB, 128)) ||
-        (rc = make_map(encode, &mVA, op.VA, m->tc_kv, op.rowsA, 128)) || (rc = make_map(encode, &mVB, op.VB, m->tc_kv, op.rowsB, 128)))
+    const int fmt = m->tc_fmt;
+    if ((rc = make_map(encode, &mSA, op.SA, m->tc_ks, op.rowsA, 128, fmt)) || (rc = make_map(encode, &mSB, op.SB, m->tc_ks, op.rowsB, 128, fmt)) ||
+        (rc = make_map(encode, &mVA, op.VA, m->tc_kv, op.rowsA, 128, fmt)) || (rc = make_map(encode, &mVB, op.VB, m->tc_kv, op.rowsB, 128, fmt)))
         return rc;
     int2* d_tiles = nullptr;
     DIPB_CUDA(pool_alloc(c, (void**)&d_tiles, sizeof(int2) * tiles.size()));
     DIPB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
     p.tiles = d_tiles; p.num_tiles = (int)tiles.size();
-    p.ns_chunks = (int)(m->tc_ks / TC_KB); p.nv_chunks = (int)(m->tc_kv / TC_KB);
+    p.ns_chunks = (int)(m->tc_ks * (fmt == 2 ? 2 : 1) / TC_KB); p.nv_chunks = (int)(m->tc_kv * (fmt == 2 ? 2 : 1) / TC_KB);
     p.nv = m->nv; p.n = m->n;
     const int use = p.num_tiles < npairs ? p.num_tiles : npairs;
     cfg.gridDim = dim3(use * 2);
     void* args[] = {&mSA, &mSB, &mVA, &mVB, &p};
-    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)msa_tc2_kernel, args);
+    cudaError_t e = cudaLaunchKernelExC(&cfg, kern2, args);
     if (e != cudaSuccess) { pool_free(c, d_tiles); set_error("msa_tc2: launch failed: %s", cudaGetErrorString(e)); return DIPB_E_CUDA; }
     c->launches++;
     DIPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -689,7 +753,7 @@ static int tc_launch(dipb_msa* m, int r0, int r1, int ncols, TileListFn make_til
     // ingest, not by L2 or DRAM (profiles/r1_ncu_tc_multicast.json) -- so independent CTAs on all 148 SMs stay the default.
     const char* e = getenv("DIPB_MSA_TC_CLUSTER");
     int cm = 1, cn = 1;
-    if (e && e[0] >= '1' && e[0] <= '4' && e[1] == 'x' && e[2] >= '1' && e[2] <= '4') { cm = e[0] - '0'; cn = e[2] - '0'; }
+    if (m->tc_fmt == 0 && e && e[0] >= '1' && e[0] <= '4' && e[1] == 'x' && e[2] >= '1' && e[2] <= '4') { cm = e[0] - '0'; cn = e[2] - '0'; }   // (int8 operands only)
     bool ok = false;
     if (cm == 4 && cn == 4) rc = tc_launch_c<4, 4>(m, op, make_tiles, arg, p, &ok);
     else if (cm == 2 && cn == 4) rc = tc_launch_c<2, 4>(m, op, make_tiles, arg, p, &ok);

@@ -161,6 +161,31 @@ def test_tensor_core_path_is_bit_identical(ctx, oracle, n, L, dist_type, pair, m
     assert np.allclose(got, oracle.msa_dist_matrix(P, L, dist_type), rtol=1e-6, atol=0, equal_nan=True)
 
 
+@pytest.mark.parametrize("fmt", ["0", "2"])
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_tensor_core_operand_formats_at_full_length(ctx, fmt, pair, monkeypatch):
+    """Both operand encodings of msa_tc.cu (int8 + kind::i8 with s32 accumulators; e2m1, 4 bits per element in HBM, unpacked by
+    the TMA, kind::f8f6f4 with f32 accumulators -- the default) against the popcount kernel at the headline sequence length:
+    near-identical sequences drive every accumulator to ~ 3 L = 90 000, past 2^16, where an inexact f32 accumulation would show."""
+    from dipper_b200 import synth
+    n, L = 600, 30000
+    rng = np.random.default_rng(5)
+    codes = np.tile(rng.integers(0, 4, L).astype(np.uint8), (n, 1))
+    mut = rng.random((n, L)) < 0.01
+    codes[mut] = rng.integers(0, 4, int(mut.sum())).astype(np.uint8)
+    codes[rng.random((n, L)) < 0.002] = 4
+    P = synth.pack4_np(codes)
+    prm = api.Param(distanceType=2, in_="m")
+    monkeypatch.setenv("DIPB_MSA_TC2", pair)
+    monkeypatch.setenv("DIPB_MSA_TC", "0")
+    ref = upload(ctx, P, L).distMatrix(prm).to_host()
+    monkeypatch.setenv("DIPB_MSA_TC", "2")
+    monkeypatch.setenv("DIPB_TC_FMT", fmt)
+    got = upload(ctx, P, L).distMatrix(prm).to_host()      # (the format is fixed at an alignment's first expansion)
+    assert np.array_equal(got, ref, equal_nan=True)
+    assert ref[1, 0] > 0 and np.isfinite(ref).all()
+
+
 @pytest.mark.parametrize("dist_type", [1, 2])
 @pytest.mark.parametrize("r0,r1,ncols", [(0, 64, 700), (100, 700, 100), (130, 515, 515), (511, 700, 257)])
 @pytest.mark.parametrize("pair", ["0", "1"])
