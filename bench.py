@@ -3,7 +3,7 @@
 
 Workload (config C3, BASELINE.json configs[2]): synthetic aligned MSA, 30 000 tips x
 30 000 sites, JC distance matrix (-d 2) then conventional NJ (-m 2).  One "step" = one
-full pass: packed sequences -> int8 operand expansion -> fp64 distance matrix -> NJ tree.
+full pass: packed sequences -> operand expansion (e2m1 simplex / validity codes) -> fp64 distance matrix -> NJ tree.
 
   value   whole-job pairs/s with the packed sequences already resident in HBM: K steps between two
           barriers + synchronize, max over ranks ("phases" are CUDA-event times inside the library).  The
@@ -14,7 +14,7 @@ full pass: packed sequences -> int8 operand expansion -> fp64 distance matrix ->
           bytes the kernel itself reads and writes (it is latency / issue bound: frac ~ 0.03); the
           reference's full-scan cost sum_n (n^2+4n)*8 B (SURVEY.md 8d yard-stick) is reported separately as
           "speedup_vs_fullscan_bytes", not as a roofline
-  dist_kernel  the tcgen05 int8 distance kernel against the tensor roofline (int8 dense
+  dist_kernel  the tcgen05 distance kernel (8-bit-container MMA rate) against the tensor roofline (int8 / fp8 dense
           peak taken as 2x the measured bf16 peak); traffic from the committed ncu capture
   cpu_baseline  the OpenMP oracle port on a bounded sample (rank 0, N=1 only)
 
@@ -142,7 +142,7 @@ def dist_algorithmic_intops(n, L):
 
 
 def dist_tensor_ops(n, L):
-    # tensor formulation (msa_tc.cu): per pair one int8 dot product of length 3L (simplex codes) and one of
+    # tensor formulation (msa_tc.cu): per pair one {-1,0,1} dot product of length 3L (simplex codes) and one of
     # length L (validity), 2 ops per multiply-add
     return n * (n - 1) / 2 * (4.0 * L) * 2.0
 
@@ -279,7 +279,7 @@ def main():
     def one_step(msa, timed):
         """resident-input step: distances (sharded) -> reduce -> NJ on rank 0. Returns (dist_ms, comm_ms, nj_ms)."""
         r0, r1 = shard(rank)
-        msa.dropOperands()                # the int8 expansion is part of every step
+        msa.dropOperands()                # the operand expansion is part of every step
         if world == 1:
             M = msa.distMatrix(prm)
         else:
@@ -409,13 +409,13 @@ def main():
         out = {
             "metric": METRIC, "value": pairs / (step_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "int8 dot products -> int32 counts -> f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "e2m1 {-1,0,1} dot products -> exact integer counts in f32 accumulators (< 2^24; bit-identical to the int8/int32 and popcount paths) -> f64", "data": "synthetic",
             "config": workload_config(n, L),
             "sharding": "distance row blocks over %d GPU(s), gathered on rank 0; NJ on rank 0 (BASELINE configs[2])" % world,
             "phases": {"dist_ms": d_ms, "reduce_ms": c_ms, "nj_ms": nj_ms,
                        "dist_pairs_per_sec": pairs / (d_ms / 1e3), "nj_wall_s": nj_ms / 1e3,
                        "nj_us_per_merge": nj_ms * 1e3 / max(n - 2, 1),
-                       "note": "dist_ms includes the int8 operand expansion of every step"},
+                       "note": "dist_ms includes the operand expansion of every step"},
             "roofline": {"bound": "hbm", "achieved": nj_ach, "peak": peak, "unit": "GB/s", "frac": nj_ach / peak,
                          "traffic": ncu_traffic("r2_ncu_nj_cluster_30k.json"), "peak_source": peak_src,
                          "kernel": "nj_cluster_kernel (one launch = all %d merges; %.0f %% of the step)" % (n - 2, 100.0 * nj_ms / step_ms),
@@ -428,9 +428,9 @@ def main():
                          "note": "not bandwidth bound: a chain of 3 cluster barriers per merge whose phases are instruction-issue and "
                                  "latency bound (profiles/r2_nj_cluster_phases.txt); fullscan_bytes = SURVEY.md 8(d) yard-stick "
                                  "(what the reference's search reads), kept apart from the roofline"},
-            "dist_kernel": {"kernel": "msa_tc2_kernel (tcgen05.mma.cta_group::2.kind::i8, 256x256 tiles per CTA pair) + msa_tc_expand_kernel", "bound": "tensor",
+            "dist_kernel": {"kernel": "msa_tc2_kernel<2> (tcgen05.mma.cta_group::2.kind::f8f6f4 on e2m1 operands unpacked by the TMA, 256x256 tiles per CTA pair; kind::i8 behind DIPB_TC_FMT=0) + msa_tc_expand_kernel", "bound": "tensor",
                             "achieved": tc_ach, "peak": 2.0 * peak_bf16, "unit": "TOP/s", "frac": tc_ach / (2.0 * peak_bf16),
-                            "peak_definition": "int8 dense = 2 x measured bf16 dense burst (%s); no measured int8 peak exists" % peak_src,
+                            "peak_definition": "8-bit dense (int8 = fp8 = f8f6f4 rate) = 2 x measured bf16 dense burst (%s); no measured 8-bit peak exists" % peak_src,
                             "algorithmic_ops": tc_ops, "traffic": ncu_traffic("r2_ncu_tc2_30k.json") or ncu_traffic("r1_ncu_tc2_30k.json"),
                             "traffic_source": "profiles/r2_ncu_tc2_30k.json if present, else r1_ncu_tc2_30k.json (dram read + write of one msa_tc2_kernel launch)",
                             "algorithmic_bytes": float(n) * ((L + 15) // 16) * 8 + float(n) * n * 8,
