@@ -102,6 +102,11 @@ __device__ __forceinline__ unsigned int half_min_u32(unsigned int v, int lane) {
 }
 __device__ __forceinline__ double warp_min_f64(double v) { return dec_f64(warp_min_u64(enc_f64(v))); }
 __device__ __forceinline__ double warp_max_f64(double v) { return -warp_min_f64(-v); }
+// Warp maximum / minimum of values that only steer the pruning (the per-merge drift of u, the upper bound of the carried
+// candidates): rounded UP to fp32 first -- larger is the safe side for both -- so that one redux does what the exact fp64
+// form needs two of, plus the 64-bit encode / decode.  (Sentinels +-1e300 become +-FLT_MAX / inf, still sentinels.)
+__device__ __forceinline__ double warp_max_up32(double v) { return (double)dec_f32(__reduce_max_sync(0xffffffffu, enc_f32(__double2float_ru(v)))); }
+__device__ __forceinline__ double warp_min_up32(double v) { return (double)dec_f32(__reduce_min_sync(0xffffffffu, enc_f32(__double2float_ru(v)))); }
 
 // (Row / column indices are never negative where an owner or a slot is derived from them: the casts to unsigned below turn
 // the divisions by the cluster size into one shift or mask each -- the signed forms cost ~5 instructions apiece, in every warp.)
@@ -504,17 +509,17 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 double pv = 1e300;
                 if (pend >= 0 && !(lane & 1)) pv = (pool_d[pc] - un) - uo2;
                 if (lane < 2 * PCW && !(lane & 1)) pool_t[pc] = pv;
-                pv = warp_min_f64(pv);
+                pv = warp_min_up32(pv);
                 if (lane == 0) s_red2[w] = pv;
             }
-            dmx = warp_max_f64(dmx);
+            dmx = warp_max_up32(dmx);
             if (lane == 0) s_red[w] = dmx;
             CL_MARK(21);
             __syncthreads();
             CL_MARK(22);
             if (w == 0) {
-                const double m = warp_max_f64(lane < NW ? s_red[lane] : -1e300);
-                const double pm = warp_min_f64(lane < NW ? s_red2[lane] : 1e300);
+                const double m = warp_max_up32(lane < NW ? s_red[lane] : -1e300);
+                const double pm = warp_min_up32(lane < NW ? s_red2[lane] : 1e300);
                 if (lane < CS) { st_peer_f64(&drift_all[rank], lane, m); st_peer_f64(&ubmin_all[rank], lane, pm); }
             }
             cur ^= 1;
@@ -547,8 +552,8 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                 if (w == NW - 1) {
                     // drift and upper bound of the cluster (pushed by every CTA in phase A): one warp, once -- every thread
                     // folding the 16 values itself cost ~800 cycles of issue
-                    const double dr = warp_max_f64(lane < CS ? drift_all[lane] : -1e300);
-                    const double um = warp_min_f64(lane < CS ? ubmin_all[lane] : 1e300);
+                    const double dr = warp_max_up32(lane < CS ? drift_all[lane] : -1e300);
+                    const double um = warp_min_up32(lane < CS ? ubmin_all[lane] : 1e300);
                     if (lane == 0) {
                         s_C = C + dr;
                         s_ub = um;

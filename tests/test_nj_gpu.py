@@ -78,6 +78,34 @@ def test_pruned_equals_fullscan_at_scale(ctx):
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("env", [{"DIPB_NJ_CLUSTER": "8"}, {"DIPB_NJ_THREADS": "256"}, {"DIPB_NJ_THREADS": "1024"}, {"DIPB_NJ_HELPERS": "0"},
+                                 {"DIPB_NJ_HELPERS": "1"}, {"DIPB_NJ_SLACK": "0"}, {"DIPB_NJ_DBG": "1"}])
+@pytest.mark.parametrize("n", [130, 1500])
+def test_cluster_kernel_variants_equal_fullscan(ctx, env, n, monkeypatch):
+    """The launch shapes and modes of nj_cluster_kernel that the default run does not take (8-CTA cluster, 256 / 1024 threads,
+    no / one helper cluster, no early unit refresh, whole-row rescans): all must give the exhaustive search's arrays.  n = 130
+    also crosses the 128-row staging tile on the first search."""
+    codes, P, _ = make_msa(n, 1200, seed=300 + n, gap_runs=False)
+    msa = api.MSADeviceArrays(ctx)
+    msa.allocateDeviceArrays(P, np.full(n, 1200, np.uint64), n, api.Param(in_="m"))
+    prm = api.Param(distanceType=2, in_="m")
+
+    def run(algo):
+        nj = api.NJDeviceArrays(ctx)
+        nj.getDismatrix(n, prm, msaDeviceArrays=msa)
+        nj.findNeighbourJoiningTree(synth.names(n), algo)
+        r = nj.result
+        nj.deallocateDeviceArrays()
+        return r
+
+    ref = run(api.NJ_FULLSCAN)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run(api.NJ_CLUSTER)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+
+
 def test_msa_to_tree_end_to_end_rf_zero(ctx, oracle):
     """-i m -d 2 -m 2: CUDA distances + CUDA NJ vs oracle distances + oracle NJ."""
     n, L = 500, 3000
