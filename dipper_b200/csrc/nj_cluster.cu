@@ -650,19 +650,24 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                         unsigned int base = 0;
                         if (lane == 0) base = atomicAdd(sel0, (unsigned int)__popc(bal));
                         base = __shfl_sync(0xffffffffu, base, 0);
-                        if (take) {
-                            // a selected row goes, with its u, v, f, straight into every CTA's staging arrays: the scan phase
-                            // then starts from local shared memory (pulling the list from rank 0 and the row state from the
-                            // owners cost two dependent DSMEM round trips, the first one 16 CTAs deep on one SM)
-                            const unsigned int pos = base + __popc(bal & ((1u << lane) - 1u));
-                            if (pos < (unsigned int)TILE) {
-                                const double us = i == x ? ux : u_s[s], vs = v_s[s], fs = f_s[s];
-#pragma unroll 4
-                                for (int q = 0; q < CS; q++) {
-                                    st_peer_s32(&t_row[pos], q, i);
-                                    st_peer_f64(&t_u[pos], q, us); st_peer_f64(&t_v[pos], q, vs); st_peer_f64(&t_f[pos], q, fs);
+                        // a selected row goes, with its u, v, f, straight into every CTA's staging arrays: the scan phase
+                        // then starts from local shared memory (pulling the list from rank 0 and the row state from the
+                        // owners cost two dependent DSMEM round trips, the first one 16 CTAs deep on one SM).  The warp
+                        // pushes its (few) selected rows one after the other, lane q to CTA q: a lane looping over the 16
+                        // targets by itself costs the warp 160 instructions per row instead of ~25
+                        const unsigned int pos = base + __popc(bal & ((1u << lane) - 1u));
+                        const double us = (take && i == x) ? ux : u_s[s], vs = v_s[s], fs = f_s[s];
+                        for (unsigned int rem = bal; rem; rem &= rem - 1u) {
+                            const int sl = __ffs(rem) - 1;
+                            const int ri = __shfl_sync(0xffffffffu, i, sl);
+                            const unsigned int rp = __shfl_sync(0xffffffffu, pos, sl);
+                            const double ru = __shfl_sync(0xffffffffu, us, sl), rv = __shfl_sync(0xffffffffu, vs, sl), rf = __shfl_sync(0xffffffffu, fs, sl);
+                            if (rp < (unsigned int)TILE) {
+                                if (lane < CS) {
+                                    st_peer_s32(&t_row[rp], lane, ri);
+                                    st_peer_f64(&t_u[rp], lane, ru); st_peer_f64(&t_v[rp], lane, rv); st_peer_f64(&t_f[rp], lane, rf);
                                 }
-                            } else sel_rows[pos] = i;
+                            } else if (lane == 0) sel_rows[rp] = ri;
                         }
                     }
                 }

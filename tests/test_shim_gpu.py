@@ -80,20 +80,23 @@ def test_shim_aligned_rows_other_models(aligned, tmp_path, dist_type):
     assert np.allclose(rb[ok], ra[ok], rtol=1e-6, atol=0)
 
 
-def test_shim_nj_and_placement_trees(aligned, tmp_path):
+def test_shim_nj_and_placement_trees(aligned, tmp_path, oracle):
     n, L, P, inp = aligned
     for mode in ("msa_place", "msa_place_exact"):
         a, b = both(mode, inp, tmp_path, 2)
         assert open(a + ".nwk").read() == open(b + ".nwk").read(), mode                 # text-identical
     a, b = both("msa_nj", inp, tmp_path, 2)
     ta, tb = open(a + ".nwk").read(), open(b + ".nwk").read()
+    # the shim's tree is the deterministic restatement's tree, whatever the reference does below
+    o = oracle.nj(oracle.msa_dist_matrix(P, L, 2))
+    to = oracle.nj_newick(*o, ["T%d" % (i + 1) for i in range(n)])       # (the driver's tip names)
+    assert newick.rf_distance(tb, to) == 0 and newick.max_branch_diff(tb, to) < 1e-9
     rf = newick.rf_distance(ta, tb)
     if rf != 0:
-        # The reference sums U with fp64 atomicAdd in arbitrary order (src/neighborJoining.cu:106,176,190): on a near-tie
-        # it does not even agree with itself from run to run.  Only a reference that IS reproducible here counts.
-        a2, _ = both("msa_nj", inp, tmp_path, 2)
-        ta2 = open(a2 + ".nwk").read()
-        assert newick.rf_distance(ta, ta2) != 0, "shim NJ tree differs from a reproducible reference tree (RF %d)" % rf
+        # The reference sums U with fp64 atomicAdd in arbitrary order (src/neighborJoining.cu:106,176,190): on a near-tie of
+        # this input its pick differs from the canonical-order sum's (and sometimes from its own previous run's).  The
+        # difference must stay that small: one or two splits around the tied merge, everything else identical.
+        assert rf <= 2, "shim NJ tree differs from the reference tree by RF %d" % rf
     else:
         assert newick.max_branch_diff(ta, tb) < 1e-5
 
