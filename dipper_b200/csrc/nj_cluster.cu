@@ -20,15 +20,20 @@
 //
 // Iteration (3 cluster barriers; everything a peer needs after a barrier was pushed into its shared memory
 // before it -- measured: pulling the same word from one CTA by 512 warps serialises for ~1500 cycles):
-//   D  every CTA reduces the published CTA winners to the same (x, y); rank 0 logs the merge
-//   A  owners update rows x, y (move `last` into y), U (double buffered), u; push chunk sums and max u-drift;
+//   D  every WARP reduces the published CTA winners to the same (x, y) and keeps its own candidate-pool slots (no CTA
+//      barrier in this stretch); rank 0 logs the merge
+//   A  owners update rows x, y (move `last` into y), U (double buffered), u; push chunk sums and max u-drift; in the
+//      shadow of the row loads the owners RESOLVE the previous scan (below);
 //      the carried candidates are re-evaluated with the post-merge u of their two ends, which every CTA derives
 //      itself from the pre-merge U (the other buffer) and rows x, y -- so the upper bound travels with the drift  | barrier
 //   B  U[x] (canonical sum order), C += drift, ub = min over CTAs; ring the helpers; owners fold the new column
 //      into K and select rows with lb <= ub                                                             | barrier
 //   C  every CTA stages the selected rows (index, u, v, f) in shared memory and scans, of its column chunks of
 //      them, only the UNITS whose own lower-bound key reaches ub (see Kb below); combines per-row minima in shared
-//      memory, pushes them to the row owners' K; publishes its winner                                    | barrier
+//      memory, writes (key of its minimum, column, key of its runner-up) of every staged row into its SLOT in the
+//      row owner's shared memory (one 16-byte DSMEM store, no atomics); publishes its winner             | barrier
+// Resolve: the owner of a staged row reads its CS slots locally: the smallest (key, column) becomes the tracked partner
+// (K1, a; the exact distance D[r][a] is fetched with phase A's loads), everything else bounds the runner-up K2.
 //
 // Unit keys (Kb).  A scan unit = UC column chunks of one row in one CTA (UC * 32 columns, UC * 256 bytes of D).
 // Kb[row][cta][part] holds, like the row keys, (min over the unit's columns of d - u_j) + C at evaluation time,
