@@ -497,8 +497,12 @@ static int mash_launch(dipb_mash* m, MashTileParams p) {
     if (rows <= 0 || ncols <= 0) return 0;
     // ---- rank-compressed, interleaved tiles (default)
     const char* er = getenv("DIPB_MASH_RANKS");   // 0: keep the 64-bit hashes (first versions, kept for comparison)
-    const char* etb = getenv("DIPB_MASH_TB");     // 16: force the 16-row tile (comparison)
-    int TB = ((size_t)(m->s + MR_PAD) * (MR_TA + 24) * sizeof(uint32_t) <= 227 * 1024 && !(etb && atoi(etb) == 16)) ? 24 : 16;
+    // 24-row tiles for whole (triangular) matrices when the sketches fit: measured 38.4 vs 42.6 ms at C2; 16-row tiles for the
+    // row blocks of placement / D&C, where the 24-row tile measured 14 % SLOWER (120 000 tips: 9.3 vs 8.1 s).  DIPB_MASH_TB=16
+    // / =24 forces one
+    const char* etb = getenv("DIPB_MASH_TB");
+    const bool fits24 = (size_t)(m->s + MR_PAD) * (MR_TA + 24) * sizeof(uint32_t) <= 227 * 1024;
+    int TB = fits24 && (etb ? atoi(etb) == 24 : p.tri != 0) ? 24 : 16;
     const size_t rk_smem = (size_t)(m->s + MR_PAD) * (MR_TA + TB) * sizeof(uint32_t);
     if (!(er && atoi(er) == 0) && (size_t)m->n * m->s < 0xFFFFFFFFull && rk_smem <= 227 * 1024) {
         if (!m->ranks) { int rc = mash_build_ranks(m); if (rc) return rc; }
