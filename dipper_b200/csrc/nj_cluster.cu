@@ -59,7 +59,7 @@ namespace dipb {
 namespace {
 
 constexpr int MAXW = 32;      // warps per CTA at most
-constexpr int CPOOL = 128;    // carried candidate pairs per CTA
+constexpr int CPOOL = 64;     // carried candidate pairs per CTA (128: 13.46 us per merge, 64: 13.29, 32: 13.29 at C3)
 constexpr int MAXCS = 16;
 constexpr int TILE = 128;     // selected rows staged in shared memory at a time
 constexpr int MAXPARTS = 32;  // units per row and CTA at most (the staged qualification mask is one word)
@@ -953,14 +953,7 @@ nj_cluster_kernel(double* __restrict__ D, size_t ld, const double* __restrict__ 
                     cluster.sync();
                 }
             }
-            // the next merge reads row n - 1 (it moves into the freed slot): pull my chunks of it into L2 now
-            if (n > 3 && lane < 2) {
-                const int pch = (n - 1 + 31) >> 5;
-                for (int lw = w; lw * CS + rank < pch; lw += NW) {
-                    const int col = (lw * CS + rank) * 32 + lane * 16;
-                    if (col < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(D + (size_t)(n - 1) * ld + col));
-                }
-            }
+            // (Prefetching the next merge's row n - 1 into L2 here measured 0.1 us per merge SLOWER than not doing it.)
             // warp winner -> CTA winner (reference order), every warp winner also feeds the candidate pool
             {
                 const int wl = warp_best_lane(bt, bi, bj, n);
