@@ -16,6 +16,7 @@ void ctx_release(dipb_ctx* c) {
     if (!c || c->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);   // frees queued by the children are stream ordered
+    if (c->stage) cudaFree(c->stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -120,9 +121,21 @@ int dipb_msa_upload_flat(dipb_ctx* c, const uint64_t* flat, size_t n, uint64_t s
     DIPB_CUDA(cudaSetDevice(c->device));
     size_t comp = (seq_len + 15) / 16;
     uint64_t* d_in = nullptr;
-    // (deliberately NOT from the stream-ordered pool: a short-lived 450 MB block there splits the free 7 GB block the next
-    // matrix wants and makes the pool grow again -- measured 90-270 ms per tree instead of 1-3 ms for this pair)
-    DIPB_CUDA(cudaMalloc(&d_in, n * comp * sizeof(uint64_t)));
+    // Staging block.  Deliberately NOT from the stream-ordered pool: a short-lived 450 MB block there splits the free 7 GB
+    // block the next matrix wants and makes the pool grow again (measured 90-270 ms per tree).  Up to 1 GB it is kept with
+    // the context and reused by the next upload; larger inputs allocate and free their own.
+    const size_t in_bytes = n * comp * sizeof(uint64_t);
+    const bool cached = in_bytes <= ((size_t)1 << 30);
+    if (cached) {
+        if (c->stage_bytes < in_bytes) {
+            if (c->stage) { cudaStreamSynchronize(c->stream); cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0; }
+            DIPB_CUDA(cudaMalloc(&c->stage, in_bytes));
+            c->stage_bytes = in_bytes;
+        }
+        d_in = static_cast<uint64_t*>(c->stage);
+    } else {
+        DIPB_CUDA(cudaMalloc(&d_in, in_bytes));
+    }
     int rc = timer_begin(c);
     if (!rc && cudaMemcpyAsync(d_in, flat, n * comp * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
         set_error("dipb_msa_upload_flat: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -132,7 +145,7 @@ int dipb_msa_upload_flat(dipb_ctx* c, const uint64_t* flat, size_t n, uint64_t s
     if (!rc) rc = msa_create(c, d_in, n, seq_len, &m);
     if (!rc) rc = timer_end(c, DIPB_T_MSA_UPLOAD);
     cudaStreamSynchronize(c->stream);
-    cudaFree(d_in);
+    if (!cached) cudaFree(d_in);
     if (rc) { dipb_msa_free(m); return rc; }
     *out = m;
     return 0;

@@ -51,6 +51,8 @@ struct dipb_ctx {
     std::atomic<int> refs{1};
     bool destroyed = false;               // dipb_destroy was called
     std::vector<int32_t> last_clusters;   // test hook storage of dipb_dc_cluster_ids (per context)
+    void* stage = nullptr;                // H2D staging block of the aligned uploads (<= 1 GB: kept and reused, a cudaMalloc /
+    size_t stage_bytes = 0;               // cudaFree pair per upload costs 10-100 ms on some hosts); freed with the context
     unsigned long long nj_occ_key = 0;    // nj_cluster launch: last (cluster size, threads, shared memory) asked of the
     int nj_occ_clusters = 0;              // occupancy calculator and its answer (the query costs ~1.5 ms per tree)
 };
