@@ -48,22 +48,24 @@ __global__ void msa_tc_expand_kernel(const uint32_t* __restrict__ planes, int ro
         // 48 bytes of S (three 16-byte runs of 32 elements) and 16 bytes of V per 32-site word
         uint8_t* so4 = reinterpret_cast<uint8_t*>(S) + (size_t)sd * ks + (size_t)w * 48;
         uint8_t* vo4 = reinterpret_cast<uint8_t*>(V) + (size_t)sd * kv + (size_t)w * 16;
-#pragma unroll 4
+        uint32_t e0[4], e1[4], e2[4], vv[4];
+#pragma unroll
         for (int q = 0; q < 4; q++) {
-            uint32_t e0 = 0, e1 = 0, e2 = 0, vv = 0;
+            e0[q] = e1[q] = e2[q] = vv[q] = 0u;
 #pragma unroll
             for (int t = 0; t < 8; t++) {
                 const int bit = 8 * q + t;
                 const int ok = (v >> bit) & 1, x0 = (b0 >> bit) & 1, x1 = (b1 >> bit) & 1;
                 const uint32_t n0 = ok ? (x1 ? 0xAu : 0x2u) : 0u, n1 = ok ? (x0 ? 0xAu : 0x2u) : 0u, n2 = ok ? ((x0 ^ x1) ? 0xAu : 0x2u) : 0u;
-                e0 |= n0 << (4 * t); e1 |= n1 << (4 * t); e2 |= n2 << (4 * t);
-                vv |= (ok ? 0x2u : 0u) << (4 * t);
+                e0[q] |= n0 << (4 * t); e1[q] |= n1 << (4 * t); e2[q] |= n2 << (4 * t);
+                vv[q] |= (ok ? 0x2u : 0u) << (4 * t);
             }
-            reinterpret_cast<uint32_t*>(so4)[q] = e0;
-            reinterpret_cast<uint32_t*>(so4 + 16)[q] = e1;
-            reinterpret_cast<uint32_t*>(so4 + 32)[q] = e2;
-            reinterpret_cast<uint32_t*>(vo4)[q] = vv;
         }
+        // (16-byte stores: a thread's 48 + 16 bytes leave in 4 instructions instead of 16)
+        reinterpret_cast<uint4*>(so4)[0] = make_uint4(e0[0], e0[1], e0[2], e0[3]);
+        reinterpret_cast<uint4*>(so4)[1] = make_uint4(e1[0], e1[1], e1[2], e1[3]);
+        reinterpret_cast<uint4*>(so4)[2] = make_uint4(e2[0], e2[1], e2[2], e2[3]);
+        reinterpret_cast<uint4*>(vo4)[0] = make_uint4(vv[0], vv[1], vv[2], vv[3]);
         return;
     }
     int8_t* so = S + (size_t)sd * ks + (size_t)w * 96;
