@@ -14,7 +14,13 @@
 //   warp 1   MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::i8 (M128 N256 K32), four per
 //            stage, D1 in TMEM columns [0,256), D2 in [256,512); tcgen05.commit frees the stage
 //   warps 2-5 epilogue: tcgen05.ld 32x32b, fp64 p / JC in the reference's expression order, D[i][j] + mirror
-// The GEMM is L2-bandwidth bound (384 operand bytes per 32 768 outputs per K byte), see DESIGN.md §4.1.
+// Operand formats (template parameter FMT, fixed per alignment at its first expansion):
+//   2 (default)  e2m1 nibbles, two elements per byte in HBM / L2; the tensor maps are CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B, so
+//                the TMA unpacks 16 nibbles into a 16-byte group of 8 data + 8 padding bytes (same shared-memory footprint,
+//                swizzle, descriptors and K = 32 step); tcgen05.mma.kind::f8f6f4 with f32 accumulators -- exact: every product
+//                is -1, 0 or 1 and every partial sum an integer < 2^24.  expect_tx counts the PACKED bytes.
+//   0            int8, kind::i8, s32 accumulators (DIPB_TC_FMT=0; the multicast cluster experiments)
+// See DESIGN.md 4.1 for the measurements (neither L2->SM nor DRAM bytes bound the kernel; the epilogue is not overlapped).
 #include <cuda.h>
 #include <algorithm>
 #include <vector>

@@ -82,7 +82,7 @@ int dipb_msa_upload(dipb_ctx *ctx, const uint64_t *const *seq4, const uint64_t *
 /* same, sequences contiguous: flat[i * ceil(seq_len/16) + w] */
 int dipb_msa_upload_flat(dipb_ctx *ctx, const uint64_t *flat, size_t n, uint64_t seq_len, dipb_msa **out);
 void dipb_msa_free(dipb_msa *msa);
-/* Releases the tensor-core operand buffers (int8 expansion of the packed sequences, 4 bytes per site) that the first
+/* Releases the tensor-core operand buffers (e2m1 / int8 expansion of the packed sequences, 2 / 4 bytes per site) that the first
  * p / JC matrix or row block builds and keeps for later calls; the next such call rebuilds them.  No reference
  * counterpart (the reference keeps only the packed sequences, src/MSA.cu:14-72); used to return 3.6 GB at 30 000 x
  * 30 000 and by bench.py so that every timed step pays for the expansion. */
